@@ -1,0 +1,140 @@
+"""TEST INFRASTRUCTURE ONLY -- seeded parity cases shared by the golden generator, the tests,
+smoke() and the bench's CPU leg.  Everything is regenerated from seeds (CPU mt19937 generator), so
+fixtures under tests/golden/ only hold *outputs* of the reference, never weights or inputs.
+
+Weights are deliberately NOT the stock init: LayerNorm gains U(.5,1.5), biases
+N(0,.1), rel-pos tables N(0,.5), c_attn U(.5,1.5) -- the stock 1/0/0.02 values hide bugs.
+"""
+from typing import Dict, List, Tuple
+
+import torch
+
+from .oracle_model import AUDIO, IMAGE, PAD, TEXT, OracleConfig, OSlot
+
+# name -> dict(cfg=..., adaptors=..., inputs spec)
+CASES = {
+    # small configs whose full logits fit in a fixture
+    "text_A": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A"),
+        adaptors=("text",), kind="text", B=3, S=24, T=16,
+    ),
+    "text_B": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="B"),
+        adaptors=("text",), kind="text", B=3, S=24, T=16,
+    ),
+    "patch_B": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="B"),
+        adaptors=("text", "image_patch_embed"), kind="patch", B=2, S=8, T=12,
+    ),
+    "audio_A": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A"),
+        adaptors=("text", "audio"), kind="audio", B=2, S=6, T=10, L=200,
+    ),
+    # BASELINE.json configs[0]: text_infilling, OFA-tiny 4L/4L d=256, seq 128, bs 2 (checksums only)
+    "cfg1_tiny": dict(
+        cfg=dict(embed_dim=256, heads=4, ffn_dim=1024, enc_layers=4, dec_layers=4, vocab=50265, mode="A"),
+        adaptors=("text",), kind="text", B=2, S=128, T=128,
+    ),
+}
+
+
+def oracle_cfg(name) -> OracleConfig:
+    return OracleConfig(**CASES[name]["cfg"])
+
+
+def synth_tensor(name: str, shape, g: torch.Generator) -> torch.Tensor:
+    """Deterministic parameter values by role (role decided from the parameter name)."""
+    shape = tuple(shape)
+    leaf = name.rsplit(".", 1)[-1]
+    if "rel_pos_table" in name:
+        return torch.randn(shape, generator=g) * 0.5
+    if leaf == "c_attn":
+        return torch.rand(shape, generator=g) + 0.5
+    is_norm = any(t in name for t in ("layer_norm", "layernorm", "_ln.", "attn_ln", ".bn", "downsample.1"))
+    if is_norm and leaf == "weight":
+        return torch.rand(shape, generator=g) + 0.5
+    if is_norm and leaf == "bias":
+        return torch.randn(shape, generator=g) * 0.1
+    if leaf == "running_mean":
+        return torch.zeros(shape)
+    if leaf == "running_var":
+        return torch.ones(shape)
+    if leaf == "bias":
+        return torch.randn(shape, generator=g) * 0.02
+    if "embed_images" in name and leaf == "weight" and len(shape) == 4:  # resnet convs: fan-in scaled
+        fan_in = shape[1] * shape[2] * shape[3]
+        return torch.randn(shape, generator=g) * (2.0 / fan_in) ** 0.5
+    if "subsample.conv" in name and leaf == "weight":
+        fan_in = shape[1] * shape[2] * shape[3]
+        return torch.randn(shape, generator=g) * (1.0 / fan_in) ** 0.5
+    if "subsample.out" in name and leaf == "weight":
+        return torch.randn(shape, generator=g) * (1.0 / shape[1]) ** 0.5
+    if "proj.weight" in name and len(shape) == 4:  # patch-embed conv
+        return torch.randn(shape, generator=g) * 0.02
+    if leaf in ("cls_token", "mask_emb"):
+        return torch.randn(shape, generator=g) * 0.02
+    # Linear / Embedding weights: BERT init (module/initialize.py:33-36)
+    return torch.randn(shape, generator=g) * 0.02
+
+
+def synth_state_dict(spec: Dict[str, Tuple[int, ...]], seed: int = 0) -> Dict[str, torch.Tensor]:
+    """spec: name -> shape for every floating-point parameter / BN buffer.  Tied tensors
+    (encoder/decoder embed_tokens) are generated once and shared."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for name in sorted(spec):
+        if name == "decoder.adaptor.embed_tokens.weight":
+            continue
+        t = synth_tensor(name, spec[name], g)
+        if name == "encoder.adaptor.embed_tokens.weight":
+            t[PAD].zero_()  # nn.Embedding(padding_idx) row (module/layer.py:8-15)
+        sd[name] = t
+    if "encoder.adaptor.embed_tokens.weight" in sd:
+        sd["decoder.adaptor.embed_tokens.weight"] = sd["encoder.adaptor.embed_tokens.weight"]
+    return sd
+
+
+def _tokens(g, B, T, V, ragged=True):
+    tok = torch.randint(4, V, (B, T), generator=g)
+    if ragged and B > 1:  # right-pad the last sequence by ~25% (collate_tokens default)
+        cut = T - max(1, T // 4)
+        tok[-1, cut:] = PAD
+    return tok
+
+
+def make_inputs(name: str, seed: int = 1234):
+    """Returns (slots: List[OSlot], target: LongTensor[B, T])."""
+    c = CASES[name]
+    g = torch.Generator().manual_seed(seed)
+    V = c["cfg"]["vocab"]
+    B, S, T = c["B"], c["S"], c["T"]
+    slots: List[OSlot] = []
+    if c["kind"] == "patch":
+        img = torch.randn(B, 3, 224, 224, generator=g)
+        slots.append(OSlot(IMAGE, True, img, adaptor="image_patch_embed"))
+    if c["kind"] == "audio":
+        L = c["L"]
+        fbank = torch.randn(B, L, 80, generator=g)
+        lens = torch.tensor([L] + [L - L // 4] * (B - 1), dtype=torch.long)
+        slots.append(OSlot(AUDIO, True, {"fbank": fbank, "fbank_lengths": lens}))
+    slots.append(OSlot(TEXT, True, _tokens(g, B, S, V)))
+    prev = _tokens(g, B, T, V)
+    prev[:, 0] = 0  # bos
+    slots.append(OSlot(TEXT, False, prev))
+    target = torch.roll(prev, -1, dims=1)
+    target[:, -1] = 2  # eos
+    target[prev == PAD] = PAD
+    target[torch.roll(prev == PAD, -1, dims=1)] = PAD
+    target[:, -1] = torch.where(prev[:, -1] == PAD, torch.tensor(PAD), torch.tensor(2))
+    return slots, target
+
+
+def param_spec_from_state_dict(sd) -> Dict[str, Tuple[int, ...]]:
+    """Floating-point tensors the synth fills (parameters + BN running stats); integer buckets and
+    the `version` buffers are derived, not synthesised."""
+    spec = {}
+    for k, v in sd.items():
+        if not v.is_floating_point() or k.endswith(".version"):
+            continue
+        spec[k] = tuple(v.shape)
+    return spec

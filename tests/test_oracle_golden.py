@@ -1,0 +1,92 @@
+"""CPU: the oracle restatement (oracle/oracle_model.py) reproduces the outputs of the reference
+code itself (fixtures made by oracle/make_golden.py from the unmodified reference files)."""
+import hashlib
+import os
+
+import pytest
+import torch
+
+from oracle import cases
+from oracle import oracle_model as om
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+SMALL = ["text_A", "text_B", "patch_B", "audio_A"]
+
+
+def rel_l2(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp_min(1e-30)).item()
+
+
+def load(name):
+    return torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_oracle_matches_reference_outputs(name):
+    g = load(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    cfg = cases.oracle_cfg(name)
+    slots, target = cases.make_inputs(name)
+    loss, logits, grads = om.loss_and_grads(sd, cfg, slots, target)
+    assert int((target != 1).sum()) == g["ntokens"]
+    # tolerances: fp32 CPU vs fp32 CPU, different op order only
+    assert rel_l2(logits, g["logits"]) <= 1e-5
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    for k, st in g["grad_stats"].items():
+        if st is None:
+            continue
+        gr = grads[k].double()
+        l2 = gr.norm().item()
+        # k_proj.bias grads are mathematically 0 (softmax shift invariance): absolute floor 1e-6
+        assert abs(l2 - st[2].item()) <= 2e-4 * st[2].item() + 1e-6, (k, l2, st[2].item())
+    for k, full in g["grad_full"].items():
+        if full.norm() <= 1e-5:
+            assert grads[k].norm() <= 2e-5, k
+        else:
+            assert rel_l2(grads[k], full) <= 2e-4, k
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_bucket_tables_bit_exact(name):
+    """Integer position machinery must be bit-exact."""
+    g = load(name)
+    cfg = cases.oracle_cfg(name)
+    for k, (shape, dig, corner) in g["ints"].items():
+        if "token_rp_bucket" in k:
+            t = om.make_token_bucket_position(cfg.token_bucket_size, cfg.max_position)
+        elif "audio_rp_bucket" in k:
+            t = om.make_token_bucket_position(cfg.max_position, 4096)
+        elif "image_rp_bucket" in k:
+            t = om.make_image_bucket_position(cfg.image_bucket_size, (2 * cfg.image_bucket_size - 1) ** 2 + 3)
+        else:
+            continue
+        assert tuple(t.shape) == shape
+        assert t.dtype == torch.int64
+        assert hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest() == dig, k
+
+
+def test_audio_length_quirk():
+    # subsample.py:37-41: L=700 -> 175 (conv really yields 174); L=998 -> 250 reported vs 248 frames
+    assert om.audio_out_lengths(torch.tensor([700, 998, 200, 150])).tolist() == [175, 250, 50, 38]
+
+
+def test_box_quantisation():
+    # box.py:101-110
+    x = torch.tensor([0.0, 255.6, 511.0, 512.0])
+    assert om.quantize_box(x).tolist() == [0, 499, 997, 999]
+
+
+def test_cfg1_tiny_text_infilling():
+    """BASELINE.json configs[0]: OFA-tiny 4L/4L d=256, S=T=128, bs=2, V=50265 (checksummed)."""
+    g = load("cfg1_tiny")
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    cfg = cases.oracle_cfg("cfg1_tiny")
+    slots, target = cases.make_inputs("cfg1_tiny")
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    loss, logits, grads = om.loss_and_grads(sd, cfg, slots, target)
+    assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
+    assert rel_l2(torch.logsumexp(logits, -1), g["lse"]) <= 1e-5
+    assert rel_l2(logits[..., g["logit_cols"]], g["logits_sampled"]) <= 1e-5
+    for k, st in g["grad_stats"].items():
+        if st is not None:
+            assert abs(grads[k].double().norm().item() - st[2].item()) <= 2e-4 * st[2].item() + 1e-6, k
