@@ -75,10 +75,10 @@ def run_case(name):
         if p.grad is None:
             grads[k] = None
             continue
-        gr = p.grad.detach().float()
+        gr = p.grad.detach().double()  # stats in fp64: fp32 norms of 1e7-element grads lose 1e-3
         grads[k] = torch.tensor([gr.sum().item(), gr.abs().sum().item(), gr.norm().item()], dtype=torch.float64)
         if any(t in k for t in SMALL_FULL) and gr.numel() <= 8192:
-            full[k] = gr.clone()
+            full[k] = gr.float().clone()
     g["grad_stats"] = grads
     g["grad_full"] = full
     ints = {}
