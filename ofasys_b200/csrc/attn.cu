@@ -1,0 +1,714 @@
+// Fused attention forward / backward (flash-style) for head_dim 64.
+//
+// Scores, position biases and probabilities live only in registers; HBM traffic is q/k/v/o (+ the
+// int32 bucket-id map shared by every head and layer).  The absolute-position term of OFA
+// (general.py:223-243: (W_q pos * s)(W_k pos)^T) rides along as 64 extra contraction columns of the
+// QK^T product (pq/pk), the relative-position term is a per-head table column staged in shared
+// memory and indexed by the bucket id of (i, j).
+//
+// Tensor-core path here is mma.sync m16n8k16 (bf16 in, fp32 accumulate): at OFA's sequence lengths
+// attention is ~1-3 % of the step FLOPs, so it is written for correctness and minimal HBM traffic
+// first; the tcgen05 budget goes to the GEMMs (gemm.cu).
+//
+// Tiles: 64 query rows x 64 keys per step, 4 warps (16 query rows each).  smem tiles are 64 rows of
+// 128 bytes with a 16-byte-chunk XOR swizzle so ldmatrix is conflict free.
+#include "common.cuh"
+
+namespace {
+
+constexpr int TILE = 64;
+constexpr int TILE_BYTES = TILE * 128;  // 64 rows x 64 bf16
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ uint32_t tile_addr(uint32_t base, int row, int chunk) {
+  return base + row * 128 + ((chunk ^ (row & 7)) << 4);
+}
+
+// async copy of rows [row0, row0+64) x 64 columns (bf16) of a strided global matrix into a swizzled tile.
+// rows >= nrows are zero-filled.  All 128 threads participate (4 chunks each).
+__device__ __forceinline__ void load_tile_async(uint32_t tile, const bf16* __restrict__ g, int64_t row_stride, int row0, int nrows) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int idx = threadIdx.x + it * 128;  // 0..511 : 64 rows x 8 chunks
+    const int r = idx >> 3, c = idx & 7;
+    const int gr = row0 + r;
+    const bool ok = gr < nrows;
+    const bf16* src = g + (int64_t)(ok ? gr : 0) * row_stride + c * 8;
+    const uint32_t dst = tile_addr(tile, r, c);
+    const int sz = ok ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+  }
+}
+__device__ __forceinline__ void cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+// A fragment: rows [r0, r0+16), k columns [kk*16, kk*16+16) of a tile
+__device__ __forceinline__ void frag_a(uint32_t tile, int r0, int kk, uint32_t (&a)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm_x4(tile_addr(tile, r0 + (l & 7) + (mi & 1) * 8, kk * 2 + (mi >> 1)), a);
+}
+// B fragments (two n-tiles) where the tile is stored [n][k]: n rows [n0, n0+16), k columns [kk*16, +16)
+__device__ __forceinline__ void frag_b(uint32_t tile, int n0, int kk, uint32_t (&b)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm_x4(tile_addr(tile, n0 + (l & 7) + (mi >> 1) * 8, kk * 2 + (mi & 1)), b);
+}
+// B fragments (two n-tiles) where the tile is stored [k][n]: k rows [k0, k0+16), n columns [nn*16, +16)
+__device__ __forceinline__ void frag_bt(uint32_t tile, int k0, int nn, uint32_t (&b)[4]) {
+  const int l = threadIdx.x & 31, mi = l >> 3;
+  ldsm_x4_t(tile_addr(tile, k0 + (l & 7) + (mi & 1) * 8, nn * 2 + (mi >> 1)), b);
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+struct AttnCommon {
+  int B, H, Tq, Tk;
+  const bf16 *q, *k, *v, *pq, *pk;
+  int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, pq_bs, pq_rs, pk_bs, pk_rs;
+  const int32_t* rp_idx;
+  const float* table;
+  int n_buckets;
+  const uint8_t* kpm;
+  int causal;
+  float scale;
+};
+
+// score post-processing shared by forward and both backward kernels:
+// s = scale*acc + table[idx] ; masked -> -inf.   (i, j) are global query / key indices.
+__device__ __forceinline__ float finish_score(const AttnCommon& p, float acc, int i, int j, int b, const float* tab_s, int& idx_out) {
+  idx_out = -1;
+  if (j >= p.Tk || i >= p.Tq) return -INFINITY;
+  float s = acc * p.scale;
+  if (p.rp_idx != nullptr) {
+    const int idx = p.rp_idx[(int64_t)i * p.Tk + j];
+    if (idx >= 0) {
+      s += tab_s[idx];
+      idx_out = idx;
+    }
+  }
+  if (p.causal && j > i) return -INFINITY;
+  if (p.kpm != nullptr && p.kpm[(int64_t)b * p.Tk + j]) return -INFINITY;
+  return s;
+}
+
+// ===================================================================================== forward
+template <bool HAS_POS>
+__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
+                                                       float* __restrict__ lse) {
+  constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);                    // NH tiles
+  const uint32_t sK = sQ + NH * TILE_BYTES;              // 2 stages x NH tiles
+  const uint32_t sV = sK + 2 * NH * TILE_BYTES;          // 2 stages x 1 tile
+  float* tab_s = reinterpret_cast<float*>(smem + (3 * NH + 2) * TILE_BYTES);
+
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = qb * TILE;
+
+  const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
+  const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
+  const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
+  const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
+  const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
+
+  if (p.rp_idx != nullptr)
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
+
+  const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
+
+  load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
+  if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
+  load_tile_async(sK, kg, p.k_rs, 0, p.Tk);
+  if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, 0, p.Tk);
+  load_tile_async(sV, vg, p.v_rs, 0, p.Tk);
+  cp_commit();
+
+  float oacc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+
+  for (int kv = 0; kv < n_kv; ++kv) {
+    const int st = kv & 1;
+    if (kv + 1 < n_kv) {
+      const int k1 = (kv + 1) * TILE;
+      load_tile_async(sK + ((st ^ 1) * NH) * TILE_BYTES, kg, p.k_rs, k1, p.Tk);
+      if (HAS_POS) load_tile_async(sK + ((st ^ 1) * NH + 1) * TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
+      load_tile_async(sV + (st ^ 1) * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
+      cp_commit();
+      cp_wait<1>();
+    } else {
+      cp_wait<0>();
+    }
+    __syncthreads();
+
+    // ---- S = Q K^T (+ PQ PK^T)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+      const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + (st * NH + hf) * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        frag_a(tq, warp * 16, kk, a);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bb[4];
+          frag_b(tk, np * 16, kk, bb);
+          mma16816(s[2 * np], a, bb[0], bb[1]);
+          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    // ---- bias / mask / online softmax
+    const int k0 = kv * TILE;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = row_g[e >> 1], j = k0 + nt * 8 + 2 * t + (e & 1);
+        int idx;
+        s[nt][e] = finish_score(p, s[nt][e], i, j, b, tab_s, idx);
+        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      }
+    float corr[2], m_use[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+      const float m_new = fmaxf(m_run[r], mx[r]);
+      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+      corr[r] = __expf(m_run[r] - m_use[r]);  // exp(-inf) = 0 on the first tile
+      m_run[r] = m_new;
+      l_run[r] *= corr[r];
+    }
+    float ps[2] = {0.f, 0.f};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float pe = __expf(s[nt][e] - m_use[e >> 1]);
+        s[nt][e] = pe;
+        ps[e >> 1] += pe;
+      }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) l_run[r] += ps[r];
+#pragma unroll
+    for (int dt = 0; dt < 8; ++dt) {
+      oacc[dt][0] *= corr[0]; oacc[dt][1] *= corr[0];
+      oacc[dt][2] *= corr[1]; oacc[dt][3] *= corr[1];
+    }
+    // ---- O += P V
+    const uint32_t tv = sV + st * TILE_BYTES;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kb][0], s[2 * kb][1]);
+      a[1] = pack_bf16(s[2 * kb][2], s[2 * kb][3]);
+      a[2] = pack_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+      a[3] = pack_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bb[4];
+        frag_bt(tv, kb * 16, dp, bb);
+        mma16816(oacc[2 * dp], a, bb[0], bb[1]);
+        mma16816(oacc[2 * dp + 1], a, bb[2], bb[3]);
+      }
+    }
+    __syncthreads();  // all warps done with stage st before it is refilled
+  }
+
+  // ---- finalize
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float l = l_run[r];
+    l += __shfl_xor_sync(0xffffffffu, l, 1);
+    l += __shfl_xor_sync(0xffffffffu, l, 2);
+    l_run[r] = l;
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = row_g[r];
+    if (i < p.Tq) {
+      const float inv = l_run[r] > 0.f ? 1.0f / l_run[r] : 0.f;
+      bf16* op = o + (int64_t)b * o_bs + (int64_t)i * o_rs + h * 64;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        const uint32_t u = pack_bf16(oacc[dt][2 * r] * inv, oacc[dt][2 * r + 1] * inv);
+        *reinterpret_cast<uint32_t*>(op + dt * 8 + 2 * t) = u;
+      }
+      if (t == 0) lse[((int64_t)b * p.H + h) * p.Tq + i] = (l_run[r] > 0.f) ? m_run[r] + __logf(l_run[r]) : -INFINITY;
+    }
+  }
+}
+
+// ===================================================================================== backward
+// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per row)
+__global__ void attn_delta_kernel(const bf16* __restrict__ d_o, int64_t do_bs, int64_t do_rs, const bf16* __restrict__ o,
+                                  int64_t o_bs, int64_t o_rs, float* __restrict__ delta, int B, int H, int Tq) {
+  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t total = (int64_t)B * H * Tq;
+  if (w >= total) return;
+  const int i = (int)(w % Tq);
+  const int h = (int)((w / Tq) % H);
+  const int b = (int)(w / ((int64_t)Tq * H));
+  const bf162 x = *reinterpret_cast<const bf162*>(d_o + (int64_t)b * do_bs + (int64_t)i * do_rs + h * 64 + lane * 2);
+  const bf162 y = *reinterpret_cast<const bf162*>(o + (int64_t)b * o_bs + (int64_t)i * o_rs + h * 64 + lane * 2);
+  const float2 fx = __bfloat1622float2(x), fy = __bfloat1622float2(y);
+  const float s = warp_sum(fx.x * fy.x + fx.y * fy.y);
+  if (lane == 0) delta[w] = s;
+}
+
+struct AttnBwdExtra {
+  const bf16* d_o;
+  int64_t do_bs, do_rs;
+  const float* lse;
+  const float* delta;
+  bf16 *dq, *dk, *dv, *dpq, *dpk;
+  int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  float* dtable;
+};
+
+// ---- dK / dV: one CTA per 64-key tile, loops over query tiles.  Works on transposed scores
+// S^T[key, query] so every accumulator row belongs to this CTA's keys.
+template <bool HAS_POS>
+__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
+  constexpr int NH = HAS_POS ? 2 : 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sK = smem_u32(smem);             // NH tiles (this CTA's keys)
+  const uint32_t sV = sK + NH * TILE_BYTES;       // 1 tile
+  const uint32_t sQ = sV + TILE_BYTES;            // NH tiles (current query tile)
+  const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1 tile
+  float* lse_s = reinterpret_cast<float*>(smem + (2 * NH + 2) * TILE_BYTES);
+  float* dlt_s = lse_s + TILE;
+  float* tab_s = dlt_s + TILE;
+
+  const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int k0 = kb * TILE;
+  const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
+  const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
+  const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
+  const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
+  const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
+  const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
+
+  if (p.rp_idx != nullptr)
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
+
+  load_tile_async(sK, kg, p.k_rs, k0, p.Tk);
+  if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
+  load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
+  cp_commit();
+
+  float dk[NH * 8][4], dv[8][4];
+#pragma unroll
+  for (int i = 0; i < NH * 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dk[i][j] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
+
+  const int n_q = (p.Tq + TILE - 1) / TILE;
+  const int q_start = p.causal ? (k0 / TILE) : 0;  // queries i < k0 never see these keys
+  const int key_g[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
+
+  for (int qt = q_start; qt < n_q; ++qt) {
+    const int q0 = qt * TILE;
+    __syncthreads();  // previous iteration finished reading sQ / sDO / lse_s
+    load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
+    if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
+    load_tile_async(sDO, dog, e.do_rs, q0, p.Tq);
+    cp_commit();
+    if (threadIdx.x < TILE) {
+      const int i = q0 + threadIdx.x;
+      lse_s[threadIdx.x] = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
+      dlt_s[threadIdx.x] = i < p.Tq ? e.delta[((int64_t)b * p.H + h) * p.Tq + i] : 0.f;
+    }
+    cp_wait<0>();
+    __syncthreads();
+
+    // S^T[key, query] = K Q^T (+ PK PQ^T)
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+      const uint32_t tk = sK + hf * TILE_BYTES, tq = sQ + hf * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        frag_a(tk, warp * 16, kk, a);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bb[4];
+          frag_b(tq, np * 16, kk, bb);
+          mma16816(s[2 * np], a, bb[0], bb[1]);
+          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    // P^T = exp(S^T - lse[query])
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int el = 0; el < 4; ++el) {
+        const int jl = nt * 8 + 2 * t + (el & 1);  // query within tile
+        const int i = q0 + jl, j = key_g[el >> 1];
+        int idx;
+        const float sc = finish_score(p, s[nt][el], i, j, b, tab_s, idx);
+        const float l = lse_s[jl];
+        s[nt][el] = (sc == -INFINITY || l == -INFINITY) ? 0.f : __expf(sc - l);
+      }
+    // dV += P^T dO
+    uint32_t pa[4][4];
+#pragma unroll
+    for (int kb2 = 0; kb2 < 4; ++kb2) {
+      pa[kb2][0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+      pa[kb2][1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+      pa[kb2][2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+      pa[kb2][3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+#pragma unroll
+      for (int dp = 0; dp < 4; ++dp) {
+        uint32_t bb[4];
+        frag_bt(sDO, kb2 * 16, dp, bb);
+        mma16816(dv[2 * dp], pa[kb2], bb[0], bb[1]);
+        mma16816(dv[2 * dp + 1], pa[kb2], bb[2], bb[3]);
+      }
+    }
+    // dP^T[key, query] = V dO^T
+    float dp_[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      frag_a(sV, warp * 16, kk, a);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bb[4];
+        frag_b(sDO, np * 16, kk, bb);
+        mma16816(dp_[2 * np], a, bb[0], bb[1]);
+        mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    // dS^T = P^T * (dP^T - delta[query]) ; pre-multiplied by scale for dK
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int el = 0; el < 4; ++el) {
+        const int jl = nt * 8 + 2 * t + (el & 1);
+        s[nt][el] = s[nt][el] * (dp_[nt][el] - dlt_s[jl]) * p.scale;
+      }
+    // dK' += dS^T Q'
+#pragma unroll
+    for (int kb2 = 0; kb2 < 4; ++kb2) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+      a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+      a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+      a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf)
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bb[4];
+          frag_bt(sQ + hf * TILE_BYTES, kb2 * 16, dp, bb);
+          mma16816(dk[hf * 8 + 2 * dp], a, bb[0], bb[1]);
+          mma16816(dk[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
+        }
+    }
+  }
+  // ---- store dK (+dPK), dV
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = key_g[r];
+    if (j < p.Tk) {
+      bf16* dkp = e.dk + (int64_t)b * e.dk_bs + (int64_t)j * e.dk_rs + h * 64;
+      bf16* dvp = e.dv + (int64_t)b * e.dv_bs + (int64_t)j * e.dv_rs + h * 64;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        *reinterpret_cast<uint32_t*>(dkp + dt * 8 + 2 * t) = pack_bf16(dk[dt][2 * r], dk[dt][2 * r + 1]);
+        *reinterpret_cast<uint32_t*>(dvp + dt * 8 + 2 * t) = pack_bf16(dv[dt][2 * r], dv[dt][2 * r + 1]);
+      }
+      if (HAS_POS) {
+        bf16* dpp = e.dpk + ((int64_t)b * p.Tk + j) * (p.H * 64) + h * 64;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+          *reinterpret_cast<uint32_t*>(dpp + dt * 8 + 2 * t) = pack_bf16(dk[(NH - 1) * 8 + dt][2 * r], dk[(NH - 1) * 8 + dt][2 * r + 1]);
+      }
+    }
+  }
+}
+
+// ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles.
+template <bool HAS_POS>
+__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
+  constexpr int NH = HAS_POS ? 2 : 1;
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t sQ = smem_u32(smem);             // NH
+  const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1
+  const uint32_t sK = sDO + TILE_BYTES;           // NH
+  const uint32_t sV = sK + NH * TILE_BYTES;       // 1
+  float* tab_s = reinterpret_cast<float*>(smem + (2 * NH + 2) * TILE_BYTES);
+  float* dtab_s = tab_s + p.n_buckets;
+
+  const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int q0 = qb * TILE;
+  const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
+  const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
+  const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
+  const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
+  const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
+  const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
+  const bool has_tab = p.rp_idx != nullptr;
+
+  if (has_tab)
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) {
+      tab_s[i] = p.table[(int64_t)i * p.H + h];
+      dtab_s[i] = 0.f;
+    }
+
+  load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
+  if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
+  load_tile_async(sDO, dog, e.do_rs, q0, p.Tq);
+  cp_commit();
+
+  const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+  float lse_r[2], dl_r[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = row_g[r];
+    lse_r[r] = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
+    dl_r[r] = i < p.Tq ? e.delta[((int64_t)b * p.H + h) * p.Tq + i] : 0.f;
+  }
+  float dq[NH * 8][4];
+#pragma unroll
+  for (int i = 0; i < NH * 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+
+  const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
+  for (int kv = 0; kv < n_kv; ++kv) {
+    const int k0 = kv * TILE;
+    __syncthreads();
+    load_tile_async(sK, kg, p.k_rs, k0, p.Tk);
+    if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
+    load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
+    cp_commit();
+    cp_wait<0>();
+    __syncthreads();
+
+    float s[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+#pragma unroll
+    for (int hf = 0; hf < NH; ++hf) {
+      const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + hf * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        frag_a(tq, warp * 16, kk, a);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          uint32_t bb[4];
+          frag_b(tk, np * 16, kk, bb);
+          mma16816(s[2 * np], a, bb[0], bb[1]);
+          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
+    // dP = dO V^T
+    float dp_[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      frag_a(sDO, warp * 16, kk, a);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        uint32_t bb[4];
+        frag_b(sV, np * 16, kk, bb);
+        mma16816(dp_[2 * np], a, bb[0], bb[1]);
+        mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+      }
+    }
+    // P, dS ; relative-position table gradient
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int el = 0; el < 4; ++el) {
+        const int i = row_g[el >> 1], j = k0 + nt * 8 + 2 * t + (el & 1);
+        int idx;
+        const float sc = finish_score(p, s[nt][el], i, j, b, tab_s, idx);
+        const float l = lse_r[el >> 1];
+        const float pe = (sc == -INFINITY || l == -INFINITY) ? 0.f : __expf(sc - l);
+        const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
+        if (has_tab && idx >= 0 && ds != 0.f) atomicAdd(dtab_s + idx, ds);
+        s[nt][el] = ds * p.scale;
+      }
+    // dQ' += dS K'
+#pragma unroll
+    for (int kb2 = 0; kb2 < 4; ++kb2) {
+      uint32_t a[4];
+      a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+      a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+      a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+      a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+#pragma unroll
+      for (int hf = 0; hf < NH; ++hf)
+#pragma unroll
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bb[4];
+          frag_bt(sK + hf * TILE_BYTES, kb2 * 16, dp, bb);
+          mma16816(dq[hf * 8 + 2 * dp], a, bb[0], bb[1]);
+          mma16816(dq[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
+        }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = row_g[r];
+    if (i < p.Tq) {
+      bf16* dqp = e.dq + (int64_t)b * e.dq_bs + (int64_t)i * e.dq_rs + h * 64;
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(dqp + dt * 8 + 2 * t) = pack_bf16(dq[dt][2 * r], dq[dt][2 * r + 1]);
+      if (HAS_POS) {
+        bf16* dpp = e.dpq + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64;
+#pragma unroll
+        for (int dt = 0; dt < 8; ++dt)
+          *reinterpret_cast<uint32_t*>(dpp + dt * 8 + 2 * t) = pack_bf16(dq[(NH - 1) * 8 + dt][2 * r], dq[(NH - 1) * 8 + dt][2 * r + 1]);
+      }
+    }
+  }
+  if (has_tab && e.dtable != nullptr) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) {
+      const float v = dtab_s[i];
+      if (v != 0.f) atomicAdd(e.dtable + (int64_t)i * p.H + h, v);
+    }
+  }
+}
+
+int fill_common(const ofab_attn_fwd_args* a, AttnCommon& c) {
+  OFAB_REQUIRE(a->B > 0 && a->H > 0 && a->Tq > 0 && a->Tk > 0, "ofab_attn: empty problem");
+  OFAB_REQUIRE(a->q && a->k && a->v, "ofab_attn: q/k/v NULL");
+  OFAB_REQUIRE((a->pq == nullptr) == (a->pk == nullptr), "ofab_attn: pq and pk must both be given or both NULL");
+  OFAB_REQUIRE((a->rp_idx == nullptr) == (a->table == nullptr), "ofab_attn: rp_idx and table must both be given or both NULL");
+  OFAB_REQUIRE(a->rp_idx == nullptr || (a->n_buckets > 0 && a->n_buckets <= 16384), "ofab_attn: n_buckets=%d out of range (1..16384)", a->n_buckets);
+  OFAB_REQUIRE(a->q_rs % 8 == 0 && a->k_rs % 8 == 0 && a->v_rs % 8 == 0 && a->q_bs % 8 == 0 && a->k_bs % 8 == 0 && a->v_bs % 8 == 0,
+               "ofab_attn: q/k/v strides must be multiples of 8 elements (16-byte rows)");
+  OFAB_REQUIRE(a->pq == nullptr || (a->pq_rs % 8 == 0 && a->pk_rs % 8 == 0 && a->pq_bs % 8 == 0 && a->pk_bs % 8 == 0),
+               "ofab_attn: pq/pk strides must be multiples of 8 elements");
+  c.B = a->B; c.H = a->H; c.Tq = a->Tq; c.Tk = a->Tk;
+  c.q = (const bf16*)a->q; c.k = (const bf16*)a->k; c.v = (const bf16*)a->v;
+  c.pq = (const bf16*)a->pq; c.pk = (const bf16*)a->pk;
+  c.q_bs = a->q_bs; c.q_rs = a->q_rs; c.k_bs = a->k_bs; c.k_rs = a->k_rs; c.v_bs = a->v_bs; c.v_rs = a->v_rs;
+  c.pq_bs = a->pq_bs; c.pq_rs = a->pq_rs; c.pk_bs = a->pk_bs; c.pk_rs = a->pk_rs;
+  c.rp_idx = a->rp_idx; c.table = a->table; c.n_buckets = a->rp_idx ? a->n_buckets : 0;
+  c.kpm = a->kpm; c.causal = a->causal; c.scale = a->scale;
+  return OFAB_OK;
+}
+
+template <typename K>
+int set_smem(K kern, int bytes, const char* what) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) return ofab_cuda_fail(e, what);
+  return OFAB_OK;
+}
+
+}  // namespace
+
+extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) {
+  AttnCommon c;
+  int rc = fill_common(a, c);
+  if (rc) return rc;
+  OFAB_REQUIRE(a->o && a->lse, "ofab_attn_fwd: o/lse NULL");
+  OFAB_REQUIRE(a->o_rs % 2 == 0 && a->o_bs % 2 == 0, "ofab_attn_fwd: o strides must be even");
+  const bool pos = a->pq != nullptr;
+  const int nh = pos ? 2 : 1;
+  const int smem = (3 * nh + 2) * TILE_BYTES + c.n_buckets * 4;
+  dim3 grid((a->Tq + TILE - 1) / TILE, a->H, a->B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pos) {
+    if ((rc = set_smem(attn_fwd_kernel<true>, smem, "ofab_attn_fwd smem"))) return rc;
+    attn_fwd_kernel<true><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);
+  } else {
+    if ((rc = set_smem(attn_fwd_kernel<false>, smem, "ofab_attn_fwd smem"))) return rc;
+    attn_fwd_kernel<false><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);
+  }
+  OFAB_LAUNCH_CHECK("ofab_attn_fwd");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) {
+  AttnCommon c;
+  int rc = fill_common(&a->f, c);
+  if (rc) return rc;
+  OFAB_REQUIRE(a->d_o && a->dq && a->dk && a->dv && a->delta && a->f.o && a->f.lse, "ofab_attn_bwd: NULL tensor");
+  const bool pos = a->f.pq != nullptr;
+  OFAB_REQUIRE(!pos || (a->dpq && a->dpk), "ofab_attn_bwd: dpq/dpk required when pq/pk are given");
+  OFAB_REQUIRE(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0, "ofab_attn_bwd: grad strides must be even");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int64_t rows = (int64_t)a->f.B * a->f.H * a->f.Tq;
+  attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)a->d_o, a->do_bs, a->do_rs, (const bf16*)a->f.o,
+                                                                       a->f.o_bs, a->f.o_rs, a->delta, a->f.B, a->f.H, a->f.Tq);
+  OFAB_LAUNCH_CHECK("ofab_attn_bwd delta");
+  AttnBwdExtra e;
+  e.d_o = (const bf16*)a->d_o; e.do_bs = a->do_bs; e.do_rs = a->do_rs;
+  e.lse = a->f.lse; e.delta = a->delta;
+  e.dq = (bf16*)a->dq; e.dk = (bf16*)a->dk; e.dv = (bf16*)a->dv; e.dpq = (bf16*)a->dpq; e.dpk = (bf16*)a->dpk;
+  e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
+  e.dtable = a->dtable;
+  const int nh = pos ? 2 : 1;
+  const int smem_kv = (2 * nh + 2) * TILE_BYTES + 2 * TILE * 4 + c.n_buckets * 4;
+  const int smem_q = (2 * nh + 2) * TILE_BYTES + 2 * c.n_buckets * 4;
+  dim3 gkv((a->f.Tk + TILE - 1) / TILE, a->f.H, a->f.B), gq((a->f.Tq + TILE - 1) / TILE, a->f.H, a->f.B);
+  if (pos) {
+    if ((rc = set_smem(attn_bwd_dkv_kernel<true>, smem_kv, "ofab_attn_bwd smem"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<true>, smem_q, "ofab_attn_bwd smem"))) return rc;
+    attn_bwd_dkv_kernel<true><<<gkv, 128, smem_kv, st>>>(c, e);
+    OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
+    attn_bwd_dq_kernel<true><<<gq, 128, smem_q, st>>>(c, e);
+  } else {
+    if ((rc = set_smem(attn_bwd_dkv_kernel<false>, smem_kv, "ofab_attn_bwd smem"))) return rc;
+    if ((rc = set_smem(attn_bwd_dq_kernel<false>, smem_q, "ofab_attn_bwd smem"))) return rc;
+    attn_bwd_dkv_kernel<false><<<gkv, 128, smem_kv, st>>>(c, e);
+    OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
+    attn_bwd_dq_kernel<false><<<gq, 128, smem_q, st>>>(c, e);
+  }
+  OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");
+  return OFAB_OK;
+}

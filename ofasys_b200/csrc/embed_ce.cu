@@ -1,0 +1,301 @@
+// Adaptor hook (embedding gather / dense rows + position + type -> LayerNorm) and the sum-CE
+// criterion kernels.  Both are HBM-bound row kernels: one 128-thread block owns a row of d <= 1024
+// (embed) or one 256-thread block a row of V logits (CE).
+#include "common.cuh"
+
+namespace {
+
+constexpr int PARTIAL_ROWS = 592;
+
+__device__ __forceinline__ float block_sum128(float v, float* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+struct EmbedArgs {
+  int B, T, d;
+  const int64_t* tokens;
+  const bf16 *E, *dense, *cls, *pos, *type, *gamma, *beta;
+  int has_cls;
+  const uint8_t* zero_mask;
+  float eps;
+};
+
+// pre-LN value of this thread's 8 columns of row (b, t)
+__device__ __forceinline__ f8 embed_pre(const EmbedArgs& a, int b, int t, int c, int64_t& tok_out) {
+  f8 v;
+  tok_out = -1;
+  if (a.tokens != nullptr) {
+    const int64_t tok = a.tokens[(int64_t)b * a.T + t];
+    tok_out = tok;
+    v = load8(a.E + tok * a.d + c);
+  } else if (a.has_cls && t == 0) {
+    v = load8(a.cls + c);
+  } else {
+    v = load8(a.dense + ((int64_t)b * (a.T - a.has_cls) + (t - a.has_cls)) * a.d + c);
+  }
+  if (a.pos != nullptr) {
+    const f8 p = load8(a.pos + (int64_t)t * a.d + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] += p.v[j];
+  }
+  if (a.type != nullptr) {
+    const f8 p = load8(a.type + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] += p.v[j];
+  }
+  return v;
+}
+
+__global__ void __launch_bounds__(128) embed_ln_fwd_kernel(const EmbedArgs a, float* __restrict__ out, int64_t out_bs,
+                                                           float* __restrict__ mean, float* __restrict__ rstd) {
+  __shared__ float red[4];
+  const int c = threadIdx.x * 8;
+  const bool col_ok = c < a.d;
+  const float inv_n = 1.0f / (float)a.d;
+  f8 g, be;
+  if (col_ok) {
+    g = load8(a.gamma + c);
+    be = load8(a.beta + c);
+  }
+  const int64_t rows = (int64_t)a.B * a.T;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / a.T), t = (int)(row % a.T);
+    f8 v;
+    float s = 0.f;
+    int64_t tok;
+    if (col_ok) {
+      v = embed_pre(a, b, t, c, tok);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v.v[j];
+    }
+    const float mu = block_sum128(s, red) * inv_n;
+    float q = 0.f;
+    if (col_ok) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float dlt = v.v[j] - mu;
+        q += dlt * dlt;
+      }
+    }
+    const float rs = rsqrtf(block_sum128(q, red) * inv_n + a.eps);
+    if (threadIdx.x == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+    const bool zero = a.zero_mask != nullptr && a.zero_mask[row];
+    if (col_ok) {
+      f8 o;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o.v[j] = zero ? 0.f : (v.v[j] - mu) * rs * g.v[j] + be.v[j];
+      store8(out + (int64_t)b * out_bs + (int64_t)t * a.d + c, o);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(128) embed_ln_bwd_kernel(const EmbedArgs a, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                           const float* __restrict__ dout, int64_t dout_bs, float* __restrict__ dE,
+                                                           int64_t padding_idx, bf16* __restrict__ ddense, float* __restrict__ dpos,
+                                                           float* __restrict__ partial) {
+  __shared__ float red[4];
+  const int c = threadIdx.x * 8;
+  const bool col_ok = c < a.d;
+  const float inv_n = 1.0f / (float)a.d;
+  f8 g, acc[4];  // dgamma, dbeta, dtype, dcls
+  if (col_ok) g = load8(a.gamma + c);
+#pragma unroll
+  for (int s = 0; s < 4; ++s)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
+  const int64_t rows = (int64_t)a.B * a.T;
+  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / a.T), t = (int)(row % a.T);
+    const bool zero = a.zero_mask != nullptr && a.zero_mask[row];
+    const float mu = mean[row], rs = rstd[row];
+    f8 xh, dy;
+    float s1 = 0.f, s2 = 0.f;
+    int64_t tok = -1;
+    if (col_ok) {
+      const f8 pre = embed_pre(a, b, t, c, tok);
+      if (zero) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dy.v[j] = 0.f;
+      } else {
+        dy = load8(dout + (int64_t)b * dout_bs + (int64_t)t * a.d + c);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        xh.v[j] = (pre.v[j] - mu) * rs;
+        acc[0].v[j] += dy.v[j] * xh.v[j];
+        acc[1].v[j] += dy.v[j];
+        dy.v[j] *= g.v[j];
+        s1 += dy.v[j] * xh.v[j];
+        s2 += dy.v[j];
+      }
+    }
+    const float c1 = block_sum128(s1, red) * inv_n;
+    const float c2 = block_sum128(s2, red) * inv_n;
+    if (col_ok) {
+      f8 dp;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) dp.v[j] = rs * (dy.v[j] - c2 - xh.v[j] * c1);
+      if (a.type != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[2].v[j] += dp.v[j];
+      }
+      if (a.pos != nullptr && dpos != nullptr && !zero) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(dpos + (int64_t)t * a.d + c + j, dp.v[j]);
+      }
+      if (a.tokens != nullptr) {
+        if (dE != nullptr && tok != padding_idx && !zero) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) atomicAdd(dE + tok * a.d + c + j, dp.v[j]);
+        }
+      } else if (a.has_cls && t == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[3].v[j] += dp.v[j];
+      } else if (ddense != nullptr) {
+        store8(ddense + ((int64_t)b * (a.T - a.has_cls) + (t - a.has_cls)) * a.d + c, dp);
+      }
+    }
+  }
+  if (col_ok) {
+#pragma unroll
+    for (int s = 0; s < 4; ++s) store8(partial + ((int64_t)s * PARTIAL_ROWS + blockIdx.x) * a.d + c, acc[s]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------ CE
+__device__ __forceinline__ void online_merge(float& m, float& s, float m2, float s2) {
+  const float mn = fmaxf(m, m2);
+  if (mn == -INFINITY) { m = mn; s = 0.f; return; }
+  s = s * __expf(m - mn) + s2 * __expf(m2 - mn);
+  m = mn;
+}
+
+__global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ target,
+                                                     int64_t ignore_index, float* __restrict__ lse, float* __restrict__ loss_sum) {
+  __shared__ float sm_m[8], sm_s[8];
+  const int64_t r = blockIdx.x;
+  const bf16* row = logits + r * ld;
+  float m = -INFINITY, s = 0.f;
+  const int64_t V8 = V / 8;
+  for (int64_t i = threadIdx.x; i < V8; i += 256) {
+    const f8 x = load8(row + i * 8);
+    float mx = x.v[0];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) mx = fmaxf(mx, x.v[j]);
+    const float mn = fmaxf(m, mx);
+    float acc = s * __expf(m - mn);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc += __expf(x.v[j] - mn);
+    m = mn;
+    s = acc;
+  }
+  for (int64_t i = V8 * 8 + threadIdx.x; i < V; i += 256) online_merge(m, s, __bfloat162float(row[i]), 1.f);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    online_merge(m, s, m2, s2);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sm_m[threadIdx.x >> 5] = m;
+    sm_s[threadIdx.x >> 5] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm_m[0], S = sm_s[0];
+    for (int w = 1; w < 8; ++w) online_merge(M, S, sm_m[w], sm_s[w]);
+    const float l = M + logf(S);
+    lse[r] = l;
+    const int64_t tg = target[r];
+    if (tg != ignore_index) atomicAdd(loss_sum, l - __bfloat162float(row[tg]));
+  }
+}
+
+__global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ target,
+                                                     int64_t ignore_index, const float* __restrict__ lse, const float* __restrict__ gscale,
+                                                     bf16* __restrict__ dlogits) {
+  const int64_t r = blockIdx.x;
+  const bf16* row = logits + r * ld;
+  bf16* drow = dlogits + r * ld;
+  const int64_t tg = target[r];
+  const bool counted = tg != ignore_index;
+  const float g = counted ? gscale[0] : 0.f;
+  const float l = lse[r];
+  const int64_t V8 = V / 8;
+  for (int64_t i = threadIdx.x; i < V8; i += 256) {
+    f8 x = load8(row + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float pr = counted ? __expf(x.v[j] - l) : 0.f;
+      x.v[j] = g * (pr - ((i * 8 + j) == tg ? 1.f : 0.f));
+    }
+    store8(drow + i * 8, x);
+  }
+  for (int64_t i = V8 * 8 + threadIdx.x; i < V; i += 256) {
+    const float pr = counted ? __expf(__bfloat162float(row[i]) - l) : 0.f;
+    drow[i] = __float2bfloat16(g * (pr - (i == tg ? 1.f : 0.f)));
+  }
+}
+
+int to_args(const ofab_embed_ln_args* a, EmbedArgs& e, const char* who) {
+  OFAB_REQUIRE(a->B > 0 && a->T > 0 && a->d >= 8 && a->d <= 1024 && a->d % 8 == 0, "%s: bad shape B=%d T=%d d=%d (d multiple of 8, <= 1024)", who, a->B, a->T, a->d);
+  OFAB_REQUIRE((a->tokens != nullptr) != (a->dense != nullptr || (a->has_cls && a->T == 1)), "%s: exactly one of tokens / dense must be given", who);
+  OFAB_REQUIRE(a->tokens == nullptr || a->E != nullptr, "%s: E is NULL", who);
+  OFAB_REQUIRE(!a->has_cls || a->cls != nullptr, "%s: has_cls without cls", who);
+  OFAB_REQUIRE(a->gamma && a->beta && a->mean && a->rstd, "%s: gamma/beta/mean/rstd NULL", who);
+  e.B = a->B; e.T = a->T; e.d = a->d;
+  e.tokens = a->tokens;
+  e.E = (const bf16*)a->E; e.dense = (const bf16*)a->dense; e.cls = (const bf16*)a->cls; e.pos = (const bf16*)a->pos;
+  e.type = (const bf16*)a->type; e.gamma = (const bf16*)a->gamma; e.beta = (const bf16*)a->beta;
+  e.has_cls = a->has_cls ? 1 : 0;
+  e.zero_mask = a->zero_mask;
+  e.eps = a->eps;
+  return OFAB_OK;
+}
+
+}  // namespace
+
+extern "C" int ofab_embed_ln_fwd(const ofab_embed_ln_args* a, ofab_stream_t stream) {
+  EmbedArgs e;
+  int rc = to_args(a, e, "ofab_embed_ln_fwd");
+  if (rc) return rc;
+  OFAB_REQUIRE(a->out != nullptr && a->out_bs >= (int64_t)a->T * a->d && a->out_bs % 4 == 0, "ofab_embed_ln_fwd: bad out / out_bs");
+  const int64_t rows = (int64_t)a->B * a->T;
+  const int64_t cap = (int64_t)ofab_sm_count() * 16;
+  embed_ln_fwd_kernel<<<(unsigned)(rows < cap ? rows : cap), 128, 0, (cudaStream_t)stream>>>(e, a->out, a->out_bs, a->mean, a->rstd);
+  OFAB_LAUNCH_CHECK("ofab_embed_ln_fwd");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_embed_ln_bwd(const ofab_embed_ln_bwd_args* a, ofab_stream_t stream) {
+  EmbedArgs e;
+  int rc = to_args(&a->f, e, "ofab_embed_ln_bwd");
+  if (rc) return rc;
+  OFAB_REQUIRE(a->dout != nullptr && a->dgb_partial != nullptr, "ofab_embed_ln_bwd: dout / dgb_partial NULL");
+  embed_ln_bwd_kernel<<<PARTIAL_ROWS, 128, 0, (cudaStream_t)stream>>>(e, a->f.mean, a->f.rstd, a->dout, a->dout_bs, a->dE, a->padding_idx,
+                                                                      (bf16*)a->ddense, a->dpos, a->dgb_partial);
+  OFAB_LAUNCH_CHECK("ofab_embed_ln_bwd");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_ce_fwd(const void* logits, int64_t rows, int64_t V, int64_t ld, const int64_t* target, int64_t ignore_index,
+                           float* lse, float* loss_sum, ofab_stream_t stream) {
+  OFAB_REQUIRE(rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "ofab_ce_fwd: bad shape rows=%lld V=%lld ld=%lld (ld multiple of 8)", (long long)rows, (long long)V, (long long)ld);
+  ce_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, loss_sum);
+  OFAB_LAUNCH_CHECK("ofab_ce_fwd");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_ce_bwd(const void* logits, int64_t rows, int64_t V, int64_t ld, const int64_t* target, int64_t ignore_index,
+                           const float* lse, const float* gscale, void* dlogits, ofab_stream_t stream) {
+  OFAB_REQUIRE(rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "ofab_ce_bwd: bad shape");
+  ce_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, gscale, (bf16*)dlogits);
+  OFAB_LAUNCH_CHECK("ofab_ce_bwd");
+  return OFAB_OK;
+}

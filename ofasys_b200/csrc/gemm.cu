@@ -1,0 +1,445 @@
+// bf16 GEMM on the 5th-generation tensor cores (tcgen05) of sm_100a.
+//
+//   D[M,N] = A[M,K] * B[N,K]^T (+ bias[N]) (+ residual[M,N]),  fp32 accumulation in TMEM.
+//
+// Persistent, warp-specialised kernel (one CTA per SM):
+//   warp 0      TMA producer: cp.async.bulk.tensor tiles of A and B into a SWIZZLE_128B smem ring
+//   warp 1      MMA issuer (one elected lane): tcgen05.mma.cta_group::1.kind::f16, UMMA 128 x BN x 16,
+//               accumulators double-buffered in tensor memory so the epilogue of tile i overlaps the
+//               main loop of tile i+1; owns tcgen05.alloc / dealloc
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 32 columns per warp) -> bias / residual -> global
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and tmem full/empty mbarriers (MMA <-> epilogue).
+//
+// Operand layouts: each operand may be "K-major" (rows of K contiguous: activations [M,K], weights
+// [N,K]) or "MN-major" (the transposed matrix read in place: dY^T, X^T for wgrad; W for dgrad), so
+// dgrad and wgrad need no transposed copies in HBM.  Both use 128-byte swizzled smem tiles; only the
+// TMA box shape and the UMMA smem/instruction descriptors differ.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+constexpr int kNumThreads = 192;
+constexpr int kSmemBudget = 200 * 1024;
+
+// ------------------------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra.uni WAIT_DONE;\n"
+      "bra.uni WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(addr),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2 at bits [61,64)), version 1 at [46,48).
+//  K-major : rows of 128 B; 8-row groups are 1024 B apart (SBO); one swizzle atom along K (LBO unused).
+//  MN-major: 64-element (128 B) MN atoms of BLOCK_K rows each; SBO = 8 K-rows (1024 B),
+//            LBO = stride between MN atoms (BLOCK_K * 128 B).
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;  // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+  return d;
+}
+
+struct GemmParams {
+  int M, N, K;
+  const bf16* bias;       // [N] or null
+  const float* residual;  // [M, ldr] or null
+  int64_t ldr;
+  void* D;
+  int64_t ldd;
+  int d_bf16;
+};
+
+template <int BN, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
+  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
+  constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+  constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "tmem columns must be a power of two");
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    for (int i = 0; i < STAGES; ++i) {
+      mbar_init(full_bar + i, 1);
+      mbar_init(empty_bar + i, 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(tmem_full + i, 1);
+      mbar_init(tmem_empty + i, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+        const int m0 = (t % m_tiles) * BLOCK_M;
+        const int n0 = (t / m_tiles) * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(empty_bar + stage, phase ^ 1);
+          mbar_expect_tx(full_bar + stage, A_BYTES + B_BYTES);
+          uint8_t* sa = smem_a + stage * A_BYTES;
+          uint8_t* sb = smem_b + stage * B_BYTES;
+          const int k0 = kb * BLOCK_K;
+          if (!A_MN) {
+            tma_load_2d(sa, &tma_a, full_bar + stage, k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * (BLOCK_K * 128), &tma_a, full_bar + stage, m0 + i * 64, k0);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (BLOCK_K * 128), &tma_b, full_bar + stage, n0 + i * 64, k0);
+          }
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
+      // N>>3 at [17,23), M>>4 at [24,29)
+      constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+      int stage = 0;
+      uint32_t phase = 0;
+      int iter = 0;
+      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+        const int as = iter & 1;
+        const uint32_t aphase = (iter >> 1) & 1;
+        mbar_wait(tmem_empty + as, aphase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + as * BN;
+        for (int kb = 0; kb < num_k_blocks; ++kb) {
+          mbar_wait(full_bar + stage, phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES);
+          const uint32_t b_addr = smem_u32(smem_b + stage * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
+            // MN-major: advance 16 K-rows of 128 B (2048 B).
+            const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc(a_addr + k * (UMMA_K * 2), 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
+                                        : make_smem_desc(b_addr + k * (UMMA_K * 2), 0, 1024);
+            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
+          if (kb == num_k_blocks - 1) umma_commit(tmem_full + as);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    int iter = 0;
+    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+      const int as = iter & 1;
+      const uint32_t aphase = (iter >> 1) & 1;
+      const int m0 = (t % m_tiles) * BLOCK_M;
+      const int n0 = (t / m_tiles) * BN;
+      mbar_wait(tmem_full + as, aphase);
+      tcgen05_fence_after();
+      const int row = m0 + q * 32 + lane;
+      const bool row_ok = row < p.M;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        __syncwarp();
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), r);
+        const int n = n0 + c0;
+        if (n < p.N && row_ok) {
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+        if (p.bias != nullptr) {
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const f8 bb = load8(p.bias + n + j);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) v[j + e] += bb.v[e];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += __bfloat162float(p.bias[n + j]);
+          }
+        }
+        if (p.residual != nullptr) {
+          const float* rp = p.residual + (int64_t)row * p.ldr + n;
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 x = *reinterpret_cast<const float4*>(rp + j);
+              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) v[j] += rp[j];
+          }
+        }
+        if (p.d_bf16) {
+          bf16* dp = reinterpret_cast<bf16*>(p.D) + (int64_t)row * p.ldd + n;
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint4 u;
+              u.x = pack_bf16(v[j], v[j + 1]);
+              u.y = pack_bf16(v[j + 2], v[j + 3]);
+              u.z = pack_bf16(v[j + 4], v[j + 5]);
+              u.w = pack_bf16(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(dp + j) = u;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) dp[j] = __float2bfloat16(v[j]);
+          }
+        } else {
+          float* dp = reinterpret_cast<float*>(p.D) + (int64_t)row * p.ldd + n;
+          if (n + 32 <= p.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n + j < p.N) dp[j] = v[j];
+          }
+        }
+        }
+      }
+      // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty + as);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+  }
+}
+
+// ------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || p == nullptr) return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2-D bf16 tensor map: `inner` contiguous elements, `outer` rows of stride ld elements.
+int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld, uint32_t box_inner, uint32_t box_outer) {
+  EncodeTiledFn fn = get_encode_fn();
+  if (!fn) {
+    ofab_set_error("ofab_gemm_bf16: cuTensorMapEncodeTiled not available from the driver");
+    return OFAB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    ofab_set_error("ofab_gemm_bf16: cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+                   (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return OFAB_ERR_CUDA;
+  }
+  return OFAB_OK;
+}
+
+template <int BN, bool A_MN, bool B_MN>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  constexpr int stage_bytes = BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2;
+  constexpr int STAGES = (kSmemBudget / stage_bytes) > 8 ? 8 : (kSmemBudget / stage_bytes);
+  constexpr int smem_bytes = STAGES * stage_bytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaFuncSetAttribute");
+    configured = true;
+  }
+  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = m_tiles * n_tiles;
+  const int sms = ofab_sm_count();
+  const int grid = tiles < sms ? tiles : sms;
+  kern<<<grid, kNumThreads, smem_bytes, st>>>(ta, tb, p);
+  OFAB_LAUNCH_CHECK("ofab_gemm_bf16 launch");
+  return OFAB_OK;
+}
+
+}  // namespace
+
+extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major, const void* B,
+                              int64_t ldb, int b_mn_major, const void* bias, const float* residual, int64_t ldr, void* D,
+                              int64_t ldd, int d_dt, ofab_stream_t stream) {
+  OFAB_REQUIRE(M > 0 && N > 0 && K > 0, "ofab_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
+  OFAB_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "ofab_gemm_bf16: dimension overflow");
+  OFAB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "ofab_gemm_bf16: lda=%lld ldb=%lld must be multiples of 8 (16-byte TMA strides)", (long long)lda, (long long)ldb);
+  OFAB_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0 && ((uintptr_t)D & 15) == 0, "ofab_gemm_bf16: A/B/D must be 16-byte aligned");
+  OFAB_REQUIRE(ldd % (d_dt == OFAB_BF16 ? 8 : 4) == 0, "ofab_gemm_bf16: ldd=%lld must keep rows 16-byte aligned", (long long)ldd);
+  OFAB_REQUIRE(residual == nullptr || (ldr % 4 == 0 && ((uintptr_t)residual & 15) == 0), "ofab_gemm_bf16: residual must be 16-byte aligned, ldr %% 4 == 0");
+  OFAB_REQUIRE(bias == nullptr || ((uintptr_t)bias & 15) == 0, "ofab_gemm_bf16: bias must be 16-byte aligned");
+  OFAB_REQUIRE(d_dt == OFAB_BF16 || d_dt == OFAB_F32, "ofab_gemm_bf16: bad d_dt");
+  OFAB_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldd >= N, "ofab_gemm_bf16: leading dimension smaller than the row");
+
+  // tile N: 256 when it divides the work well, else 128 (keeps wave quantisation low for N = 768)
+  const int sms = ofab_sm_count();
+  const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+  auto waves = [&](int bn) {
+    const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
+    const int64_t w = (tiles + sms - 1) / sms;
+    return (double)w * bn;  // time ~ waves x tile width
+  };
+  const int BN = (N > 128 && waves(256) <= waves(128)) ? 256 : 128;
+
+  CUtensorMap ta, tb;
+  int rc;
+  if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M);
+  else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BLOCK_K);
+  if (rc) return rc;
+  if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN);
+  else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BLOCK_K);
+  if (rc) return rc;
+
+  GemmParams p;
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.bias = (const bf16*)bias;
+  p.residual = residual;
+  p.ldr = ldr;
+  p.D = D;
+  p.ldd = ldd;
+  p.d_bf16 = d_dt == OFAB_BF16;
+  cudaStream_t st = (cudaStream_t)stream;
+#define GO(BNV, AM, BM) return launch<BNV, AM, BM>(ta, tb, p, st)
+  if (BN == 256) {
+    if (!a_mn_major && !b_mn_major) GO(256, false, false);
+    if (!a_mn_major && b_mn_major) GO(256, false, true);
+    if (a_mn_major && !b_mn_major) GO(256, true, false);
+    GO(256, true, true);
+  } else {
+    if (!a_mn_major && !b_mn_major) GO(128, false, false);
+    if (!a_mn_major && b_mn_major) GO(128, false, true);
+    if (a_mn_major && !b_mn_major) GO(128, true, false);
+    GO(128, true, true);
+  }
+#undef GO
+}

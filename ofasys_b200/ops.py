@@ -1,0 +1,664 @@
+"""torch.autograd.Function wrappers over the C ABI (include/ofab.h).
+
+PyTorch supplies device memory (caching allocator), the current CUDA stream and autograd's graph
+walk; every kernel that runs is ours.  All functions require CUDA tensors and raise otherwise --
+there is no CPU or eager fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import BF16, F32
+
+_DT = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.OfabError("ofasys_b200 ops need CUDA tensors (no CPU fallback); got a CPU tensor")
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------ reductions
+def colsum(x2d, out_dtype=torch.bfloat16, out=None, accumulate=False):
+    """out[c] (+)= sum_r x2d[r, c]; x2d may have a row stride (last dim contiguous)."""
+    assert x2d.dim() == 2 and x2d.stride(1) == 1
+    rows, cols = x2d.shape
+    if out is None:
+        out = torch.empty(cols, dtype=out_dtype, device=x2d.device)
+    scratch = torch.empty(_lib.lib().ofab_colsum_scratch_elems(cols), dtype=torch.float32, device=x2d.device)
+    _lib.call("ofab_colsum", _p(x2d), _DT[x2d.dtype], rows, cols, x2d.stride(0), _p(out), _DT[out.dtype], int(accumulate), _p(scratch), _s())
+    return out
+
+
+def _reduce_partials(partial, slab, cols, dtype):
+    pr = partial.shape[1]
+    return colsum(partial[slab].view(pr, cols), dtype)
+
+
+def cast_bf16(x):
+    _need_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x, dtype=torch.bfloat16)
+    _lib.call("ofab_cast_f32_bf16", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+def cast_f32(x):
+    _need_cuda(x)
+    x = _c(x)
+    y = torch.empty_like(x, dtype=torch.float32)
+    _lib.call("ofab_cast_bf16_f32", _p(x), _p(y), x.numel(), _s())
+    return y
+
+
+class _CastFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, to_f32):
+        ctx.to_f32 = to_f32
+        return cast_f32(x) if to_f32 else cast_bf16(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return (cast_bf16(g) if ctx.to_f32 else cast_f32(g)), None
+
+
+def to_f32(x):
+    return x if x.dtype == torch.float32 else _CastFn.apply(x, True)
+
+
+def to_bf16(x):
+    return x if x.dtype == torch.bfloat16 else _CastFn.apply(x, False)
+
+
+# ------------------------------------------------------------------------------------ LayerNorm
+def _partial_rows():
+    return _lib.lib().ofab_ln_partial_rows()
+
+
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps, gelu, out_dtype):
+        _need_cuda(x, weight, bias)
+        x = _c(x)
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+        _lib.call("ofab_ln_fwd", _p(x), _DT[x.dtype], _p(weight), _p(bias), _p(y), _DT[out_dtype], _p(mean), _p(rstd), rows, cols, eps, int(gelu), _s())
+        ctx.save_for_backward(x, weight, mean, rstd)
+        ctx.gelu = gelu
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, mean, rstd = ctx.saved_tensors
+        dy = _c(dy)
+        cols = x.shape[-1]
+        rows = x.numel() // cols
+        dx = torch.empty_like(x)
+        partial = torch.empty((2, _partial_rows(), cols), dtype=torch.float32, device=x.device)
+        _lib.call("ofab_ln_bwd", _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(weight), _p(mean), _p(rstd), _p(dx), _DT[dx.dtype], 0,
+                  _p(partial), rows, cols, int(ctx.gelu), _s())
+        dw = _reduce_partials(partial, 0, cols, weight.dtype)
+        db = _reduce_partials(partial, 1, cols, weight.dtype)
+        return dx, dw, db, None, None, None
+
+
+def layer_norm(x, weight, bias, eps=1e-5, gelu=False, out_dtype=torch.bfloat16):
+    """LN(gelu?(x)).  x fp32 -> bf16/fp32, or bf16 -> bf16/fp32 (gelu only bf16 -> bf16)."""
+    return _LayerNormFn.apply(x, weight, bias, eps, gelu, out_dtype)
+
+
+class _LnResLnFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, x, w1, b1, w2, b2, eps):
+        _need_cuda(a, x)
+        a, x = _c(a), _c(x)
+        assert a.dtype == torch.bfloat16 and x.dtype == torch.float32
+        cols = a.shape[-1]
+        rows = a.numel() // cols
+        x_new = torch.empty_like(x)
+        y = torch.empty_like(a)
+        stats = torch.empty((4, rows), dtype=torch.float32, device=a.device)
+        _lib.call("ofab_ln_res_ln_fwd", _p(a), _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(x_new), _p(y), _p(stats), rows, cols, eps, _s())
+        ctx.save_for_backward(a, x_new, w1, w2, stats)
+        return x_new, y
+
+    @staticmethod
+    def backward(ctx, dx_new, dy):
+        a, x_new, w1, w2, stats = ctx.saved_tensors
+        cols = a.shape[-1]
+        rows = a.numel() // cols
+        dx_new = torch.zeros_like(x_new) if dx_new is None else _c(dx_new)
+        dy = torch.zeros_like(a) if dy is None else _c(dy)
+        dx_tot = torch.empty_like(x_new)
+        da = torch.empty_like(a)
+        partial = torch.empty((4, _partial_rows(), cols), dtype=torch.float32, device=a.device)
+        _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _s())
+        g = [_reduce_partials(partial, i, cols, w1.dtype) for i in range(4)]
+        return da, dx_tot, g[0], g[1], g[2], g[3], None
+
+
+def ln_res_ln(a, x, w1, b1, w2, b2, eps=1e-5):
+    """x_new = x + LN1(a); y = LN2(x_new).  Returns (x_new fp32, y bf16)."""
+    return _LnResLnFn.apply(a, x, w1, b1, w2, b2, eps)
+
+
+# ------------------------------------------------------------------------------------ GEMM
+def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldd, bias=None, residual=None, ldr=0):
+    """out[M,N] = A * B^T (+bias)(+residual) on tcgen05 (see include/ofab.h)."""
+    _lib.call("ofab_gemm_bf16", M, N, K, _p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), _p(bias), _p(residual), ldr, _p(out), ldd, _DT[out.dtype], _s())
+    return out
+
+
+def _as2d(x):
+    if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0:
+        return x
+    return _c(x).view(-1, x.shape[-1])
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual):
+        _need_cuda(x, weight)
+        assert x.dtype == torch.bfloat16 and weight.dtype == torch.bfloat16
+        x2 = _as2d(x)
+        M, K = x2.shape
+        N = weight.shape[0]
+        w = _c(weight)
+        Np = (N + 7) // 8 * 8
+        if residual is not None:
+            r2 = _c(residual).view(M, N)
+            buf = torch.empty((M, N), dtype=torch.float32, device=x.device)
+            gemm(M, N, K, x2, x2.stride(0), 0, w, K, 0, buf, N, bias=bias, residual=r2, ldr=N)
+            out = buf
+        else:
+            buf = torch.empty((M, Np), dtype=torch.bfloat16, device=x.device)
+            gemm(M, N, K, x2, x2.stride(0), 0, w, K, 0, buf, Np, bias=bias)
+            out = buf if Np == N else buf[:, :N]
+        ctx.save_for_backward(x2, w)
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.xshape = x.shape
+        return out.view(*x.shape[:-1], N) if Np == N else out.unflatten(0, x.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w = ctx.saved_tensors
+        M, K = x2.shape
+        N = w.shape[0]
+        d_res = dy if ctx.has_res else None
+        dyb = dy if dy.dtype == torch.bfloat16 else cast_bf16(dy)
+        dy2 = dyb.reshape(M, N) if dyb.is_contiguous() else _as2d(dyb.reshape(M, N))
+        ld = dy2.stride(0)
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
+            gemm(M, K, N, dy2, ld, 0, w, K, 1, dx, K)  # dX = dY * W   (W read MN-major in place)
+            dx = dx.view(ctx.xshape)
+        if ctx.needs_input_grad[1]:
+            dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
+            gemm(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = colsum(dy2, torch.bfloat16)
+        return dx, dw, db, d_res
+
+
+def linear(x, weight, bias=None, residual=None):
+    """y = x W^T + b (bf16) ; with `residual` (fp32): y = residual + x W^T + b in fp32."""
+    return _LinearFn.apply(x, weight, bias, residual)
+
+
+class _ScaleColsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, W, c, group):
+        W, c = _c(W), _c(c)
+        out = torch.empty_like(W)
+        _lib.call("ofab_scale_cols", _p(W), _p(c), _p(out), W.shape[0], W.shape[1], group, _s())
+        ctx.save_for_backward(W, c)
+        ctx.group = group
+        return out
+
+    @staticmethod
+    def backward(ctx, dWe):
+        W, c = ctx.saved_tensors
+        dWe = _c(dWe)
+        dW = torch.empty_like(W)
+        dc = torch.zeros(c.shape, dtype=torch.float32, device=W.device)
+        _lib.call("ofab_scale_cols_bwd", _p(dWe), _p(W), _p(c), _p(dW), _p(dc), W.shape[0], W.shape[1], ctx.group, _s())
+        return dW, cast_bf16(dc), None
+
+
+def scale_cols(W, c, group):
+    """W_eff[n, k] = W[n, k] * c[k // group]: folds the per-head c_attn into out_proj."""
+    return _ScaleColsFn.apply(W, c, group)
+
+
+# ------------------------------------------------------------------------------------ attention
+class PositionBias:
+    """Structured replacement of the reference's dense attn_bias [B*H, T, S]:
+    pq/pk : bf16 [1 or B, T, d] absolute-position projections (scale applied in-kernel), or None
+    rp_idx: int32 [Tq, Tk] bucket ids (-1 = no relative bias), or None
+    table : bf16 [n_buckets, H] this layer's relative-position table(s), or None
+    """
+
+    def __init__(self, pq=None, pk=None, rp_idx=None, table=None):
+        self.pq, self.pk, self.rp_idx, self.table = pq, pk, rp_idx, table
+
+
+def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse):
+    args.B, args.H, args.Tq, args.Tk = B, H, Tq, Tk
+    args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
+    args.q_bs, args.q_rs = q.stride(0), q.stride(1)
+    args.k_bs, args.k_rs = k.stride(0), k.stride(1)
+    args.v_bs, args.v_rs = v.stride(0), v.stride(1)
+    if pq is not None:
+        args.pq, args.pk = pq.data_ptr(), pk.data_ptr()
+        args.pq_bs = 0 if pq.shape[0] == 1 else pq.stride(0)
+        args.pq_rs = pq.stride(1)
+        args.pk_bs = 0 if pk.shape[0] == 1 else pk.stride(0)
+        args.pk_rs = pk.stride(1)
+    else:
+        args.pq = args.pk = None
+    if rp_idx is not None:
+        args.rp_idx, args.table, args.n_buckets = rp_idx.data_ptr(), table_f32.data_ptr(), table_f32.shape[0]
+    else:
+        args.rp_idx = args.table = None
+        args.n_buckets = 0
+    args.kpm = None if kpm is None else kpm.data_ptr()
+    args.causal = int(causal)
+    args.scale = scale
+    args.o, args.o_bs, args.o_rs = o.data_ptr(), o.stride(0), o.stride(1)
+    args.lse = lse.data_ptr()
+
+
+class _AttentionFn(torch.autograd.Function):
+    """q_src: self-attention -> packed qkv [B, T, 3d]; cross-attention -> q [B, Tq, d] with kv_src [B, Tk, 2d]."""
+
+    @staticmethod
+    def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H):
+        _need_cuda(q_src)
+        q_src = _c(q_src)
+        d = H * 64
+        B = q_src.shape[0]
+        if kv_src is None:
+            assert q_src.shape[-1] == 3 * d
+            q, k, v = q_src[..., :d], q_src[..., d:2 * d], q_src[..., 2 * d:]
+        else:
+            kv_src = _c(kv_src)
+            assert q_src.shape[-1] == d and kv_src.shape[-1] == 2 * d
+            q, k, v = q_src, kv_src[..., :d], kv_src[..., d:]
+        Tq, Tk = q.shape[1], k.shape[1]
+        if pq is not None:
+            pq, pk = _c(pq), _c(pk)
+        table_f = None
+        if rp_idx is not None:
+            assert rp_idx.dtype == torch.int32 and rp_idx.shape == (Tq, Tk) and rp_idx.is_contiguous()
+            table_f = cast_f32(table)
+        if kpm is not None:
+            kpm = _c(kpm.to(torch.uint8) if kpm.dtype != torch.uint8 else kpm)
+        o = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=q_src.device)
+        lse = torch.empty((B, H, Tq), dtype=torch.float32, device=q_src.device)
+        a = _lib.AttnFwdArgs()
+        _fill_attn(a, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse)
+        _lib.call("ofab_attn_fwd", ctypes.byref(a), _s())
+        ctx.save_for_backward(q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse)
+        ctx.meta = (causal, scale, H, None if table is None else table.dtype)
+        return o
+
+    @staticmethod
+    def backward(ctx, d_o):
+        q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse = ctx.saved_tensors
+        causal, scale, H, table_dtype = ctx.meta
+        d = H * 64
+        B = q_src.shape[0]
+        d_o = _c(d_o)
+        if kv_src is None:
+            q, k, v = q_src[..., :d], q_src[..., d:2 * d], q_src[..., 2 * d:]
+            dq_src = torch.empty_like(q_src)
+            dq, dk, dv = dq_src[..., :d], dq_src[..., d:2 * d], dq_src[..., 2 * d:]
+            dkv_src = None
+        else:
+            q, k, v = q_src, kv_src[..., :d], kv_src[..., d:]
+            dq_src = torch.empty_like(q_src)
+            dkv_src = torch.empty_like(kv_src)
+            dq, dk, dv = dq_src, dkv_src[..., :d], dkv_src[..., d:]
+        Tq, Tk = q.shape[1], k.shape[1]
+        a = _lib.AttnBwdArgs()
+        _fill_attn(a.f, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse)
+        a.d_o, a.do_bs, a.do_rs = d_o.data_ptr(), d_o.stride(0), d_o.stride(1)
+        a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+        a.dq_bs, a.dq_rs = dq.stride(0), dq.stride(1)
+        a.dk_bs, a.dk_rs = dk.stride(0), dk.stride(1)
+        a.dv_bs, a.dv_rs = dv.stride(0), dv.stride(1)
+        dpq = dpk = dtab = None
+        if pq is not None:
+            dpq = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=d_o.device)
+            dpk = torch.empty((B, Tk, d), dtype=torch.bfloat16, device=d_o.device)
+            a.dpq, a.dpk = dpq.data_ptr(), dpk.data_ptr()
+        else:
+            a.dpq = a.dpk = None
+        if rp_idx is not None:
+            dtab = torch.zeros_like(table_f)
+            a.dtable = dtab.data_ptr()
+        else:
+            a.dtable = None
+        delta = torch.empty((B, H, Tq), dtype=torch.float32, device=d_o.device)
+        a.delta = delta.data_ptr()
+        _lib.call("ofab_attn_bwd", ctypes.byref(a), _s())
+        if pq is not None:
+            if pq.shape[0] == 1 and B > 1:  # broadcast positions: sum the per-sample grads
+                dpq = colsum(dpq.view(B, Tq * d), torch.bfloat16).view(1, Tq, d)
+            if pk.shape[0] == 1 and B > 1:
+                dpk = colsum(dpk.view(B, Tk * d), torch.bfloat16).view(1, Tk, d)
+        if dtab is not None:
+            dtab = cast_bf16(dtab) if table_dtype == torch.bfloat16 else dtab
+        return dq_src, dkv_src, dpq, dpk, dtab, None, None, None, None, None
+
+
+def attention(q_src, kv_src, H, scale, bias: PositionBias = None, key_padding_mask=None, causal=False):
+    b = bias or PositionBias()
+    return _AttentionFn.apply(q_src, kv_src, b.pq, b.pk, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H)
+
+
+# ------------------------------------------------------------------------------------ adaptor hook
+class _EmbedLnFn(torch.autograd.Function):
+    """out = LN(src + pos + type) (fp32 [B, T, d]); src = E[tokens] or [cls; dense]."""
+
+    @staticmethod
+    def forward(ctx, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx):
+        dev = gamma.device
+        _need_cuda(gamma)
+        if tokens is not None:
+            tokens = _c(tokens)
+            B, T = tokens.shape
+            d = E.shape[1]
+            E = _c(E)
+        else:
+            dense = _c(dense)
+            B, d = dense.shape[0], dense.shape[-1]
+            T = dense.shape[1] + (1 if cls is not None else 0)
+        if pos is not None:
+            pos = _c(pos)
+            assert pos.shape[0] >= T and pos.shape[-1] == d
+        if zero_mask is not None:
+            zero_mask = _c(zero_mask.to(torch.uint8))
+        out = torch.empty((B, T, d), dtype=torch.float32, device=dev)
+        mean = torch.empty(B * T, dtype=torch.float32, device=dev)
+        rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
+        a = _lib.EmbedLnArgs()
+        _EmbedLnFn._fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd)
+        _lib.call("ofab_embed_ln_fwd", ctypes.byref(a), _s())
+        ctx.save_for_backward(tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, mean, rstd)
+        ctx.meta = (B, T, d, eps, padding_idx)
+        return out
+
+    @staticmethod
+    def _fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd):
+        a.B, a.T, a.d = B, T, d
+        a.tokens = None if tokens is None else tokens.data_ptr()
+        a.E = None if E is None or tokens is None else E.data_ptr()
+        a.dense = None if dense is None else dense.data_ptr()
+        a.cls = None if cls is None else cls.data_ptr()
+        a.has_cls = int(cls is not None)
+        a.pos = None if pos is None else pos.data_ptr()
+        a.type = None if type_vec is None else type_vec.data_ptr()
+        a.gamma, a.beta = gamma.data_ptr(), beta.data_ptr()
+        a.zero_mask = None if zero_mask is None else zero_mask.data_ptr()
+        a.eps = eps
+        a.out = None if out is None else out.data_ptr()
+        a.out_bs = T * d
+        a.mean, a.rstd = mean.data_ptr(), rstd.data_ptr()
+
+    @staticmethod
+    def backward(ctx, dout):
+        tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, mean, rstd = ctx.saved_tensors
+        B, T, d, eps, padding_idx = ctx.meta
+        dev = gamma.device
+        dout = _c(dout)
+        a = _lib.EmbedLnBwdArgs()
+        _EmbedLnFn._fill(a.f, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, None, mean, rstd)
+        a.dout, a.dout_bs = dout.data_ptr(), T * d
+        dE = ddense = dpos = None
+        if tokens is not None and ctx.needs_input_grad[1]:
+            dE = torch.zeros(E.shape, dtype=torch.float32, device=dev)
+            a.dE = dE.data_ptr()
+        else:
+            a.dE = None
+        a.padding_idx = -1 if padding_idx is None else padding_idx
+        if dense is not None:
+            ddense = torch.empty_like(dense)
+            a.ddense = ddense.data_ptr()
+        else:
+            a.ddense = None
+        if pos is not None and ctx.needs_input_grad[4]:
+            dpos = torch.zeros((pos.shape[0], d), dtype=torch.float32, device=dev)
+            a.dpos = dpos.data_ptr()
+        else:
+            a.dpos = None
+        partial = torch.empty((4, _partial_rows(), d), dtype=torch.float32, device=dev)
+        a.dgb_partial = partial.data_ptr()
+        _lib.call("ofab_embed_ln_bwd", ctypes.byref(a), _s())
+        dgamma = _reduce_partials(partial, 0, d, gamma.dtype)
+        dbeta = _reduce_partials(partial, 1, d, gamma.dtype)
+        dtype_vec = _reduce_partials(partial, 2, d, type_vec.dtype).view(type_vec.shape) if type_vec is not None else None
+        dcls = _reduce_partials(partial, 3, d, cls.dtype).view(cls.shape) if cls is not None else None
+        if dE is not None:
+            dE = cast_bf16(dE)
+        if dpos is not None:
+            dpos = cast_bf16(dpos).view(pos.shape)
+        return None, dE, ddense, dcls, dpos, dtype_vec, dgamma, dbeta, None, None, None
+
+
+def embed_ln(gamma, beta, tokens=None, E=None, dense=None, cls=None, pos=None, type_vec=None, zero_mask=None, eps=1e-5, padding_idx=None):
+    return _EmbedLnFn.apply(tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx)
+
+
+# ------------------------------------------------------------------------------------ criterion
+class _CrossEntropyFn(torch.autograd.Function):
+    """sum-reduced CE over rows whose target != ignore_index; logits bf16 [..., V] (row stride % 8 == 0)."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index):
+        _need_cuda(logits, target)
+        V = logits.shape[-1]
+        l2 = logits.reshape(-1, V) if logits.dim() != 2 else logits
+        if l2.stride(1) != 1 or l2.stride(0) % 8 != 0:
+            Vp = (V + 7) // 8 * 8
+            buf = torch.empty((l2.shape[0], Vp), dtype=torch.bfloat16, device=logits.device)
+            buf[:, :V].copy_(l2)
+            l2 = buf[:, :V]
+        rows, ld = l2.shape[0], l2.stride(0)
+        tgt = _c(target.reshape(-1))
+        lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        _lib.call("ofab_ce_fwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(loss), _s())
+        ctx.save_for_backward(l2, tgt, lse)
+        ctx.meta = (ignore_index, logits.shape)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        l2, tgt, lse = ctx.saved_tensors
+        ignore_index, shape = ctx.meta
+        rows, V = l2.shape
+        ld = l2.stride(0)
+        dl = torch.empty((rows, ld), dtype=torch.bfloat16, device=l2.device)
+        gs = _c(g.reshape(1).to(torch.float32))
+        _lib.call("ofab_ce_bwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(gs), _p(dl), _s())
+        return dl[:, :V].view(shape) if ld == V else dl[:, :V].unflatten(0, shape[:-1]), None, None
+
+
+def cross_entropy_sum(logits, target, ignore_index=1):
+    return _CrossEntropyFn.apply(logits, target, ignore_index)
+
+
+class _LinearCrossEntropyFn(torch.autograd.Function):
+    """loss = sum-CE(x E^T, target): the tied output projection (adaptor/base.py:131) fused with the
+    criterion (cross_entropy.py:62-67) so the [rows, V] logits live only as one bf16 scratch."""
+
+    @staticmethod
+    def forward(ctx, x, E, target, ignore_index):
+        _need_cuda(x, E, target)
+        x2 = _as2d(x)
+        M, K = x2.shape
+        V = E.shape[0]
+        Vp = (V + 7) // 8 * 8
+        E = _c(E)
+        logits = torch.empty((M, Vp), dtype=torch.bfloat16, device=x.device)
+        gemm(M, V, K, x2, x2.stride(0), 0, E, K, 0, logits, Vp)
+        tgt = _c(target.reshape(-1))
+        lse = torch.empty(M, dtype=torch.float32, device=x.device)
+        loss = torch.zeros(1, dtype=torch.float32, device=x.device)
+        _lib.call("ofab_ce_fwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(loss), _s())
+        ctx.save_for_backward(x2, E, tgt, lse, logits)
+        ctx.meta = (ignore_index, x.shape)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, E, tgt, lse, logits = ctx.saved_tensors
+        ignore_index, xshape = ctx.meta
+        M, K = x2.shape
+        V = E.shape[0]
+        Vp = logits.shape[1]
+        gs = _c(g.reshape(1).to(torch.float32))
+        _lib.call("ofab_ce_bwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(gs), _p(logits), _s())  # in place
+        dx = dE = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=torch.bfloat16, device=x2.device)
+            gemm(M, K, V, logits, Vp, 0, E, K, 1, dx, K)
+            dx = dx.view(xshape)
+        if ctx.needs_input_grad[1]:
+            dE = torch.empty((V, K), dtype=torch.bfloat16, device=x2.device)
+            gemm(V, K, M, logits, Vp, 1, x2, x2.stride(0), 1, dE, K)
+        return dx, dE, None, None
+
+
+def linear_cross_entropy(x, E, target, ignore_index=1):
+    return _LinearCrossEntropyFn.apply(x, E, target, ignore_index)
+
+
+# ------------------------------------------------------------------------------------ adaptors' convs
+def patch_im2col(img, patch, ldk):
+    """[B, C, H, W] (fp32/bf16) -> bf16 [B*(H/p)*(W/p), ldk]; no gradient (the image is data)."""
+    _need_cuda(img)
+    img = _c(img)
+    B, C, H, W = img.shape
+    cols = torch.empty((B * (H // patch) * (W // patch), ldk), dtype=torch.bfloat16, device=img.device)
+    _lib.call("ofab_patch_im2col", _p(img), _DT[img.dtype], B, C, H, W, patch, _p(cols), ldk, _s())
+    return cols
+
+
+class _TransposeLast2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, w3):
+        w3 = _c(w3)
+        O, A, Bd = w3.shape
+        out = torch.empty((O, Bd, A), dtype=w3.dtype, device=w3.device)
+        _lib.call("ofab_transpose_last2", _p(w3), _p(out), O, A, Bd, _s())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        O, Bd, A = g.shape
+        out = torch.empty((O, A, Bd), dtype=g.dtype, device=g.device)
+        _lib.call("ofab_transpose_last2", _p(g), _p(out), O, Bd, A, _s())
+        return out
+
+
+def transpose_last2(w3):
+    return _TransposeLast2Fn.apply(w3)
+
+
+class _Conv1ReluFn(torch.autograd.Function):
+    """Conv2d(1, C, 3, stride 2) + ReLU on fbank [B, L, F] -> bf16 [B, H1, W1, C] (channel-last)."""
+
+    @staticmethod
+    def forward(ctx, fbank, w, b):
+        _need_cuda(fbank, w)
+        fbank = _c(fbank)
+        B, L, F = fbank.shape
+        C = w.shape[0]
+        w9 = _c(w).view(C, 9)
+        H1, W1 = (L - 3) // 2 + 1, (F - 3) // 2 + 1
+        out = torch.empty((B, H1, W1, C), dtype=torch.bfloat16, device=fbank.device)
+        _lib.call("ofab_conv1_relu_fwd", _p(fbank), _DT[fbank.dtype], B, L, F, _p(w9), _p(b), C, _p(out), _s())
+        ctx.save_for_backward(fbank, out)
+        ctx.wshape = w.shape
+        return out
+
+    @staticmethod
+    def backward(ctx, dy):
+        fbank, y = ctx.saved_tensors
+        dy = _c(dy)
+        B, L, F = fbank.shape
+        C = y.shape[-1]
+        dw = torch.zeros((C, 9), dtype=torch.float32, device=dy.device)
+        db = torch.zeros(C, dtype=torch.float32, device=dy.device)
+        _lib.call("ofab_conv1_relu_bwd", _p(fbank), _DT[fbank.dtype], B, L, F, _p(y), _p(dy), C, _p(dw), _p(db), _s())
+        return None, cast_bf16(dw).view(ctx.wshape), cast_bf16(db)
+
+
+def conv1_relu(fbank, w, b):
+    return _Conv1ReluFn.apply(fbank, w, b)
+
+
+class _Im2col3x3s2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, Hin, Win, C = x.shape
+        Ho, Wo = (Hin - 3) // 2 + 1, (Win - 3) // 2 + 1
+        cols = torch.empty((B * Ho * Wo, 9 * C), dtype=torch.bfloat16, device=x.device)
+        _lib.call("ofab_im2col_3x3s2", _p(x), B, Hin, Win, C, _p(cols), _s())
+        ctx.shape = x.shape
+        return cols
+
+    @staticmethod
+    def backward(ctx, dcols):
+        dcols = _c(dcols)
+        B, Hin, Win, C = ctx.shape
+        dx = torch.empty(ctx.shape, dtype=torch.bfloat16, device=dcols.device)
+        _lib.call("ofab_col2im_3x3s2", _p(dcols), B, Hin, Win, C, _p(dx), _s())
+        return dx
+
+
+def im2col_3x3s2(x):
+    return _Im2col3x3s2Fn.apply(x)
+
+
+class _ReluFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = _c(x).clone() if x.requires_grad or True else x
+        _lib.call("ofab_relu_inplace", _p(y), y.numel(), _s())
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        dy = _c(dy).clone()
+        _lib.call("ofab_relu_bwd_inplace", _p(y), _p(dy), dy.numel(), _s())
+        return dy
+
+
+def relu(x):
+    return _ReluFn.apply(x)

@@ -1,0 +1,137 @@
+"""CPU (no GPU): host-side logic of the product -- registry, state-dict contract, integer position
+machinery (bit-exact vs the reference's own tables), C-ABI export table, loud failure without CUDA."""
+import ctypes
+import hashlib
+import os
+import re
+
+import pytest
+import torch
+
+import ofasys_b200 as ob
+from ofasys_b200 import _lib
+from ofasys_b200.adaptor.audio import make_audio_bucket_1d
+from ofasys_b200.adaptor.text import make_token_bucket_position
+from oracle import cases
+from oracle import oracle_model as om
+
+from util import TTS_ONLY, build_product, load_golden
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "cfg1_tiny"])
+def test_state_dict_contract(name):
+    """Parameter names / shapes equal the reference's (golden `spec` was dumped from its state_dict)."""
+    g = load_golden(name)
+    m = build_product(name)
+    ours = {k: tuple(v.shape) for k, v in m.state_dict().items() if v.is_floating_point() and not k.endswith(".version")}
+    ref = {k: v for k, v in g["spec"].items() if not any(t in k.split(".") for t in TTS_ONLY)}
+    assert set(ours) == set(ref), (sorted(set(ours) - set(ref))[:5], sorted(set(ref) - set(ours))[:5])
+    for k in ref:
+        assert ours[k] == tuple(ref[k]), k
+    # reference state dicts (incl. its derived buffers / TTS-only tensors) load
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.endswith("rp_bucket") or k.endswith("version") for k in missing), missing
+    # tied embedding is one tensor (general.py:191-221)
+    assert m.encoder.adaptor.embed_tokens.weight.data_ptr() == m.decoder.adaptor.embed_tokens.weight.data_ptr()
+
+
+def test_registry():
+    st = ob.ConfigStore()
+    assert st.get("ofasys.model", "unify").target is ob.GeneralistModel
+    for n in ("text", "image_patch_embed", "audio_fbank"):
+        assert st.contain("ofasys.adaptor", n)
+
+
+def test_token_bucket_bit_exact():
+    g = load_golden("text_A")
+    shape, dig, corner = g["ints"]["encoder.adaptor.text.token_rp_bucket"]
+    t = make_token_bucket_position(256, 1024)
+    assert t.dtype == torch.int64 and tuple(t.shape) == shape
+    assert hashlib.sha256(t.contiguous().numpy().tobytes()).hexdigest() == dig
+    m = build_product("text_A")
+    assert torch.equal(m.encoder.adaptor.text.token_rp_bucket, t)
+    assert torch.equal(m.encoder.adaptor.text.rel_idx(24).long(), t[:24, :24])
+
+
+def test_audio_bucket_bit_exact():
+    """1-D (i - j) table reproduces the reference's 4096 x 4096 buffer bit for bit."""
+    g = load_golden("audio_A")
+    shape, dig, corner = g["ints"]["encoder.adaptor.audio_fbank.audio_rp_bucket"]
+    one = make_audio_bucket_1d(1024)
+    i = torch.arange(4096)
+    full = one[i[:, None] - i[None, :] + 4095]
+    assert tuple(full.shape) == shape
+    assert hashlib.sha256(full.contiguous().numpy().tobytes()).hexdigest() == dig
+    m = build_product("audio_A")
+    assert torch.equal(m.encoder.adaptor.audio_fbank.rel_idx(49).long(), full[:49, :49])
+
+
+def test_audio_lengths_and_box_bins():
+    from ofasys_b200.adaptor.audio import Conv2dSubsampling4
+    from ofasys_b200.preprocessor import quantize_box
+
+    s = Conv2dSubsampling4(80, 8)
+    lens = torch.tensor([700, 998, 200, 150, 3, 4])
+    assert torch.equal(s.get_out_seq_lens_tensor(lens), om.audio_out_lengths(lens))
+    x = torch.tensor([0.0, 255.6, 511.0, 512.0, 100.25])
+    assert torch.equal(quantize_box(x), om.quantize_box(x))
+
+
+def test_global_rel_idx_block_diagonal():
+    """concat(): slot-local bucket ids are offset into the concatenated table; -1 elsewhere."""
+    m = build_product("audio_A")
+    ga = m.encoder.adaptor
+    from ofasys_b200.adaptor.base import AdaptorOutput
+
+    a = ga.audio_fbank.rel_idx(5)
+    t = ga.text.rel_idx(3)
+    outs = [
+        AdaptorOutput(torch.zeros(1, 5, 8), torch.zeros(1, 5, dtype=torch.bool), None, None, rel_idx=a, rel_tables=[torch.zeros(2047, 2)]),
+        AdaptorOutput(torch.zeros(1, 3, 8), torch.zeros(1, 3, dtype=torch.bool), None, None, rel_idx=t, rel_tables=[torch.zeros(511, 2)]),
+    ]
+    idx = ga._global_idx(outs)
+    assert idx.shape == (8, 8) and idx.dtype == torch.int32
+    assert torch.equal(idx[:5, :5], a) and torch.equal(idx[5:, 5:], t + 2047)
+    assert (idx[:5, 5:] == -1).all() and (idx[5:, :5] == -1).all()
+
+
+def test_cabi_exports_every_declared_symbol():
+    """libofab.so loads without a GPU and exports exactly what include/ofab.h declares."""
+    hdr = open(os.path.join(ROOT, "include", "ofab.h")).read()
+    declared = set(re.findall(r"\b(ofab_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    assert os.path.exists(_lib.LIB_PATH), "libofab.so not built (run __graft_entry__.build())"
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for sym in sorted(declared):
+        assert hasattr(L, sym), f"{sym} declared in ofab.h but not exported"
+    assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
+    lib = _lib.lib()
+    assert lib.ofab_version() >= 100
+    assert lib.ofab_ln_partial_rows() == 592
+
+
+def test_no_cpu_fallback():
+    """The product refuses CPU tensors instead of silently computing elsewhere."""
+    from ofasys_b200 import ops
+
+    x = torch.randn(4, 64)
+    w = torch.ones(64, dtype=torch.bfloat16)
+    with pytest.raises(_lib.OfabError):
+        ops.layer_norm(x, w, w)
+
+
+def test_product_never_imports_oracle():
+    import subprocess
+    import sys
+
+    code = "import sys, ofasys_b200, ofasys_b200.ops; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+    for dp, _, fs in os.walk(os.path.join(ROOT, "ofasys_b200")):
+        for f in fs:
+            if f.endswith(".py"):
+                src = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in src and "from oracle" not in src, f

@@ -1,0 +1,420 @@
+"""GPU: every kernel family of libofab against a plain PyTorch fp32 restatement of the same op on
+the same (bf16-rounded) inputs.  Tolerances: fp32 outputs 2e-5 rel-L2 (accumulation order); bf16
+outputs 6e-3 (one bf16 rounding, eps = 7.8e-3 per element)."""
+import math
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from util import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 2e-5
+TOL16 = 6e-3
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def g():
+    return torch.Generator(device="cpu").manual_seed(0)
+
+
+def rnd(*shape, dtype=torch.bfloat16, scale=1.0, gen=None):
+    return (torch.randn(*shape, generator=gen or g()) * scale).to(dtype).to(dev())
+
+
+def setup_module(module):
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    from ofasys_b200 import _lib
+
+    _lib.check(_lib.lib().ofab_device_check(0), "device check")
+
+
+# ----------------------------------------------------------------------------------------- LN
+@pytest.mark.parametrize("cols", [64, 128, 256, 768, 1024, 2048, 3072, 4096])
+@pytest.mark.parametrize("rows", [1, 37, 1031])
+def test_layer_norm_fwd_bwd(rows, cols):
+    from ofasys_b200 import ops
+
+    gen = g()
+    x = rnd(rows, cols, dtype=torch.float32, gen=gen).requires_grad_(True)
+    w = (torch.rand(cols, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    b = (torch.randn(cols, generator=gen) * 0.1).bfloat16().to(dev()).requires_grad_(True)
+    dy = rnd(rows, cols, gen=gen)
+    y = ops.layer_norm(x, w, b)
+    y.backward(dy)
+    xr = x.detach().clone().requires_grad_(True)
+    wr, br = w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    yr = F.layer_norm(xr, (cols,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    assert rel_l2(y, yr) <= TOL16
+    assert rel_l2(x.grad, xr.grad) <= 1e-4
+    assert rel_l2(w.grad, wr.grad) <= TOL16 and rel_l2(b.grad, br.grad) <= TOL16
+
+
+@pytest.mark.parametrize("cols", [512, 1024, 3072, 4096])
+def test_gelu_layer_norm(cols):
+    from ofasys_b200 import ops
+
+    gen = g()
+    rows = 517
+    h = rnd(rows, cols, gen=gen).requires_grad_(True)
+    w = (torch.rand(cols, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    b = (torch.randn(cols, generator=gen) * 0.1).bfloat16().to(dev()).requires_grad_(True)
+    dy = rnd(rows, cols, gen=gen)
+    y = ops.layer_norm(h, w, b, gelu=True)
+    y.backward(dy)
+    hr = h.detach().float().requires_grad_(True)
+    wr, br = w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    yr = F.layer_norm(F.gelu(hr), (cols,), wr, br, 1e-5)
+    yr.backward(dy.float())
+    assert rel_l2(y, yr) <= TOL16
+    assert rel_l2(h.grad, hr.grad) <= TOL16
+    assert rel_l2(w.grad, wr.grad) <= TOL16 and rel_l2(b.grad, br.grad) <= TOL16
+
+
+@pytest.mark.parametrize("cols", [128, 256, 768, 1024])
+def test_ln_res_ln(cols):
+    from ofasys_b200 import ops
+
+    gen = g()
+    rows = 333
+    a = rnd(rows, cols, gen=gen).requires_grad_(True)
+    x = rnd(rows, cols, dtype=torch.float32, gen=gen).requires_grad_(True)
+    ps = []
+    for _ in range(2):
+        ps.append((torch.rand(cols, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True))
+        ps.append((torch.randn(cols, generator=gen) * 0.1).bfloat16().to(dev()).requires_grad_(True))
+    dxn = rnd(rows, cols, dtype=torch.float32, gen=gen)
+    dy = rnd(rows, cols, gen=gen)
+    xn, y = ops.ln_res_ln(a, x, *ps)
+    torch.autograd.backward([xn, y], [dxn, dy])
+    ar, xr = a.detach().float().requires_grad_(True), x.detach().clone().requires_grad_(True)
+    pr = [p.detach().float().requires_grad_(True) for p in ps]
+    xnr = xr + F.layer_norm(ar, (cols,), pr[0], pr[1], 1e-5)
+    yr = F.layer_norm(xnr, (cols,), pr[2], pr[3], 1e-5)
+    torch.autograd.backward([xnr, yr], [dxn, dy.float()])
+    assert rel_l2(xn, xnr) <= TOL32 and rel_l2(y, yr) <= TOL16
+    assert rel_l2(x.grad, xr.grad) <= 1e-4 and rel_l2(a.grad, ar.grad) <= TOL16
+    for p, q in zip(ps, pr):
+        assert rel_l2(p.grad, q.grad) <= TOL16
+
+
+def test_colsum():
+    from ofasys_b200 import ops
+
+    x = rnd(5000, 200, dtype=torch.float32)
+    assert rel_l2(ops.colsum(x, torch.float32), x.sum(0)) <= 1e-5
+    xb = rnd(777, 96)
+    assert rel_l2(ops.colsum(xb, torch.float32), xb.float().sum(0)) <= 1e-5
+
+
+# --------------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 136, 72), (1000, 768, 768), (257, 2304, 768), (520, 3072, 128), (64, 50265 // 8 * 8 + 8, 256), (768, 768, 1000)])
+def test_gemm_layouts(M, N, K, a_mn, b_mn):
+    """All four operand-major combinations (fwd: K/K, dgrad: K/MN, wgrad: MN/MN), ragged M/N/K tiles."""
+    from ofasys_b200 import ops
+
+    if a_mn and M % 8:
+        M = (M + 7) // 8 * 8
+    if b_mn and N % 8:
+        N = (N + 7) // 8 * 8
+    gen = g()
+    A = rnd(M, K, gen=gen)
+    B = rnd(N, K, gen=gen)
+    Am = A.t().contiguous() if a_mn else A
+    Bm = B.t().contiguous() if b_mn else B
+    out = torch.empty(M, N, dtype=torch.float32, device=dev())
+    ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, N)
+    ref = A.float() @ B.float().t()
+    assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn)
+
+
+def test_gemm_epilogues():
+    from ofasys_b200 import ops
+
+    gen = g()
+    M, N, K = 300, 776, 192
+    A, B = rnd(M, K, gen=gen), rnd(N, K, gen=gen)
+    bias = rnd(N, gen=gen)
+    res = rnd(M, N, dtype=torch.float32, gen=gen)
+    ref = A.float() @ B.float().t()
+    o1 = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+    ops.gemm(M, N, K, A, K, 0, B, K, 0, o1, N, bias=bias)
+    assert rel_l2(o1, ref + bias.float()) <= TOL16
+    o2 = torch.empty(M, N, dtype=torch.float32, device=dev())
+    ops.gemm(M, N, K, A, K, 0, B, K, 0, o2, N, bias=bias, residual=res, ldr=N)
+    assert rel_l2(o2, ref + bias.float() + res) <= TOL32
+    # padded leading dimension (logits layout)
+    o3 = torch.full((M, N + 8), 7.0, dtype=torch.bfloat16, device=dev())
+    ops.gemm(M, N - 3, K, A, K, 0, B, K, 0, o3, N + 8)
+    assert rel_l2(o3[:, : N - 3], ref[:, : N - 3]) <= TOL16
+    assert (o3[:, N - 3:] == 7.0).all(), "columns beyond N must not be written"
+
+
+def test_gemm_many_tiles_persistent():
+    """more tiles than SMs: exercises the persistent loop, smem ring wrap and both TMEM stages."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    M, N, K = 4096 + 40, 2304, 768
+    A, B = rnd(M, K, gen=gen, scale=0.5), rnd(N, K, gen=gen, scale=0.5)
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+    ops.gemm(M, N, K, A, K, 0, B, K, 0, out, N)
+    assert rel_l2(out, A.float() @ B.float().t()) <= TOL16
+
+
+@pytest.mark.parametrize("with_res", [False, True])
+def test_linear_autograd(with_res):
+    from ofasys_b200 import ops
+
+    gen = g()
+    Bz, T, K, N = 3, 50, 256, 384
+    x = rnd(Bz, T, K, gen=gen).requires_grad_(True)
+    W = rnd(N, K, gen=gen, scale=0.05).requires_grad_(True)
+    b = rnd(N, gen=gen, scale=0.1).requires_grad_(True)
+    res = rnd(Bz, T, N, dtype=torch.float32, gen=gen).requires_grad_(True) if with_res else None
+    dy = rnd(Bz, T, N, dtype=torch.float32 if with_res else torch.bfloat16, gen=gen)
+    y = ops.linear(x, W, b, residual=res)
+    y.backward(dy)
+    xr, Wr, br = (t.detach().float().requires_grad_(True) for t in (x, W, b))
+    yr = F.linear(xr, Wr, br)
+    if with_res:
+        rr = res.detach().clone().requires_grad_(True)
+        yr = yr + rr
+    dyr = dy.float() if not with_res else dy.bfloat16().float()  # backward GEMMs consume bf16 dY
+    yr.backward(dyr)
+    assert rel_l2(y, yr) <= (TOL32 if with_res else TOL16)
+    assert rel_l2(x.grad, xr.grad) <= TOL16 and rel_l2(W.grad, Wr.grad) <= TOL16 and rel_l2(b.grad, br.grad) <= TOL16
+    if with_res:
+        assert torch.equal(res.grad, dy)
+
+
+# ---------------------------------------------------------------------------------- attention
+def attn_ref(q, k, v, pq, pk, table, idx, kpm, causal, scale, H):
+    """fp32 restatement of multihead_attention.py:308-338 with the bias written out densely."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    dh = 64
+    sp = lambda t: t.view(t.shape[0], t.shape[1], H, dh).transpose(1, 2)
+    s = torch.matmul(sp(q), sp(k).transpose(2, 3))
+    if pq is not None:
+        s = s + torch.matmul(sp(pq), sp(pk).transpose(2, 3))
+    s = s * scale
+    if idx is not None:
+        bias = table[idx.clamp_min(0).long()]  # Tq x Tk x H
+        bias = torch.where((idx >= 0).unsqueeze(-1), bias, torch.zeros_like(bias))
+        s = s + bias.permute(2, 0, 1).unsqueeze(0)
+    if causal:
+        s = s + torch.triu(torch.full((Tq, Tk), float("-inf"), device=s.device), 1)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    p = torch.softmax(s, dim=-1)
+    return torch.matmul(p, sp(v)).transpose(1, 2).reshape(B, Tq, d)
+
+
+@pytest.mark.parametrize("mode", ["self", "cross"])
+@pytest.mark.parametrize("Tq,Tk", [(64, 64), (24, 24), (130, 130), (16, 265), (257, 257)])
+@pytest.mark.parametrize("variant", ["plain", "pos", "pos_rel", "pos_rel_kpm_causal", "kpm", "causal"])
+def test_attention(mode, Tq, Tk, variant):
+    from ofasys_b200 import ops
+
+    if mode == "self" and Tq != Tk:
+        pytest.skip("self-attention needs Tq == Tk")
+    if mode == "cross" and "causal" in variant:
+        pytest.skip("no causal cross-attention")
+    gen = g()
+    B, H = 2, 2
+    d = H * 64
+    scale = 128 ** -0.5
+    if mode == "self":
+        qkv = rnd(B, Tq, 3 * d, gen=gen).requires_grad_(True)
+        kv = None
+    else:
+        qkv = rnd(B, Tq, d, gen=gen).requires_grad_(True)
+        kv = rnd(B, Tk, 2 * d, gen=gen).requires_grad_(True)
+    pq = pk = table = idx = kpm = None
+    if "pos" in variant:
+        pq = rnd(1, Tq, d, gen=gen).requires_grad_(True)
+        pk = rnd(1, Tk, d, gen=gen).requires_grad_(True)
+    if "rel" in variant:
+        nb = 37
+        table = rnd(nb, H, gen=gen, scale=0.5).requires_grad_(True)
+        idx = torch.randint(-1, nb, (Tq, Tk), generator=gen).to(torch.int32).to(dev())
+    if "kpm" in variant:
+        kpm = torch.zeros(B, Tk, dtype=torch.bool)
+        kpm[1, Tk - max(1, Tk // 4):] = True
+        if Tk > 8:
+            kpm[0, 3] = True  # interior pad (concatenated slots)
+        kpm = kpm.to(dev())
+    causal = "causal" in variant
+    do = rnd(B, Tq, d, gen=gen)
+    o = ops.attention(qkv, kv, H, scale, ops.PositionBias(pq, pk, idx, table), kpm, causal)
+    o.backward(do)
+
+    leaves = [t for t in (qkv, kv, pq, pk, table) if t is not None]
+    refs = {id(t): t.detach().float().requires_grad_(True) for t in leaves}
+    R = lambda t: None if t is None else refs[id(t)]
+    if mode == "self":
+        q_, k_, v_ = R(qkv)[..., :d], R(qkv)[..., d:2 * d], R(qkv)[..., 2 * d:]
+    else:
+        q_, k_, v_ = R(qkv), R(kv)[..., :d], R(kv)[..., d:]
+    pq_ = None if pq is None else R(pq).expand(B, -1, -1)
+    pk_ = None if pk is None else R(pk).expand(B, -1, -1)
+    orf = attn_ref(q_, k_, v_, pq_, pk_, R(table), idx, kpm, causal, scale, H)
+    orf.backward(do.float())
+    assert rel_l2(o, orf) <= 1e-2, (mode, Tq, Tk, variant)
+    for t in leaves:
+        assert rel_l2(t.grad, refs[id(t)].grad) <= 2e-2, (mode, Tq, Tk, variant, tuple(t.shape))
+
+
+# ------------------------------------------------------------------------------- embed / CE
+@pytest.mark.parametrize("d", [128, 256, 768])
+@pytest.mark.parametrize("entangle,is_src", [(False, True), (True, True), (True, False)])
+def test_embed_ln_gather(d, entangle, is_src):
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, T, V = 3, 19, 97
+    E = rnd(V, d, gen=gen, scale=0.5).requires_grad_(True)
+    pos = rnd(T + 5, d, gen=gen, scale=0.5).requires_grad_(True)
+    typ = rnd(1, d, gen=gen, scale=0.5).requires_grad_(True)
+    gam = (torch.rand(d, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    bet = rnd(d, gen=gen, scale=0.1).requires_grad_(True)
+    tok = torch.randint(2, V, (B, T), generator=gen)
+    tok[1, -4:] = 1
+    tok = tok.to(dev())
+    mask = tok.eq(1)
+    dout = rnd(B, T, d, dtype=torch.float32, gen=gen)
+    out = ops.embed_ln(gam, bet, tokens=tok, E=E, pos=pos if entangle else None, type_vec=typ if is_src else None,
+                       zero_mask=mask if is_src else None, padding_idx=1)
+    out.backward(dout)
+    Er, pr, tr, gr, br = (t.detach().float().requires_grad_(True) for t in (E, pos, typ, gam, bet))
+    pre = F.embedding(tok, Er, padding_idx=1)
+    if entangle:
+        pre = pre + pr[:T]
+    if is_src:
+        pre = pre + tr.squeeze()
+    ref = F.layer_norm(pre, (d,), gr, br, 1e-5)
+    if is_src:
+        ref = ref * (1 - mask.unsqueeze(-1).float())
+    ref.backward(dout)
+    assert rel_l2(out, ref) <= TOL32
+    assert rel_l2(E.grad, Er.grad) <= TOL16
+    assert rel_l2(gam.grad, gr.grad) <= TOL16 and rel_l2(bet.grad, br.grad) <= TOL16
+    if entangle:
+        assert rel_l2(pos.grad, pr.grad) <= TOL16
+    if is_src:
+        assert rel_l2(typ.grad, tr.grad) <= TOL16
+
+
+@pytest.mark.parametrize("has_cls", [False, True])
+def test_embed_ln_dense(has_cls):
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, P, d = 2, 9, 256
+    dense = rnd(B, P, d, gen=gen).requires_grad_(True)
+    cls = rnd(1, 1, d, gen=gen).requires_grad_(True) if has_cls else None
+    T = P + int(has_cls)
+    pos = rnd(T, d, gen=gen).requires_grad_(True)
+    typ = rnd(1, d, gen=gen).requires_grad_(True)
+    gam = (torch.rand(d, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    bet = rnd(d, gen=gen, scale=0.1).requires_grad_(True)
+    dout = rnd(B, T, d, dtype=torch.float32, gen=gen)
+    out = ops.embed_ln(gam, bet, dense=dense, cls=cls, pos=pos, type_vec=typ)
+    out.backward(dout)
+    leaves = [t for t in (dense, cls, pos, typ, gam, bet) if t is not None]
+    R = {id(t): t.detach().float().requires_grad_(True) for t in leaves}
+    x = R[id(dense)]
+    if has_cls:
+        x = torch.cat([R[id(cls)].expand(B, -1, -1), x], dim=1)
+    ref = F.layer_norm(x + R[id(pos)][:T] + R[id(typ)].squeeze(), (d,), R[id(gam)], R[id(bet)], 1e-5)
+    ref.backward(dout)
+    assert rel_l2(out, ref) <= TOL32
+    for t in leaves:
+        assert rel_l2(t.grad, R[id(t)].grad) <= TOL16, tuple(t.shape)
+
+
+@pytest.mark.parametrize("V", [512, 50265])
+def test_cross_entropy_and_fused_projection(V):
+    from ofasys_b200 import ops
+
+    gen = g()
+    M, d = 77, 128
+    x = rnd(M, d, gen=gen).requires_grad_(True)
+    E = rnd(V, d, gen=gen, scale=0.3).requires_grad_(True)
+    tgt = torch.randint(2, V, (M,), generator=gen)
+    tgt[::7] = 1
+    tgt = tgt.to(dev())
+    loss = ops.linear_cross_entropy(x, E, tgt, 1)
+    (loss * 0.5).backward()
+    xr, Er = x.detach().float().requires_grad_(True), E.detach().float().requires_grad_(True)
+    logits = (xr @ Er.t()).bfloat16().float()  # the kernel reads bf16 logits
+    lr = F.cross_entropy(logits, tgt, ignore_index=1, reduction="sum")
+    lref = F.cross_entropy(xr @ Er.t(), tgt, ignore_index=1, reduction="sum")
+    (lref * 0.5).backward()
+    assert abs(loss.item() - lr.item()) <= 1e-4 * abs(lr.item())
+    assert abs(loss.item() - lref.item()) <= 2e-3 * abs(lref.item())
+    assert rel_l2(x.grad, xr.grad) <= 1e-2 and rel_l2(E.grad, Er.grad) <= 1e-2
+    # stand-alone criterion on model logits
+    lg = ops.linear(x.detach(), E.detach()).requires_grad_(True)
+    l2 = ops.cross_entropy_sum(lg, tgt, 1)
+    l2.backward()
+    lgr = lg.detach().float().requires_grad_(True)
+    F.cross_entropy(lgr, tgt, ignore_index=1, reduction="sum").backward()
+    assert abs(l2.item() - lr.item()) <= 1e-4 * abs(lr.item())
+    assert rel_l2(lg.grad, lgr.grad) <= TOL16
+
+
+def test_scale_cols():
+    from ofasys_b200 import ops
+
+    gen = g()
+    W = rnd(128, 128, gen=gen).requires_grad_(True)
+    c = (torch.rand(2, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    dW = rnd(128, 128, gen=gen)
+    We = ops.scale_cols(W, c, 64)
+    We.backward(dW)
+    Wr, cr = W.detach().float().requires_grad_(True), c.detach().float().requires_grad_(True)
+    (Wr * cr.repeat_interleave(64)[None, :]).backward(dW.float())
+    assert rel_l2(We, Wr * cr.repeat_interleave(64)[None, :]) <= TOL16
+    assert rel_l2(W.grad, Wr.grad) <= TOL16 and rel_l2(c.grad, cr.grad) <= TOL16
+
+
+# ------------------------------------------------------------------------------- audio convs
+def test_audio_subsampler_pieces():
+    from ofasys_b200 import ops
+    from ofasys_b200.adaptor.audio import Conv2dSubsampling4
+
+    gen = g()
+    B, L, Fd, C = 2, 61, 80, 64
+    sub = Conv2dSubsampling4(Fd, C).to(dev())
+    with torch.no_grad():
+        for p in sub.parameters():
+            p.copy_(torch.randn(p.shape, generator=gen) * (0.3 if p.dim() > 1 else 0.1))
+    ref = [p.detach().clone().float().requires_grad_(True) for p in sub.parameters()]
+    sub = sub.to(torch.bfloat16)
+    for p, r in zip(sub.parameters(), ref):
+        r.data.copy_(p.detach().float())
+    x = rnd(B, L, Fd, dtype=torch.float32, gen=gen)
+    lens = torch.tensor([L, L - 9], device=dev())
+    out, ol = sub(x, lens)
+    dy = rnd(*out.shape, gen=gen)
+    out.backward(dy)
+    w1, b1, w2, b2, wl, bl = ref
+    h = F.relu(F.conv2d(x.unsqueeze(1), w1, b1, stride=2)).bfloat16().float()
+    h = F.relu(F.conv2d(h, w2, b2, stride=2)).bfloat16().float()
+    b_, c_, t_, f_ = h.shape
+    yr = F.linear(h.transpose(1, 2).contiguous().view(b_, t_, c_ * f_), wl, bl)
+    yr.backward(dy.float())
+    assert tuple(out.shape) == tuple(yr.shape)
+    assert rel_l2(out, yr) <= 1e-2
+    for p, r in zip(sub.parameters(), ref):
+        assert rel_l2(p.grad, r.grad) <= 3e-2, tuple(p.shape)
