@@ -1,0 +1,373 @@
+"""bench.py -- seq/s of the OFASys unified encoder-decoder fwd+bwd hot path on B200.
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+Workload (BASELINE.json configs[1]): image_caption, OFA-base 12L/12L d=768, 224^2 patch-embed
+(257 tokens) + 8-token prompt -> 64-token caption, bf16, per-GPU batch 32, synthetic data, random-init
+weights of that architecture.  A step = forward + sum-CE loss + backward of every parameter gradient
+(+ the gradient all-reduce when N > 1); optimizer excluded.
+
+One JSON line on stdout (rank 0):
+  value      seq/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e        same metric through the public API with pinned HOST buffers: H2D of the step's inputs and
+             D2H of the loss inside the timed region
+  roofline   tcgen05 GEMM (dominant kernel): algorithmic FLOPs / per-launch CUDA-event time vs the
+             measured bf16 peak of MEASURED_PEAKS.json
+  cpu_baseline  the oracle (CPU restatement of the reference, oracle/oracle_model.py) timed on host cores
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = "seq/s enc-dec fwd+bwd, OFA-base mixed-modality"
+WORKLOAD = "image_caption OFA-base 12L/12L d=768, 224^2 patch-embed(257 tok)+8-tok prompt -> 64-tok caption"
+V = 50265
+CFG = dict(embed_dim=768, heads=12, ffn_dim=3072, enc_layers=12, dec_layers=12, vocab=V, mode="B")
+PROMPT, TGT = 8, 64
+FWD_GFLOP_PER_SEQ = 71.15  # SURVEY.md 8d (FlopCounterMode on the reference, cfg2a)
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]), hbm=d["hbm_gbs"], src="measured")
+    return dict(tf_burst=1590.0, tf_sustained=1400.0, hbm=6650.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------------ model / data
+def build_model(dev):
+    import ofasys_b200 as ob
+
+    cfg = ob.GeneralistModelConfig.default()
+    cfg.dropout = 0.0
+    cfg.use_self_attn_bias = False
+    cfg.entangle_position_embedding = True
+    cfg.arch = "base"
+    m = ob.GeneralistModel(cfg)
+    m.cfg.encoder.layers = m.cfg.decoder.layers = 12  # "OFA-base 12L/12L" (reference preset is 6/6; SURVEY.md header)
+    for n in ("text", "image_patch_embed"):
+        a = getattr(m.cfg.adaptor, n)
+        a.is_active = True
+        a.entangle_position_embedding = True
+    m.cfg.adaptor.image_patch_embed.embed_dim = 768
+    torch.manual_seed(0)
+    m.initialize(ob.Dictionary(n_dummy=V - 4))
+    return m.to(torch.bfloat16).to(dev).train()
+
+
+def host_batch(B, seed, pin):
+    g = torch.Generator().manual_seed(seed)
+    img = torch.randn(B, 3, 224, 224, generator=g)
+    prompt = torch.randint(4, V, (B, PROMPT), generator=g)
+    prev = torch.randint(4, V, (B, TGT), generator=g)
+    prev[:, 0] = 0
+    n_short = max(1, B // 10)  # 10 % of the sequences shortened and right-padded
+    prev[:n_short, TGT - TGT // 4:] = 1
+    tgt = torch.roll(prev, -1, 1)
+    tgt[:, -1] = 2
+    tgt[prev == 1] = 1
+    tgt[torch.roll(prev == 1, -1, 1)] = 1
+    out = dict(img=img, prompt=prompt, prev=prev, tgt=tgt)
+    if pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+def to_slots(b):
+    import ofasys_b200 as ob
+
+    MT = ob.ModalityType
+    return [ob.Slot(MT.IMAGE, True, b["img"], attributes="adaptor=image_patch_embed"), ob.Slot(MT.TEXT, True, b["prompt"]),
+            ob.Slot(MT.TEXT, False, b["prev"])]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.rows = []
+        self.stop = False
+        self.index = index
+        self.t = threading.Thread(target=self.run, daemon=True)
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop:
+            try:
+                r = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5)
+                parts = [x.strip() for x in r.stdout.strip().split(",")]
+                if len(parts) >= 6:
+                    self.rows.append(parts)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(int(float(r[0])) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": int(float(self.rows[0][1])), "reasons": reasons, "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------ CPU arms
+def cpu_oracle_run(steps, warmup, batch, threads):
+    """fwd+bwd of the oracle (reference algorithm, fp32) on host cores: bounded sample of the workload."""
+    from oracle import cases
+    from oracle import oracle_model as om
+
+    torch.set_num_threads(threads)
+    cfg = om.OracleConfig(**CFG)
+    spec = _spec_cache()
+    sd = cases.synth_state_dict(spec, seed=0)
+    hb = host_batch(batch, 1234, pin=False)
+    slots = [om.OSlot(om.IMAGE, True, hb["img"], adaptor="image_patch_embed"), om.OSlot(om.TEXT, True, hb["prompt"]), om.OSlot(om.TEXT, False, hb["prev"])]
+    times = []
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        om.loss_and_grads(sd, cfg, slots, hb["tgt"])
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    times.sort()
+    med = times[len(times) // 2]
+    return batch / med, med
+
+
+def _spec_cache():
+    """parameter name -> shape of the benchmark model (CPU construction only; no kernels run)."""
+    import ofasys_b200 as ob
+    import ofasys_b200.model.ofa as ofa_mod
+
+    cfg = ob.GeneralistModelConfig.default()
+    cfg.dropout = 0.0
+    cfg.use_self_attn_bias = False
+    cfg.entangle_position_embedding = True
+    cfg.arch = "base"
+    m = ob.GeneralistModel(cfg)
+    m.cfg.encoder.layers = m.cfg.decoder.layers = 12
+    for n in ("text", "image_patch_embed"):
+        a = getattr(m.cfg.adaptor, n)
+        a.is_active = True
+        a.entangle_position_embedding = True
+    m.cfg.adaptor.image_patch_embed.embed_dim = 768
+    orig = ofa_mod.init_bert_params
+    try:
+        ofa_mod.init_bert_params = lambda mod: None  # shapes only
+        m.initialize(ob.Dictionary(n_dummy=V - 4))
+    finally:
+        ofa_mod.init_bert_params = orig
+    return {k: tuple(v.shape) for k, v in m.state_dict().items() if v.is_floating_point() and not k.endswith(".version")}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    batch = 4
+    sps, med = cpu_oracle_run(max(1, min(args.steps, 3)), min(args.warmup, 1), batch, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": sps, "unit": "seq/s", "n_gpus": args.gpus, "steps": max(1, min(args.steps, 3)),
+        "warmup": min(args.warmup, 1), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "global_batch": batch, "parallelism": "cpu"},
+        "cpu_baseline": {"value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
+                         "sample": f"batch {batch} fwd+bwd, fp32, torch {torch.__version__} CPU, median of {max(1, min(args.steps, 3))} steps"},
+        "e2e": {"value": sps, "unit": "seq/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------ GPU arm
+def grad_arena(model):
+    """All gradients live in one contiguous bf16 arena (gradient_as_bucket_view): autograd accumulates
+    into views of it and the all-reduce runs on slices of it."""
+    params = [p for p in model.parameters() if p.requires_grad]
+    n = sum(p.numel() for p in params)
+    arena = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+    off = 0
+    for p in params:
+        p.grad = arena[off:off + p.numel()].view_as(p)
+        off += p.numel()
+    return arena
+
+
+def run_gpu(args, rank, world, local_rank):
+    import torch.distributed as dist
+
+    from ofasys_b200 import _lib
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.lib().ofab_device_check(local_rank), "device check")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    model = build_model(dev)
+    arena = grad_arena(model)
+    n_buckets = 8
+    edges = [arena.numel() * i // n_buckets for i in range(n_buckets + 1)]
+    hb = host_batch(B, 1234 + rank, pin=True)
+    db = {k: v.to(dev) for k, v in hb.items()}
+    ntok = int((hb["tgt"] != 1).sum())
+
+    def step_resident():
+        arena.zero_()
+        loss = model.forward_loss(to_slots(db), db["tgt"])
+        loss.backward()
+        if world > 1:
+            for i in range(n_buckets):
+                dist.all_reduce(arena[edges[i]:edges[i + 1]], op=dist.ReduceOp.AVG)
+        return loss
+
+    def step_e2e():
+        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
+        arena.zero_()
+        loss = model.forward_loss(to_slots(d), d["tgt"])
+        loss.backward()
+        if world > 1:
+            for i in range(n_buckets):
+                dist.all_reduce(arena[edges[i]:edges[i + 1]], op=dist.ReduceOp.AVG)
+        return loss.item()  # D2H read of the step result
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0 = _lib.launch_count
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = e0.elapsed_time(e1)
+        t = torch.tensor([ms], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, (_lib.launch_count - c0) // steps
+
+    with ClockSampler(local_rank) as cs:
+        ms_step, launches = timed(step_resident, args.steps, args.warmup)
+    clocks = cs.summary()
+    ms_e2e, _ = timed(step_e2e, args.steps, max(1, args.warmup // 2))
+
+    # ---- roofline of the dominant kernel (tcgen05 GEMM): per-launch CUDA events on the launch stream
+    roof = None
+    if rank == 0:
+        pk = peaks()
+        recs = []
+        orig = _lib.call
+
+        def call(name, *a):
+            if name != "ofab_gemm_bf16":
+                return orig(name, *a)
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *a)
+            e.record()
+            recs.append((2.0 * a[0] * a[1] * a[2], s, e))
+
+        _lib.call = call
+        import ofasys_b200.ops as ops_mod
+
+        try:
+            for _ in range(2):
+                step_resident()
+            torch.cuda.synchronize()
+            recs.clear()
+            for _ in range(max(2, min(args.steps, 5))):
+                step_resident()
+            torch.cuda.synchronize()
+        finally:
+            _lib.call = orig
+        fl = sum(r[0] for r in recs)
+        tm = sum(r[1].elapsed_time(r[2]) for r in recs) * 1e-3
+        ach = fl / tm / 1e12
+        roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
+                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                "gemm_launches_per_step": len(recs) // max(2, min(args.steps, 5)), "gemm_ms_per_step": tm * 1e3 / max(2, min(args.steps, 5))}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 or True:
+            threads = os.cpu_count() or 1
+            try:
+                sps, med = cpu_oracle_run(2, 1, 4, threads)
+                cpu = {"value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
+                       "sample": "oracle (CPU restatement of the reference), batch 4 fwd+bwd fp32, median of 2 steps after 1 warm-up"}
+            except Exception as ex:  # never hide the GPU number behind a CPU-side failure
+                cpu = {"value": None, "unit": "seq/s", "cores": threads, "kind": "port", "sample": f"failed: {ex}"}
+        gb = B * world
+        value = gb / (ms_step * 1e-3)
+        pk = peaks()
+        h2d = sum(v.numel() * v.element_size() for v in hb.values())
+        line = {
+            "metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "src_len": 257 + PROMPT, "tgt_len": TGT,
+                       "parallelism": f"dp{world}", "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
+                       "algorithmic_gflop_per_seq": 3 * FWD_GFLOP_PER_SEQ, "ntokens_per_rank": ntok},
+            "clocks": clocks,
+            "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
+            "gpu_launches": launches,
+            "model_tflops": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world,
+            "model_frac_of_bf16_peak": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world / pk["tf_sustained"],
+            "roofline": roof,
+            "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--impl", default="ofab", choices=["ofab", "reference"])
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -148,7 +148,7 @@ def mha(sd, prefix, cfg: OracleConfig, query, key, kpm, attn_mask, attn_bias, fa
         w = w + attn_bias  # :311-312
     if attn_mask is not None:
         w = torch.nan_to_num(w)  # :314-317
-        w = w + attn_mask.unsqueeze(0)
+        w = w + attn_mask.to(w.dtype).unsqueeze(0)  # buffered_future_mask is cast to the activations (transformer.py:537)
     if kpm is not None:
         w = w.view(B, H, T, S).masked_fill(kpm.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
         w = w.view(B * H, T, S)  # :319-326
@@ -472,7 +472,7 @@ def loss_and_grads(sd, cfg, slots, target):
         v = sd[k]
         key = v.data_ptr()
         if key not in leaf:
-            leaf[key] = v.detach().clone().requires_grad_(True)
+            leaf[key] = v.detach().requires_grad_(True)  # shares storage: no 1 GB copy per step
         params[k] = leaf[key]
     full = dict(sd)
     full.update(params)
