@@ -184,7 +184,7 @@ def _spec_cache():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
+    threads = min(os.cpu_count() or 1, 32)  # more threads slow torch's CPU kernels down on these shapes
     batch = 4
     sps, med = cpu_oracle_run(max(1, min(args.steps, 3)), min(args.warmup, 1), batch, threads)
     line = {
@@ -201,17 +201,14 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def grad_arena(model):
-    """All gradients live in one contiguous bf16 arena (gradient_as_bucket_view): autograd accumulates
-    into views of it and the all-reduce runs on slices of it."""
-    params = [p for p in model.parameters() if p.requires_grad]
-    n = sum(p.numel() for p in params)
-    arena = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+def _allreduce_bucket(tensors, dist):
+    """average one bucket of gradient tensors across ranks with a single NCCL all-reduce."""
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
     off = 0
-    for p in params:
-        p.grad = arena[off:off + p.numel()].view_as(p)
-        off += p.numel()
-    return arena
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
 
 
 def run_gpu(args, rank, world, local_rank):
@@ -226,30 +223,69 @@ def run_gpu(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     model = build_model(dev)
-    arena = grad_arena(model)
-    n_buckets = 8
-    edges = [arena.numel() * i // n_buckets for i in range(n_buckets + 1)]
+    params = [p for p in model.parameters() if p.requires_grad]
     hb = host_batch(B, 1234 + rank, pin=True)
-    db = {k: v.to(dev) for k, v in hb.items()}
+    db = {k: v.to(dev) for k, v in hb.items()}  # static device inputs (graph replays read these addresses)
     ntok = int((hb["tgt"] != 1).sum())
+    state = {"loss": None, "graph": None}
 
-    def step_resident():
-        arena.zero_()
+    def fwd_bwd():
+        for p in params:
+            p.grad = None
         loss = model.forward_loss(to_slots(db), db["tgt"])
         loss.backward()
-        if world > 1:
-            for i in range(n_buckets):
-                dist.all_reduce(arena[edges[i]:edges[i + 1]], op=dist.ReduceOp.AVG)
+        return loss
+
+    def reduce_grads():
+        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink), bucketed
+            grads = [p.grad for p in params if p.grad is not None]
+            bucket, size = [], 0
+            for g_ in grads:
+                bucket.append(g_)
+                size += g_.numel()
+                if size >= (32 << 20):
+                    _allreduce_bucket(bucket, dist)
+                    bucket, size = [], 0
+            if bucket:
+                _allreduce_bucket(bucket, dist)
+
+    use_graph = not args.no_graph
+    if use_graph:
+        # CUDA graph of the whole fwd+bwd: ~2000 kernel launches per step are replayed without host work
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                fwd_bwd()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        try:
+            c0 = _lib.launch_count
+            g = torch.cuda.CUDAGraph()
+            for p in params:
+                p.grad = None
+            with torch.cuda.graph(g):
+                state["loss"] = fwd_bwd()
+            state["graph"] = g
+            state["launches"] = _lib.launch_count - c0
+        except Exception as ex:  # stay correct: fall back to eager launches and say so
+            print(f"[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
+            use_graph = False
+            torch.cuda.synchronize()
+
+    def step_resident():
+        if use_graph:
+            state["graph"].replay()
+            loss = state["loss"]
+        else:
+            loss = fwd_bwd()
+        reduce_grads()
         return loss
 
     def step_e2e():
-        d = {k: v.to(dev, non_blocking=True) for k, v in hb.items()}
-        arena.zero_()
-        loss = model.forward_loss(to_slots(d), d["tgt"])
-        loss.backward()
-        if world > 1:
-            for i in range(n_buckets):
-                dist.all_reduce(arena[edges[i]:edges[i + 1]], op=dist.ReduceOp.AVG)
+        for k in db:  # H2D of this step's inputs from pinned host memory into the static device buffers
+            db[k].copy_(hb[k], non_blocking=True)
+        loss = step_resident()
         return loss.item()  # D2H read of the step result
 
     def timed(fn, steps, warmup):
@@ -272,7 +308,8 @@ def run_gpu(args, rank, world, local_rank):
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return t.item() / steps, (_lib.launch_count - c0) // steps
+        n_l = state.get("launches") if use_graph else (_lib.launch_count - c0) // steps
+        return t.item() / steps, n_l
 
     with ClockSampler(local_rank) as cs:
         ms_step, launches = timed(step_resident, args.steps, args.warmup)
@@ -300,11 +337,11 @@ def run_gpu(args, rank, world, local_rank):
 
         try:
             for _ in range(2):
-                step_resident()
+                fwd_bwd()
             torch.cuda.synchronize()
             recs.clear()
             for _ in range(max(2, min(args.steps, 5))):
-                step_resident()
+                fwd_bwd()
             torch.cuda.synchronize()
         finally:
             _lib.call = orig
@@ -315,10 +352,47 @@ def run_gpu(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "gemm_launches_per_step": len(recs) // max(2, min(args.steps, 5)), "gemm_ms_per_step": tm * 1e3 / max(2, min(args.steps, 5))}
 
+    if rank == 0 and args.breakdown:
+        # per-entry-point device time (CUDA events around every C-ABI call): where the step goes
+        recs = []
+        orig = _lib.call
+
+        def call_all(name, *a):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            orig(name, *a)
+            e.record()
+            recs.append((name, s, e))
+
+        _lib.call = call_all
+        try:
+            fwd_bwd()
+            torch.cuda.synchronize()
+            recs.clear()
+            t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(3):
+                fwd_bwd()
+            t1.record()
+            torch.cuda.synchronize()
+        finally:
+            _lib.call = orig
+        agg = {}
+        for name, s, e in recs:
+            a = agg.setdefault(name, [0, 0.0])
+            a[0] += 1
+            a[1] += s.elapsed_time(e)
+        tot = t0.elapsed_time(t1) / 3
+        out = {k: {"calls_per_step": v[0] / 3, "ms_per_step": v[1] / 3} for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])}
+        out["_sum_ms"] = sum(v[1] for v in agg.values()) / 3
+        out["_step_ms_with_events"] = tot
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "breakdown.json"), "w"), indent=1)
+
     if rank == 0:
         cpu = None
-        if world == 1 or True:
-            threads = os.cpu_count() or 1
+        if not args.no_cpu:
+            threads = min(os.cpu_count() or 1, 32)  # more threads slow torch's CPU kernels down on these shapes
             try:
                 sps, med = cpu_oracle_run(2, 1, 4, threads)
                 cpu = {"value": sps, "unit": "seq/s", "cores": threads, "kind": "port",
@@ -333,7 +407,7 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "src_len": 257 + PROMPT, "tgt_len": TGT,
-                       "parallelism": f"dp{world}", "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "algorithmic_gflop_per_seq": 3 * FWD_GFLOP_PER_SEQ, "ntokens_per_rank": ntok},
             "clocks": clocks,
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -355,6 +429,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--impl", default="ofab", choices=["ofab", "reference"])
+    ap.add_argument("--breakdown", action="store_true", help="also write gpurun_out/breakdown.json (per entry point device time)")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

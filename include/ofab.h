@@ -83,6 +83,10 @@ int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const void* a, const
  * Deterministic (two-stage, no atomics). */
 int ofab_colsum(const void* in, int in_dt, int64_t rows, int64_t cols, int64_t ld, void* out,
                 int out_dt, int accumulate, float* scratch, ofab_stream_t stream);
+/* out[s, c] = sum over the ofab_ln_partial_rows() rows of slab s of partial[nslabs, rows, cols]:
+ * finishes dgamma / dbeta (and dtype / dcls) of one backward kernel in a single launch. */
+int ofab_reduce_partials(const float* partial, int nslabs, int cols, void* out, int out_dt,
+                         ofab_stream_t stream);
 /* floats of `scratch` ofab_colsum needs for `cols` columns */
 int64_t ofab_colsum_scratch_elems(int64_t cols);
 

@@ -67,6 +67,7 @@ _SIGS = {
     "ofab_ln_res_ln_bwd": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_void_p]),
     "ofab_colsum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ofab_colsum_scratch_elems": (c_int64, [c_int64]),
+    "ofab_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ofab_gemm_bf16": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "ofab_attn_fwd": (c_int, [POINTER(AttnFwdArgs), c_void_p]),
     "ofab_attn_bwd": (c_int, [POINTER(AttnBwdArgs), c_void_p]),
@@ -120,7 +121,10 @@ def check(rc, what=""):
         raise OfabError(f"libofab call failed ({rc}) {what}: {msg}")
 
 
+_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 3}
+
+
 def call(name, *args):
     global launch_count
-    launch_count += 1
+    launch_count += _KERNELS_PER_CALL.get(name, 1)
     check(getattr(lib(), name)(*args), name)

@@ -83,38 +83,74 @@ struct AttnCommon {
   float scale;
 };
 
-// score post-processing shared by forward and both backward kernels:
-// s = scale*acc + table[idx] ; masked -> -inf.   (i, j) are global query / key indices.
-__device__ __forceinline__ float finish_score(const AttnCommon& p, float acc, int i, int j, int b, const float* tab_s, int& idx_out) {
-  idx_out = -1;
-  if (j >= p.Tk || i >= p.Tq) return -INFINITY;
-  float s = acc * p.scale;
-  if (p.rp_idx != nullptr) {
-    const int idx = p.rp_idx[(int64_t)i * p.Tk + j];
-    if (idx >= 0) {
-      s += tab_s[idx];
-      idx_out = idx;
-    }
+// Key-validity mask of one 64-key tile (bit jl set <=> key k0+jl is in range and not padding), built
+// cooperatively by warps 0 and 1 while the tile's cp.async copies are in flight.
+__device__ __forceinline__ void build_kmask(const AttnCommon& p, int b, int k0, uint32_t* dst /* smem [2] */) {
+  if (threadIdx.x < 64) {
+    const int j = k0 + threadIdx.x;
+    bool ok = j < p.Tk;
+    if (ok && p.kpm != nullptr) ok = p.kpm[(int64_t)b * p.Tk + j] == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) dst[threadIdx.x >> 5] = m;
   }
-  if (p.causal && j > i) return -INFINITY;
-  if (p.kpm != nullptr && p.kpm[(int64_t)b * p.Tk + j]) return -INFINITY;
-  return s;
+}
+
+// Score post-processing shared by forward and both backward kernels, on one warp's 16 x 64 accumulator
+// tile:  s = scale*acc (+ table[bucket(i,j)]) ; masked -> -inf.
+//   TRANSPOSED = false: accumulator rows are queries (row0 = first query row of the warp), columns keys.
+//   TRANSPOSED = true : accumulator rows are keys   (row0 = first key row of the warp),   columns queries.
+// Fast path (no table, no masked key in the tile, tile not on the causal diagonal): one FMUL per element.
+template <bool TRANSPOSED, typename F>
+__device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4], int q0, int k0, int row0, uint64_t kmask,
+                                            const float* tab_s, F&& on_idx) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const bool has_tab = p.rp_idx != nullptr;
+  const bool diag = p.causal && (k0 + TILE - 1 > q0);  // some (i, j) of this CTA tile may have j > i
+  if (!has_tab && !diag && kmask == ~0ull) {
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s[nt][e] *= p.scale;
+    return;
+  }
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = row0 + g + 8 * (e >> 1), c = nt * 8 + 2 * t + (e & 1);
+      const int il = TRANSPOSED ? c : r, jl = TRANSPOSED ? r : c;
+      const int i = q0 + il, j = k0 + jl;
+      bool ok = (kmask >> jl) & 1ull;
+      if (p.causal) ok = ok && (j <= i);
+      float v = s[nt][e] * p.scale;
+      if (has_tab && ok && i < p.Tq) {
+        const int idx = p.rp_idx[(int64_t)i * p.Tk + j];
+        if (idx >= 0) {
+          v += tab_s[idx];
+          on_idx(nt, e, idx);
+        }
+      }
+      s[nt][e] = ok ? v : -INFINITY;
+    }
 }
 
 // ===================================================================================== forward
+// smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | kmask [2 stages][2] u32 | table column (n_buckets floats)
 template <bool HAS_POS>
 __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
                                                        float* __restrict__ lse) {
   constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
   extern __shared__ __align__(128) uint8_t smem[];
-  const uint32_t sQ = smem_u32(smem);                    // NH tiles
-  const uint32_t sK = sQ + NH * TILE_BYTES;              // 2 stages x NH tiles
-  const uint32_t sV = sK + 2 * NH * TILE_BYTES;          // 2 stages x 1 tile
-  float* tab_s = reinterpret_cast<float*>(smem + (3 * NH + 2) * TILE_BYTES);
+  const uint32_t sQ = smem_u32(smem);
+  const uint32_t sK = sQ + NH * TILE_BYTES;
+  const uint32_t sV = sK + 2 * NH * TILE_BYTES;
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + (3 * NH + 2) * TILE_BYTES);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + 4);
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qb * TILE;
+  const bool warp_live = q0 + warp * 16 < p.Tq;  // tail tile: warps without valid query rows only help loading
 
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
@@ -133,6 +169,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
   if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, 0, p.Tk);
   load_tile_async(sV, vg, p.v_rs, 0, p.Tk);
   cp_commit();
+  build_kmask(p, b, 0, kmask_s);
 
   float oacc[8][4];
 #pragma unroll
@@ -150,94 +187,101 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
       if (HAS_POS) load_tile_async(sK + ((st ^ 1) * NH + 1) * TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
       load_tile_async(sV + (st ^ 1) * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
       cp_commit();
+      build_kmask(p, b, k1, kmask_s + 2 * (st ^ 1));
       cp_wait<1>();
     } else {
       cp_wait<0>();
     }
     __syncthreads();
 
-    // ---- S = Q K^T (+ PQ PK^T)
-    float s[8][4];
+    if (warp_live) {
+      const int k0 = kv * TILE;
+      const int nk = min(TILE, p.Tk - k0);          // valid keys in this tile
+      const int np_n = (nk + 15) >> 4;               // 16-key groups that hold a valid key
+      const uint64_t kmask = (uint64_t)kmask_s[2 * st] | ((uint64_t)kmask_s[2 * st + 1] << 32);
+      // ---- S = Q K^T (+ PQ PK^T)
+      float s[8][4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-    for (int hf = 0; hf < NH; ++hf) {
-      const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + (st * NH + hf) * TILE_BYTES;
+      for (int hf = 0; hf < NH; ++hf) {
+        const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + (st * NH + hf) * TILE_BYTES;
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t a[4];
-        frag_a(tq, warp * 16, kk, a);
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a[4];
+          frag_a(tq, warp * 16, kk, a);
 #pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          uint32_t bb[4];
-          frag_b(tk, np * 16, kk, bb);
-          mma16816(s[2 * np], a, bb[0], bb[1]);
-          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          for (int np = 0; np < 4; ++np) {
+            if (np < np_n) {
+              uint32_t bb[4];
+              frag_b(tk, np * 16, kk, bb);
+              mma16816(s[2 * np], a, bb[0], bb[1]);
+              mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+            }
+          }
         }
       }
-    }
-    // ---- bias / mask / online softmax
-    const int k0 = kv * TILE;
-    float mx[2] = {-INFINITY, -INFINITY};
+      // ---- bias / mask / online softmax
+      finish_tile<false>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+      float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int i = row_g[e >> 1], j = k0 + nt * 8 + 2 * t + (e & 1);
-        int idx;
-        s[nt][e] = finish_score(p, s[nt][e], i, j, b, tab_s, idx);
-        mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+        for (int e = 0; e < 4; ++e) mx[e >> 1] = fmaxf(mx[e >> 1], s[nt][e]);
+      float corr[2], m_use[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float m_new = fmaxf(m_run[r], mx[r]);
+        m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
+        corr[r] = __expf(m_run[r] - m_use[r]);  // exp(-inf) = 0 on the first tile
+        m_run[r] = m_new;
+        l_run[r] *= corr[r];
       }
-    float corr[2], m_use[2];
+      float ps[2] = {0.f, 0.f};
 #pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
-      mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-      const float m_new = fmaxf(m_run[r], mx[r]);
-      m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-      corr[r] = __expf(m_run[r] - m_use[r]);  // exp(-inf) = 0 on the first tile
-      m_run[r] = m_new;
-      l_run[r] *= corr[r];
-    }
-    float ps[2] = {0.f, 0.f};
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
+        for (int e = 0; e < 4; ++e) {
+          const float pe = __expf(s[nt][e] - m_use[e >> 1]);
+          s[nt][e] = pe;
+          ps[e >> 1] += pe;
+        }
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float pe = __expf(s[nt][e] - m_use[e >> 1]);
-        s[nt][e] = pe;
-        ps[e >> 1] += pe;
+      for (int r = 0; r < 2; ++r) l_run[r] += ps[r];
+#pragma unroll
+      for (int dt = 0; dt < 8; ++dt) {
+        oacc[dt][0] *= corr[0]; oacc[dt][1] *= corr[0];
+        oacc[dt][2] *= corr[1]; oacc[dt][3] *= corr[1];
       }
+      // ---- O += P V
+      const uint32_t tv = sV + st * TILE_BYTES;
 #pragma unroll
-    for (int r = 0; r < 2; ++r) l_run[r] += ps[r];
+      for (int kb = 0; kb < 4; ++kb) {
+        if (kb < np_n) {
+          uint32_t a[4];
+          a[0] = pack_bf16(s[2 * kb][0], s[2 * kb][1]);
+          a[1] = pack_bf16(s[2 * kb][2], s[2 * kb][3]);
+          a[2] = pack_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
+          a[3] = pack_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
 #pragma unroll
-    for (int dt = 0; dt < 8; ++dt) {
-      oacc[dt][0] *= corr[0]; oacc[dt][1] *= corr[0];
-      oacc[dt][2] *= corr[1]; oacc[dt][3] *= corr[1];
-    }
-    // ---- O += P V
-    const uint32_t tv = sV + st * TILE_BYTES;
-#pragma unroll
-    for (int kb = 0; kb < 4; ++kb) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kb][0], s[2 * kb][1]);
-      a[1] = pack_bf16(s[2 * kb][2], s[2 * kb][3]);
-      a[2] = pack_bf16(s[2 * kb + 1][0], s[2 * kb + 1][1]);
-      a[3] = pack_bf16(s[2 * kb + 1][2], s[2 * kb + 1][3]);
-#pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t bb[4];
-        frag_bt(tv, kb * 16, dp, bb);
-        mma16816(oacc[2 * dp], a, bb[0], bb[1]);
-        mma16816(oacc[2 * dp + 1], a, bb[2], bb[3]);
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t bb[4];
+            frag_bt(tv, kb * 16, dp, bb);
+            mma16816(oacc[2 * dp], a, bb[0], bb[1]);
+            mma16816(oacc[2 * dp + 1], a, bb[2], bb[3]);
+          }
+        }
       }
     }
     __syncthreads();  // all warps done with stage st before it is refilled
   }
 
   // ---- finalize
+  if (!warp_live) return;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float l = l_run[r];
@@ -301,11 +345,13 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
   const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1 tile
   float* lse_s = reinterpret_cast<float*>(smem + (2 * NH + 2) * TILE_BYTES);
   float* dlt_s = lse_s + TILE;
-  float* tab_s = dlt_s + TILE;
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(dlt_s + TILE);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + 2);
 
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = kb * TILE;
+  const bool warp_live = k0 + warp * 16 < p.Tk;
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
   const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
@@ -320,6 +366,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
   if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
   load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
   cp_commit();
+  build_kmask(p, b, k0, kmask_s);
 
   float dk[NH * 8][4], dv[8][4];
 #pragma unroll
@@ -349,6 +396,11 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
     }
     cp_wait<0>();
     __syncthreads();
+    if (!warp_live) continue;
+
+    const int nq = min(TILE, p.Tq - q0);
+    const int np_n = (nq + 15) >> 4;  // 16-query groups holding a valid query
+    const uint64_t kmask = (uint64_t)kmask_s[0] | ((uint64_t)kmask_s[1] << 32);
 
     // S^T[key, query] = K Q^T (+ PK PQ^T)
     float s[8][4];
@@ -365,39 +417,40 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
         frag_a(tk, warp * 16, kk, a);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
-          uint32_t bb[4];
-          frag_b(tq, np * 16, kk, bb);
-          mma16816(s[2 * np], a, bb[0], bb[1]);
-          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          if (np < np_n) {
+            uint32_t bb[4];
+            frag_b(tq, np * 16, kk, bb);
+            mma16816(s[2 * np], a, bb[0], bb[1]);
+            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          }
         }
       }
     }
     // P^T = exp(S^T - lse[query])
+    finish_tile<true>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int el = 0; el < 4; ++el) {
-        const int jl = nt * 8 + 2 * t + (el & 1);  // query within tile
-        const int i = q0 + jl, j = key_g[el >> 1];
-        int idx;
-        const float sc = finish_score(p, s[nt][el], i, j, b, tab_s, idx);
-        const float l = lse_s[jl];
-        s[nt][el] = (sc == -INFINITY || l == -INFINITY) ? 0.f : __expf(sc - l);
+        const float l = lse_s[nt * 8 + 2 * t + (el & 1)];
+        s[nt][el] = (s[nt][el] == -INFINITY || l == -INFINITY) ? 0.f : __expf(s[nt][el] - l);
       }
     // dV += P^T dO
-    uint32_t pa[4][4];
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
-      pa[kb2][0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
-      pa[kb2][1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
-      pa[kb2][2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
-      pa[kb2][3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+      if (kb2 < np_n) {
+        uint32_t pa[4];
+        pa[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+        pa[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+        pa[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+        pa[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
 #pragma unroll
-      for (int dp = 0; dp < 4; ++dp) {
-        uint32_t bb[4];
-        frag_bt(sDO, kb2 * 16, dp, bb);
-        mma16816(dv[2 * dp], pa[kb2], bb[0], bb[1]);
-        mma16816(dv[2 * dp + 1], pa[kb2], bb[2], bb[3]);
+        for (int dp = 0; dp < 4; ++dp) {
+          uint32_t bb[4];
+          frag_bt(sDO, kb2 * 16, dp, bb);
+          mma16816(dv[2 * dp], pa, bb[0], bb[1]);
+          mma16816(dv[2 * dp + 1], pa, bb[2], bb[3]);
+        }
       }
     }
     // dP^T[key, query] = V dO^T
@@ -412,10 +465,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
       frag_a(sV, warp * 16, kk, a);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        frag_b(sDO, np * 16, kk, bb);
-        mma16816(dp_[2 * np], a, bb[0], bb[1]);
-        mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        if (np < np_n) {
+          uint32_t bb[4];
+          frag_b(sDO, np * 16, kk, bb);
+          mma16816(dp_[2 * np], a, bb[0], bb[1]);
+          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        }
       }
     }
     // dS^T = P^T * (dP^T - delta[query]) ; pre-multiplied by scale for dK
@@ -429,20 +484,22 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
     // dK' += dS^T Q'
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
-      a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
-      a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
-      a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+      if (kb2 < np_n) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+        a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+        a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+        a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
 #pragma unroll
-      for (int hf = 0; hf < NH; ++hf)
+        for (int hf = 0; hf < NH; ++hf)
 #pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-          uint32_t bb[4];
-          frag_bt(sQ + hf * TILE_BYTES, kb2 * 16, dp, bb);
-          mma16816(dk[hf * 8 + 2 * dp], a, bb[0], bb[1]);
-          mma16816(dk[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
-        }
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t bb[4];
+            frag_bt(sQ + hf * TILE_BYTES, kb2 * 16, dp, bb);
+            mma16816(dk[hf * 8 + 2 * dp], a, bb[0], bb[1]);
+            mma16816(dk[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
+          }
+      }
     }
   }
   // ---- store dK (+dPK), dV
@@ -476,12 +533,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
   const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1
   const uint32_t sK = sDO + TILE_BYTES;           // NH
   const uint32_t sV = sK + NH * TILE_BYTES;       // 1
-  float* tab_s = reinterpret_cast<float*>(smem + (2 * NH + 2) * TILE_BYTES);
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + (2 * NH + 2) * TILE_BYTES);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + 2);
   float* dtab_s = tab_s + p.n_buckets;
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qb * TILE;
+  const bool warp_live = q0 + warp * 16 < p.Tq;
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
   const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
@@ -523,8 +582,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
     if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
     load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
     cp_commit();
+    build_kmask(p, b, k0, kmask_s);
     cp_wait<0>();
     __syncthreads();
+    if (!warp_live) continue;
+
+    const int nk = min(TILE, p.Tk - k0);
+    const int np_n = (nk + 15) >> 4;
+    const uint64_t kmask = (uint64_t)kmask_s[0] | ((uint64_t)kmask_s[1] << 32);
 
     float s[8][4];
 #pragma unroll
@@ -540,10 +605,12 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
         frag_a(tq, warp * 16, kk, a);
 #pragma unroll
         for (int np = 0; np < 4; ++np) {
-          uint32_t bb[4];
-          frag_b(tk, np * 16, kk, bb);
-          mma16816(s[2 * np], a, bb[0], bb[1]);
-          mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          if (np < np_n) {
+            uint32_t bb[4];
+            frag_b(tk, np * 16, kk, bb);
+            mma16816(s[2 * np], a, bb[0], bb[1]);
+            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          }
         }
       }
     }
@@ -559,57 +626,70 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
       frag_a(sDO, warp * 16, kk, a);
 #pragma unroll
       for (int np = 0; np < 4; ++np) {
-        uint32_t bb[4];
-        frag_b(sV, np * 16, kk, bb);
-        mma16816(dp_[2 * np], a, bb[0], bb[1]);
-        mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        if (np < np_n) {
+          uint32_t bb[4];
+          frag_b(sV, np * 16, kk, bb);
+          mma16816(dp_[2 * np], a, bb[0], bb[1]);
+          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        }
       }
     }
     // P, dS ; relative-position table gradient
+    int idxs[8][4];
+    if (has_tab) {
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int el = 0; el < 4; ++el) idxs[nt][el] = -1;
+    }
+    finish_tile<false>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { idxs[nt][el] = idx; });
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int el = 0; el < 4; ++el) {
-        const int i = row_g[el >> 1], j = k0 + nt * 8 + 2 * t + (el & 1);
-        int idx;
-        const float sc = finish_score(p, s[nt][el], i, j, b, tab_s, idx);
         const float l = lse_r[el >> 1];
-        const float pe = (sc == -INFINITY || l == -INFINITY) ? 0.f : __expf(sc - l);
+        const float pe = (s[nt][el] == -INFINITY || l == -INFINITY) ? 0.f : __expf(s[nt][el] - l);
         const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
-        if (has_tab && idx >= 0 && ds != 0.f) atomicAdd(dtab_s + idx, ds);
+        if (has_tab) {
+          if (idxs[nt][el] >= 0 && ds != 0.f) atomicAdd(dtab_s + idxs[nt][el], ds);
+        }
         s[nt][el] = ds * p.scale;
       }
     // dQ' += dS K'
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
-      uint32_t a[4];
-      a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
-      a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
-      a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
-      a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+      if (kb2 < np_n) {
+        uint32_t a[4];
+        a[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+        a[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+        a[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+        a[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
 #pragma unroll
-      for (int hf = 0; hf < NH; ++hf)
+        for (int hf = 0; hf < NH; ++hf)
 #pragma unroll
-        for (int dp = 0; dp < 4; ++dp) {
-          uint32_t bb[4];
-          frag_bt(sK + hf * TILE_BYTES, kb2 * 16, dp, bb);
-          mma16816(dq[hf * 8 + 2 * dp], a, bb[0], bb[1]);
-          mma16816(dq[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
-        }
+          for (int dp = 0; dp < 4; ++dp) {
+            uint32_t bb[4];
+            frag_bt(sK + hf * TILE_BYTES, kb2 * 16, dp, bb);
+            mma16816(dq[hf * 8 + 2 * dp], a, bb[0], bb[1]);
+            mma16816(dq[hf * 8 + 2 * dp + 1], a, bb[2], bb[3]);
+          }
+      }
     }
   }
+  if (warp_live) {
 #pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    const int i = row_g[r];
-    if (i < p.Tq) {
-      bf16* dqp = e.dq + (int64_t)b * e.dq_bs + (int64_t)i * e.dq_rs + h * 64;
+    for (int r = 0; r < 2; ++r) {
+      const int i = row_g[r];
+      if (i < p.Tq) {
+        bf16* dqp = e.dq + (int64_t)b * e.dq_bs + (int64_t)i * e.dq_rs + h * 64;
 #pragma unroll
-      for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(dqp + dt * 8 + 2 * t) = pack_bf16(dq[dt][2 * r], dq[dt][2 * r + 1]);
-      if (HAS_POS) {
-        bf16* dpp = e.dpq + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64;
+        for (int dt = 0; dt < 8; ++dt) *reinterpret_cast<uint32_t*>(dqp + dt * 8 + 2 * t) = pack_bf16(dq[dt][2 * r], dq[dt][2 * r + 1]);
+        if (HAS_POS) {
+          bf16* dpp = e.dpq + ((int64_t)b * p.Tq + i) * (p.H * 64) + h * 64;
 #pragma unroll
-        for (int dt = 0; dt < 8; ++dt)
-          *reinterpret_cast<uint32_t*>(dpp + dt * 8 + 2 * t) = pack_bf16(dq[(NH - 1) * 8 + dt][2 * r], dq[(NH - 1) * 8 + dt][2 * r + 1]);
+          for (int dt = 0; dt < 8; ++dt)
+            *reinterpret_cast<uint32_t*>(dpp + dt * 8 + 2 * t) = pack_bf16(dq[(NH - 1) * 8 + dt][2 * r], dq[(NH - 1) * 8 + dt][2 * r + 1]);
+        }
       }
     }
   }
@@ -659,7 +739,7 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
   OFAB_REQUIRE(a->o_rs % 2 == 0 && a->o_bs % 2 == 0, "ofab_attn_fwd: o strides must be even");
   const bool pos = a->pq != nullptr;
   const int nh = pos ? 2 : 1;
-  const int smem = (3 * nh + 2) * TILE_BYTES + c.n_buckets * 4;
+  const int smem = (3 * nh + 2) * TILE_BYTES + 16 + c.n_buckets * 4;
   dim3 grid((a->Tq + TILE - 1) / TILE, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
   if (pos) {
@@ -693,8 +773,8 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
   e.dtable = a->dtable;
   const int nh = pos ? 2 : 1;
-  const int smem_kv = (2 * nh + 2) * TILE_BYTES + 2 * TILE * 4 + c.n_buckets * 4;
-  const int smem_q = (2 * nh + 2) * TILE_BYTES + 2 * c.n_buckets * 4;
+  const int smem_kv = (2 * nh + 2) * TILE_BYTES + 2 * TILE * 4 + 8 + c.n_buckets * 4;
+  const int smem_q = (2 * nh + 2) * TILE_BYTES + 8 + 2 * c.n_buckets * 4;
   dim3 gkv((a->f.Tk + TILE - 1) / TILE, a->f.H, a->f.B), gq((a->f.Tq + TILE - 1) / TILE, a->f.H, a->f.B);
   if (pos) {
     if ((rc = set_smem(attn_bwd_dkv_kernel<true>, smem_kv, "ofab_attn_bwd smem"))) return rc;

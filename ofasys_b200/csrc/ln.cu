@@ -410,6 +410,26 @@ __global__ void colsum_stage2(const float* __restrict__ partial, int64_t cols, T
 
 }  // namespace
 
+// out[s, c] = sum_r partial[s, r, c] for the OFAB_LN_PARTIAL_ROWS rows of every slab: one launch finishes
+// dgamma / dbeta (/ dtype / dcls) of a backward kernel.  grid (ceil(cols/32), ns), block (32, 8).
+template <typename TO>
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int cols, TO* __restrict__ out) {
+  __shared__ float sm[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const float* base = partial + (int64_t)blockIdx.y * OFAB_LN_PARTIAL_ROWS * cols;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = threadIdx.y; r < OFAB_LN_PARTIAL_ROWS; r += 8) s += base[(int64_t)r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    out[(int64_t)blockIdx.y * cols + c] = (TO)t;
+  }
+}
+
 // ---------------------------------------------------------------------------------- dispatch
 #define LN_SHAPE_DISPATCH(cols, CALL)                 \
   if ((cols) <= 256) { CALL(32, 1); }                 \
@@ -535,5 +555,16 @@ extern "C" int ofab_colsum(const void* in, int in_dt, int64_t rows, int64_t cols
   else
     colsum_stage2<bf16><<<g2, 256, 0, st>>>(scratch, cols, (bf16*)out, accumulate);
   OFAB_LAUNCH_CHECK("ofab_colsum stage2");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_reduce_partials(const float* partial, int nslabs, int cols, void* out, int out_dt, ofab_stream_t stream) {
+  OFAB_REQUIRE(nslabs > 0 && cols > 0, "ofab_reduce_partials: bad shape");
+  dim3 grid((cols + 31) / 32, nslabs), block(32, 8);
+  if (out_dt == OFAB_F32)
+    reduce_partials_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(partial, cols, (float*)out);
+  else
+    reduce_partials_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(partial, cols, (bf16*)out);
+  OFAB_LAUNCH_CHECK("ofab_reduce_partials");
   return OFAB_OK;
 }

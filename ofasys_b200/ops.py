@@ -44,9 +44,12 @@ def colsum(x2d, out_dtype=torch.bfloat16, out=None, accumulate=False):
     return out
 
 
-def _reduce_partials(partial, slab, cols, dtype):
-    pr = partial.shape[1]
-    return colsum(partial[slab].view(pr, cols), dtype)
+def _reduce_partials(partial, dtype):
+    """[ns, rows, cols] fp32 partial slabs -> [ns, cols] `dtype` in one launch."""
+    ns, _, cols = partial.shape
+    out = torch.empty((ns, cols), dtype=dtype, device=partial.device)
+    _lib.call("ofab_reduce_partials", _p(partial), ns, cols, _p(out), _DT[dtype], _s())
+    return out
 
 
 def cast_bf16(x):
@@ -114,9 +117,8 @@ class _LayerNormFn(torch.autograd.Function):
         partial = torch.empty((2, _partial_rows(), cols), dtype=torch.float32, device=x.device)
         _lib.call("ofab_ln_bwd", _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(weight), _p(mean), _p(rstd), _p(dx), _DT[dx.dtype], 0,
                   _p(partial), rows, cols, int(ctx.gelu), _s())
-        dw = _reduce_partials(partial, 0, cols, weight.dtype)
-        db = _reduce_partials(partial, 1, cols, weight.dtype)
-        return dx, dw, db, None, None, None
+        g = _reduce_partials(partial, weight.dtype)
+        return dx, g[0], g[1], None, None, None
 
 
 def layer_norm(x, weight, bias, eps=1e-5, gelu=False, out_dtype=torch.bfloat16):
@@ -150,7 +152,7 @@ class _LnResLnFn(torch.autograd.Function):
         da = torch.empty_like(a)
         partial = torch.empty((4, _partial_rows(), cols), dtype=torch.float32, device=a.device)
         _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _s())
-        g = [_reduce_partials(partial, i, cols, w1.dtype) for i in range(4)]
+        g = _reduce_partials(partial, w1.dtype)
         return da, dx_tot, g[0], g[1], g[2], g[3], None
 
 
@@ -454,10 +456,10 @@ class _EmbedLnFn(torch.autograd.Function):
         partial = torch.empty((4, _partial_rows(), d), dtype=torch.float32, device=dev)
         a.dgb_partial = partial.data_ptr()
         _lib.call("ofab_embed_ln_bwd", ctypes.byref(a), _s())
-        dgamma = _reduce_partials(partial, 0, d, gamma.dtype)
-        dbeta = _reduce_partials(partial, 1, d, gamma.dtype)
-        dtype_vec = _reduce_partials(partial, 2, d, type_vec.dtype).view(type_vec.shape) if type_vec is not None else None
-        dcls = _reduce_partials(partial, 3, d, cls.dtype).view(cls.shape) if cls is not None else None
+        g = _reduce_partials(partial, gamma.dtype)
+        dgamma, dbeta = g[0], g[1]
+        dtype_vec = g[2].view(type_vec.shape) if type_vec is not None else None
+        dcls = g[3].view(cls.shape) if cls is not None else None
         if dE is not None:
             dE = cast_bf16(dE)
         if dpos is not None:
