@@ -201,16 +201,6 @@ def run_reference(args, rank, world):
 
 
 # ------------------------------------------------------------------------------------ GPU arm
-def _allreduce_bucket(tensors, dist):
-    """average one bucket of gradient tensors across ranks with a single NCCL all-reduce."""
-    flat = torch.cat([t.reshape(-1) for t in tensors])
-    dist.all_reduce(flat, op=dist.ReduceOp.AVG)
-    off = 0
-    for t in tensors:
-        t.copy_(flat[off:off + t.numel()].view_as(t))
-        off += t.numel()
-
-
 def run_gpu(args, rank, world, local_rank):
     import torch.distributed as dist
 
@@ -236,18 +226,13 @@ def run_gpu(args, rank, world, local_rank):
         loss.backward()
         return loss
 
+    from ofasys_b200.distributed import allreduce_grads, build_buckets
+
+    buckets = build_buckets(params) if world > 1 else None
+
     def reduce_grads():
-        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink), bucketed
-            grads = [p.grad for p in params if p.grad is not None]
-            bucket, size = [], 0
-            for g_ in grads:
-                bucket.append(g_)
-                size += g_.numel()
-                if size >= (32 << 20):
-                    _allreduce_bucket(bucket, dist)
-                    bucket, size = [], 0
-            if bucket:
-                _allreduce_bucket(bucket, dist)
+        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink), ~32 MB buckets
+            allreduce_grads(buckets)
 
     use_graph = not args.no_graph
     if use_graph:

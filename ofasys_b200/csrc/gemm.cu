@@ -15,6 +15,7 @@
 // dgrad and wgrad need no transposed copies in HBM.  Both use 128-byte swizzled smem tiles; only the
 // TMA box shape and the UMMA smem/instruction descriptors differ.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -409,7 +410,11 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
     const int64_t w = (tiles + sms - 1) / sms;
     return (double)w * bn;  // time ~ waves x tile width
   };
-  const int BN = (N > 128 && waves(256) <= waves(128)) ? 256 : 128;
+  int BN = (N > 128 && waves(256) <= waves(128)) ? 256 : 128;
+  if (const char* ov = getenv("OFAB_GEMM_BN")) {  // development override for tile-shape experiments
+    const int v = atoi(ov);
+    if (v == 128 || v == 256) BN = v;
+  }
 
   CUtensorMap ta, tb;
   int rc;
