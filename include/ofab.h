@@ -68,7 +68,9 @@ int ofab_ln_partial_rows(void);
 
 /* Fused "normformer" junction of every attention block (transformer_layer.py:175-186,428-436):
  *   a_ln = LN1(a);  x_new = x + a_ln;  y = LN2(x_new)
- * a: bf16 [rows, cols]; x, x_new: fp32; y: bf16.  stats: fp32 [4, rows] = mean1,rstd1,mean2,rstd2. */
+ * a: bf16 [rows, cols]; x, x_new: fp32; y: bf16.  stats: fp32 [4, rows] = mean1,rstd1,mean2,rstd2.
+ * g1 == b1 == NULL: no first LayerNorm, x_new = x + a (the FFN's deferred residual add fused with the next
+ * block's pre-LayerNorm, transformer_layer.py:203-209 + :170); dg1/db1 partial slabs are then zero. */
 int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1, const void* b1, const void* g2,
                        const void* b2, float* x_new, void* y, float* stats, int64_t rows, int cols,
                        float eps, ofab_stream_t stream);

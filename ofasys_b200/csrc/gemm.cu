@@ -22,10 +22,9 @@
 namespace {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;   // 64 bf16 = 128 bytes = one swizzle row
 constexpr int UMMA_K = 16;
 constexpr int kNumThreads = 192;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemMax = 227 * 1024;  // opt-in dynamic shared memory per CTA on sm_100
 
 // ------------------------------------------------------------------------------- PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -60,6 +59,52 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
       "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// 2-CTA (cta_group::2) variants -----------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// TMA load issued by either CTA of a pair; completion bytes are signalled on the LEADER's barrier
+// (peer bit 24 of the shared::cluster address cleared).
+__device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(mbar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -90,8 +135,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2 at bits [61,64)), version 1 at [46,48).
 //  K-major : rows of 128 B; 8-row groups are 1024 B apart (SBO); one swizzle atom along K (LBO unused).
-//  MN-major: 64-element (128 B) MN atoms of BLOCK_K rows each; SBO = 8 K-rows (1024 B),
-//            LBO = stride between MN atoms (BLOCK_K * 128 B).
+//  MN-major: 64-element (128 B) MN atoms of BK rows each; SBO = 8 K-rows (1024 B),
+//            LBO = stride between MN atoms (BK * 128 B).
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
@@ -110,22 +155,40 @@ struct GemmParams {
   void* D;
   int64_t ldd;
   int d_bf16;
+  int tma_store;  // epilogue writes bf16 tiles through swizzled smem + TMA (coalesced); else direct st.global
+  int dbg;        // development: 1 = no global stores, 2 = no TMEM reads, 4 = no MMA issue, 8 = no TMA loads
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(smem_u32(src)), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+
+// CG = 1: one CTA per 128 x BN tile.  CG = 2: a CTA pair (cluster of 2, cta_group::2) owns a 256 x BN tile;
+// each CTA stages its 128 rows of A and HALF of the B tile, the leader issues UMMA 256 x BN x 16 that reads
+// both CTAs' shared memory, so per-SM smem traffic per MMA is halved.
+// BK = K elements per pipeline stage (64 or 128): one mbarrier hand-shake per BK/16 MMAs; with BK = 128 a
+// K-major operand stage holds two 64-wide swizzle atoms.
+template <int BN, bool A_MN, bool B_MN, int CG, int BK, int STAGES>
 __global__ void __launch_bounds__(kNumThreads, 1)
-gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b, const GemmParams p) {
-  constexpr uint32_t A_BYTES = BLOCK_M * BLOCK_K * 2;
-  constexpr uint32_t B_BYTES = BN * BLOCK_K * 2;
+gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+                 const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
+  constexpr int BNL = BN / CG;  // B rows staged by this CTA
+  constexpr int KA = BK / 64;   // 64-wide K atoms per stage
+  constexpr uint32_t A_BYTES = BLOCK_M * BK * 2;
+  constexpr uint32_t B_BYTES = BNL * BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512 || TMEM_COLS == 128, "tmem columns must be a power of two");
+  constexpr uint32_t STG_BYTES = BLOCK_M * 128;  // one 128-row x 64-col bf16 store tile
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "tmem columns must be a power of two");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_b + STAGES * B_BYTES);
+  uint8_t* smem_st = smem_b + STAGES * B_BYTES;  // 2 store staging tiles
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem_st + 2 * STG_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
@@ -133,30 +196,41 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M;
+  const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);  // tiles of 128*CG rows
   const int n_tiles = (p.N + BN - 1) / BN;
   const int num_tiles = m_tiles * n_tiles;
-  const int num_k_blocks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int num_k_blocks = (p.K + BK - 1) / BK;
+  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const bool leader = rank == 0;
+  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
+    if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_d) : "memory");
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full_bar + i, 1);
+      mbar_init(full_bar + i, CG);  // leader's barrier: one producer arrival per CTA of the pair
       mbar_init(empty_bar + i, 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
-      mbar_init(tmem_empty + i, 4);  // one arrival per epilogue warp
+      mbar_init(tmem_empty + i, 4 * CG);  // one arrival per epilogue warp (of both CTAs, on the leader)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  if (CG == 2) cluster_sync_all();  // both CTAs are resident before the paired TMEM allocation
   if (warp == 1) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(TMEM_COLS));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
@@ -165,26 +239,34 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % m_tiles) * BLOCK_M;
-        const int n0 = (t / m_tiles) * BN;
+      for (int t = tile0; t < num_tiles; t += tile_step) {
+        const int m0 = (t % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;  // this CTA's 128 rows
+        const int n0 = (t / m_tiles) * BN + (int)rank * BNL;                   // this CTA's slice of the B tile
         for (int kb = 0; kb < num_k_blocks; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
-          mbar_expect_tx(full_bar + stage, A_BYTES + B_BYTES);
+          if (leader) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
+          else mbar_arrive_remote(full_bar + stage, 0);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
-          const int k0 = kb * BLOCK_K;
+          const int k0 = kb * BK;
+          auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
+            if (p.dbg & 8) return;
+            if (CG == 1) tma_load_2d(dst, map, full_bar + stage, c0, c1);
+            else tma_load_2d_2sm(dst, map, full_bar + stage, c0, c1);
+          };
           if (!A_MN) {
-            tma_load_2d(sa, &tma_a, full_bar + stage, k0, m0);
+#pragma unroll
+            for (int a = 0; a < KA; ++a) load(sa + a * (BLOCK_M * 128), &tma_a, k0 + a * 64, m0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BLOCK_M / 64; ++i) tma_load_2d(sa + i * (BLOCK_K * 128), &tma_a, full_bar + stage, m0 + i * 64, k0);
+            for (int i = 0; i < BLOCK_M / 64; ++i) load(sa + i * (BK * 128), &tma_a, m0 + i * 64, k0);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tma_b, full_bar + stage, k0, n0);
+#pragma unroll
+            for (int a = 0; a < KA; ++a) load(sb + a * (BNL * 128), &tma_b, k0 + a * 64, n0);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (BLOCK_K * 128), &tma_b, full_bar + stage, n0 + i * 64, k0);
+            for (int i = 0; i < BNL / 64; ++i) load(sb + i * (BK * 128), &tma_b, n0 + i * 64, k0);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -194,16 +276,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    if (lane == 0) {
+    // ===================================================================== MMA issuer (leader CTA only)
+    if (lane == 0 && leader) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
       // N>>3 at [17,23), M>>4 at [24,29)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+                                 ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+      for (int t = tile0; t < num_tiles; t += tile_step, ++iter) {
         const int as = iter & 1;
         const uint32_t aphase = (iter >> 1) & 1;
         mbar_wait(tmem_empty + as, aphase ^ 1);
@@ -215,17 +297,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES);
           const uint32_t b_addr = smem_u32(smem_b + stage * B_BYTES);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            // K-major: advance 16 elements (32 B) inside the 128 B swizzle row.
-            // MN-major: advance 16 K-rows of 128 B (2048 B).
-            const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                        : make_smem_desc(a_addr + k * (UMMA_K * 2), 0, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), BLOCK_K * 128, 1024)
-                                        : make_smem_desc(b_addr + k * (UMMA_K * 2), 0, 1024);
-            umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // K-major: 64-wide atom (k / 4), then 16 elements (32 B) inside the 128 B swizzle row.
+            // MN-major: 16 K-rows of 128 B (2048 B) per step; atoms along MN are BK*128 B apart (LBO).
+            const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), BK * 128, 1024)
+                                        : make_smem_desc(a_addr + (k >> 2) * (BLOCK_M * 128) + (k & 3) * (UMMA_K * 2), 0, 1024);
+            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), BK * 128, 1024)
+                                        : make_smem_desc(b_addr + (k >> 2) * (BNL * 128) + (k & 3) * (UMMA_K * 2), 0, 1024);
+            if (p.dbg & 4) continue;
+            if (CG == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            else umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(empty_bar + stage);  // frees the smem slot when these MMAs retire
-          if (kb == num_k_blocks - 1) umma_commit(tmem_full + as);
+          // frees the smem slot (in both CTAs when paired) once these MMAs retire
+          if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage);
+          if (kb == num_k_blocks - 1) {
+            if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -236,96 +323,159 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int etid = (warp - 2) * 32 + lane;  // 0..127
+    const int rloc = q * 32 + lane;           // row of the 128-row tile held by this thread
     int iter = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++iter) {
+    int sbuf = 0;
+    for (int t = tile0; t < num_tiles; t += tile_step, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const int m0 = (t % m_tiles) * BLOCK_M;
+      const int m0 = (t % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
       const int n0 = (t / m_tiles) * BN;
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
-      const int row = m0 + q * 32 + lane;
+      const int row = m0 + rloc;
       const bool row_ok = row < p.M;
+      if (p.tma_store) {
+        // ---- coalesced path: 64-column bf16 chunks -> 128B-swizzled smem tile -> TMA store (clips M / N tails)
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        __syncwarp();
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), r);
-        const int n = n0 + c0;
-        if (n < p.N && row_ok) {
-        float v[32];
+        for (int c64 = 0; c64 < BN; c64 += 64) {
+          if (n0 + c64 >= p.N) break;  // uniform
+          uint8_t* stg = smem_st + sbuf * STG_BYTES;
+          if (etid == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");  // staging tile sbuf is free again
+          asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-        if (p.bias != nullptr) {
-          if (n + 32 <= p.N) {
+          for (int hf = 0; hf < 2; ++hf) {
+            uint32_t r[32];
+            const int c0 = c64 + hf * 32;
+            __syncwarp();
+            if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), r);
+            else { for (int j = 0; j < 32; ++j) r[j] = 0; }
+            const int n = n0 + c0;
+            float v[32];
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              const f8 bb = load8(p.bias + n + j);
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr && n < p.N) {
+              if (n + 32 <= p.N) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) v[j + e] += bb.v[e];
+                for (int j = 0; j < 32; j += 8) {
+                  const f8 bb = load8(p.bias + n + j);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[j + e] += bb.v[e];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) v[j] += __bfloat162float(p.bias[n + j]);
+              }
             }
-          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) v[j] += __bfloat162float(p.bias[n + j]);
-          }
-        }
-        if (p.residual != nullptr) {
-          const float* rp = p.residual + (int64_t)row * p.ldr + n;
-          if (n + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 x = *reinterpret_cast<const float4*>(rp + j);
-              v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) v[j] += rp[j];
-          }
-        }
-        if (p.d_bf16) {
-          bf16* dp = reinterpret_cast<bf16*>(p.D) + (int64_t)row * p.ldd + n;
-          if (n + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
+            for (int j = 0; j < 4; ++j) {
               uint4 u;
-              u.x = pack_bf16(v[j], v[j + 1]);
-              u.y = pack_bf16(v[j + 2], v[j + 3]);
-              u.z = pack_bf16(v[j + 4], v[j + 5]);
-              u.w = pack_bf16(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(dp + j) = u;
+              u.x = pack_bf16(v[8 * j], v[8 * j + 1]);
+              u.y = pack_bf16(v[8 * j + 2], v[8 * j + 3]);
+              u.z = pack_bf16(v[8 * j + 4], v[8 * j + 5]);
+              u.w = pack_bf16(v[8 * j + 6], v[8 * j + 7]);
+              const int ci = hf * 4 + j;  // 16-byte chunk inside the 128-byte row
+              *reinterpret_cast<uint4*>(stg + rloc * 128 + ((ci ^ (rloc & 7)) << 4)) = u;
             }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) dp[j] = __float2bfloat16(v[j]);
           }
-        } else {
-          float* dp = reinterpret_cast<float*>(p.D) + (int64_t)row * p.ldd + n;
-          if (n + 32 <= p.N) {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n + j < p.N) dp[j] = v[j];
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy smem writes -> async proxy
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          if (etid == 0 && !(p.dbg & 1)) {
+            tma_store_2d(&tma_d, stg, n0 + c64, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
+          sbuf ^= 1;
         }
+      } else {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          uint32_t r[32];
+          __syncwarp();
+          if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN + c0), r);
+          else { for (int j = 0; j < 32; ++j) r[j] = 0; }
+          const int n = n0 + c0;
+          if (n < p.N && row_ok && !(p.dbg & 1)) {
+            float v[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+            if (p.bias != nullptr) {
+              if (n + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  const f8 bb = load8(p.bias + n + j);
+#pragma unroll
+                  for (int e = 0; e < 8; ++e) v[j + e] += bb.v[e];
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) v[j] += __bfloat162float(p.bias[n + j]);
+              }
+            }
+            if (p.residual != nullptr) {
+              const float* rp = p.residual + (int64_t)row * p.ldr + n;
+              if (n + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 x = *reinterpret_cast<const float4*>(rp + j);
+                  v[j] += x.x; v[j + 1] += x.y; v[j + 2] += x.z; v[j + 3] += x.w;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) v[j] += rp[j];
+              }
+            }
+            if (p.d_bf16) {
+              bf16* dp = reinterpret_cast<bf16*>(p.D) + (int64_t)row * p.ldd + n;
+              if (n + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 u;
+                  u.x = pack_bf16(v[j], v[j + 1]);
+                  u.y = pack_bf16(v[j + 2], v[j + 3]);
+                  u.z = pack_bf16(v[j + 4], v[j + 5]);
+                  u.w = pack_bf16(v[j + 6], v[j + 7]);
+                  *reinterpret_cast<uint4*>(dp + j) = u;
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) dp[j] = __float2bfloat16(v[j]);
+              }
+            } else {
+              float* dp = reinterpret_cast<float*>(p.D) + (int64_t)row * p.ldd + n;
+              if (n + 32 <= p.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n + j < p.N) dp[j] = v[j];
+              }
+            }
+          }
         }
       }
       // all TMEM reads of this accumulator stage are complete (tcgen05.wait::ld above)
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tmem_empty + as);
+      if (lane == 0) {
+        if (CG == 1) mbar_arrive(tmem_empty + as);
+        else mbar_arrive_remote(tmem_empty + as, 0);  // the MMA issuer waits on the leader's barrier
+      }
     }
+    if (p.tma_store && etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before smem dies
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
     tcgen05_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
   }
 }
 
@@ -366,24 +516,39 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, 
   return OFAB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  constexpr int stage_bytes = BLOCK_M * BLOCK_K * 2 + BN * BLOCK_K * 2;
-  constexpr int STAGES = (kSmemBudget / stage_bytes) > 8 ? 8 : (kSmemBudget / stage_bytes);
-  constexpr int smem_bytes = STAGES * stage_bytes + 1024 /*barriers*/ + 1024 /*alignment slack*/;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+template <int BN, bool A_MN, bool B_MN, int CG>
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
+  constexpr int BK = CG == 2 ? 128 : 64;
+  constexpr int stage_bytes = BLOCK_M * BK * 2 + (BN / CG) * BK * 2;
+  constexpr int kFixed = 2 * BLOCK_M * 128 /*store staging*/ + 1024 /*barriers*/ + 1024 /*alignment slack*/;
+  constexpr int STAGES = ((kSmemMax - kFixed) / stage_bytes) > 8 ? 8 : ((kSmemMax - kFixed) / stage_bytes);
+  static_assert(STAGES >= 2, "pipeline needs at least two stages");
+  constexpr int smem_bytes = STAGES * stage_bytes + kFixed;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CG, BK, STAGES>;
   static bool configured = false;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaFuncSetAttribute");
     configured = true;
   }
-  const int m_tiles = (p.M + BLOCK_M - 1) / BLOCK_M, n_tiles = (p.N + BN - 1) / BN;
+  const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG), n_tiles = (p.N + BN - 1) / BN;
   const int tiles = m_tiles * n_tiles;
-  const int sms = ofab_sm_count();
-  const int grid = tiles < sms ? tiles : sms;
-  kern<<<grid, kNumThreads, smem_bytes, st>>>(ta, tb, p);
-  OFAB_LAUNCH_CHECK("ofab_gemm_bf16 launch");
+  const int units = ofab_sm_count() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
+  const int grid = (tiles < units ? tiles : units) * CG;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kNumThreads);
+  cfg.dynamicSmemBytes = smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p);
+  if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16 launch");
   return OFAB_OK;
 }
 
@@ -402,28 +567,56 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   OFAB_REQUIRE(d_dt == OFAB_BF16 || d_dt == OFAB_F32, "ofab_gemm_bf16: bad d_dt");
   OFAB_REQUIRE(lda >= (a_mn_major ? M : K) && ldb >= (b_mn_major ? N : K) && ldd >= N, "ofab_gemm_bf16: leading dimension smaller than the row");
 
-  // tile N: 256 when it divides the work well, else 128 (keeps wave quantisation low for N = 768)
+  // Tile selection.  CTA pairs (cta_group::2, 256 x BN tiles) halve shared-memory traffic per MMA and are
+  // preferred; BN and the 1-CTA form are chosen by wave quantisation (time ~ waves x tile width, with the
+  // 1-CTA form derated for its smem-bound main loop).
   const int sms = ofab_sm_count();
-  const int64_t m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
-  auto waves = [&](int bn) {
-    const int64_t tiles = m_tiles * ((N + bn - 1) / bn);
-    const int64_t w = (tiles + sms - 1) / sms;
-    return (double)w * bn;  // time ~ waves x tile width
+  auto cost = [&](int bn, int cg) {
+    const int64_t mt = (M + BLOCK_M * cg - 1) / (BLOCK_M * cg);
+    const int64_t tiles = mt * ((N + bn - 1) / bn);
+    const int64_t units = sms / cg;
+    const double waves = (double)((tiles + units - 1) / units);
+    return waves * bn * (cg == 1 ? 1.35 : 1.0);
   };
-  int BN = (N > 128 && waves(256) <= waves(128)) ? 256 : 128;
-  if (const char* ov = getenv("OFAB_GEMM_BN")) {  // development override for tile-shape experiments
+  int BN = 256, CG = 2;
+  double best = 1e30;
+  const int bns[2] = {256, 128};
+  for (int cg = 2; cg >= 1; --cg)
+    for (int bi = 0; bi < 2; ++bi) {
+      const int bn = bns[bi];
+      if (b_mn_major && (bn / cg) % 64 != 0) continue;  // MN-major B is staged in 64-wide atoms
+      const double c = cost(bn, cg);
+      if (c < best - 1e-9) { best = c; BN = bn; CG = cg; }
+    }
+  if (const char* ov = getenv("OFAB_GEMM_BN")) {  // development overrides for tile-shape experiments
     const int v = atoi(ov);
     if (v == 128 || v == 256) BN = v;
   }
+  if (const char* ov = getenv("OFAB_GEMM_CG")) {
+    const int v = atoi(ov);
+    if (v == 1 || v == 2) CG = v;
+  }
+  if (b_mn_major && (BN / CG) % 64 != 0) CG = 1;
 
   CUtensorMap ta, tb;
   int rc;
-  if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, BLOCK_K, BLOCK_M);
-  else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BLOCK_K);
+  // K-major operands are loaded as 64-wide (128 B) K atoms x rows; MN-major operands as 64-wide MN atoms x BK rows
+  const uint32_t BK = CG == 2 ? 128 : 64;
+  if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BLOCK_M);
+  else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   if (rc) return rc;
-  if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, BLOCK_K, (uint32_t)BN);
-  else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BLOCK_K);
+  if (!b_mn_major) rc = make_map(&tb, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 64, (uint32_t)(BN / CG));
+  else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
+  // bf16 outputs without a residual leave through swizzled smem + TMA stores of 128 x 64 tiles (coalesced 128 B rows)
+  const int tma_store = (d_dt == OFAB_BF16 && residual == nullptr) ? 1 : 0;
+  CUtensorMap td;
+  if (tma_store) {
+    rc = make_map(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, BLOCK_M);
+    if (rc) return rc;
+  } else {
+    td = ta;  // unused
+  }
 
   GemmParams p;
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
@@ -433,8 +626,15 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   p.D = D;
   p.ldd = ldd;
   p.d_bf16 = d_dt == OFAB_BF16;
+  p.tma_store = tma_store;
+  p.dbg = 0;
+  if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
   cudaStream_t st = (cudaStream_t)stream;
-#define GO(BNV, AM, BM) return launch<BNV, AM, BM>(ta, tb, p, st)
+#define GO(BNV, AM, BM)                                   \
+  do {                                                    \
+    if (CG == 2) return launch<BNV, AM, BM, 2>(ta, tb, td, p, st); \
+    return launch<BNV, AM, BM, 1>(ta, tb, td, p, st);          \
+  } while (0)
   if (BN == 256) {
     if (!a_mn_major && !b_mn_major) GO(256, false, false);
     if (!a_mn_major && b_mn_major) GO(256, false, true);

@@ -200,7 +200,9 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
 }
 
 // ---------------------------------------------------------------- fused LN -> +res -> LN
-template <int TPR, int NV>
+// HAS_LN1 = false: x_new = x + a (no first LayerNorm): the deferred residual add of an FFN output fused
+// with the next block's pre-LayerNorm.
+template <int TPR, int NV, bool HAS_LN1>
 __global__ void __launch_bounds__(128) ln_res_ln_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ x,
                                                             const bf16* __restrict__ g1, const bf16* __restrict__ b1,
                                                             const bf16* __restrict__ g2, const bf16* __restrict__ b2,
@@ -226,32 +228,39 @@ __global__ void __launch_bounds__(128) ln_res_ln_fwd_kernel(const bf16* __restri
         for (int j = 0; j < 8; ++j) s += v[i].v[j];
       }
     }
-    const float m1 = row_sum<TPR>(s, red) * inv_n;
-    float q = 0.f;
+    float m1 = 0.f, r1 = 1.f, q = 0.f;
+    if (HAS_LN1) {
+      m1 = row_sum<TPR>(s, red) * inv_n;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      const int c = (lane + i * TPR) * 8;
-      if (live && c < cols) {
+      for (int i = 0; i < NV; ++i) {
+        const int c = (lane + i * TPR) * 8;
+        if (live && c < cols) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float d = v[i].v[j] - m1;
-          q += d * d;
+          for (int j = 0; j < 8; ++j) {
+            const float d = v[i].v[j] - m1;
+            q += d * d;
+          }
         }
       }
+      r1 = rsqrtf(row_sum<TPR>(q, red) * inv_n + eps);
     }
-    const float r1 = rsqrtf(row_sum<TPR>(q, red) * inv_n + eps);
-    // x_new = x + LN1(a)
+    // x_new = x + LN1(a)   (or x + a)
     s = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + i * TPR) * 8;
       if (live && c < cols) {
-        const f8 gg = load8(g1 + c), bb = load8(b1 + c), xx = load8(x + row * cols + c);
+        const f8 xx = load8(x + row * cols + c);
+        if (HAS_LN1) {
+          const f8 gg = load8(g1 + c), bb = load8(b1 + c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[i].v[j] = xx.v[j] + ((v[i].v[j] - m1) * r1 * gg.v[j] + bb.v[j]);
-          s += v[i].v[j];
+          for (int j = 0; j < 8; ++j) v[i].v[j] = xx.v[j] + ((v[i].v[j] - m1) * r1 * gg.v[j] + bb.v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[i].v[j] += xx.v[j];
         }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += v[i].v[j];
         store8(x_new + row * cols + c, v[i]);
       }
     }
@@ -291,7 +300,7 @@ __global__ void __launch_bounds__(128) ln_res_ln_fwd_kernel(const bf16* __restri
   }
 }
 
-template <int TPR, int NV>
+template <int TPR, int NV, bool HAS_LN1>
 __global__ void __launch_bounds__(128) ln_res_ln_bwd_kernel(const float* __restrict__ dxn, const bf16* __restrict__ dy,
                                                             const bf16* __restrict__ a, const float* __restrict__ x_new,
                                                             const bf16* __restrict__ g1, const bf16* __restrict__ g2,
@@ -345,25 +354,33 @@ __global__ void __launch_bounds__(128) ln_res_ln_bwd_kernel(const float* __restr
     for (int i = 0; i < NV; ++i) {
       const int c = (lane + i * TPR) * 8;
       if (live && c < cols) {
-        const f8 up = load8(dxn + row * cols + c), aa = load8(a + row * cols + c), gg = load8(g1 + c);
+        const f8 up = load8(dxn + row * cols + c);
         f8 tot;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          tot.v[j] = up.v[j] + r2 * (d[i].v[j] - c2 - xh[i].v[j] * c1);
-          xh[i].v[j] = (aa.v[j] - m1) * r1;
-          acc[0][i].v[j] += tot.v[j] * xh[i].v[j];
-          acc[1][i].v[j] += tot.v[j];
-          const float t = tot.v[j] * gg.v[j];
-          d[i].v[j] = t;
-          s1 += t * xh[i].v[j];
-          s2 += t;
-        }
+        for (int j = 0; j < 8; ++j) tot.v[j] = up.v[j] + r2 * (d[i].v[j] - c2 - xh[i].v[j] * c1);
         store8(dxt + row * cols + c, tot);
+        if (HAS_LN1) {
+          const f8 aa = load8(a + row * cols + c), gg = load8(g1 + c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            xh[i].v[j] = (aa.v[j] - m1) * r1;
+            acc[0][i].v[j] += tot.v[j] * xh[i].v[j];
+            acc[1][i].v[j] += tot.v[j];
+            const float t = tot.v[j] * gg.v[j];
+            d[i].v[j] = t;
+            s1 += t * xh[i].v[j];
+            s2 += t;
+          }
+        } else {
+          store8(da + row * cols + c, tot);  // d a = d x_new
+        }
       }
     }
-    c1 = row_sum<TPR>(s1, red) * inv_n;
-    c2 = row_sum<TPR>(s2, red) * inv_n;
-    if (live) {
+    if (HAS_LN1) {
+      c1 = row_sum<TPR>(s1, red) * inv_n;
+      c2 = row_sum<TPR>(s2, red) * inv_n;
+    }
+    if (live && HAS_LN1) {
 #pragma unroll
       for (int i = 0; i < NV; ++i) {
         const int c = (lane + i * TPR) * 8;
@@ -515,7 +532,10 @@ extern "C" int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1,
   if (rows == 0) return OFAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(TPR, NV)                                                                                       \
-  ln_res_ln_fwd_kernel<TPR, NV><<<ln_fwd_grid(rows, TPR), 128, 0, st>>>((const bf16*)a, x, (const bf16*)g1, (const bf16*)b1, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps);
+  if (g1 != nullptr)                                                                                        \
+    ln_res_ln_fwd_kernel<TPR, NV, true><<<ln_fwd_grid(rows, TPR), 128, 0, st>>>((const bf16*)a, x, (const bf16*)g1, (const bf16*)b1, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps); \
+  else                                                                                                      \
+    ln_res_ln_fwd_kernel<TPR, NV, false><<<ln_fwd_grid(rows, TPR), 128, 0, st>>>((const bf16*)a, x, nullptr, nullptr, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps);
   LN_SHAPE_DISPATCH(cols, CALL)
 #undef CALL
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_fwd");
@@ -528,7 +548,10 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_res_ln_bwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   cudaStream_t st = (cudaStream_t)stream;
 #define CALL(TPR, NV)                                                                                       \
-  ln_res_ln_bwd_kernel<TPR, NV><<<OFAB_LN_PARTIAL_ROWS, 128, 0, st>>>(dx_new, (const bf16*)dy, (const bf16*)a, x_new, (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols);
+  if (g1 != nullptr)                                                                                        \
+    ln_res_ln_bwd_kernel<TPR, NV, true><<<OFAB_LN_PARTIAL_ROWS, 128, 0, st>>>(dx_new, (const bf16*)dy, (const bf16*)a, x_new, (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols); \
+  else                                                                                                      \
+    ln_res_ln_bwd_kernel<TPR, NV, false><<<OFAB_LN_PARTIAL_ROWS, 128, 0, st>>>(dx_new, (const bf16*)dy, nullptr, x_new, nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols);
   LN_SHAPE_DISPATCH(cols, CALL)
 #undef CALL
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_bwd");

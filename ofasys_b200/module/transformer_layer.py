@@ -24,14 +24,23 @@ def _check(cfg, side):
         raise NotImplementedError("modal_ffn / scale_resids are off in every BASELINE config and not implemented")
 
 
-def _ffn(layer, x_res, x2):
-    """x_res fp32 residual, x2 = final_layer_norm(x_res) bf16 -> x_res + fc2(ffn_ln(gelu(fc1 x2)))."""
+def _ffn(layer, x2):
+    """x2 = final_layer_norm(x) bf16 -> fc2(ffn_ln(gelu(fc1 x2))) bf16.  The residual add is deferred: it is
+    fused with the next block's pre-LayerNorm (ops.ln_res_ln with no first LN), so the GEMM epilogue stays a
+    plain coalesced bf16 TMA store."""
     h = ops.linear(x2, layer.fc1.weight, layer.fc1.bias)
     if layer.ffn_layernorm is not None:
         h = ops.layer_norm(h, layer.ffn_layernorm.weight, layer.ffn_layernorm.bias, layer.ffn_layernorm.eps, gelu=True)
     else:
         raise NotImplementedError("scale_fc=False")
-    return ops.linear(h, layer.fc2.weight, layer.fc2.bias, residual=x_res)
+    return ops.linear(h, layer.fc2.weight, layer.fc2.bias)
+
+
+def _enter(x, pending, ln):
+    """(x, pending FFN output of the previous layer) -> (x + pending, ln(x + pending))."""
+    if pending is None:
+        return x, ln(x)
+    return ops.ln_res_ln(pending, x, None, None, ln.weight, ln.bias, ln.eps)
 
 
 def _junction(attn_out, x_res, ln_attn, ln_next):
@@ -64,17 +73,22 @@ class TransformerEncoderLayer(nn.Module):
         self.drop_path_rate = float(drop_path_rate)
 
     def forward(self, x, encoder_padding_mask=None, attn_mask=None, self_attn_bias=None, need_attn=False, modal_mask=None,
-                batch_first=False):
-        """x: T x B x C (reference layout) or B x T x C with batch_first=True; fp32 residual stream."""
+                batch_first=False, pending=None, defer=False):
+        """x: T x B x C (reference layout) or B x T x C with batch_first=True; fp32 residual stream.
+        Internal fast path (used by TransformerEncoder): `pending` = previous layer's FFN output whose residual add
+        is still owed; with defer=True this layer returns ((x, pending'), None) instead of adding its own."""
         if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
             raise NotImplementedError("dropout / drop-path > 0: parity and headline runs use p=0 (SURVEY 8d)")
         if not batch_first:
             x = x.transpose(0, 1).contiguous()
         x = ops.to_f32(x)
-        x1 = self.self_attn_layer_norm(x)
+        x, x1 = _enter(x, pending, self.self_attn_layer_norm)
         a, _ = self.self_attn(x1, key_padding_mask=encoder_padding_mask, attn_bias=self_attn_bias, batch_first=True, causal=attn_mask is not None)
         x, x2 = _junction(a, x, self.attn_ln, self.final_layer_norm)
-        x = _ffn(self, x, x2)
+        y = _ffn(self, x2)
+        if defer:
+            return (x, y), None
+        x = ops.add_residual(x, y)
         if not batch_first:
             x = x.transpose(0, 1)
         return x, None
@@ -112,7 +126,7 @@ class TransformerDecoderLayer(nn.Module):
 
     def forward(self, x, encoder_out=None, encoder_padding_mask=None, incremental_state=None, prev_self_attn_state=None,
                 prev_attn_state=None, self_attn_mask=None, self_attn_padding_mask=None, need_attn=False, need_head_weights=False,
-                self_attn_bias=None, cross_attn_bias=None, modal_mask=None, batch_first=False):
+                self_attn_bias=None, cross_attn_bias=None, modal_mask=None, batch_first=False, pending=None, defer=False):
         if incremental_state is not None or prev_self_attn_state is not None or prev_attn_state is not None:
             raise NotImplementedError("incremental decoding is outside the fwd+bwd hot path")
         if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
@@ -121,7 +135,7 @@ class TransformerDecoderLayer(nn.Module):
             x = x.transpose(0, 1).contiguous()
             encoder_out = encoder_out.transpose(0, 1).contiguous()
         x = ops.to_f32(x)
-        x1 = self.self_attn_layer_norm(x)
+        x, x1 = _enter(x, pending, self.self_attn_layer_norm)
         # the decoder passes False (not None) when biases are off -> manual path (transformer.py:476-477)
         a, _ = self.self_attn(x1, key_padding_mask=self_attn_padding_mask, attn_bias=self_attn_bias if self_attn_bias is not None else False,
                               batch_first=True, causal=self_attn_mask is not None)
@@ -129,7 +143,10 @@ class TransformerDecoderLayer(nn.Module):
         c, _ = self.encoder_attn(x2, key=encoder_out, value=encoder_out, key_padding_mask=encoder_padding_mask, static_kv=True,
                                  attn_bias=cross_attn_bias, batch_first=True, causal=False)
         x, x3 = _junction(c, x, self.cross_attn_ln, self.final_layer_norm)
-        x = _ffn(self, x, x3)
+        y = _ffn(self, x3)
+        if defer:
+            return (x, y), None, None
+        x = ops.add_residual(x, y)
         if not batch_first:
             x = x.transpose(0, 1)
         return x, None, None

@@ -138,27 +138,48 @@ class _LnResLnFn(torch.autograd.Function):
         y = torch.empty_like(a)
         stats = torch.empty((4, rows), dtype=torch.float32, device=a.device)
         _lib.call("ofab_ln_res_ln_fwd", _p(a), _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(x_new), _p(y), _p(stats), rows, cols, eps, _s())
-        ctx.save_for_backward(a, x_new, w1, w2, stats)
+        ctx.save_for_backward(a if w1 is not None else None, x_new, w1, w2, stats)
+        ctx.shape_a = a.shape
         return x_new, y
 
     @staticmethod
     def backward(ctx, dx_new, dy):
         a, x_new, w1, w2, stats = ctx.saved_tensors
-        cols = a.shape[-1]
-        rows = a.numel() // cols
+        cols = x_new.shape[-1]
+        rows = x_new.numel() // cols
         dx_new = torch.zeros_like(x_new) if dx_new is None else _c(dx_new)
-        dy = torch.zeros_like(a) if dy is None else _c(dy)
+        dy = torch.zeros(ctx.shape_a, dtype=torch.bfloat16, device=x_new.device) if dy is None else _c(dy)
         dx_tot = torch.empty_like(x_new)
-        da = torch.empty_like(a)
-        partial = torch.empty((4, _partial_rows(), cols), dtype=torch.float32, device=a.device)
+        da = torch.empty(ctx.shape_a, dtype=torch.bfloat16, device=x_new.device)
+        partial = torch.empty((4, _partial_rows(), cols), dtype=torch.float32, device=x_new.device)
         _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _s())
-        g = _reduce_partials(partial, w1.dtype)
+        g = _reduce_partials(partial, w2.dtype)
+        if w1 is None:
+            return da, dx_tot, None, None, g[2], g[3], None
         return da, dx_tot, g[0], g[1], g[2], g[3], None
 
 
 def ln_res_ln(a, x, w1, b1, w2, b2, eps=1e-5):
-    """x_new = x + LN1(a); y = LN2(x_new).  Returns (x_new fp32, y bf16)."""
+    """x_new = x + LN1(a); y = LN2(x_new).  Returns (x_new fp32, y bf16).  w1 = b1 = None: x_new = x + a."""
     return _LnResLnFn.apply(a, x, w1, b1, w2, b2, eps)
+
+
+class _AddFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, y):
+        x, y = _c(x), _c(y)
+        out = torch.empty_like(x)
+        _lib.call("ofab_add_f32", _p(x), _p(y), _p(out), x.numel(), _s())
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, g
+
+
+def add_residual(x, y):
+    """x (fp32) + y (bf16 or fp32) -> fp32: the un-fused residual add of the reference-layout API path."""
+    return _AddFn.apply(x, to_f32(y))
 
 
 # ------------------------------------------------------------------------------------ GEMM

@@ -105,6 +105,28 @@ def test_ln_res_ln(cols):
         assert rel_l2(p.grad, q.grad) <= TOL16
 
 
+def test_res_ln_no_first_norm():
+    """x_new = x + a ; y = LN(x_new): the deferred FFN residual add fused with the next pre-LN."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    rows, cols = 301, 768
+    a = rnd(rows, cols, gen=gen).requires_grad_(True)
+    x = rnd(rows, cols, dtype=torch.float32, gen=gen).requires_grad_(True)
+    w = (torch.rand(cols, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    b = (torch.randn(cols, generator=gen) * 0.1).bfloat16().to(dev()).requires_grad_(True)
+    dxn, dy = rnd(rows, cols, dtype=torch.float32, gen=gen), rnd(rows, cols, gen=gen)
+    xn, y = ops.ln_res_ln(a, x, None, None, w, b)
+    torch.autograd.backward([xn, y], [dxn, dy])
+    ar, xr, wr, br = a.detach().float().requires_grad_(True), x.detach().clone().requires_grad_(True), w.detach().float().requires_grad_(True), b.detach().float().requires_grad_(True)
+    xnr = xr + ar
+    yr = F.layer_norm(xnr, (cols,), wr, br, 1e-5)
+    torch.autograd.backward([xnr, yr], [dxn, dy.float()])
+    assert rel_l2(xn, xnr) <= TOL32 and rel_l2(y, yr) <= TOL16
+    assert rel_l2(x.grad, xr.grad) <= 1e-4 and rel_l2(a.grad, ar.grad) <= TOL16
+    assert rel_l2(w.grad, wr.grad) <= TOL16 and rel_l2(b.grad, br.grad) <= TOL16
+
+
 def test_colsum():
     from ofasys_b200 import ops
 
@@ -134,6 +156,32 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, N)
     ref = A.float() @ B.float().t()
     assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn)
+
+
+@pytest.mark.parametrize("cg", [1, 2])
+@pytest.mark.parametrize("bn", [128, 256])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg):
+    """Every (BN, cta_group) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles and
+    CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair)."""
+    from ofasys_b200 import ops
+
+    monkeypatch.setenv("OFAB_GEMM_BN", str(bn))
+    monkeypatch.setenv("OFAB_GEMM_CG", str(cg))
+    gen = g()
+    for (M, N, K) in [(1000, 776, 200), (8480 // 4, 2304, 768), (300, 136, 3072)]:
+        if a_mn:
+            M = (M + 7) // 8 * 8
+        if b_mn:
+            N = (N + 7) // 8 * 8
+        A, B = rnd(M, K, gen=gen), rnd(N, K, gen=gen)
+        Am = A.t().contiguous() if a_mn else A
+        Bm = B.t().contiguous() if b_mn else B
+        bias = rnd(N, gen=gen)
+        out = torch.empty(M, N, dtype=torch.float32, device=dev())
+        ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, N, bias=bias)
+        ref = A.float() @ B.float().t() + bias.float()
+        assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn, bn, cg)
 
 
 def test_gemm_epilogues():

@@ -54,9 +54,9 @@ def main():
     rows.append(bench("dec.crosskv.fwd", 8480, 1536, 768, 0, 0))
     rows.append(bench("dec.crosskv.dgrad", 8480, 768, 1536, 0, 1))
     rows.append(bench("dec.crosskv.wgrad", 1536, 768, 8480, 1, 1))
-    rows.append(bench("logits.fwd", 2048, 50265, 768, 0, 0))
-    rows.append(bench("logits.dgrad", 2048, 768, 50265, 0, 1))
-    rows.append(bench("logits.wgrad", 50265, 768, 2048, 1, 1))
+    rows.append(bench("logits.fwd", 2048, 50264, 768, 0, 0))
+    rows.append(bench("logits.dgrad", 2048, 768, 50264, 0, 1))
+    rows.append(bench("logits.wgrad", 50264, 768, 2048, 1, 1))
     tot = sum(r["us"] for r in rows if not r["name"].startswith("logits") and "crosskv" not in r["name"]) * 12
     tot += sum(r["us"] for r in rows if "crosskv" in r["name"]) * 12 + sum(r["us"] for r in rows if r["name"].startswith("logits"))
     for r in rows:

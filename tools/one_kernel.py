@@ -1,0 +1,34 @@
+"""Run a few launches of one kernel family in isolation (for `ncu --set full` captures)."""
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from ofasys_b200 import ops  # noqa: E402
+
+dev = torch.device("cuda:0")
+which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
+if which == "gemm":  # encoder fc1 forward of the benchmark step: M=8480 N=3072 K=768 (+bias)
+    M, N, K = 8480, 3072, 768
+    A = torch.randn(M, K, device=dev).bfloat16()
+    B = torch.randn(N, K, device=dev).bfloat16()
+    bias = torch.randn(N, device=dev).bfloat16()
+    out = torch.empty(M, N, dtype=torch.bfloat16, device=dev)
+    for _ in range(5):
+        ops.gemm(M, N, K, A, K, 0, B, K, 0, out, N, bias=bias)
+elif which == "attn":  # encoder self-attention of the benchmark step: B=32 H=12 T=265
+    B, T, H = 32, 265, 12
+    qkv = torch.randn(B, T, 3 * H * 64, device=dev).bfloat16().requires_grad_(True)
+    kpm = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    for _ in range(3):
+        o = ops.attention(qkv, None, H, 0.125, None, kpm, False)
+        o.backward(torch.randn_like(o))
+elif which == "ln":  # GELU + ffn_layernorm of the benchmark step: rows 8480 x 3072
+    x = torch.randn(8480, 3072, device=dev).bfloat16().requires_grad_(True)
+    w = torch.ones(3072, device=dev).bfloat16().requires_grad_(True)
+    b = torch.zeros(3072, device=dev).bfloat16().requires_grad_(True)
+    for _ in range(3):
+        y = ops.layer_norm(x, w, b, gelu=True)
+        y.backward(torch.randn_like(y))
+torch.cuda.synchronize()
