@@ -59,8 +59,9 @@ int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const void* beta, vo
                 ofab_stream_t stream);
 
 /* backward of ofab_ln_fwd.  dx (dx_dt) = d act(x) * LN'(dy); if `dx_accum` != 0, dx += (fp32 only).
- * dgb_partial: fp32 [2, ofab_ln_partial_rows(), cols] scratch that receives per-block partial sums
- * of dgamma (slab 0) and dbeta (slab 1); reduce with ofab_colsum_partials. */
+ * dgb_partial: fp32 [3, ofab_ln_partial_rows(), cols] scratch that receives per-block partial sums
+ * of dgamma (slab 0), dbeta (slab 1) and of dx itself (slab 2: column sums of dx = the bias gradient of
+ * the Linear layer that produced x, nn.Linear backward); finish with ofab_reduce_partials. */
 int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const void* gamma,
                 const float* mean, const float* rstd, void* dx, int dx_dt, int dx_accum,
                 float* dgb_partial, int64_t rows, int cols, int gelu, ofab_stream_t stream);
@@ -75,7 +76,8 @@ int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1, const void
                        const void* b2, float* x_new, void* y, float* stats, int64_t rows, int cols,
                        float eps, ofab_stream_t stream);
 /* backward: dx_tot = dx_new + LN2'(dy);  da = LN1'(dx_tot).  dx_new may alias dx_tot.
- * dgb_partial: fp32 [4, ofab_ln_partial_rows(), cols] = dg1, db1, dg2, db2 partials. */
+ * dgb_partial: fp32 [5, ofab_ln_partial_rows(), cols] = dg1, db1, dg2, db2 partials and the column sums of
+ * da (bias gradient of the Linear that produced a). */
 int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const void* a, const float* x_new,
                        const void* g1, const void* g2, const float* stats, float* dx_tot, void* da,
                        float* dgb_partial, int64_t rows, int cols, ofab_stream_t stream);

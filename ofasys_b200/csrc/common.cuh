@@ -84,7 +84,7 @@ __device__ __forceinline__ void store8(float* p, const f8& r) {
 // exp + 5 FMA + 1 rcp instead of erff's long path; the exp is shared with the pdf term of the gradient.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // MUFU.RCP
   const float e = __expf(-z * z);  // = exp(-x^2/2)
   const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
   const float erf_abs = fmaf(-poly, e, 1.0f);

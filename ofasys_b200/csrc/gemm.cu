@@ -609,9 +609,12 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   else rc = make_map(&tb, B, (uint64_t)N, (uint64_t)K, (uint64_t)ldb, 64, BK);
   if (rc) return rc;
   // bf16 outputs without a residual leave through swizzled smem + TMA stores of 128 x 64 tiles (coalesced 128 B rows)
-  const int tma_store = (d_dt == OFAB_BF16 && residual == nullptr) ? 1 : 0;
+  // (N % 8: only whole 16-byte chunks are sent through the bulk-tensor store; ragged N takes the direct path)
+  const int tma_store = (d_dt == OFAB_BF16 && residual == nullptr && N % 8 == 0) ? 1 : 0;
+  int tma_store_f = tma_store;
+  if (getenv("OFAB_GEMM_FORCE_TMA_STORE") && d_dt == OFAB_BF16 && residual == nullptr) tma_store_f = 1;  // development probe
   CUtensorMap td;
-  if (tma_store) {
+  if (tma_store_f) {
     rc = make_map(&td, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 64, BLOCK_M);
     if (rc) return rc;
   } else {
@@ -626,7 +629,7 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   p.D = D;
   p.ldd = ldd;
   p.d_bf16 = d_dt == OFAB_BF16;
-  p.tma_store = tma_store;
+  p.tma_store = tma_store_f;
   p.dbg = 0;
   if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
   cudaStream_t st = (cudaStream_t)stream;

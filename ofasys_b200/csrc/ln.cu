@@ -143,11 +143,11 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
   const int lane = threadIdx.x % TPR;
   const int rib = threadIdx.x / TPR;
   const float inv_n = 1.0f / (float)cols;
-  f8 acc[2][NV];
+  f8 acc[3][NV];  // dgamma, dbeta, column sums of dx (= bias gradient of the Linear that produced x)
 #pragma unroll
   for (int i = 0; i < NV; ++i)
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc[0][i].v[j] = acc[1][i].v[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[0][i].v[j] = acc[1][i].v[j] = acc[2][i].v[j] = 0.f;
   const int64_t nblk_rows = (rows + RPB - 1) / RPB;
   for (int64_t rb = blockIdx.x; rb < nblk_rows; rb += gridDim.x) {
     const int64_t row = rb * RPB + rib;
@@ -165,7 +165,13 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
         const f8 g = load8(gamma + c);  // L1-resident; not kept in registers
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float a = GELU ? gelu_f(pre[i].v[j]) : pre[i].v[j];
+          float a = pre[i].v[j];
+          if (GELU) {  // one erf evaluation serves both gelu(x) and gelu'(x); `pre` keeps the derivative from here on
+            float cdf, px;
+            gelu_parts(a, cdf, px);
+            pre[i].v[j] = cdf + px;
+            a *= cdf;
+          }
           xh[i].v[j] = (a - mu) * rs;
           acc[0][i].v[j] += d[i].v[j] * xh[i].v[j];
           acc[1][i].v[j] += d[i].v[j];
@@ -188,7 +194,8 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             float t = rs * (d[i].v[j] - c2 - xh[i].v[j] * c1);
-            if (GELU) t *= gelu_grad_f(pre[i].v[j]);
+            if (GELU) t *= pre[i].v[j];
+            acc[2][i].v[j] += t;
             o.v[j] = ACCUM ? o.v[j] + t : t;
           }
           store8(dx + row * cols + c, o);
@@ -196,7 +203,7 @@ __global__ void __launch_bounds__(128) ln_bwd_kernel(const TDY* __restrict__ dy,
       }
     }
   }
-  flush_partials<TPR, NV, 2>(acc, partial, cols);
+  flush_partials<TPR, NV, 3>(acc, partial, cols);
 }
 
 // ---------------------------------------------------------------- fused LN -> +res -> LN
@@ -312,9 +319,9 @@ __global__ void __launch_bounds__(128) ln_res_ln_bwd_kernel(const float* __restr
   const int lane = threadIdx.x % TPR;
   const int rib = threadIdx.x / TPR;
   const float inv_n = 1.0f / (float)cols;
-  f8 acc[4][NV];  // dg1, db1, dg2, db2
+  f8 acc[5][NV];  // dg1, db1, dg2, db2, column sums of da (bias gradient of the Linear that produced a)
 #pragma unroll
-  for (int s = 0; s < 4; ++s)
+  for (int s = 0; s < 5; ++s)
 #pragma unroll
     for (int i = 0; i < NV; ++i)
 #pragma unroll
@@ -373,6 +380,8 @@ __global__ void __launch_bounds__(128) ln_res_ln_bwd_kernel(const float* __restr
           }
         } else {
           store8(da + row * cols + c, tot);  // d a = d x_new
+#pragma unroll
+          for (int j = 0; j < 8; ++j) acc[4][i].v[j] += tot.v[j];
         }
       }
     }
@@ -387,13 +396,16 @@ __global__ void __launch_bounds__(128) ln_res_ln_bwd_kernel(const float* __restr
         if (c < cols) {
           f8 o;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) o.v[j] = r1 * (d[i].v[j] - c2 - xh[i].v[j] * c1);
+          for (int j = 0; j < 8; ++j) {
+            o.v[j] = r1 * (d[i].v[j] - c2 - xh[i].v[j] * c1);
+            acc[4][i].v[j] += o.v[j];
+          }
           store8(da + row * cols + c, o);
         }
       }
     }
   }
-  flush_partials<TPR, NV, 4>(acc, partial, cols);
+  flush_partials<TPR, NV, 5>(acc, partial, cols);
 }
 
 // ------------------------------------------------------------------------------------ colsum
@@ -428,21 +440,21 @@ __global__ void colsum_stage2(const float* __restrict__ partial, int64_t cols, T
 }  // namespace
 
 // out[s, c] = sum_r partial[s, r, c] for the OFAB_LN_PARTIAL_ROWS rows of every slab: one launch finishes
-// dgamma / dbeta (/ dtype / dcls) of a backward kernel.  grid (ceil(cols/32), ns), block (32, 8).
+// dgamma / dbeta (/ dtype / dcls) of a backward kernel.  grid (ceil(cols/32), ns), block (32, 32).
 template <typename TO>
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int cols, TO* __restrict__ out) {
-  __shared__ float sm[8][33];
+  __shared__ float sm[32][33];
   const int c = blockIdx.x * 32 + threadIdx.x;
   const float* base = partial + (int64_t)blockIdx.y * OFAB_LN_PARTIAL_ROWS * cols;
   float s = 0.f;
   if (c < cols)
-    for (int r = threadIdx.y; r < OFAB_LN_PARTIAL_ROWS; r += 8) s += base[(int64_t)r * cols + c];
+    for (int r = threadIdx.y; r < OFAB_LN_PARTIAL_ROWS; r += 32) s += base[(int64_t)r * cols + c];
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += sm[k][threadIdx.x];
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
     out[(int64_t)blockIdx.y * cols + c] = (TO)t;
   }
 }
@@ -583,7 +595,7 @@ extern "C" int ofab_colsum(const void* in, int in_dt, int64_t rows, int64_t cols
 
 extern "C" int ofab_reduce_partials(const float* partial, int nslabs, int cols, void* out, int out_dt, ofab_stream_t stream) {
   OFAB_REQUIRE(nslabs > 0 && cols > 0, "ofab_reduce_partials: bad shape");
-  dim3 grid((cols + 31) / 32, nslabs), block(32, 8);
+  dim3 grid((cols + 31) / 32, nslabs), block(32, 32);
   if (out_dt == OFAB_F32)
     reduce_partials_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(partial, cols, (float*)out);
   else

@@ -52,6 +52,23 @@ def _reduce_partials(partial, dtype):
     return out
 
 
+# Bias-gradient side channel: the LayerNorm backward kernels already hold every element of the gradient they
+# emit (dx / da) in registers, so they also accumulate its column sums -- which is exactly the bias gradient of the
+# Linear layer that consumes that gradient next in backward.  The hint is keyed by the gradient's storage.
+_BIAS_HINTS = {}
+
+
+def _hint_bias_grad(grad_tensor, colsum_vec):
+    if len(_BIAS_HINTS) > 64:
+        _BIAS_HINTS.clear()
+    _BIAS_HINTS[(grad_tensor.data_ptr(), grad_tensor.numel())] = colsum_vec
+
+
+def _take_bias_hint(grad_tensor, n):
+    v = _BIAS_HINTS.pop((grad_tensor.data_ptr(), grad_tensor.numel()), None)
+    return v if v is not None and v.numel() == n else None
+
+
 def cast_bf16(x):
     _need_cuda(x)
     x = _c(x)
@@ -114,10 +131,12 @@ class _LayerNormFn(torch.autograd.Function):
         cols = x.shape[-1]
         rows = x.numel() // cols
         dx = torch.empty_like(x)
-        partial = torch.empty((2, _partial_rows(), cols), dtype=torch.float32, device=x.device)
+        partial = torch.empty((3, _partial_rows(), cols), dtype=torch.float32, device=x.device)
         _lib.call("ofab_ln_bwd", _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(weight), _p(mean), _p(rstd), _p(dx), _DT[dx.dtype], 0,
                   _p(partial), rows, cols, int(ctx.gelu), _s())
         g = _reduce_partials(partial, weight.dtype)
+        if dx.dtype == torch.bfloat16:
+            _hint_bias_grad(dx, g[2])
         return dx, g[0], g[1], None, None, None
 
 
@@ -151,9 +170,10 @@ class _LnResLnFn(torch.autograd.Function):
         dy = torch.zeros(ctx.shape_a, dtype=torch.bfloat16, device=x_new.device) if dy is None else _c(dy)
         dx_tot = torch.empty_like(x_new)
         da = torch.empty(ctx.shape_a, dtype=torch.bfloat16, device=x_new.device)
-        partial = torch.empty((4, _partial_rows(), cols), dtype=torch.float32, device=x_new.device)
+        partial = torch.empty((5, _partial_rows(), cols), dtype=torch.float32, device=x_new.device)
         _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _s())
         g = _reduce_partials(partial, w2.dtype)
+        _hint_bias_grad(da, g[4])
         if w1 is None:
             return da, dx_tot, None, None, g[2], g[3], None
         return da, dx_tot, g[0], g[1], g[2], g[3], None
@@ -212,7 +232,9 @@ class _LinearFn(torch.autograd.Function):
             out = buf
         else:
             buf = torch.empty((M, Np), dtype=torch.bfloat16, device=x.device)
-            gemm(M, N, K, x2, x2.stride(0), 0, w, K, 0, buf, Np, bias=bias)
+            # ragged N without bias (the tied vocabulary projection): compute the padded width -- rows of W beyond N
+            # are zero-filled by TMA, so the pad columns hold zeros and the coalesced TMA-store epilogue applies
+            gemm(M, Np if bias is None else N, K, x2, x2.stride(0), 0, w, K, 0, buf, Np, bias=bias)
             out = buf if Np == N else buf[:, :N]
         ctx.save_for_backward(x2, w)
         ctx.has_bias = bias is not None
@@ -238,7 +260,9 @@ class _LinearFn(torch.autograd.Function):
             dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
             gemm(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = colsum(dy2, torch.bfloat16)
+            db = _take_bias_hint(dy, N)  # produced for free by the LayerNorm backward that emitted dy
+            if db is None:
+                db = colsum(dy2, torch.bfloat16)
         return dx, dw, db, d_res
 
 
@@ -544,7 +568,7 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
         Vp = (V + 7) // 8 * 8
         E = _c(E)
         logits = torch.empty((M, Vp), dtype=torch.bfloat16, device=x.device)
-        gemm(M, V, K, x2, x2.stride(0), 0, E, K, 0, logits, Vp)
+        gemm(M, Vp, K, x2, x2.stride(0), 0, E, K, 0, logits, Vp)  # pad columns [V, Vp) = 0 (TMA zero-fills rows of E beyond V)
         tgt = _c(target.reshape(-1))
         lse = torch.empty(M, dtype=torch.float32, device=x.device)
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
