@@ -121,7 +121,7 @@ def check(rc, what=""):
         raise OfabError(f"libofab call failed ({rc}) {what}: {msg}")
 
 
-_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 3}
+_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2}
 
 
 def call(name, *args):

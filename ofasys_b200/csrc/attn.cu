@@ -100,11 +100,11 @@ __device__ __forceinline__ void build_kmask(const AttnCommon& p, int b, int k0, 
 //   TRANSPOSED = false: accumulator rows are queries (row0 = first query row of the warp), columns keys.
 //   TRANSPOSED = true : accumulator rows are keys   (row0 = first key row of the warp),   columns queries.
 // Fast path (no table, no masked key in the tile, tile not on the causal diagonal): one FMUL per element.
-template <bool TRANSPOSED, typename F>
+template <bool TRANSPOSED, bool HAS_TAB, typename F>
 __device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4], int q0, int k0, int row0, uint64_t kmask,
                                             const float* tab_s, F&& on_idx) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-  const bool has_tab = p.rp_idx != nullptr;
+  constexpr bool has_tab = HAS_TAB;
   const bool diag = p.causal && (k0 + TILE - 1 > q0);  // some (i, j) of this CTA tile may have j > i
   if (!has_tab && !diag && kmask == ~0ull) {
 #pragma unroll
@@ -136,16 +136,18 @@ __device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4
 
 // ===================================================================================== forward
 // smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | kmask [2 stages][2] u32 | table column (n_buckets floats)
-template <bool HAS_POS>
-__global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
-                                                       float* __restrict__ lse) {
+// K/V ring: 3 stages, one __syncthreads per key tile (the stage refilled in iteration kv was consumed in kv-1).
+template <bool HAS_POS, bool HAS_TAB>
+__global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
+                                                                        float* __restrict__ lse) {
   constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
+  constexpr int NST = 3;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + NH * TILE_BYTES;
-  const uint32_t sV = sK + 2 * NH * TILE_BYTES;
-  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + (3 * NH + 2) * TILE_BYTES);
-  float* tab_s = reinterpret_cast<float*>(kmask_s + 4);
+  const uint32_t sV = sK + NST * NH * TILE_BYTES;
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + ((NST + 1) * NH + NST) * TILE_BYTES);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + 2 * NST);
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -158,18 +160,23 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
   const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
   const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
 
-  if (p.rp_idx != nullptr)
+  if (HAS_TAB)
     for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
 
   const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
 
+  auto load_kv = [&](int kvi) {
+    const int stg = kvi % NST, k1 = kvi * TILE;
+    load_tile_async(sK + (stg * NH) * TILE_BYTES, kg, p.k_rs, k1, p.Tk);
+    if (HAS_POS) load_tile_async(sK + (stg * NH + 1) * TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
+    load_tile_async(sV + stg * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
+    cp_commit();
+    build_kmask(p, b, k1, kmask_s + 2 * stg);
+  };
   load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
   if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
-  load_tile_async(sK, kg, p.k_rs, 0, p.Tk);
-  if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, 0, p.Tk);
-  load_tile_async(sV, vg, p.v_rs, 0, p.Tk);
-  cp_commit();
-  build_kmask(p, b, 0, kmask_s);
+  load_kv(0);
+  if (n_kv > 1) load_kv(1);
 
   float oacc[8][4];
 #pragma unroll
@@ -180,19 +187,10 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
   const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
 
   for (int kv = 0; kv < n_kv; ++kv) {
-    const int st = kv & 1;
-    if (kv + 1 < n_kv) {
-      const int k1 = (kv + 1) * TILE;
-      load_tile_async(sK + ((st ^ 1) * NH) * TILE_BYTES, kg, p.k_rs, k1, p.Tk);
-      if (HAS_POS) load_tile_async(sK + ((st ^ 1) * NH + 1) * TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
-      load_tile_async(sV + (st ^ 1) * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
-      cp_commit();
-      build_kmask(p, b, k1, kmask_s + 2 * (st ^ 1));
-      cp_wait<1>();
-    } else {
-      cp_wait<0>();
-    }
-    __syncthreads();
+    const int st = kv % NST;
+    if (kv + 1 < n_kv) cp_wait<1>(); else cp_wait<0>();  // tile kv has landed (tile kv+1 may still be in flight)
+    __syncthreads();                                      // ... for every thread; and everyone finished tile kv-1
+    if (kv + 2 < n_kv) load_kv(kv + 2);                   // refill the stage consumed in iteration kv-1
 
     if (warp_live) {
       const int k0 = kv * TILE;
@@ -224,7 +222,7 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
         }
       }
       // ---- bias / mask / online softmax
-      finish_tile<false>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+      finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -277,7 +275,6 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
         }
       }
     }
-    __syncthreads();  // all warps done with stage st before it is refilled
   }
 
   // ---- finalize
@@ -306,28 +303,13 @@ __global__ void __launch_bounds__(128) attn_fwd_kernel(const AttnCommon p, bf16*
 }
 
 // ===================================================================================== backward
-// delta[b,h,i] = sum_d dO[b,i,h,d] * O[b,i,h,d]   (one warp per row)
-__global__ void attn_delta_kernel(const bf16* __restrict__ d_o, int64_t do_bs, int64_t do_rs, const bf16* __restrict__ o,
-                                  int64_t o_bs, int64_t o_rs, float* __restrict__ delta, int B, int H, int Tq) {
-  const int64_t w = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  const int64_t total = (int64_t)B * H * Tq;
-  if (w >= total) return;
-  const int i = (int)(w % Tq);
-  const int h = (int)((w / Tq) % H);
-  const int b = (int)(w / ((int64_t)Tq * H));
-  const bf162 x = *reinterpret_cast<const bf162*>(d_o + (int64_t)b * do_bs + (int64_t)i * do_rs + h * 64 + lane * 2);
-  const bf162 y = *reinterpret_cast<const bf162*>(o + (int64_t)b * o_bs + (int64_t)i * o_rs + h * 64 + lane * 2);
-  const float2 fx = __bfloat1622float2(x), fy = __bfloat1622float2(y);
-  const float s = warp_sum(fx.x * fy.x + fx.y * fy.y);
-  if (lane == 0) delta[w] = s;
-}
-
 struct AttnBwdExtra {
   const bf16* d_o;
   int64_t do_bs, do_rs;
+  const bf16* o;  // forward output (for delta = rowsum(dO * O))
+  int64_t o_bs, o_rs;
   const float* lse;
-  const float* delta;
+  float* delta;   // written by the dQ kernel, read by the dK/dV kernel that runs after it
   bf16 *dq, *dk, *dv, *dpq, *dpk;
   int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   float* dtable;
@@ -335,8 +317,8 @@ struct AttnBwdExtra {
 
 // ---- dK / dV: one CTA per 64-key tile, loops over query tiles.  Works on transposed scores
 // S^T[key, query] so every accumulator row belongs to this CTA's keys.
-template <bool HAS_POS>
-__global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
+template <bool HAS_POS, bool HAS_TAB>
+__global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sK = smem_u32(smem);             // NH tiles (this CTA's keys)
@@ -359,7 +341,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
   const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
   const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
 
-  if (p.rp_idx != nullptr)
+  if (HAS_TAB)
     for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
 
   load_tile_async(sK, kg, p.k_rs, k0, p.Tk);
@@ -427,7 +409,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
       }
     }
     // P^T = exp(S^T - lse[query])
-    finish_tile<true>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+    finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -525,8 +507,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dkv_kernel(const AttnCommon p, c
 }
 
 // ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles.
-template <bool HAS_POS>
-__global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
+template <bool HAS_POS, bool HAS_TAB>
+__global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);             // NH
@@ -547,7 +529,7 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
   const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
   const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
   const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
-  const bool has_tab = p.rp_idx != nullptr;
+  constexpr bool has_tab = HAS_TAB;
 
   if (has_tab)
     for (int i = threadIdx.x; i < p.n_buckets; i += 128) {
@@ -564,9 +546,24 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
   float lse_r[2], dl_r[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
+    // delta[i] = sum_d dO[i,d] * O[i,d]: the 4 lanes of a quad split the 64 columns of row i (16 each)
     const int i = row_g[r];
+    float dsum = 0.f;
+    if (i < p.Tq) {
+      const bf16* dop = dog + (int64_t)i * e.do_rs + t * 16;
+      const bf16* op = e.o + (int64_t)b * e.o_bs + (int64_t)i * e.o_rs + h * 64 + t * 16;
+#pragma unroll
+      for (int c = 0; c < 16; c += 8) {
+        const f8 x = load8(dop + c), y = load8(op + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) dsum += x.v[j] * y.v[j];
+      }
+    }
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
+    dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
     lse_r[r] = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
-    dl_r[r] = i < p.Tq ? e.delta[((int64_t)b * p.H + h) * p.Tq + i] : 0.f;
+    dl_r[r] = dsum;
+    if (i < p.Tq && t == 0) e.delta[((int64_t)b * p.H + h) * p.Tq + i] = dsum;  // for the dK/dV kernel
   }
   float dq[NH * 8][4];
 #pragma unroll
@@ -635,14 +632,14 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
       }
     }
     // P, dS ; relative-position table gradient
-    int idxs[8][4];
+    int idxs[has_tab ? 8 : 1][4];
     if (has_tab) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+      for (int nt = 0; nt < (has_tab ? 8 : 1); ++nt)
 #pragma unroll
         for (int el = 0; el < 4; ++el) idxs[nt][el] = -1;
     }
-    finish_tile<false>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { idxs[nt][el] = idx; });
+    finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { if (has_tab) idxs[has_tab ? nt : 0][el] = idx; });
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -651,7 +648,8 @@ __global__ void __launch_bounds__(128) attn_bwd_dq_kernel(const AttnCommon p, co
         const float pe = (s[nt][el] == -INFINITY || l == -INFINITY) ? 0.f : __expf(s[nt][el] - l);
         const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
         if (has_tab) {
-          if (idxs[nt][el] >= 0 && ds != 0.f) atomicAdd(dtab_s + idxs[nt][el], ds);
+          const int ix = idxs[has_tab ? nt : 0][el];
+          if (ix >= 0 && ds != 0.f) atomicAdd(dtab_s + ix, ds);
         }
         s[nt][el] = ds * p.scale;
       }
@@ -737,18 +735,18 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
   if (rc) return rc;
   OFAB_REQUIRE(a->o && a->lse, "ofab_attn_fwd: o/lse NULL");
   OFAB_REQUIRE(a->o_rs % 2 == 0 && a->o_bs % 2 == 0, "ofab_attn_fwd: o strides must be even");
-  const bool pos = a->pq != nullptr;
+  const bool pos = a->pq != nullptr, tab = a->rp_idx != nullptr;
   const int nh = pos ? 2 : 1;
-  const int smem = (3 * nh + 2) * TILE_BYTES + 16 + c.n_buckets * 4;
+  const int smem = (4 * nh + 3) * TILE_BYTES + 24 + c.n_buckets * 4;
   dim3 grid((a->Tq + TILE - 1) / TILE, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (pos) {
-    if ((rc = set_smem(attn_fwd_kernel<true>, smem, "ofab_attn_fwd smem"))) return rc;
-    attn_fwd_kernel<true><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);
-  } else {
-    if ((rc = set_smem(attn_fwd_kernel<false>, smem, "ofab_attn_fwd smem"))) return rc;
-    attn_fwd_kernel<false><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);
+#define FWD(P, T)                                                                                  \
+  {                                                                                                \
+    if ((rc = set_smem(attn_fwd_kernel<P, T>, smem, "ofab_attn_fwd smem"))) return rc;             \
+    attn_fwd_kernel<P, T><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);      \
   }
+  if (pos && tab) FWD(true, true) else if (pos) FWD(true, false) else if (tab) FWD(false, true) else FWD(false, false)
+#undef FWD
   OFAB_LAUNCH_CHECK("ofab_attn_fwd");
   return OFAB_OK;
 }
@@ -758,16 +756,14 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   int rc = fill_common(&a->f, c);
   if (rc) return rc;
   OFAB_REQUIRE(a->d_o && a->dq && a->dk && a->dv && a->delta && a->f.o && a->f.lse, "ofab_attn_bwd: NULL tensor");
-  const bool pos = a->f.pq != nullptr;
+  const bool pos = a->f.pq != nullptr, tab = a->f.rp_idx != nullptr;
   OFAB_REQUIRE(!pos || (a->dpq && a->dpk), "ofab_attn_bwd: dpq/dpk required when pq/pk are given");
   OFAB_REQUIRE(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0, "ofab_attn_bwd: grad strides must be even");
+  OFAB_REQUIRE(a->do_rs % 8 == 0 && a->do_bs % 8 == 0 && a->f.o_rs % 8 == 0 && a->f.o_bs % 8 == 0, "ofab_attn_bwd: dO / O strides must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;
-  const int64_t rows = (int64_t)a->f.B * a->f.H * a->f.Tq;
-  attn_delta_kernel<<<(unsigned)((rows * 32 + 255) / 256), 256, 0, st>>>((const bf16*)a->d_o, a->do_bs, a->do_rs, (const bf16*)a->f.o,
-                                                                       a->f.o_bs, a->f.o_rs, a->delta, a->f.B, a->f.H, a->f.Tq);
-  OFAB_LAUNCH_CHECK("ofab_attn_bwd delta");
   AttnBwdExtra e;
   e.d_o = (const bf16*)a->d_o; e.do_bs = a->do_bs; e.do_rs = a->do_rs;
+  e.o = (const bf16*)a->f.o; e.o_bs = a->f.o_bs; e.o_rs = a->f.o_rs;
   e.lse = a->f.lse; e.delta = a->delta;
   e.dq = (bf16*)a->dq; e.dk = (bf16*)a->dk; e.dv = (bf16*)a->dv; e.dpq = (bf16*)a->dpq; e.dpk = (bf16*)a->dpk;
   e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
@@ -776,19 +772,17 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   const int smem_kv = (2 * nh + 2) * TILE_BYTES + 2 * TILE * 4 + 8 + c.n_buckets * 4;
   const int smem_q = (2 * nh + 2) * TILE_BYTES + 8 + 2 * c.n_buckets * 4;
   dim3 gkv((a->f.Tk + TILE - 1) / TILE, a->f.H, a->f.B), gq((a->f.Tq + TILE - 1) / TILE, a->f.H, a->f.B);
-  if (pos) {
-    if ((rc = set_smem(attn_bwd_dkv_kernel<true>, smem_kv, "ofab_attn_bwd smem"))) return rc;
-    if ((rc = set_smem(attn_bwd_dq_kernel<true>, smem_q, "ofab_attn_bwd smem"))) return rc;
-    attn_bwd_dkv_kernel<true><<<gkv, 128, smem_kv, st>>>(c, e);
-    OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
-    attn_bwd_dq_kernel<true><<<gq, 128, smem_q, st>>>(c, e);
-  } else {
-    if ((rc = set_smem(attn_bwd_dkv_kernel<false>, smem_kv, "ofab_attn_bwd smem"))) return rc;
-    if ((rc = set_smem(attn_bwd_dq_kernel<false>, smem_q, "ofab_attn_bwd smem"))) return rc;
-    attn_bwd_dkv_kernel<false><<<gkv, 128, smem_kv, st>>>(c, e);
-    OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
-    attn_bwd_dq_kernel<false><<<gq, 128, smem_q, st>>>(c, e);
+  // dQ first: it also computes delta = rowsum(dO * O) that the dK/dV kernel needs
+#define BWD(P, T)                                                                                   \
+  {                                                                                                 \
+    if ((rc = set_smem(attn_bwd_dq_kernel<P, T>, smem_q, "ofab_attn_bwd smem"))) return rc;         \
+    if ((rc = set_smem(attn_bwd_dkv_kernel<P, T>, smem_kv, "ofab_attn_bwd smem"))) return rc;       \
+    attn_bwd_dq_kernel<P, T><<<gq, 128, smem_q, st>>>(c, e);                                        \
+    OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");                                                          \
+    attn_bwd_dkv_kernel<P, T><<<gkv, 128, smem_kv, st>>>(c, e);                                     \
   }
-  OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");
+  if (pos && tab) BWD(true, true) else if (pos) BWD(true, false) else if (tab) BWD(false, true) else BWD(false, false)
+#undef BWD
+  OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
   return OFAB_OK;
 }

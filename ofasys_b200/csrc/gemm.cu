@@ -576,7 +576,9 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
     const int64_t tiles = mt * ((N + bn - 1) / bn);
     const int64_t units = sms / cg;
     const double waves = (double)((tiles + units - 1) / units);
-    return waves * bn * (cg == 1 ? 1.35 : 1.0);
+    // per-tile efficiency factors fitted to the measured sweep (profiles/r01_gemm_sweep_v4.json)
+    const double eff = cg == 2 ? (bn == 256 ? 1.0 : 1.25) : (bn == 256 ? 1.1 : 1.3);
+    return waves * bn * eff;
   };
   int BN = 256, CG = 2;
   double best = 1e30;
