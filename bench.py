@@ -337,6 +337,29 @@ def run_gpu(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "gemm_launches_per_step": len(recs) // max(2, min(args.steps, 5)), "gemm_ms_per_step": tm * 1e3 / max(2, min(args.steps, 5))}
 
+    if rank == 0 and args.kprofile:
+        # kernel-level timeline of the replayed step (CUPTI via torch.profiler): hot caches, real back-to-back execution
+        from torch.profiler import ProfilerActivity, profile
+
+        for _ in range(2):
+            step_resident()
+        torch.cuda.synchronize()
+        nrep = 5
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(nrep):
+                step_resident()
+            torch.cuda.synchronize()
+        agg = {}
+        for evt in prof.events():
+            if evt.device_type is not None and "cuda" in str(evt.device_type).lower():
+                a = agg.setdefault(evt.name, [0, 0.0])
+                a[0] += 1
+                a[1] += evt.device_time if hasattr(evt, "device_time") else evt.cuda_time
+        rows = sorted(((k, v[0] / nrep, v[1] / nrep / 1e3) for k, v in agg.items()), key=lambda r: -r[2])
+        out = {"step_kernel_ms": sum(r[2] for r in rows), "kernels": [{"name": k[:160], "launches_per_step": n, "ms_per_step": ms} for k, n, ms in rows]}
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kprofile.json"), "w"), indent=1)
+
     if rank == 0 and args.breakdown:
         # per-entry-point device time (CUDA events around every C-ABI call): where the step goes
         recs = []
@@ -415,6 +438,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
     ap.add_argument("--impl", default="ofab", choices=["ofab", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="also write gpurun_out/breakdown.json (per entry point device time)")
+    ap.add_argument("--kprofile", action="store_true", help="also write gpurun_out/kprofile.json (per-kernel device time of the replayed step, CUPTI)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()

@@ -111,7 +111,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     lib = _lib.lib()
     assert lib.ofab_version() >= 100
-    assert lib.ofab_ln_partial_rows() == 592
+    assert lib.ofab_ln_partial_rows() == 444
 
 
 def test_no_cpu_fallback():
