@@ -261,6 +261,44 @@ int ofab_transpose_last2(const void* in, void* out, int64_t O, int A, int Bdim, 
 int ofab_relu_bwd_inplace(const void* y, void* dy, int64_t n, ofab_stream_t stream);
 int ofab_relu_inplace(void* y, int64_t n, ofab_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * ResNet backbone of the image / video adaptors (ofasys/module/resnet.py:116-246; adaptor/image_resnet.py:
+ * 166-202).  Activations are channel-last bf16 [B, H, W, C] == token rows [B*H*W, C]: 1x1 convolutions are
+ * ofab_gemm_bf16 directly, k x k convolutions are im2col + ofab_gemm_bf16 (weights permuted [Co,Ci,k*k] ->
+ * [Co,k*k,Ci] with ofab_transpose_last2).
+ * ------------------------------------------------------------------------------------------- */
+/* stem: img [B,C,H,W] (img_dt) -> cols bf16 [B*Ho*Wo, ldk], column = c*k*k + i*k + j (the weight's own
+ * flattening, resnet.py:167 conv1 7x7 s2 p3), zero padding, columns >= C*k*k zero. */
+int ofab_im2col_nchw(const void* img, int img_dt, int B, int C, int H, int W, int k, int stride, int pad,
+                     void* cols, int64_t ldk, ofab_stream_t stream);
+/* x bf16 [B,H,W,C] -> cols [B*Ho*Wo, k*k*C], column = (i*k + j)*C + c, zero padding (conv3x3, resnet.py:20-32) */
+int ofab_im2col_nhwc(const void* x, int B, int H, int W, int C, int k, int stride, int pad, void* cols,
+                     ofab_stream_t stream);
+/* adjoint of ofab_im2col_nhwc: dx [B,H,W,C] (overwritten) */
+int ofab_col2im_nhwc(const void* dcols, int B, int H, int W, int C, int k, int stride, int pad, void* dx,
+                     ofab_stream_t stream);
+/* spatial stride-2 row selection of a 1x1 stride-2 convolution (downsample, resnet.py:207-210).
+ * backward == 0: x [B,H,W,C] -> y [B,ceil(H/2),ceil(W/2),C]; backward != 0: x = dy, y = dx (zero-filled scatter). */
+int ofab_subsample2(const void* x, int B, int H, int W, int C, void* y, int backward, ofab_stream_t stream);
+/* nn.MaxPool2d(3, stride 2, padding 1) on [B,H,W,C]; argmax: uint8 tap index (first maximum) for backward */
+int ofab_maxpool3x3s2_fwd(const void* x, int B, int H, int W, int C, void* y, uint8_t* argmax, ofab_stream_t stream);
+int ofab_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int B, int H, int W, int C, void* dx, ofab_stream_t stream);
+/* nn.BatchNorm2d in training mode on x bf16 [R, C] (R = B*H*W): batch mean / biased variance (fp32 out), momentum
+ * update of running_mean / running_var (unbiased), run_dt = dtype of the running buffers (NULL to skip).
+ * scratch: ofab_bn_scratch_elems(C) floats. */
+int64_t ofab_bn_scratch_elems(int C);
+int ofab_bn_stats(const void* x, int64_t R, int C, float* mean, float* var, void* run_mean, void* run_var,
+                  int run_dt, float momentum, float* scratch, ofab_stream_t stream);
+/* y = relu?( (x - mean) * rsqrt(var + eps) * gamma + beta (+ residual) )  -- the bottleneck tail
+ * `out = identity + bn3(conv3(..)); relu` (resnet.py:131-134) is one pass. */
+int ofab_bn_apply(const void* x, const float* mean, const float* var, const void* gamma, const void* beta,
+                  const void* residual, void* y, int64_t R, int C, float eps, int relu, ofab_stream_t stream);
+/* backward of stats+apply: g = dy * (y > 0 if relu); sums[0..C) = sum g (= dbeta), sums[C..2C) = sum g*xhat
+ * (= dgamma); dx = gamma*rstd*(g - sum_g/R - xhat*sum_gxhat/R); dres (optional) = g. */
+int ofab_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* var,
+                const void* gamma, float* sums, void* dx, void* dres, int64_t R, int C, float eps, int relu,
+                float* scratch, ofab_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

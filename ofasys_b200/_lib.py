@@ -88,6 +88,16 @@ _SIGS = {
     "ofab_transpose_last2": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p]),
     "ofab_relu_bwd_inplace": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_relu_inplace": (c_int, [c_void_p, c_int64, c_void_p]),
+    "ofab_im2col_nchw": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int64, c_void_p]),
+    "ofab_im2col_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ofab_col2im_nhwc": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ofab_subsample2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "ofab_maxpool3x3s2_fwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "ofab_maxpool3x3s2_bwd": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "ofab_bn_scratch_elems": (c_int64, [c_int]),
+    "ofab_bn_stats": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "ofab_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
+    "ofab_bn_bwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -121,7 +131,7 @@ def check(rc, what=""):
         raise OfabError(f"libofab call failed ({rc}) {what}: {msg}")
 
 
-_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2}
+_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2, "ofab_bn_stats": 2, "ofab_bn_bwd": 3}
 
 
 def call(name, *args):

@@ -11,7 +11,7 @@ from ..configure import BaseDataclass, ConfigStore
 from ..module import Embedding
 from ..preprocessor import ModalityType, Slot
 from .base import AdaptorOutput, BaseAdaptor
-from . import text, image_patch_embed, audio  # noqa: F401  (registers the adaptors)
+from . import text, image_resnet, image_patch_embed, audio  # noqa: F401  (registers the adaptors)
 
 _ORDER = ["text", "image_resnet", "image_patch_embed", "audio_fbank", "video_image_sequence"]
 

@@ -7,7 +7,7 @@
 // dgamma/dbeta partial sums stay in registers and leave as one row per block.
 #include "common.cuh"
 
-#define OFAB_LN_PARTIAL_ROWS 444  // 3 x 148 SMs: persistent backward grid (3 blocks of 384 threads per SM)
+#define OFAB_LN_PARTIAL_ROWS 888  // 6 x 148 SMs: persistent backward grid
 
 extern "C" int ofab_ln_partial_rows(void) { return OFAB_LN_PARTIAL_ROWS; }
 
@@ -422,14 +422,14 @@ struct LnLaunch {
 static inline LnLaunch ln_launch(int cols) {
   LnLaunch l;
   l.tpr = ((cols / 8) + 31) / 32 * 32;           // threads per row: one 8-column vector each
-  l.block = l.tpr > 384 ? 512 : 384;             // cols > 3072 -> 512-thread blocks
+  l.block = l.tpr >= 96 ? l.tpr : 384;           // one row per block (3..16 warps); narrow rows share a block
   l.smem = l.block * 8 * (int)sizeof(float);     // row-group combine buffer of the backward kernels
   return l;
 }
 static inline int ln_fwd_grid(int64_t rows, const LnLaunch& l) {
   const int rpb = l.block / l.tpr;
   int64_t nb = (rows + rpb - 1) / rpb;
-  const int64_t cap = (int64_t)ofab_sm_count() * 8;
+  const int64_t cap = (int64_t)ofab_sm_count() * 16;
   return (int)(nb < cap ? (nb > 0 ? nb : 1) : cap);
 }
 

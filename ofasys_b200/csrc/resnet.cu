@@ -1,0 +1,369 @@
+// ResNet backbone pieces of the image / video adaptors (ofasys/module/resnet.py:116-246) around the tcgen05
+// GEMM.  Activations are channel-last bf16 [B, H, W, C] (= token rows [B*H*W, C]), so 1x1 convolutions are plain
+// GEMMs, 3x3 / 7x7 convolutions are im2col (vector copies) + GEMM, and BatchNorm (training mode: batch statistics,
+// resnet.py keeps nn.BatchNorm2d in train mode unless freeze_resnet) is a column reduction + an elementwise pass
+// fused with the residual add and ReLU of the bottleneck.
+#include "common.cuh"
+
+namespace {
+
+inline int ew_grid(int64_t work, int threads) {
+  int64_t b = (work + threads - 1) / threads;
+  const int64_t cap = (int64_t)ofab_sm_count() * 16;
+  return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---- im2col from an NCHW image (stem conv 7x7 s2 p3): cols[(b,ho,wo), c*kh*kw + i*kw + j] (weight's own flattening)
+template <typename T>
+__global__ void im2col_nchw_kernel(const T* __restrict__ img, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
+                                   bf16* __restrict__ cols, int64_t ldk) {
+  const int kk = C * k * k;
+  const int64_t total = (int64_t)B * Ho * Wo * ldk;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / ldk;
+    const int col = (int)(i % ldk);
+    float v = 0.f;
+    if (col < kk) {
+      const int c = col / (k * k), ki = (col / k) % k, kj = col % k;
+      const int wo = (int)(row % Wo), ho = (int)((row / Wo) % Ho), b = (int)(row / ((int64_t)Wo * Ho));
+      const int y = ho * stride - pad + ki, x = wo * stride - pad + kj;
+      if (y >= 0 && y < H && x >= 0 && x < W) v = (float)img[(((int64_t)b * C + c) * H + y) * W + x];
+    }
+    cols[i] = __float2bfloat16(v);
+  }
+}
+
+// ---- im2col on channel-last activations, square kernel k, stride, zero padding:
+// cols[(b,ho,wo), (i*k + j)*C + c] = x[b, ho*stride - pad + i, wo*stride - pad + j, c]
+__global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                                   bf16* __restrict__ cols) {
+  const int C8 = C / 8, kk = k * k;
+  const int64_t total = (int64_t)B * Ho * Wo * kk * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int t = (int)((i / C8) % kk);
+    const int64_t r = i / ((int64_t)C8 * kk);
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((int64_t)Wo * Ho));
+    const int y = ho * stride - pad + t / k, xx = wo * stride - pad + t % k;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 0 && y < H && xx >= 0 && xx < W) v = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + y) * W + xx) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(cols + (r * kk + t) * C + c8 * 8) = v;
+  }
+}
+// adjoint (gather form, no atomics): dx[b,y,x,c] = sum over taps (i,j) and outputs (ho,wo) with ho*stride - pad + i == y ...
+__global__ void col2im_nhwc_kernel(const bf16* __restrict__ dcols, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
+                                   bf16* __restrict__ dx) {
+  const int C8 = C / 8, kk = k * k;
+  const int64_t total = (int64_t)B * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int64_t r = i / C8;
+    const int xx = (int)(r % W), y = (int)((r / W) % H), b = (int)(r / ((int64_t)W * H));
+    f8 acc;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc.v[j] = 0.f;
+    for (int ti = 0; ti < k; ++ti) {
+      const int yy = y + pad - ti;
+      if (yy < 0 || yy % stride != 0 || yy / stride >= Ho) continue;
+      for (int tj = 0; tj < k; ++tj) {
+        const int xw = xx + pad - tj;
+        if (xw < 0 || xw % stride != 0 || xw / stride >= Wo) continue;
+        const f8 v = load8(dcols + ((((int64_t)b * Ho + yy / stride) * Wo + xw / stride) * kk + ti * k + tj) * C + c8 * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc.v[j] += v.v[j];
+      }
+    }
+    store8(dx + r * C + c8 * 8, acc);
+  }
+}
+
+// ---- spatial stride-2 subsampling (1x1 stride-2 downsample convs) and its adjoint
+__global__ void subsample2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ y, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const int64_t total = (int64_t)B * Ho * Wo * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int64_t r = i / C8;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((int64_t)Wo * Ho));
+    *reinterpret_cast<uint4*>(y + r * C + c8 * 8) = *reinterpret_cast<const uint4*>(x + (((int64_t)b * H + 2 * ho) * W + 2 * wo) * C + c8 * 8);
+  }
+}
+__global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, int B, int H, int W, int C, bf16* __restrict__ dx, int Ho, int Wo) {
+  const int C8 = C / 8;
+  const int64_t total = (int64_t)B * H * W * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c8 = (int)(i % C8);
+    const int64_t r = i / C8;
+    const int xx = (int)(r % W), y = (int)((r / W) % H), b = (int)(r / ((int64_t)W * H));
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!(y & 1) && !(xx & 1) && y / 2 < Ho && xx / 2 < Wo) v = *reinterpret_cast<const uint4*>(dy + (((int64_t)b * Ho + y / 2) * Wo + xx / 2) * C + c8 * 8);
+    *reinterpret_cast<uint4*>(dx + r * C + c8 * 8) = v;
+  }
+}
+
+// ---- max pooling 3x3 stride 2 pad 1 (channel-last); argmax tap (0..8, first maximum as torch) saved for backward
+__global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ y, uint8_t* __restrict__ arg, int Ho, int Wo) {
+  const int64_t total = (int64_t)B * Ho * Wo * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int wo = (int)(r % Wo), ho = (int)((r / Wo) % Ho), b = (int)(r / ((int64_t)Wo * Ho));
+    float best = -INFINITY;
+    int bi = 0;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {
+      const int y = 2 * ho - 1 + t / 3, xx = 2 * wo - 1 + t % 3;
+      if (y >= 0 && y < H && xx >= 0 && xx < W) {
+        const float v = __bfloat162float(x[(((int64_t)b * H + y) * W + xx) * C + c]);
+        if (v > best) { best = v; bi = t; }
+      }
+    }
+    y[i] = __float2bfloat16(best);
+    arg[i] = (uint8_t)bi;
+  }
+}
+__global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ arg, int B, int H, int W, int C, bf16* __restrict__ dx, int Ho, int Wo) {
+  const int64_t total = (int64_t)B * H * W * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const int64_t r = i / C;
+    const int xx = (int)(r % W), y = (int)((r / W) % H), b = (int)(r / ((int64_t)W * H));
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 9; ++t) {  // output (ho, wo) whose tap t lands on (y, xx)
+      const int yy = y + 1 - t / 3, xw = xx + 1 - t % 3;
+      if (yy < 0 || (yy & 1) || yy / 2 >= Ho || xw < 0 || (xw & 1) || xw / 2 >= Wo) continue;
+      const int64_t o = ((((int64_t)b * Ho + yy / 2) * Wo + xw / 2) * C) + c;
+      if (arg[o] == t) s += __bfloat162float(dy[o]);
+    }
+    dx[i] = __float2bfloat16(s);
+  }
+}
+
+// ---- BatchNorm (training): per-channel statistics over the R = B*H*W rows of x [R, C]
+// stage 1: partial (sum, sum of squares) of (x - shift[c]) per row chunk; shift = first row (conditioning)
+#define BN_CHUNKS 64
+__global__ void bn_stats_stage1(const bf16* __restrict__ x, int64_t R, int C, float* __restrict__ part /* [2][CHUNKS][C] */) {
+  __shared__ float s1[4][64], s2[4][64];
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
+  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(R, r0 + per);
+  float a = 0.f, q = 0.f;
+  if (c < C) {
+    const float sh = __bfloat162float(x[c]);
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
+      const float v = __bfloat162float(x[r * C + c]) - sh;
+      a += v;
+      q += v * v;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    part[(int64_t)blockIdx.y * C + c] = s1[0][threadIdx.x] + s1[1][threadIdx.x] + s1[2][threadIdx.x] + s1[3][threadIdx.x];
+    part[((int64_t)BN_CHUNKS + blockIdx.y) * C + c] = s2[0][threadIdx.x] + s2[1][threadIdx.x] + s2[2][threadIdx.x] + s2[3][threadIdx.x];
+  }
+}
+// stage 2: mean / biased variance; momentum update of the running statistics (unbiased variance), as nn.BatchNorm2d
+template <typename TR>
+__global__ void bn_stats_stage2(const bf16* __restrict__ x, const float* __restrict__ part, int64_t R, int C, float* __restrict__ mean,
+                                float* __restrict__ var, TR* __restrict__ run_mean, TR* __restrict__ run_var, float momentum) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, q = 0.f;
+  for (int k = 0; k < BN_CHUNKS; ++k) {
+    a += part[(int64_t)k * C + c];
+    q += part[((int64_t)BN_CHUNKS + k) * C + c];
+  }
+  const float sh = __bfloat162float(x[c]);
+  const float m = a / (float)R;
+  const float v = fmaxf(q / (float)R - m * m, 0.f);
+  mean[c] = m + sh;
+  var[c] = v;
+  if (run_mean != nullptr) {
+    const float unb = R > 1 ? v * (float)R / (float)(R - 1) : v;
+    run_mean[c] = (TR)((1.f - momentum) * (float)run_mean[c] + momentum * (m + sh));
+    run_var[c] = (TR)((1.f - momentum) * (float)run_var[c] + momentum * unb);
+  }
+}
+// y = relu?( (x - mean) * rstd * gamma + beta (+ residual) )
+__global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var, const bf16* __restrict__ gamma,
+                                const bf16* __restrict__ beta, const bf16* __restrict__ res, bf16* __restrict__ y, int64_t R, int C, float eps, int relu) {
+  const int C8 = C / 8;
+  const int64_t total = R * C8;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    f8 v = load8(x + i * 8);
+    const f8 g = load8(gamma + c), b = load8(beta + c);
+    f8 rr;
+    if (res != nullptr) rr = load8(res + i * 8);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float o = (v.v[j] - mean[c + j]) * rsqrtf(var[c + j] + eps) * g.v[j] + b.v[j];
+      if (res != nullptr) o += rr.v[j];
+      v.v[j] = relu ? fmaxf(o, 0.f) : o;
+    }
+    store8(y + i * 8, v);
+  }
+}
+// backward stage 1: per-channel partial sums of g and g*xhat, g = dy * (y > 0 if relu)
+__global__ void bn_bwd_stage1(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
+                              const float* __restrict__ var, int64_t R, int C, float eps, int relu, float* __restrict__ part) {
+  __shared__ float s1[4][64], s2[4][64];
+  const int c = blockIdx.x * 64 + threadIdx.x;
+  const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
+  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(R, r0 + per);
+  float a = 0.f, q = 0.f;
+  if (c < C) {
+    const float m = mean[c], rs = rsqrtf(var[c] + eps);
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
+      float g = __bfloat162float(dy[r * C + c]);
+      if (relu && !(__bfloat162float(y[r * C + c]) > 0.f)) g = 0.f;
+      a += g;
+      q += g * (__bfloat162float(x[r * C + c]) - m) * rs;
+    }
+  }
+  s1[threadIdx.y][threadIdx.x] = a;
+  s2[threadIdx.y][threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < C) {
+    part[(int64_t)blockIdx.y * C + c] = s1[0][threadIdx.x] + s1[1][threadIdx.x] + s1[2][threadIdx.x] + s1[3][threadIdx.x];
+    part[((int64_t)BN_CHUNKS + blockIdx.y) * C + c] = s2[0][threadIdx.x] + s2[1][threadIdx.x] + s2[2][threadIdx.x] + s2[3][threadIdx.x];
+  }
+}
+__global__ void bn_bwd_stage2(const float* __restrict__ part, int C, float* __restrict__ sums /* [2][C]: sum g, sum g*xhat */) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float a = 0.f, q = 0.f;
+  for (int k = 0; k < BN_CHUNKS; ++k) {
+    a += part[(int64_t)k * C + c];
+    q += part[((int64_t)BN_CHUNKS + k) * C + c];
+  }
+  sums[c] = a;
+  sums[C + c] = q;
+}
+// dx = gamma * rstd * (g - sum_g/R - xhat * sum_gxhat/R);  dres = g
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
+                                    const float* __restrict__ var, const bf16* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ dx,
+                                    bf16* __restrict__ dres, int64_t R, int C, float eps, int relu) {
+  const int C8 = C / 8;
+  const int64_t total = R * C8;
+  const float invR = 1.0f / (float)R;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C8) * 8;
+    f8 g = load8(dy + i * 8);
+    const f8 xv = load8(x + i * 8), gm = load8(gamma + c);
+    if (relu) {
+      const f8 yv = load8(y + i * 8);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) g.v[j] = yv.v[j] > 0.f ? g.v[j] : 0.f;
+    }
+    if (dres != nullptr) store8(dres + i * 8, g);
+    f8 o;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rs = rsqrtf(var[c + j] + eps);
+      const float xh = (xv.v[j] - mean[c + j]) * rs;
+      o.v[j] = gm.v[j] * rs * (g.v[j] - sums[c + j] * invR - xh * sums[C + c + j] * invR);
+    }
+    store8(dx + i * 8, o);
+  }
+}
+
+}  // namespace
+
+extern "C" int ofab_im2col_nchw(const void* img, int img_dt, int B, int C, int H, int W, int k, int stride, int pad, void* cols, int64_t ldk,
+                                ofab_stream_t stream) {
+  OFAB_REQUIRE(k > 0 && stride > 0 && pad >= 0 && ldk >= (int64_t)C * k * k && ldk % 8 == 0, "ofab_im2col_nchw: bad geometry");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * ldk;
+  if (img_dt == OFAB_F32)
+    im2col_nchw_kernel<float><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
+  else
+    im2col_nchw_kernel<bf16><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
+  OFAB_LAUNCH_CHECK("ofab_im2col_nchw");
+  return OFAB_OK;
+}
+extern "C" int ofab_im2col_nhwc(const void* x, int B, int H, int W, int C, int k, int stride, int pad, void* cols, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0 && k > 0 && stride > 0 && pad >= 0, "ofab_im2col_nhwc: bad geometry (C %% 8 == 0)");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * k * k * (C / 8);
+  im2col_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)cols);
+  OFAB_LAUNCH_CHECK("ofab_im2col_nhwc");
+  return OFAB_OK;
+}
+extern "C" int ofab_col2im_nhwc(const void* dcols, int B, int H, int W, int C, int k, int stride, int pad, void* dx, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0 && k > 0 && stride > 0 && pad >= 0, "ofab_col2im_nhwc: bad geometry (C %% 8 == 0)");
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+  const int64_t total = (int64_t)B * H * W * (C / 8);
+  col2im_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dcols, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)dx);
+  OFAB_LAUNCH_CHECK("ofab_col2im_nhwc");
+  return OFAB_OK;
+}
+extern "C" int ofab_subsample2(const void* x, int B, int H, int W, int C, void* y, int backward, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0, "ofab_subsample2: C %% 8 != 0");
+  const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
+  if (!backward) {
+    const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
+    subsample2_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
+  } else {  // x = dy [B,Ho,Wo,C], y = dx [B,H,W,C]
+    const int64_t total = (int64_t)B * H * W * (C / 8);
+    subsample2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
+  }
+  OFAB_LAUNCH_CHECK("ofab_subsample2");
+  return OFAB_OK;
+}
+extern "C" int ofab_maxpool3x3s2_fwd(const void* x, int B, int H, int W, int C, void* y, uint8_t* argmax, ofab_stream_t stream) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * Ho * Wo * C;
+  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, argmax, Ho, Wo);
+  OFAB_LAUNCH_CHECK("ofab_maxpool3x3s2_fwd");
+  return OFAB_OK;
+}
+extern "C" int ofab_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int B, int H, int W, int C, void* dx, ofab_stream_t stream) {
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const int64_t total = (int64_t)B * H * W * C;
+  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, argmax, B, H, W, C, (bf16*)dx, Ho, Wo);
+  OFAB_LAUNCH_CHECK("ofab_maxpool3x3s2_bwd");
+  return OFAB_OK;
+}
+extern "C" int64_t ofab_bn_scratch_elems(int C) { return (int64_t)2 * BN_CHUNKS * C; }
+
+extern "C" int ofab_bn_stats(const void* x, int64_t R, int C, float* mean, float* var, void* run_mean, void* run_var, int run_dt,
+                             float momentum, float* scratch, ofab_stream_t stream) {
+  OFAB_REQUIRE(R > 0 && C > 0 && scratch != nullptr, "ofab_bn_stats: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+  bn_stats_stage1<<<grid, block, 0, st>>>((const bf16*)x, R, C, scratch);
+  OFAB_LAUNCH_CHECK("ofab_bn_stats stage1");
+  if (run_dt == OFAB_F32)
+    bn_stats_stage2<float><<<(C + 127) / 128, 128, 0, st>>>((const bf16*)x, scratch, R, C, mean, var, (float*)run_mean, (float*)run_var, momentum);
+  else
+    bn_stats_stage2<bf16><<<(C + 127) / 128, 128, 0, st>>>((const bf16*)x, scratch, R, C, mean, var, (bf16*)run_mean, (bf16*)run_var, momentum);
+  OFAB_LAUNCH_CHECK("ofab_bn_stats stage2");
+  return OFAB_OK;
+}
+extern "C" int ofab_bn_apply(const void* x, const float* mean, const float* var, const void* gamma, const void* beta, const void* residual,
+                             void* y, int64_t R, int C, float eps, int relu, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0, "ofab_bn_apply: C %% 8 != 0");
+  bn_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, var, (const bf16*)gamma, (const bf16*)beta,
+                                                                              (const bf16*)residual, (bf16*)y, R, C, eps, relu);
+  OFAB_LAUNCH_CHECK("ofab_bn_apply");
+  return OFAB_OK;
+}
+extern "C" int ofab_bn_bwd(const void* dy, const void* x, const void* y, const float* mean, const float* var, const void* gamma, float* sums,
+                           void* dx, void* dres, int64_t R, int C, float eps, int relu, float* scratch, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0 && scratch != nullptr && sums != nullptr, "ofab_bn_bwd: bad arguments");
+  OFAB_REQUIRE(!relu || y != nullptr, "ofab_bn_bwd: relu needs the forward output");
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+  bn_bwd_stage1<<<grid, block, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
+  OFAB_LAUNCH_CHECK("ofab_bn_bwd stage1");
+  bn_bwd_stage2<<<(C + 127) / 128, 128, 0, st>>>(scratch, C, sums);
+  OFAB_LAUNCH_CHECK("ofab_bn_bwd stage2");
+  bn_bwd_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
+                                                                (bf16*)dx, (bf16*)dres, R, C, eps, relu);
+  OFAB_LAUNCH_CHECK("ofab_bn_bwd apply");
+  return OFAB_OK;
+}

@@ -709,3 +709,132 @@ class _ReluFn(torch.autograd.Function):
 
 def relu(x):
     return _ReluFn.apply(x)
+
+
+# ------------------------------------------------------------------------------------ ResNet pieces (NHWC bf16)
+def im2col_nchw(img, k, stride, pad, ldk):
+    """stem im2col from the NCHW image (data: no gradient)."""
+    _need_cuda(img)
+    img = _c(img)
+    B, C, H, W = img.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    cols = torch.empty((B * Ho * Wo, ldk), dtype=torch.bfloat16, device=img.device)
+    _lib.call("ofab_im2col_nchw", _p(img), _DT[img.dtype], B, C, H, W, k, stride, pad, _p(cols), ldk, _s())
+    return cols, Ho, Wo
+
+
+class _Im2colNhwcFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        x = _c(x)
+        B, H, W, C = x.shape
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        cols = torch.empty((B * Ho * Wo, k * k * C), dtype=torch.bfloat16, device=x.device)
+        _lib.call("ofab_im2col_nhwc", _p(x), B, H, W, C, k, stride, pad, _p(cols), _s())
+        ctx.meta = (x.shape, k, stride, pad)
+        return cols
+
+    @staticmethod
+    def backward(ctx, dcols):
+        shape, k, stride, pad = ctx.meta
+        B, H, W, C = shape
+        dcols = _c(dcols)
+        dx = torch.empty(shape, dtype=torch.bfloat16, device=dcols.device)
+        _lib.call("ofab_col2im_nhwc", _p(dcols), B, H, W, C, k, stride, pad, _p(dx), _s())
+        return dx, None, None, None
+
+
+def im2col_nhwc(x, k, stride, pad):
+    return _Im2colNhwcFn.apply(x, k, stride, pad)
+
+
+class _Subsample2Fn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, C = x.shape
+        y = torch.empty((B, (H - 1) // 2 + 1, (W - 1) // 2 + 1, C), dtype=x.dtype, device=x.device)
+        _lib.call("ofab_subsample2", _p(x), B, H, W, C, _p(y), 0, _s())
+        ctx.shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        B, H, W, C = ctx.shape
+        dy = _c(dy)
+        dx = torch.empty(ctx.shape, dtype=dy.dtype, device=dy.device)
+        _lib.call("ofab_subsample2", _p(dy), B, H, W, C, _p(dx), 1, _s())
+        return dx
+
+
+def subsample2(x):
+    return _Subsample2Fn.apply(x)
+
+
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = _c(x)
+        B, H, W, C = x.shape
+        Ho, Wo = (H - 1) // 2 + 1, (W - 1) // 2 + 1
+        y = torch.empty((B, Ho, Wo, C), dtype=x.dtype, device=x.device)
+        arg = torch.empty((B, Ho, Wo, C), dtype=torch.uint8, device=x.device)
+        _lib.call("ofab_maxpool3x3s2_fwd", _p(x), B, H, W, C, _p(y), _p(arg), _s())
+        ctx.save_for_backward(arg)
+        ctx.shape = x.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (arg,) = ctx.saved_tensors
+        B, H, W, C = ctx.shape
+        dy = _c(dy)
+        dx = torch.empty(ctx.shape, dtype=dy.dtype, device=dy.device)
+        _lib.call("ofab_maxpool3x3s2_bwd", _p(dy), _p(arg), B, H, W, C, _p(dx), _s())
+        return dx
+
+
+def maxpool3x3s2(x):
+    return _MaxPoolFn.apply(x)
+
+
+class _BatchNormFn(torch.autograd.Function):
+    """Training-mode BatchNorm over the rows of x [.., C] fused with (+residual) and ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, relu, eps, momentum, run_mean, run_var):
+        x = _c(x)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dev = x.device
+        mean = torch.empty(C, dtype=torch.float32, device=dev)
+        var = torch.empty(C, dtype=torch.float32, device=dev)
+        scratch = torch.empty(_lib.lib().ofab_bn_scratch_elems(C), dtype=torch.float32, device=dev)
+        rdt = _DT[run_mean.dtype] if run_mean is not None else F32
+        _lib.call("ofab_bn_stats", _p(x), R, C, _p(mean), _p(var), _p(run_mean), _p(run_var), rdt, momentum, _p(scratch), _s())
+        res = None if residual is None else _c(residual)
+        y = torch.empty_like(x)
+        _lib.call("ofab_bn_apply", _p(x), _p(mean), _p(var), _p(gamma), _p(beta), _p(res), _p(y), R, C, eps, int(relu), _s())
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, var)
+        ctx.meta = (relu, eps, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, var = ctx.saved_tensors
+        relu, eps, has_res = ctx.meta
+        dy = _c(dy)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dev = x.device
+        sums = torch.empty((2, C), dtype=torch.float32, device=dev)
+        scratch = torch.empty(_lib.lib().ofab_bn_scratch_elems(C), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        _lib.call("ofab_bn_bwd", _p(dy), _p(x), _p(y), _p(mean), _p(var), _p(gamma), _p(sums), _p(dx), _p(dres), R, C, eps, int(relu), _p(scratch), _s())
+        g = cast_bf16(sums) if gamma.dtype == torch.bfloat16 else sums
+        return dx, g[1], g[0], dres, None, None, None, None, None
+
+
+def batch_norm_train(x, gamma, beta, residual=None, relu=False, eps=1e-5, momentum=0.1, run_mean=None, run_var=None):
+    return _BatchNormFn.apply(x, gamma, beta, residual, relu, eps, momentum, run_mean, run_var)

@@ -30,6 +30,11 @@ CASES = {
         cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A"),
         adaptors=("text", "audio"), kind="audio", B=2, S=6, T=10, L=200,
     ),
+    # image_resnet (ResNet-50 as in the reference's `tiny` preset, train-mode BatchNorm) + text, Mode A, 64x64 image
+    "resnet_A": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A", resnet_type="resnet50"),
+        adaptors=("text", "image_resnet"), kind="resnet", B=4, S=8, T=12, image=64,
+    ),
     # BASELINE.json configs[0]: text_infilling, OFA-tiny 4L/4L d=256, seq 128, bs 2 (checksums only)
     "cfg1_tiny": dict(
         cfg=dict(embed_dim=256, heads=4, ffn_dim=1024, enc_layers=4, dec_layers=4, vocab=50265, mode="A"),
@@ -112,6 +117,9 @@ def make_inputs(name: str, seed: int = 1234):
     if c["kind"] == "patch":
         img = torch.randn(B, 3, 224, 224, generator=g)
         slots.append(OSlot(IMAGE, True, img, adaptor="image_patch_embed"))
+    if c["kind"] == "resnet":
+        img = torch.randn(B, 3, c["image"], c["image"], generator=g)
+        slots.append(OSlot(IMAGE, True, img, adaptor="image_resnet"))
     if c["kind"] == "audio":
         L = c["L"]
         fbank = torch.randn(B, L, 80, generator=g)

@@ -46,6 +46,8 @@ def run_case(name):
         arch="tiny", enc_layers=cfg["enc_layers"], dec_layers=cfg["dec_layers"], vocab=cfg["vocab"],
         adaptors=c["adaptors"], mode=cfg["mode"], dims=(cfg["embed_dim"], cfg["heads"], cfg["ffn_dim"]),
     )
+    if "resnet_type" in cfg:
+        assert m.cfg.adaptor.image_resnet.resnet_type == cfg["resnet_type"]
     ref_sd = m.state_dict()
     spec = cases.param_spec_from_state_dict(ref_sd)
     sd = cases.synth_state_dict(spec, seed=0)

@@ -20,7 +20,7 @@ from util import TTS_ONLY, build_product, load_golden
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "cfg1_tiny"])
+@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "cfg1_tiny"])
 def test_state_dict_contract(name):
     """Parameter names / shapes equal the reference's (golden `spec` was dumped from its state_dict)."""
     g = load_golden(name)
@@ -111,7 +111,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     lib = _lib.lib()
     assert lib.ofab_version() >= 100
-    assert lib.ofab_ln_partial_rows() == 444
+    assert lib.ofab_ln_partial_rows() == 888
 
 
 def test_no_cpu_fallback():

@@ -19,7 +19,7 @@ from oracle import oracle_model as om
 from util import bf16_round_state_dict, build_product, load_golden, rel_l2, to_product_slots
 
 pytestmark = pytest.mark.gpu
-SMALL = ["text_A", "text_B", "patch_B", "audio_A"]
+SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A"]
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
 
 

@@ -466,3 +466,129 @@ def test_audio_subsampler_pieces():
     assert rel_l2(out, yr) <= 1e-2
     for p, r in zip(sub.parameters(), ref):
         assert rel_l2(p.grad, r.grad) <= 3e-2, tuple(p.shape)
+
+
+# ------------------------------------------------------------------------------- ResNet pieces
+@pytest.mark.parametrize("k,stride,pad,H,W,C", [(3, 1, 1, 14, 14, 64), (3, 2, 1, 15, 13, 32), (3, 2, 1, 56, 56, 64)])
+def test_conv_kxk_im2col_gemm(k, stride, pad, H, W, C):
+    """k x k convolution = im2col (channel-last) + tcgen05 GEMM with the [Co,Ci,k*k] -> [Co,k*k,Ci] weight permute."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, Co = 3, 48
+    x = rnd(B, H, W, C, gen=gen).requires_grad_(True)
+    w = rnd(Co, C, k, k, gen=gen, scale=0.05).requires_grad_(True)
+    cols = ops.im2col_nhwc(x, k, stride, pad)
+    wp = ops.transpose_last2(w.reshape(Co, C, k * k)).reshape(Co, k * k * C)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = ops.linear(cols, wp, None).view(B, Ho, Wo, Co)
+    dy = rnd(B, Ho, Wo, Co, gen=gen)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    wr = w.detach().float().requires_grad_(True)
+    yr = F.conv2d(xr, wr, stride=stride, padding=pad)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(y.permute(0, 3, 1, 2), yr) <= TOL16
+    assert rel_l2(x.grad.permute(0, 3, 1, 2), xr.grad) <= 1e-2
+    assert rel_l2(w.grad, wr.grad) <= 1e-2
+
+
+def test_stem_maxpool_subsample():
+    from ofasys_b200 import ops
+
+    gen = g()
+    B = 2
+    img = rnd(B, 3, 64, 48, dtype=torch.float32, gen=gen)
+    w = rnd(64, 3, 7, 7, gen=gen, scale=0.1).requires_grad_(True)
+    cols, Ho, Wo = ops.im2col_nchw(img, 7, 2, 3, 152)
+    y = ops.linear(cols, F.pad(w.reshape(64, 147), (0, 5)), None).view(B, Ho, Wo, 64)
+    yr = F.conv2d(img.bfloat16().float(), w.detach().float(), stride=2, padding=3)
+    assert rel_l2(y.permute(0, 3, 1, 2), yr) <= TOL16
+    # maxpool
+    x = rnd(B, 17, 15, 64, gen=gen).requires_grad_(True)
+    p = ops.maxpool3x3s2(x)
+    dp = rnd(*p.shape, gen=gen)
+    p.backward(dp)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    pr = F.max_pool2d(xr, 3, 2, 1)
+    pr.backward(dp.float().permute(0, 3, 1, 2))
+    assert torch.equal(p.permute(0, 3, 1, 2).float(), pr)
+    assert rel_l2(x.grad.permute(0, 3, 1, 2), xr.grad) <= TOL16
+    # stride-2 subsample
+    x2 = rnd(B, 9, 8, 32, gen=gen).requires_grad_(True)
+    s = ops.subsample2(x2)
+    assert torch.equal(s, x2[:, ::2, ::2])
+    ds = rnd(*s.shape, gen=gen)
+    s.backward(ds)
+    ref = torch.zeros_like(x2)
+    ref[:, ::2, ::2] = ds
+    assert torch.equal(x2.grad, ref)
+
+
+@pytest.mark.parametrize("relu,with_res", [(False, False), (True, False), (True, True)])
+def test_batch_norm_train(relu, with_res):
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, H, W, C = 4, 7, 9, 64
+    x = (rnd(B, H, W, C, gen=gen).float() * 2 + 0.7).bfloat16().requires_grad_(True)
+    res = rnd(B, H, W, C, gen=gen).requires_grad_(True) if with_res else None
+    gam = (torch.rand(C, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(True)
+    bet = rnd(C, gen=gen, scale=0.1).requires_grad_(True)
+    rm, rv = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    y = ops.batch_norm_train(x, gam, bet, res, relu, 1e-5, 0.1, rm, rv)
+    dy = rnd(B, H, W, C, gen=gen)
+    y.backward(dy)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gam.detach().float().requires_grad_(True), bet.detach().float().requires_grad_(True)
+    rmr, rvr = torch.zeros(C, device=dev()), torch.ones(C, device=dev())
+    yr = F.batch_norm(xr, rmr, rvr, gr, br, True, 0.1, 1e-5)
+    if with_res:
+        rr = res.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(y.permute(0, 3, 1, 2), yr) <= TOL16
+    assert rel_l2(x.grad.permute(0, 3, 1, 2), xr.grad) <= 2e-2
+    assert rel_l2(gam.grad, gr.grad) <= 2e-2 and rel_l2(bet.grad, br.grad) <= 2e-2
+    assert rel_l2(rm, rmr) <= 1e-4 and rel_l2(rv, rvr) <= 1e-3
+    if with_res:
+        assert rel_l2(res.grad.permute(0, 3, 1, 2), rr.grad) <= TOL16
+
+
+def test_resnet50_backbone_vs_oracle():
+    """whole C1..C4 backbone (train-mode BN) against the oracle's restatement run on the GPU in fp32."""
+    from ofasys_b200.module.resnet import resnet50_backbone
+    from oracle import oracle_model as om
+
+    gen = g()
+    net = resnet50_backbone().to(dev())
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if p.dim() == 4:
+                fan = p.shape[1] * p.shape[2] * p.shape[3]
+                p.copy_(torch.randn(p.shape, generator=gen) * (2.0 / fan) ** 0.5)
+            elif n.endswith("weight"):
+                p.copy_(torch.rand(p.shape, generator=gen) + 0.5)
+            else:
+                p.copy_(torch.randn(p.shape, generator=gen) * 0.1)
+    net = net.to(torch.bfloat16).train()
+    sd = {"r." + k: v.detach().float() for k, v in net.state_dict().items() if v.is_floating_point()}
+    ref_leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items() if "running" not in k}
+    sd_ref = dict(sd)
+    sd_ref.update(ref_leaves)
+    img = rnd(4, 3, 64, 64, dtype=torch.float32, gen=gen)
+    y = net(img)
+    dy = rnd(*y.shape, gen=gen)
+    y.backward(dy)
+    yr = om.resnet_backbone(img, sd_ref, "r", "resnet50", training=True)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    e = rel_l2(y.permute(0, 3, 1, 2), yr)
+    assert e <= 3e-2, e
+    worst = 0.0
+    for k, p in net.named_parameters():
+        gr = ref_leaves["r." + k].grad
+        if gr.norm() > 1e-3:
+            worst = max(worst, rel_l2(p.grad, gr))
+    assert worst <= 0.15, worst

@@ -37,6 +37,7 @@ def build_product(name, device=None, dtype=None):
     m.cfg.decoder.input_dim = m.cfg.decoder.output_dim = d
     m.cfg.encoder.attention_heads = m.cfg.decoder.attention_heads = h
     m.cfg.encoder.layers, m.cfg.decoder.layers = cc["enc_layers"], cc["dec_layers"]
+    keep_resnet = cc.get("resnet_type")
     for a in c["adaptors"]:
         a = "audio_fbank" if a == "audio" else a
         acfg = getattr(m.cfg.adaptor, a)
@@ -45,6 +46,8 @@ def build_product(name, device=None, dtype=None):
             acfg.entangle_position_embedding = True
         if a == "image_patch_embed":
             acfg.embed_dim = d
+        if a == "image_resnet" and "resnet_type" in cc:
+            acfg.resnet_type = cc["resnet_type"]
     if cc["mode"] == "B":
         m.cfg.adaptor.text.entangle_position_embedding = True
     m.initialize(ob.Dictionary(n_dummy=cc["vocab"] - 4))
