@@ -226,13 +226,13 @@ def run_gpu(args, rank, world, local_rank):
         loss.backward()
         return loss
 
-    from ofasys_b200.distributed import allreduce_grads, build_buckets
+    from ofasys_b200.distributed import GradBuckets
 
-    buckets = build_buckets(params) if world > 1 else None
+    buckets = GradBuckets(params) if world > 1 else None
 
     def reduce_grads():
-        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink), ~32 MB buckets
-            allreduce_grads(buckets)
+        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink/NVSwitch), flat 64 MB buckets
+            buckets.allreduce()
 
     use_graph = not args.no_graph
     if use_graph:

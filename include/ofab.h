@@ -226,6 +226,11 @@ int ofab_ce_bwd(const void* logits, int64_t rows, int64_t V, int64_t ld, const i
 int ofab_cast_f32_bf16(const float* x, void* y, int64_t n, ofab_stream_t stream);
 int ofab_cast_bf16_f32(const void* x, float* y, int64_t n, ofab_stream_t stream);
 /* out = a + b (fp32) */
+/* Multi-tensor copy (data-parallel exchange step): `chunks` is a DEVICE array of n_chunks records
+ * {const void* src; void* dst; uint64 bytes} (24 bytes each); one launch copies them all.  Used to pack the
+ * per-parameter gradients of a bucket into the flat all-reduce buffer and back (replaces the per-bucket flatten /
+ * unflatten of c10d DDP's Reducer that the reference relies on: distributed_model_dispatcher.py:49-75). */
+int ofab_multi_copy(const void* chunks, int64_t n_chunks, ofab_stream_t stream);
 int ofab_add_f32(const float* a, const float* b, float* out, int64_t n, ofab_stream_t stream);
 /* W_eff[n, k] = W[n, k] * c[k / group]  (per-head c_attn folded into out_proj,
  * ofasys/module/multihead_attention.py:342-346).  bf16 in/out, c bf16 [cols/group]. */

@@ -155,6 +155,37 @@ extern "C" int ofab_cast_bf16_f32(const void* x, float* y, int64_t n, ofab_strea
   OFAB_LAUNCH_CHECK("ofab_cast_bf16_f32");
   return OFAB_OK;
 }
+// ---- multi-tensor copy: one launch moves a whole gradient bucket between parameter-shaped tensors and a flat buffer
+struct MultiCopyChunk {
+  const void* src;
+  void* dst;
+  unsigned long long bytes;
+};
+namespace {
+__global__ void multi_copy_kernel(const MultiCopyChunk* __restrict__ chunks, int64_t n) {
+  for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const MultiCopyChunk c = chunks[i];
+    const char* s = (const char*)c.src;
+    char* d = (char*)c.dst;
+    const unsigned long long nb = c.bytes;
+    if ((((uintptr_t)s | (uintptr_t)d) & 15) == 0) {
+      const unsigned long long nv = nb / 16;
+      for (unsigned long long j = threadIdx.x; j < nv; j += blockDim.x) ((uint4*)d)[j] = __ldg(((const uint4*)s) + j);
+      for (unsigned long long j = nv * 16 + threadIdx.x; j < nb; j += blockDim.x) d[j] = s[j];
+    } else {
+      for (unsigned long long j = threadIdx.x; j < nb; j += blockDim.x) d[j] = s[j];
+    }
+  }
+}
+}  // namespace
+extern "C" int ofab_multi_copy(const void* chunks, int64_t n_chunks, ofab_stream_t stream) {
+  if (n_chunks <= 0) return OFAB_OK;
+  OFAB_REQUIRE(chunks != nullptr, "ofab_multi_copy: null chunk table");
+  const int64_t grid = n_chunks < 148 * 16 ? n_chunks : 148 * 16;
+  multi_copy_kernel<<<(unsigned)grid, 256, 0, (cudaStream_t)stream>>>((const MultiCopyChunk*)chunks, n_chunks);
+  OFAB_LAUNCH_CHECK("ofab_multi_copy");
+  return OFAB_OK;
+}
 extern "C" int ofab_add_f32(const float* a, const float* b, float* out, int64_t n, ofab_stream_t stream) {
   if (n <= 0) return OFAB_OK;
   add_f32_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n);

@@ -607,3 +607,44 @@ def test_resnet50_backbone_vs_oracle():
         den += gr.pow(2).sum().item()
     ours, ref16 = (n1 / den) ** 0.5, (n2 / den) ** 0.5
     assert ours <= 1.5 * ref16 + 1e-2, (ours, ref16)
+
+
+def test_multi_copy_pack_unpack():
+    """flat-bucket pack / unpack of odd-sized gradient tensors (ofab_multi_copy) is a bit-exact round trip."""
+    from ofasys_b200 import _lib
+    from ofasys_b200.distributed import GradBuckets
+
+    gen = g()
+    shapes = [(768,), (3, 5, 7), (1000, 768), (1,), (257, 33), (131072 + 3,)]
+    params = [torch.nn.Parameter(rnd(*s, gen=gen)) for s in shapes]
+    for p in params:
+        p.grad = rnd(*p.shape, gen=gen)
+    ref = [p.grad.clone() for p in params]
+    gb = GradBuckets(params, bucket_bytes=1 << 20)
+    st = torch.cuda.current_stream().cuda_stream
+    for i, bucket in enumerate(gb.buckets):
+        grads = [p.grad for p in bucket]
+        tp, tu = gb._tables(i, grads)
+        _lib.call("ofab_multi_copy", tp.data_ptr(), tp.shape[0], st)
+        flat = gb._flat[i]
+        off = 0
+        for gr in grads:  # packed at 16-byte aligned offsets, bit-exact
+            assert torch.equal(flat[off:off + gr.numel()].view_as(gr), gr)
+            off += (gr.numel() * 2 + 15) // 16 * 8
+        flat.mul_(2.0)
+        _lib.call("ofab_multi_copy", tu.data_ptr(), tu.shape[0], st)
+    for p, r in zip(params, ref):
+        assert torch.equal(p.grad, (r.float() * 2).bfloat16())
+
+
+def test_dp_nccl_two_gpus():
+    """world-size-2 NCCL run of the data-parallel exchange (skipped on a one-GPU box)."""
+    import subprocess, sys, os
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tests", "dp_nccl_worker.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DP_NCCL_OK" in r.stdout
