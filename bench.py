@@ -228,20 +228,29 @@ def run_gpu(args, rank, world, local_rank):
 
     from ofasys_b200.distributed import GradBuckets
 
-    buckets = GradBuckets(params) if world > 1 else None
+    # N > 1: the backward is cut at the encoder/decoder boundary; the decoder-side gradients are averaged (NCCL, side
+    # stream) while the encoder backward runs, the rest after it.  N == 1: one graph, no exchange.
+    split = world > 1 and not args.no_overlap
+    side = torch.cuda.Stream()
 
-    def reduce_grads():
-        if world > 1:  # DP exchange step: average gradients over ranks (NCCL over NVLink/NVSwitch), flat 64 MB buckets
-            buckets.allreduce()
+    def fwd_bwd_begin():
+        for p in params:
+            p.grad = None
+        loss, early, finish = model.forward_backward_split(to_slots(db), db["tgt"])
+        state["early"], state["finish"] = early, finish
+        return loss
 
     use_graph = not args.no_graph
     if use_graph:
-        # CUDA graph of the whole fwd+bwd: ~2000 kernel launches per step are replayed without host work
-        side = torch.cuda.Stream()
+        # CUDA graph(s) of the whole fwd+bwd: ~1000 kernel launches per step are replayed without host work
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             for _ in range(2):
-                fwd_bwd()
+                if split:
+                    fwd_bwd_begin()
+                    state["finish"]()
+                else:
+                    fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         try:
@@ -249,8 +258,16 @@ def run_gpu(args, rank, world, local_rank):
             g = torch.cuda.CUDAGraph()
             for p in params:
                 p.grad = None
-            with torch.cuda.graph(g):
-                state["loss"] = fwd_bwd()
+            if split:
+                with torch.cuda.graph(g):
+                    state["loss"] = fwd_bwd_begin()
+                g2 = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g2, pool=g.pool()):
+                    state["finish"]()
+                state["graph2"] = g2
+            else:
+                with torch.cuda.graph(g):
+                    state["loss"] = fwd_bwd()
             state["graph"] = g
             state["launches"] = _lib.launch_count - c0
         except Exception as ex:  # stay correct: fall back to eager launches and say so
@@ -258,13 +275,40 @@ def run_gpu(args, rank, world, local_rank):
             use_graph = False
             torch.cuda.synchronize()
 
+    buckets = early_b = late_b = None
+
     def step_resident():
+        nonlocal buckets, early_b, late_b
+        if not split:
+            if use_graph:
+                state["graph"].replay()
+                loss = state["loss"]
+            else:
+                loss = fwd_bwd()
+            if world > 1:  # unoverlapped exchange (--no-overlap)
+                if buckets is None:
+                    buckets = GradBuckets(params)
+                buckets.allreduce()
+            return loss
         if use_graph:
             state["graph"].replay()
             loss = state["loss"]
         else:
-            loss = fwd_bwd()
-        reduce_grads()
+            loss = fwd_bwd_begin()
+        if early_b is None:
+            ids = {id(p) for p in state["early"]}
+            early_b = GradBuckets(state["early"])
+            late_b = GradBuckets([p for p in params if id(p) not in ids])
+        cur = torch.cuda.current_stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            early_b.allreduce()
+        if use_graph:
+            state["graph2"].replay()
+        else:
+            state["finish"]()
+        late_b.allreduce()
+        cur.wait_stream(side)
         return loss
 
     def step_e2e():
@@ -293,7 +337,7 @@ def run_gpu(args, rank, world, local_rank):
         t = torch.tensor([ms], device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        n_l = state.get("launches") if use_graph else (_lib.launch_count - c0) // steps
+        n_l = (_lib.launch_count - c0) // steps + (state.get("launches") if use_graph else 0)  # graph nodes + eager pack/unpack
         return t.item() / steps, n_l
 
     with ClockSampler(local_rank) as cs:
@@ -337,7 +381,7 @@ def run_gpu(args, rank, world, local_rank):
                 "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "gemm_launches_per_step": len(recs) // max(2, min(args.steps, 5)), "gemm_ms_per_step": tm * 1e3 / max(2, min(args.steps, 5))}
 
-    if rank == 0 and args.kprofile:
+    if args.kprofile:  # every rank runs the steps (collectives), rank 0 writes
         # kernel-level timeline of the replayed step (CUPTI via torch.profiler): hot caches, real back-to-back execution
         from torch.profiler import ProfilerActivity, profile
 
@@ -357,8 +401,15 @@ def run_gpu(args, rank, world, local_rank):
                 a[1] += evt.device_time if hasattr(evt, "device_time") else evt.cuda_time
         rows = sorted(((k, v[0] / nrep, v[1] / nrep / 1e3) for k, v in agg.items()), key=lambda r: -r[2])
         out = {"step_kernel_ms": sum(r[2] for r in rows), "kernels": [{"name": k[:160], "launches_per_step": n, "ms_per_step": ms} for k, n, ms in rows]}
-        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
-        json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kprofile.json"), "w"), indent=1)
+        if world > 1:  # where the exchange kernels sit on the timeline (us from the first kernel of the profile)
+            devs = [e for e in prof.events() if e.device_type is not None and "cuda" in str(e.device_type).lower()]
+            t0 = min(e.time_range.start for e in devs)
+            out["span_ms_per_step"] = (max(e.time_range.end for e in devs) - t0) / nrep / 1e3
+            out["exchange_timeline"] = [{"name": e.name[:60], "start_us": e.time_range.start - t0, "dur_us": e.time_range.end - e.time_range.start}
+                                        for e in devs if ("nccl" in e.name.lower() or "multi_copy" in e.name)][:200]
+        if rank == 0:
+            os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+            json.dump(out, open(os.path.join(ROOT, "gpurun_out", "kprofile.json"), "w"), indent=1)
 
     if rank == 0 and args.breakdown:
         # per-entry-point device time (CUDA events around every C-ABI call): where the step goes
@@ -415,7 +466,8 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "src_len": 257 + PROMPT, "tgt_len": TGT,
-                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
+                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                       "grad_exchange": (None if world == 1 else "NCCL all-reduce(avg) of flat 64 MB buckets" + ("; decoder-side buckets overlap the encoder backward" if split else "")), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "algorithmic_gflop_per_seq": 3 * FWD_GFLOP_PER_SEQ, "ntokens_per_rank": ntok},
             "clocks": clocks,
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e},
@@ -440,6 +492,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="also write gpurun_out/breakdown.json (per entry point device time)")
     ap.add_argument("--kprofile", action="store_true", help="also write gpurun_out/kprofile.json (per-kernel device time of the replayed step, CUPTI)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-overlap", action="store_true", help="N>1: average all gradients after the whole backward (no split)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -164,6 +164,50 @@ class GeneralistModel(nn.Module):
         pad = self.global_dict.pad() if ignore_index is None else ignore_index
         return ops.linear_cross_entropy(feats, self.decoder.adaptor.embed_tokens.weight, target, pad)
 
+    def forward_backward_split(self, slots: List[Slot], target: torch.Tensor, ignore_index: Optional[int] = None):
+        """fwd + bwd of the measured path with the backward cut at the encoder/decoder boundary, for data-parallel
+        overlap (the reference gets this from c10d DDP's bucket hooks, distributed_model_dispatcher.py:49-75):
+
+            loss, early, finish = model.forward_backward_split(slots, target)
+            ... start averaging `early` (decoder-side parameters; their .grad is final) ...
+            finish()        # encoder backward; afterwards every other parameter's .grad is final
+
+        Parameters shared with the encoder (the tied embedding) are finished by `finish()`."""
+        enc_out = self.encoder([s for s in slots if s.is_src])
+        # cut the autograd graph at the boundary: the decoder sees detached leaves, stage 2 feeds their gradients back
+        cut, leaves, dec_in = [], [], {}
+
+        def leaf(t):
+            if not (torch.is_tensor(t) and t.requires_grad):
+                return t
+            d = t.detach().requires_grad_(True)
+            cut.append(t)
+            leaves.append(d)
+            return d
+
+        for k, v in enc_out.items():
+            if k == "encoder_out" and "_encoder_out_bt" in enc_out:
+                continue  # T x B x C view of `_encoder_out_bt`, rebuilt below from the detached leaf
+            dec_in[k] = [leaf(t) for t in v] if isinstance(v, (list, tuple)) else leaf(v)
+        if "_encoder_out_bt" in enc_out:
+            dec_in["encoder_out"] = [dec_in["_encoder_out_bt"].transpose(0, 1)]
+        feats, _ = self.decoder([s for s in slots if not s.is_src], encoder_out=dec_in, features_only=True)
+        pad = self.global_dict.pad() if ignore_index is None else ignore_index
+        loss = ops.linear_cross_entropy(feats, self.decoder.adaptor.embed_tokens.weight, target, pad)
+        enc_ids = {id(p) for p in self.encoder.parameters()}
+        early = [p for p in self.parameters() if p.requires_grad and id(p) not in enc_ids]
+        shared = [p for p in self.decoder.parameters() if p.requires_grad and id(p) in enc_ids]
+        grads = torch.autograd.grad(loss, leaves + early + shared, allow_unused=True)
+        for p, g in zip(early + shared, grads[len(cut):]):
+            p.grad = g
+        todo = [(t, g) for t, g in zip(cut, grads[:len(cut)]) if g is not None]
+
+        def finish():
+            if todo:
+                torch.autograd.backward([t for t, _ in todo], [g for _, g in todo])
+
+        return loss, early, finish
+
     def get_normalized_probs(self, net_output, log_probs: bool, sample=None):
         return self.active_executor.get_normalized_probs(self, net_output, log_probs, sample)
 

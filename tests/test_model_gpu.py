@@ -178,3 +178,42 @@ def test_cfg1_tiny_text_infilling_gpu():
     _report(name, {"sampled_logits_rel_l2": e1, "lse_rel_l2": e2, "loss_rel": e3, "bad_grad_norms": bad})
     assert e1 <= 1.5e-2 and e2 <= 2e-3 and e3 <= 2e-3
     assert not bad, bad
+
+
+@pytest.mark.parametrize("name", ["text_A", "patch_B"])
+def test_split_backward_equals_plain(name):
+    """forward_backward_split (backward cut at the encoder/decoder boundary for data-parallel overlap) produces the
+    same gradients as loss.backward(); decoder-side parameters are final before finish()."""
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    m = build_product(name)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(torch.bfloat16).to(dev).train()
+    slots, target = cases.make_inputs(name)
+    pslots = to_product_slots(slots, dev)
+    tgt = target.to(dev)
+    m.zero_grad(set_to_none=True)
+    loss = m.forward_loss(pslots, tgt)
+    loss.backward()
+    ref = {k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None}
+    m.zero_grad(set_to_none=True)
+    loss2, early, finish = m.forward_backward_split(pslots, tgt)
+    assert abs(loss2.item() - loss.item()) <= 1e-5 * abs(loss.item())  # the sum-NLL reduction uses float atomics
+    early_ids = {id(p) for p in early}
+    names = {id(p): k for k, p in m.named_parameters()}
+    assert early and all(names[i].startswith("decoder.") for i in early_ids)
+    for p in early:
+        if names[id(p)] in ref:
+            assert torch.equal(p.grad, ref[names[id(p)]]), names[id(p)]
+        else:
+            assert p.grad is None
+    finish()
+    for k, p in m.named_parameters():
+        if k not in ref:
+            assert p.grad is None or not p.grad.any()
+            continue
+        if id(p) in early_ids:
+            assert torch.equal(p.grad, ref[k]), k  # untouched by finish()
+        else:
+            assert rel_l2(p.grad, ref[k]) <= 4e-3, (k, rel_l2(p.grad, ref[k]))
