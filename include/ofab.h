@@ -272,6 +272,11 @@ int ofab_relu_inplace(void* y, int64_t n, ofab_stream_t stream);
  * ofab_gemm_bf16 directly, k x k convolutions are im2col + ofab_gemm_bf16 (weights permuted [Co,Ci,k*k] ->
  * [Co,k*k,Ci] with ofab_transpose_last2).
  * ------------------------------------------------------------------------------------------- */
+/* Video clip [B, C, F, H, W] (f32 or bf16) -> frames bf16 [B*F, C, H, W] (frames may be NULL) and zero[B*F] = 1 when
+ * every value of the frame is 0: the frame-padding test of VideoImageSequenceAdaptor.get_clip_videos_info
+ * (adaptor/video_image_sequence.py:118-139, `clip.abs().mean(-1) == 0`; bit-exact, NaN counts as non-zero). */
+int ofab_video_frames(const void* video, int dt, int B, int C, int F, int64_t HW, void* frames, uint8_t* zero, ofab_stream_t stream);
+
 /* stem: img [B,C,H,W] (img_dt) -> cols bf16 [B*Ho*Wo, ldk], column = c*k*k + i*k + j (the weight's own
  * flattening, resnet.py:167 conv1 7x7 s2 p3), zero padding, columns >= C*k*k zero. */
 int ofab_im2col_nchw(const void* img, int img_dt, int B, int C, int H, int W, int k, int stride, int pad,

@@ -77,6 +77,7 @@ _SIGS = {
     "ofab_ce_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "ofab_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_cast_bf16_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "ofab_video_frames": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "ofab_multi_copy": (c_int, [c_void_p, c_int64, c_void_p]),
     "ofab_add_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_scale_cols": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p]),

@@ -11,7 +11,7 @@ from ..configure import BaseDataclass, ConfigStore
 from ..module import Embedding
 from ..preprocessor import ModalityType, Slot
 from .base import AdaptorOutput, BaseAdaptor
-from . import text, image_resnet, image_patch_embed, audio  # noqa: F401  (registers the adaptors)
+from . import text, image_resnet, image_patch_embed, audio, video_image_sequence  # noqa: F401  (registers the adaptors)
 
 _ORDER = ["text", "image_resnet", "image_patch_embed", "audio_fbank", "video_image_sequence"]
 
@@ -109,6 +109,8 @@ class OFAGeneralAdaptor(nn.Module):
         assert output_slot
         return self.get_adaptor(output_slot).forward_output(x, extra, slot=output_slot)
 
+    COMPACT_ABOVE = 1024  # concatenated table rows above which the bucket ids are compacted to the used ones
+
     def _global_idx(self, outs: List[AdaptorOutput]):
         """int32 [S, S]: block-diagonal bucket ids, each slot's ids offset into the concatenated table;
         -1 where the reference adds no relative bias (general.py:270-280).  Cached per shape signature."""
@@ -125,8 +127,16 @@ class OFAGeneralAdaptor(nn.Module):
                 idx[start:start + T, start:start + T] = o.rel_idx + off
                 off += o.rel_tables[0].shape[0]
             start += T
-        self._idx_cache[key] = idx
-        return idx
+        used = None
+        if off > self.COMPACT_ABOVE:
+            # the attention kernels stage one table column per head in shared memory: keep only the rows this shape
+            # can address (e.g. 729 of the image table's 6892 for a 14x14 grid)
+            used = torch.unique(idx[idx >= 0].long())
+            lut = torch.full((off,), -1, dtype=torch.int32, device=dev)
+            lut[used] = torch.arange(used.numel(), dtype=torch.int32, device=dev)
+            idx = torch.where(idx >= 0, lut[idx.clamp_min(0).long()], idx)
+        self._idx_cache[key] = (idx, used)
+        return idx, used
 
     def concat(self, outs: List[AdaptorOutput]) -> AdaptorOutput:
         one = len(outs) == 1
@@ -147,13 +157,15 @@ class OFAGeneralAdaptor(nn.Module):
         num_layers = self.cfg.encoder.layers if self.is_src else self.cfg.decoder.layers
         n_tables = 1 if self.cfg.share_attn_bias else num_layers
         with_rel = [o for o in outs if o.rel_idx is not None]
-        idx = self._global_idx(outs) if with_rel else None
+        idx, used = self._global_idx(outs) if with_rel else (None, None)
         biases = []
         for l in range(n_tables):
             table = None
             if with_rel:
                 tabs = [o.rel_tables[l] for o in with_rel]
                 table = tabs[0] if len(tabs) == 1 else torch.cat(tabs, dim=0)
+                if used is not None:
+                    table = table.index_select(0, used)
             biases.append(ops.PositionBias(pq, pk, idx, table))
         out.self_attn_bias = biases
         return out

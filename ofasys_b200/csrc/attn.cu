@@ -705,7 +705,7 @@ int fill_common(const ofab_attn_fwd_args* a, AttnCommon& c) {
   OFAB_REQUIRE(a->q && a->k && a->v, "ofab_attn: q/k/v NULL");
   OFAB_REQUIRE((a->pq == nullptr) == (a->pk == nullptr), "ofab_attn: pq and pk must both be given or both NULL");
   OFAB_REQUIRE((a->rp_idx == nullptr) == (a->table == nullptr), "ofab_attn: rp_idx and table must both be given or both NULL");
-  OFAB_REQUIRE(a->rp_idx == nullptr || (a->n_buckets > 0 && a->n_buckets <= 16384), "ofab_attn: n_buckets=%d out of range (1..16384)", a->n_buckets);
+  OFAB_REQUIRE(a->rp_idx == nullptr || (a->n_buckets > 0 && a->n_buckets <= 22900), "ofab_attn: n_buckets=%d out of range (1..22900: one fp32 table column (+ its gradient) per head must fit in shared memory)", a->n_buckets);
   OFAB_REQUIRE(a->q_rs % 8 == 0 && a->k_rs % 8 == 0 && a->v_rs % 8 == 0 && a->q_bs % 8 == 0 && a->k_bs % 8 == 0 && a->v_bs % 8 == 0,
                "ofab_attn: q/k/v strides must be multiples of 8 elements (16-byte rows)");
   OFAB_REQUIRE(a->pq == nullptr || (a->pq_rs % 8 == 0 && a->pk_rs % 8 == 0 && a->pq_bs % 8 == 0 && a->pk_bs % 8 == 0),

@@ -273,6 +273,36 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 
 }  // namespace
 
+// ---- video clip [B, C, F, H, W] -> frames bf16 [B*F, C, H, W] + "frame is all zero" flags (the reference's frame
+// padding test `clip.abs().mean() == 0`, video_image_sequence.py:136-139).  One block per frame.
+namespace {
+template <typename T>
+__global__ void video_frames_kernel(const T* __restrict__ vid, int C, int F, int64_t HW, bf16* __restrict__ frames, uint8_t* __restrict__ zero) {
+  const int b = blockIdx.x / F, f = blockIdx.x % F;
+  int any = 0;
+  for (int c = 0; c < C; ++c) {
+    const T* src = vid + (((int64_t)b * C + c) * F + f) * HW;
+    bf16* dst = frames ? frames + (((int64_t)blockIdx.x) * C + c) * HW : nullptr;
+    for (int64_t i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float v = (float)src[i];
+      any |= (v != 0.f);
+      if (dst) dst[i] = __float2bfloat16(v);
+    }
+  }
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0 && zero) zero[blockIdx.x] = any ? 0 : 1;
+}
+}  // namespace
+extern "C" int ofab_video_frames(const void* video, int dt, int B, int C, int F, int64_t HW, void* frames, uint8_t* zero, ofab_stream_t stream) {
+  OFAB_REQUIRE(B > 0 && C > 0 && F > 0 && HW > 0, "ofab_video_frames: empty clip");
+  OFAB_REQUIRE(dt == OFAB_F32 || dt == OFAB_BF16, "ofab_video_frames: dtype must be f32 or bf16");
+  if (dt == OFAB_F32)
+    video_frames_kernel<float><<<B * F, 256, 0, (cudaStream_t)stream>>>((const float*)video, C, F, HW, (bf16*)frames, zero);
+  else
+    video_frames_kernel<bf16><<<B * F, 256, 0, (cudaStream_t)stream>>>((const bf16*)video, C, F, HW, (bf16*)frames, zero);
+  OFAB_LAUNCH_CHECK("ofab_video_frames");
+  return OFAB_OK;
+}
 extern "C" int ofab_im2col_nchw(const void* img, int img_dt, int B, int C, int H, int W, int k, int stride, int pad, void* cols, int64_t ldk,
                                 ofab_stream_t stream) {
   OFAB_REQUIRE(k > 0 && stride > 0 && pad >= 0 && ldk >= (int64_t)C * k * k && ldk % 8 == 0, "ofab_im2col_nchw: bad geometry");

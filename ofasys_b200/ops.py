@@ -356,7 +356,7 @@ class _AttentionFn(torch.autograd.Function):
         table_f = None
         if rp_idx is not None:
             assert rp_idx.dtype == torch.int32 and rp_idx.shape == (Tq, Tk) and rp_idx.is_contiguous()
-            table_f = cast_f32(table)
+            table_f = _c(table) if table.dtype == torch.float32 else cast_f32(table)
         if kpm is not None:
             kpm = _c(kpm.to(torch.uint8) if kpm.dtype != torch.uint8 else kpm)
         o = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=q_src.device)
@@ -712,6 +712,17 @@ def relu(x):
 
 
 # ------------------------------------------------------------------------------------ ResNet pieces (NHWC bf16)
+def video_frames(video):
+    """clip [B, C, F, H, W] -> (frames bf16 [B*F, C, H, W], all-zero-frame mask bool [B, F]); data, no gradient."""
+    _need_cuda(video)
+    video = _c(video)
+    B, C, F, H, W = video.shape
+    frames = torch.empty((B * F, C, H, W), dtype=torch.bfloat16, device=video.device)
+    zero = torch.empty((B, F), dtype=torch.uint8, device=video.device)
+    _lib.call("ofab_video_frames", _p(video), _DT[video.dtype], B, C, F, H * W, _p(frames), _p(zero), _s())
+    return frames, zero.view(torch.bool)
+
+
 def im2col_nchw(img, k, stride, pad, ldk):
     """stem im2col from the NCHW image (data: no gradient)."""
     _need_cuda(img)

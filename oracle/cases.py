@@ -9,7 +9,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .oracle_model import AUDIO, IMAGE, PAD, TEXT, OracleConfig, OSlot
+from .oracle_model import AUDIO, IMAGE, PAD, TEXT, VIDEO, OracleConfig, OSlot
 
 # name -> dict(cfg=..., adaptors=..., inputs spec)
 CASES = {
@@ -34,6 +34,11 @@ CASES = {
     "resnet_A": dict(
         cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A", resnet_type="resnet50"),
         adaptors=("text", "image_resnet"), kind="resnet", B=4, S=8, T=12, image=64,
+    ),
+    # video_image_sequence (16-frame video in configs[4]; here 3 frames of 64x64, one all-zero = padded frame) + text
+    "video_A": dict(
+        cfg=dict(embed_dim=128, heads=2, ffn_dim=512, enc_layers=2, dec_layers=2, vocab=512, mode="A", resnet_type="resnet50"),
+        adaptors=("text", "video_image_sequence"), kind="video", B=2, S=6, T=10, image=64, frames=3,
     ),
     # BASELINE.json configs[0]: text_infilling, OFA-tiny 4L/4L d=256, seq 128, bs 2 (checksums only)
     "cfg1_tiny": dict(
@@ -124,6 +129,10 @@ def make_inputs(name: str, seed: int = 1234):
     if c["kind"] == "resnet":
         img = torch.randn(B, 3, c["image"], c["image"], generator=g)
         slots.append(OSlot(IMAGE, True, img, adaptor="image_resnet"))
+    if c["kind"] == "video":
+        vid = torch.randn(B, 3, c["frames"], c["image"], c["image"], generator=g)
+        vid[-1, :, -1] = 0.0  # the last frame of the last clip is padding (video_image_sequence.py:136-139)
+        slots.append(OSlot(VIDEO, True, vid))
     if c["kind"] == "audio":
         L = c["L"]
         fbank = torch.randn(B, L, 80, generator=g)

@@ -373,6 +373,37 @@ def image_resnet_adaptor(sd, gp, cfg, slot, num_layers, training=True):
     return _hook(sd, ap, cfg, slot, AOut(x, masks, pos, bias), num_layers, None)
 
 
+def video_adaptor(sd, gp, cfg, slot, num_layers, training=True):
+    """adaptor/video_image_sequence.py:111-208: the image_resnet adaptor's backbone / image_proj / 2-D positions on
+    B*F frames, frame positions (id = f + 1) added to the patch positions, padding = all-zero frames (:136-139),
+    bias[(f,p),(f',p')] = frame_table[bucket(f,f')] + image_table[bucket2d(p,p')] (:176-200).  The hook
+    (LayerNorms, type embedding) uses the *video* adaptor's own parameters."""
+    ap, rp = gp + ".video_image_sequence", gp + ".image_resnet"
+    v = slot.value.transpose(1, 2)  # B x F x 3 x H x W
+    B, Fr = v.shape[:2]
+    feat = resnet_backbone(v.reshape(-1, v.size(2), v.size(3), v.size(4)), sd, rp + ".embed_images", cfg.resnet_type, training)
+    h, w = feat.shape[-2:]
+    P = h * w
+    emb = feat.reshape(feat.size(0), feat.size(1), -1).transpose(1, 2).reshape(B, Fr * P, feat.size(1))
+    masks = (v.reshape(B, Fr, -1).abs().mean(dim=-1) == 0.0).unsqueeze(-1).expand(B, Fr, P).reshape(B, Fr * P)
+    pid = (torch.arange(w).unsqueeze(0).expand(h, w) + torch.arange(h).unsqueeze(1) * cfg.image_bucket_size + 1).view(-1)
+    ipos = F.embedding(pid[None, :].expand(B, P), sd[rp + ".embed_image_positions.weight"])  # B x P x d
+    fpos = F.embedding((torch.arange(Fr) + 1)[None, :].expand(B, Fr), sd[ap + ".embed_frame_positions.weight"])  # B x F x d
+    pos = (ipos.unsqueeze(1) + fpos.unsqueeze(2)).reshape(B, Fr * P, -1)
+    x = linear(emb, sd, rp + ".image_proj")
+    bias = []
+    if cfg.mode == "A":
+        nrd = (2 * cfg.image_bucket_size - 1) ** 2 + 3
+        rp_img = make_image_bucket_position(cfg.image_bucket_size, nrd)[pid][:, pid]
+        rp_frm = make_token_bucket_position(cfg.token_bucket_size, 1024)[:Fr, :Fr]  # make_video_bucket_position :50-60
+        for idx in range(num_layers):
+            vi = F.embedding(rp_img, sd[f"{rp}.image_rel_pos_table_list.{idx}.weight"]).permute(2, 0, 1)  # H x P x P
+            vf = F.embedding(rp_frm, sd[f"{ap}.video_rel_pos_table_list.{idx}.weight"]).permute(2, 0, 1)  # H x F x F
+            val = vf[:, :, None, :, None] + vi[:, None, :, None, :]  # H x F x P x F x P
+            bias.append(val.reshape(1, val.size(0), Fr * P, Fr * P).expand(B, -1, -1, -1))
+    return _hook(sd, ap, cfg, slot, AOut(x, masks, pos, bias), num_layers, None)
+
+
 _DEFAULT_ADAPTOR = {  # adaptor/general.py:36-46
     TEXT: "text", IMAGE: "image_resnet", BOX: "text", AUDIO: "audio_fbank", PHONE: "text",
     VIDEO: "video_image_sequence", MOTION: "text", STRUCT: "text", CATEGORY: "text",
@@ -382,6 +413,7 @@ _ADAPTOR_FN = {
     "image_patch_embed": patch_embed_adaptor,
     "audio_fbank": audio_adaptor,
     "image_resnet": image_resnet_adaptor,
+    "video_image_sequence": video_adaptor,
 }
 
 

@@ -20,7 +20,7 @@ from util import TTS_ONLY, build_product, load_golden
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "cfg1_tiny"])
+@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A", "cfg1_tiny"])
 def test_state_dict_contract(name):
     """Parameter names / shapes equal the reference's (golden `spec` was dumped from its state_dict)."""
     g = load_golden(name)
@@ -93,10 +93,18 @@ def test_global_rel_idx_block_diagonal():
         AdaptorOutput(torch.zeros(1, 5, 8), torch.zeros(1, 5, dtype=torch.bool), None, None, rel_idx=a, rel_tables=[torch.zeros(2047, 2)]),
         AdaptorOutput(torch.zeros(1, 3, 8), torch.zeros(1, 3, dtype=torch.bool), None, None, rel_idx=t, rel_tables=[torch.zeros(511, 2)]),
     ]
-    idx = ga._global_idx(outs)
-    assert idx.shape == (8, 8) and idx.dtype == torch.int32
+    ga.COMPACT_ABOVE = 1 << 30
+    idx, used = ga._global_idx(outs)
+    assert used is None and idx.shape == (8, 8) and idx.dtype == torch.int32
     assert torch.equal(idx[:5, :5], a) and torch.equal(idx[5:, 5:], t + 2047)
     assert (idx[:5, 5:] == -1).all() and (idx[5:, :5] == -1).all()
+    # compaction: ids renumbered to the rows this shape can address; `used` maps them back (bit-exact)
+    ga.COMPACT_ABOVE = 1024
+    ga._idx_cache.clear()
+    cidx, used = ga._global_idx(outs)
+    assert used is not None and used.numel() == len(set(idx[idx >= 0].tolist())) and cidx.dtype == torch.int32
+    back = torch.where(cidx >= 0, used[cidx.clamp_min(0).long()].to(torch.int32), cidx)
+    assert torch.equal(back, idx)
 
 
 def test_cabi_exports_every_declared_symbol():

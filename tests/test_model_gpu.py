@@ -19,7 +19,7 @@ from oracle import oracle_model as om
 from util import bf16_round_state_dict, build_product, load_golden, rel_l2, to_product_slots
 
 pytestmark = pytest.mark.gpu
-SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A"]
+SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A"]
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
 
 
@@ -65,7 +65,7 @@ def test_model_fwd_bwd_parity(name):
     loss_ref, logits_ref, grads_ref = om.loss_and_grads(sd_r, cfg, slots, target)
     err16 = _oracle_bf16_error(sd_r, cfg, slots, logits_ref)
     sim = None
-    if name == "resnet_A":
+    if name in ("resnet_A", "video_A"):
         # A ReLU network's gradient is discontinuous in forward perturbations: with bf16 activation storage ~0.2 % of the
         # masks flip per ReLU (4-5 % gradient rel-L2 each, adding in quadrature over 49 ReLUs).  The yardstick for the
         # ResNet parameters is therefore the error of the reference algorithm itself under bf16 storage with fp32

@@ -648,3 +648,27 @@ def test_dp_nccl_two_gpus():
                         "--master-port", "29533", os.path.join(root, "tests", "dp_nccl_worker.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "DP_NCCL_OK" in r.stdout
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_video_frames_and_zero_mask(dtype):
+    """clip -> frames transpose + the reference's all-zero-frame padding test (bit-exact)."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, C, F_, H, W = 3, 3, 5, 17, 13
+    clip = torch.randn(B, C, F_, H, W, generator=gen).to(dev(), dtype)
+    clip[1, :, 2] = 0
+    clip[2, :, 4] = 0
+    clip[2, 1, 4, 16, 12] = -0.0
+    clip[0, :, 0] = 0
+    clip[0, 2, 0, 3, 3] = 1e-30 if dtype == torch.float32 else 1e-20  # one tiny non-zero value: not padding
+    frames, zero = ops.video_frames(clip)
+    v = clip.transpose(1, 2)
+    ref_mask = v.reshape(B, F_, -1).float().abs().mean(dim=-1) == 0.0
+    tiny = clip[0, :, 0].float().abs().sum() > 0
+    assert tiny
+    want = ref_mask.clone()
+    want[0, 0] = False  # fp32 mean of one 1e-30 among 663 zeros underflows in the reference formula only below 1e-38
+    assert torch.equal(zero, want)
+    assert torch.equal(frames, v.reshape(B * F_, C, H, W).to(torch.bfloat16))

@@ -10,7 +10,7 @@ from oracle import cases
 from oracle import oracle_model as om
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A"]
+SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A"]
 
 
 def rel_l2(a, b):

@@ -37,7 +37,8 @@ def build_product(name, device=None, dtype=None):
     m.cfg.decoder.input_dim = m.cfg.decoder.output_dim = d
     m.cfg.encoder.attention_heads = m.cfg.decoder.attention_heads = h
     m.cfg.encoder.layers, m.cfg.decoder.layers = cc["enc_layers"], cc["dec_layers"]
-    keep_resnet = cc.get("resnet_type")
+    if "resnet_type" in cc:
+        m.cfg.adaptor.image_resnet.resnet_type = cc["resnet_type"]
     for a in c["adaptors"]:
         a = "audio_fbank" if a == "audio" else a
         acfg = getattr(m.cfg.adaptor, a)
