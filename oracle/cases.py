@@ -45,6 +45,23 @@ CASES = {
         cfg=dict(embed_dim=256, heads=4, ffn_dim=1024, enc_layers=4, dec_layers=4, vocab=50265, mode="A"),
         adaptors=("text",), kind="text", B=2, S=128, T=128,
     ),
+    # BASELINE.json configs[1] at its full model size: image_caption, OFA-base 12L/12L d=768 H=12, 224^2 patch-embed (257
+    # tokens) + 8-token prompt -> 64-token caption, V=50265 (bench.py's workload at B=2; checksums only)
+    "cfg2_base": dict(
+        cfg=dict(embed_dim=768, heads=12, ffn_dim=3072, enc_layers=12, dec_layers=12, vocab=50265, mode="B"),
+        adaptors=("text", "image_patch_embed"), kind="patch", B=2, S=8, T=64,
+    ),
+    # BASELINE.json configs[2] at its full model size: ASR, OFA-base, 10 s fbank [998,80] (ragged lengths) + 12-token
+    # prompt -> 128-token transcript, Mode A (audio rel-pos table over 2047 buckets)
+    "cfg3_asr_base": dict(
+        cfg=dict(embed_dim=768, heads=12, ffn_dim=3072, enc_layers=12, dec_layers=12, vocab=50265, mode="A"),
+        adaptors=("text", "audio"), kind="audio", B=2, S=12, T=128, L=998,
+    ),
+    # OFA-large layer geometry (configs[4]: d=1024, H=16, F=4096) on a shallow 3L/2L stack
+    "large_A": dict(
+        cfg=dict(embed_dim=1024, heads=16, ffn_dim=4096, enc_layers=3, dec_layers=2, vocab=512, mode="A"),
+        adaptors=("text",), kind="text", B=3, S=40, T=24,
+    ),
 }
 
 
