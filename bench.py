@@ -4,7 +4,7 @@
   python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
 
 Workload (BASELINE.json configs[1]): image_caption, OFA-base 12L/12L d=768, 224^2 patch-embed
-(257 tokens) + 8-token prompt -> 64-token caption, bf16, per-GPU batch 32, synthetic data, random-init
+(257 tokens) + 8-token prompt -> 64-token caption, bf16, per-GPU batch 64 ("B=32 (also 64)"; --batch 32 reproduces the smaller one), synthetic data, random-init
 weights of that architecture.  A step = forward + sum-CE loss + backward of every parameter gradient
 (+ the gradient all-reduce when N > 1); optimizer excluded.
 
@@ -487,7 +487,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=32, help="per-GPU batch")
+    ap.add_argument("--batch", type=int, default=64, help="per-GPU batch (SURVEY 8d: 32 or 64; measured 1.20x seq/s at 64 vs 32, 1.03x more at 128)")
     ap.add_argument("--impl", default="ofab", choices=["ofab", "reference"])
     ap.add_argument("--breakdown", action="store_true", help="also write gpurun_out/breakdown.json (per entry point device time)")
     ap.add_argument("--kprofile", action="store_true", help="also write gpurun_out/kprofile.json (per-kernel device time of the replayed step, CUPTI)")

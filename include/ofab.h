@@ -109,6 +109,17 @@ int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, 
                    const float* residual, int64_t ldr, void* D, int64_t ldd, int d_dt,
                    ofab_stream_t stream);
 
+/* Split-K form for outputs with too few tiles to fill the chip and a long contraction -- the weight gradients
+ * dW[N_out, K_in] = dY^T X of nn.Linear backward (autograd of the F.linear calls above), whose tile count does not
+ * grow with the batch while K = B*T does.  D = A * B^T (no bias / residual); the K loop is cut into ranges that run
+ * as separate work items writing fp32 partial slabs into `workspace`, then one reduction pass writes D (bf16/fp32).
+ * The number of ranges is chosen internally; ofab_gemm_splitk_workspace_elems() returns the fp32 elements of
+ * workspace this call needs for (M, N, K) -- 0 means the plain kernel is used and workspace may be NULL. */
+int64_t ofab_gemm_splitk_workspace_elems(int64_t M, int64_t N, int64_t K);
+int ofab_gemm_bf16_splitk(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major,
+                          const void* B, int64_t ldb, int b_mn_major, void* D, int64_t ldd, int d_dt,
+                          float* workspace, int64_t workspace_elems, ofab_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Fused attention (flash-style; scores, bias and probabilities never touch HBM).
  * Replaces MultiheadAttention.forward's bmm/+bias/mask/softmax/bmm chain

@@ -69,6 +69,8 @@ _SIGS = {
     "ofab_colsum_scratch_elems": (c_int64, [c_int64]),
     "ofab_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ofab_gemm_bf16": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
+    "ofab_gemm_splitk_workspace_elems": (c_int64, [c_int64, c_int64, c_int64]),
+    "ofab_gemm_bf16_splitk": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "ofab_attn_fwd": (c_int, [POINTER(AttnFwdArgs), c_void_p]),
     "ofab_attn_bwd": (c_int, [POINTER(AttnBwdArgs), c_void_p]),
     "ofab_embed_ln_fwd": (c_int, [POINTER(EmbedLnArgs), c_void_p]),

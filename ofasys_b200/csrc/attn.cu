@@ -95,24 +95,40 @@ __device__ __forceinline__ void build_kmask(const AttnCommon& p, int b, int k0, 
   }
 }
 
-// Score post-processing shared by forward and both backward kernels, on one warp's 16 x 64 accumulator
-// tile:  s = scale*acc (+ table[bucket(i,j)]) ; masked -> -inf.
+// Key-validity bitmap of the whole key axis, built once per CTA: bit j of word j/32 set <=> key j is in range and
+// not padding.  (One pass of coalesced byte loads in the prologue instead of a dependent global load per key tile.)
+__device__ __forceinline__ void build_kmask_all(const AttnCommon& p, int b, uint32_t* dst /* smem [ceil(Tk/64)*2] */) {
+  const int words = ((p.Tk + 63) >> 6) * 2;
+  for (int w0 = (threadIdx.x >> 5); w0 < words; w0 += (blockDim.x >> 5)) {
+    const int j = w0 * 32 + (threadIdx.x & 31);
+    bool ok = j < p.Tk;
+    if (ok && p.kpm != nullptr) ok = p.kpm[(int64_t)b * p.Tk + j] == 0;
+    const uint32_t m = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) dst[w0] = m;
+  }
+}
+
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+// Score post-processing shared by forward and both backward kernels, on one warp's 16 x 64 accumulator tile.
+// Everything downstream works in the LOG2 domain: x2 = log2(e) * (scale * acc + table[bucket(i, j)]), masked -> -inf,
+// so that a probability is ONE ffma + ONE ex2:  p = ex2(x * mult - m2).
+//   return value `mult`: the factor that takes the tile's values to the log2 domain --
+//     fast path (no table, no masked key in the tile, tile not on the causal diagonal): the accumulators are left
+//       untouched and mult = scale * log2(e);
+//     otherwise the values are rewritten as x2 (bias added, mask applied) and mult = 1.
 //   TRANSPOSED = false: accumulator rows are queries (row0 = first query row of the warp), columns keys.
 //   TRANSPOSED = true : accumulator rows are keys   (row0 = first key row of the warp),   columns queries.
-// Fast path (no table, no masked key in the tile, tile not on the causal diagonal): one FMUL per element.
+//   tab_s holds the table column pre-multiplied by log2(e).
 template <bool TRANSPOSED, bool HAS_TAB, typename F>
-__device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4], int q0, int k0, int row0, uint64_t kmask,
-                                            const float* tab_s, F&& on_idx) {
+__device__ __forceinline__ float finish_tile(const AttnCommon& p, float (&s)[8][4], int q0, int k0, int row0, uint64_t kmask,
+                                             const float* tab_s, F&& on_idx) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr bool has_tab = HAS_TAB;
+  const float c2 = p.scale * kLog2e;
   const bool diag = p.causal && (k0 + TILE - 1 > q0);  // some (i, j) of this CTA tile may have j > i
-  if (!has_tab && !diag && kmask == ~0ull) {
-#pragma unroll
-    for (int nt = 0; nt < 8; ++nt)
-#pragma unroll
-      for (int e = 0; e < 4; ++e) s[nt][e] *= p.scale;
-    return;
-  }
+  if (!has_tab && !diag && kmask == ~0ull) return c2;
 #pragma unroll
   for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -122,7 +138,7 @@ __device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4
       const int i = q0 + il, j = k0 + jl;
       bool ok = (kmask >> jl) & 1ull;
       if (p.causal) ok = ok && (j <= i);
-      float v = s[nt][e] * p.scale;
+      float v = s[nt][e] * c2;
       if (has_tab && ok && i < p.Tq) {
         const int idx = p.rp_idx[(int64_t)i * p.Tk + j];
         if (idx >= 0) {
@@ -132,22 +148,23 @@ __device__ __forceinline__ void finish_tile(const AttnCommon& p, float (&s)[8][4
       }
       s[nt][e] = ok ? v : -INFINITY;
     }
+  return 1.0f;
 }
 
 // ===================================================================================== forward
-// smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | kmask [2 stages][2] u32 | table column (n_buckets floats)
-// K/V ring: 3 stages, one __syncthreads per key tile (the stage refilled in iteration kv was consumed in kv-1).
+// smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | key-validity bitmap (Tk bits) | table column (n_buckets floats)
+// K/V ring: 2 stages, one __syncthreads per key tile: tile kv+1 is fetched (cp.async) while tile kv is consumed.
 template <bool HAS_POS, bool HAS_TAB>
 __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
                                                                         float* __restrict__ lse) {
   constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
-  constexpr int NST = 3;
+  constexpr int NST = 2;
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK = sQ + NH * TILE_BYTES;
   const uint32_t sV = sK + NST * NH * TILE_BYTES;
   uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + ((NST + 1) * NH + NST) * TILE_BYTES);
-  float* tab_s = reinterpret_cast<float*>(kmask_s + 2 * NST);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + ((p.Tk + 63) >> 6) * 2);
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -160,9 +177,6 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
   const bf16* pqg = HAS_POS ? p.pq + (int64_t)b * p.pq_bs + h * 64 : nullptr;
   const bf16* pkg = HAS_POS ? p.pk + (int64_t)b * p.pk_bs + h * 64 : nullptr;
 
-  if (HAS_TAB)
-    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
-
   const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
 
   auto load_kv = [&](int kvi) {
@@ -171,32 +185,33 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
     if (HAS_POS) load_tile_async(sK + (stg * NH + 1) * TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
     load_tile_async(sV + stg * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
     cp_commit();
-    build_kmask(p, b, k1, kmask_s + 2 * stg);
   };
   load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
   if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
   load_kv(0);
-  if (n_kv > 1) load_kv(1);
+  if (HAS_TAB)
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h] * kLog2e;
+  build_kmask_all(p, b, kmask_s);
 
   float oacc[8][4];
 #pragma unroll
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
-  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+  float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // running max (log2 domain) and sum per query row
   const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
 
   for (int kv = 0; kv < n_kv; ++kv) {
     const int st = kv % NST;
-    if (kv + 1 < n_kv) cp_wait<1>(); else cp_wait<0>();  // tile kv has landed (tile kv+1 may still be in flight)
-    __syncthreads();                                      // ... for every thread; and everyone finished tile kv-1
-    if (kv + 2 < n_kv) load_kv(kv + 2);                   // refill the stage consumed in iteration kv-1
+    cp_wait<0>();      // tile kv has landed ...
+    __syncthreads();   // ... for every thread; and everyone finished tile kv-1 (and, first time, the bitmap / table)
+    if (kv + 1 < n_kv) load_kv(kv + 1);  // refill the stage consumed in iteration kv-1
 
     if (warp_live) {
       const int k0 = kv * TILE;
       const int nk = min(TILE, p.Tk - k0);          // valid keys in this tile
       const int np_n = (nk + 15) >> 4;               // 16-key groups that hold a valid key
-      const uint64_t kmask = (uint64_t)kmask_s[2 * st] | ((uint64_t)kmask_s[2 * st + 1] << 32);
+      const uint64_t kmask = (uint64_t)kmask_s[2 * kv] | ((uint64_t)kmask_s[2 * kv + 1] << 32);
       // ---- S = Q K^T (+ PQ PK^T)
       float s[8][4];
 #pragma unroll
@@ -221,8 +236,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
           }
         }
       }
-      // ---- bias / mask / online softmax
-      finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+      // ---- bias / mask / online softmax (log2 domain: p = ex2(s * mult - m), one FFMA + one MUFU per score)
+      const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -233,9 +248,9 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
       for (int r = 0; r < 2; ++r) {
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
         mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
-        const float m_new = fmaxf(m_run[r], mx[r]);
+        const float m_new = fmaxf(m_run[r], mx[r] * mult);  // mult > 0: the max commutes with the scaling
         m_use[r] = (m_new == -INFINITY) ? 0.f : m_new;
-        corr[r] = __expf(m_run[r] - m_use[r]);  // exp(-inf) = 0 on the first tile
+        corr[r] = fast_ex2(m_run[r] - m_use[r]);  // ex2(-inf) = 0 on the first tile
         m_run[r] = m_new;
         l_run[r] *= corr[r];
       }
@@ -244,7 +259,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          const float pe = __expf(s[nt][e] - m_use[e >> 1]);
+          const float pe = fast_ex2(fmaf(s[nt][e], mult, -m_use[e >> 1]));
           s[nt][e] = pe;
           ps[e >> 1] += pe;
         }
@@ -297,7 +312,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
         const uint32_t u = pack_bf16(oacc[dt][2 * r] * inv, oacc[dt][2 * r + 1] * inv);
         *reinterpret_cast<uint32_t*>(op + dt * 8 + 2 * t) = u;
       }
-      if (t == 0) lse[((int64_t)b * p.H + h) * p.Tq + i] = (l_run[r] > 0.f) ? m_run[r] + __logf(l_run[r]) : -INFINITY;
+      // natural-log log-sum-exp of the (scaled, biased) scores
+      if (t == 0) lse[((int64_t)b * p.H + h) * p.Tq + i] = (l_run[r] > 0.f) ? (m_run[r] + __log2f(l_run[r])) * kLn2 : -INFINITY;
     }
   }
 }
@@ -317,17 +333,20 @@ struct AttnBwdExtra {
 
 // ---- dK / dV: one CTA per 64-key tile, loops over query tiles.  Works on transposed scores
 // S^T[key, query] so every accumulator row belongs to this CTA's keys.
+// Query-side operands (Q, dO, lse, delta) are double-buffered when no table column competes for shared memory
+// (NSB = 2: tile qt+1 is fetched while tile qt is consumed, one barrier per tile).
 template <bool HAS_POS, bool HAS_TAB>
 __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
+  constexpr int NSB = HAS_TAB ? 1 : 2;
+  constexpr int QST = (NH + 1) * TILE_BYTES;      // one query-side stage: Q (NH tiles) | dO
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sK = smem_u32(smem);             // NH tiles (this CTA's keys)
   const uint32_t sV = sK + NH * TILE_BYTES;       // 1 tile
-  const uint32_t sQ = sV + TILE_BYTES;            // NH tiles (current query tile)
-  const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1 tile
-  float* lse_s = reinterpret_cast<float*>(smem + (2 * NH + 2) * TILE_BYTES);
-  float* dlt_s = lse_s + TILE;
-  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(dlt_s + TILE);
+  const uint32_t sQ0 = sV + TILE_BYTES;           // NSB stages
+  float* lse_s = reinterpret_cast<float*>(smem + (NH + 1) * TILE_BYTES + NSB * QST);  // [NSB][TILE] lse * log2(e)
+  float* dlt_s = lse_s + NSB * TILE;                                                   // [NSB][TILE] delta * scale
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(dlt_s + NSB * TILE);
   float* tab_s = reinterpret_cast<float*>(kmask_s + 2);
 
   const int kb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -342,13 +361,31 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
   const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
 
   if (HAS_TAB)
-    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h];
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) tab_s[i] = p.table[(int64_t)i * p.H + h] * kLog2e;
+
+  const int n_q = (p.Tq + TILE - 1) / TILE;
+  const int q_start = p.causal ? (k0 / TILE) : 0;  // queries i < k0 never see these keys
+  auto load_q = [&](int qt, int stg) {
+    const int q1 = qt * TILE;
+    const uint32_t sQ = sQ0 + stg * QST;
+    load_tile_async(sQ, qg, p.q_rs, q1, p.Tq);
+    if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q1, p.Tq);
+    load_tile_async(sQ + NH * TILE_BYTES, dog, e.do_rs, q1, p.Tq);
+    cp_commit();
+    if (threadIdx.x < TILE) {
+      const int i = q1 + threadIdx.x;
+      const float l = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
+      // rows without any visible key (or past Tq) get a huge finite lse: every probability becomes ex2(-huge) = 0
+      lse_s[stg * TILE + threadIdx.x] = (l == -INFINITY) ? 1e30f : l * kLog2e;
+      dlt_s[stg * TILE + threadIdx.x] = i < p.Tq ? e.delta[((int64_t)b * p.H + h) * p.Tq + i] * p.scale : 0.f;
+    }
+  };
 
   load_tile_async(sK, kg, p.k_rs, k0, p.Tk);
   if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
   load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
-  cp_commit();
   build_kmask(p, b, k0, kmask_s);
+  if (q_start < n_q) load_q(q_start, 0);  // one commit group together with K / V
 
   float dk[NH * 8][4], dv[8][4];
 #pragma unroll
@@ -359,26 +396,27 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
   for (int i = 0; i < 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
-
-  const int n_q = (p.Tq + TILE - 1) / TILE;
-  const int q_start = p.causal ? (k0 / TILE) : 0;  // queries i < k0 never see these keys
   const int key_g[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
 
   for (int qt = q_start; qt < n_q; ++qt) {
     const int q0 = qt * TILE;
-    __syncthreads();  // previous iteration finished reading sQ / sDO / lse_s
-    load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
-    if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
-    load_tile_async(sDO, dog, e.do_rs, q0, p.Tq);
-    cp_commit();
-    if (threadIdx.x < TILE) {
-      const int i = q0 + threadIdx.x;
-      lse_s[threadIdx.x] = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
-      dlt_s[threadIdx.x] = i < p.Tq ? e.delta[((int64_t)b * p.H + h) * p.Tq + i] : 0.f;
+    const int stg = NSB == 2 ? ((qt - q_start) & 1) : 0;
+    if (NSB == 2) {
+      cp_wait<0>();      // tile qt has landed ...
+      __syncthreads();   // ... for every thread; and everyone finished tile qt-1
+      if (qt + 1 < n_q) load_q(qt + 1, stg ^ 1);
+    } else {
+      if (qt > q_start) {
+        __syncthreads();  // previous iteration finished reading the query-side stage
+        load_q(qt, 0);
+      }
+      cp_wait<0>();
+      __syncthreads();
     }
-    cp_wait<0>();
-    __syncthreads();
     if (!warp_live) continue;
+    const uint32_t sQ = sQ0 + stg * QST, sDO = sQ + NH * TILE_BYTES;
+    const float* lse2 = lse_s + stg * TILE;
+    const float* dls = dlt_s + stg * TILE;
 
     const int nq = min(TILE, p.Tq - q0);
     const int np_n = (nq + 15) >> 4;  // 16-query groups holding a valid query
@@ -408,15 +446,12 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
         }
       }
     }
-    // P^T = exp(S^T - lse[query])
-    finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+    // P^T = ex2(S^T * mult - lse2[query])   (masked scores are -inf -> 0)
+    const float mult = finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int el = 0; el < 4; ++el) {
-        const float l = lse_s[nt * 8 + 2 * t + (el & 1)];
-        s[nt][el] = (s[nt][el] == -INFINITY || l == -INFINITY) ? 0.f : __expf(s[nt][el] - l);
-      }
+      for (int el = 0; el < 4; ++el) s[nt][el] = fast_ex2(fmaf(s[nt][el], mult, -lse2[nt * 8 + 2 * t + (el & 1)]));
     // dV += P^T dO
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
@@ -455,14 +490,11 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
         }
       }
     }
-    // dS^T = P^T * (dP^T - delta[query]) ; pre-multiplied by scale for dK
+    // scale * dS^T = P^T * (scale * dP^T - scale * delta[query])
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int el = 0; el < 4; ++el) {
-        const int jl = nt * 8 + 2 * t + (el & 1);
-        s[nt][el] = s[nt][el] * (dp_[nt][el] - dlt_s[jl]) * p.scale;
-      }
+      for (int el = 0; el < 4; ++el) s[nt][el] *= fmaf(dp_[nt][el], p.scale, -dls[nt * 8 + 2 * t + (el & 1)]);
     // dK' += dS^T Q'
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
@@ -506,17 +538,19 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
   }
 }
 
-// ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles.
+// ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles (K / V double-buffered when no
+// table column competes for shared memory).
 template <bool HAS_POS, bool HAS_TAB>
 __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
+  constexpr int NSB = HAS_TAB ? 1 : 2;
+  constexpr int KST = (NH + 1) * TILE_BYTES;      // one key-side stage: K (NH tiles) | V
   extern __shared__ __align__(128) uint8_t smem[];
   const uint32_t sQ = smem_u32(smem);             // NH
   const uint32_t sDO = sQ + NH * TILE_BYTES;      // 1
-  const uint32_t sK = sDO + TILE_BYTES;           // NH
-  const uint32_t sV = sK + NH * TILE_BYTES;       // 1
-  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + (2 * NH + 2) * TILE_BYTES);
-  float* tab_s = reinterpret_cast<float*>(kmask_s + 2);
+  const uint32_t sK0 = sDO + TILE_BYTES;          // NSB stages
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(smem + (NH + 1) * TILE_BYTES + NSB * KST);
+  float* tab_s = reinterpret_cast<float*>(kmask_s + ((p.Tk + 63) >> 6) * 2);
   float* dtab_s = tab_s + p.n_buckets;
 
   const int qb = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -531,19 +565,28 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
   const bf16* dog = e.d_o + (int64_t)b * e.do_bs + h * 64;
   constexpr bool has_tab = HAS_TAB;
 
-  if (has_tab)
-    for (int i = threadIdx.x; i < p.n_buckets; i += 128) {
-      tab_s[i] = p.table[(int64_t)i * p.H + h];
-      dtab_s[i] = 0.f;
-    }
-
+  auto load_kv = [&](int kvi, int stg) {
+    const int k1 = kvi * TILE;
+    const uint32_t sK = sK0 + stg * KST;
+    load_tile_async(sK, kg, p.k_rs, k1, p.Tk);
+    if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k1, p.Tk);
+    load_tile_async(sK + NH * TILE_BYTES, vg, p.v_rs, k1, p.Tk);
+    cp_commit();
+  };
   load_tile_async(sQ, qg, p.q_rs, q0, p.Tq);
   if (HAS_POS) load_tile_async(sQ + TILE_BYTES, pqg, p.pq_rs, q0, p.Tq);
   load_tile_async(sDO, dog, e.do_rs, q0, p.Tq);
-  cp_commit();
+  load_kv(0, 0);  // one commit group together with Q / dO
+
+  if (has_tab)
+    for (int i = threadIdx.x; i < p.n_buckets; i += 128) {
+      tab_s[i] = p.table[(int64_t)i * p.H + h] * kLog2e;
+      dtab_s[i] = 0.f;
+    }
+  build_kmask_all(p, b, kmask_s);
 
   const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
-  float lse_r[2], dl_r[2];
+  float lse2_r[2], dl_r[2], dls_r[2];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     // delta[i] = sum_d dO[i,d] * O[i,d]: the 4 lanes of a quad split the 64 columns of row i (16 each)
@@ -561,8 +604,10 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
     }
     dsum += __shfl_xor_sync(0xffffffffu, dsum, 1);
     dsum += __shfl_xor_sync(0xffffffffu, dsum, 2);
-    lse_r[r] = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
+    const float l = i < p.Tq ? e.lse[((int64_t)b * p.H + h) * p.Tq + i] : -INFINITY;
+    lse2_r[r] = (l == -INFINITY) ? 1e30f : l * kLog2e;  // no visible key / past Tq: every probability becomes 0
     dl_r[r] = dsum;
+    dls_r[r] = dsum * p.scale;
     if (i < p.Tq && t == 0) e.delta[((int64_t)b * p.H + h) * p.Tq + i] = dsum;  // for the dK/dV kernel
   }
   float dq[NH * 8][4];
@@ -574,19 +619,25 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
   const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
   for (int kv = 0; kv < n_kv; ++kv) {
     const int k0 = kv * TILE;
-    __syncthreads();
-    load_tile_async(sK, kg, p.k_rs, k0, p.Tk);
-    if (HAS_POS) load_tile_async(sK + TILE_BYTES, pkg, p.pk_rs, k0, p.Tk);
-    load_tile_async(sV, vg, p.v_rs, k0, p.Tk);
-    cp_commit();
-    build_kmask(p, b, k0, kmask_s);
-    cp_wait<0>();
-    __syncthreads();
+    const int stg = NSB == 2 ? (kv & 1) : 0;
+    if (NSB == 2) {
+      cp_wait<0>();      // tile kv has landed ...
+      __syncthreads();   // ... for every thread; and everyone finished tile kv-1 (first time: bitmap / table staged)
+      if (kv + 1 < n_kv) load_kv(kv + 1, stg ^ 1);
+    } else {
+      if (kv > 0) {
+        __syncthreads();
+        load_kv(kv, 0);
+      }
+      cp_wait<0>();
+      __syncthreads();
+    }
     if (!warp_live) continue;
+    const uint32_t sK = sK0 + stg * KST, sV = sK + NH * TILE_BYTES;
 
     const int nk = min(TILE, p.Tk - k0);
     const int np_n = (nk + 15) >> 4;
-    const uint64_t kmask = (uint64_t)kmask_s[0] | ((uint64_t)kmask_s[1] << 32);
+    const uint64_t kmask = (uint64_t)kmask_s[2 * kv] | ((uint64_t)kmask_s[2 * kv + 1] << 32);
 
     float s[8][4];
 #pragma unroll
@@ -639,19 +690,20 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
 #pragma unroll
         for (int el = 0; el < 4; ++el) idxs[nt][el] = -1;
     }
-    finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { if (has_tab) idxs[has_tab ? nt : 0][el] = idx; });
+    const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { if (has_tab) idxs[has_tab ? nt : 0][el] = idx; });
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int el = 0; el < 4; ++el) {
-        const float l = lse_r[el >> 1];
-        const float pe = (s[nt][el] == -INFINITY || l == -INFINITY) ? 0.f : __expf(s[nt][el] - l);
-        const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
+        const float pe = fast_ex2(fmaf(s[nt][el], mult, -lse2_r[el >> 1]));  // masked scores are -inf -> 0
         if (has_tab) {
+          const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
           const int ix = idxs[has_tab ? nt : 0][el];
           if (ix >= 0 && ds != 0.f) atomicAdd(dtab_s + ix, ds);
+          s[nt][el] = ds * p.scale;
+        } else {
+          s[nt][el] = pe * fmaf(dp_[nt][el], p.scale, -dls_r[el >> 1]);  // scale * dS
         }
-        s[nt][el] = ds * p.scale;
       }
     // dQ' += dS K'
 #pragma unroll
@@ -737,7 +789,8 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
   OFAB_REQUIRE(a->o_rs % 2 == 0 && a->o_bs % 2 == 0, "ofab_attn_fwd: o strides must be even");
   const bool pos = a->pq != nullptr, tab = a->rp_idx != nullptr;
   const int nh = pos ? 2 : 1;
-  const int smem = (4 * nh + 3) * TILE_BYTES + 24 + c.n_buckets * 4;
+  const int kwords = ((a->Tk + 63) / 64) * 2;  // key-validity bitmap
+  const int smem = (3 * nh + 2) * TILE_BYTES + kwords * 4 + c.n_buckets * 4;
   dim3 grid((a->Tq + TILE - 1) / TILE, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
 #define FWD(P, T)                                                                                  \
@@ -769,8 +822,10 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
   e.dtable = a->dtable;
   const int nh = pos ? 2 : 1;
-  const int smem_kv = (2 * nh + 2) * TILE_BYTES + 2 * TILE * 4 + 8 + c.n_buckets * 4;
-  const int smem_q = (2 * nh + 2) * TILE_BYTES + 8 + 2 * c.n_buckets * 4;
+  const int nsb = tab ? 1 : 2;  // query- / key-side stages (double-buffered unless a table column needs the space)
+  const int kwords = ((a->f.Tk + 63) / 64) * 2;
+  const int smem_kv = (nh + 1) * (1 + nsb) * TILE_BYTES + nsb * 2 * TILE * 4 + 8 + c.n_buckets * 4;
+  const int smem_q = (nh + 1) * (1 + nsb) * TILE_BYTES + kwords * 4 + 2 * c.n_buckets * 4;
   dim3 gkv((a->f.Tk + TILE - 1) / TILE, a->f.H, a->f.B), gq((a->f.Tq + TILE - 1) / TILE, a->f.H, a->f.B);
   // dQ first: it also computes delta = rowsum(dO * O) that the dK/dV kernel needs
 #define BWD(P, T)                                                                                   \

@@ -47,8 +47,7 @@ struct f8 {
   float v[8];
 };
 
-__device__ __forceinline__ f8 load8(const bf16* p) {
-  uint4 u = *reinterpret_cast<const uint4*>(p);
+__device__ __forceinline__ f8 unpack8(const uint4& u) {  // 8 packed bf16 -> 8 floats
   const bf162* h = reinterpret_cast<const bf162*>(&u);
   f8 r;
 #pragma unroll
@@ -59,6 +58,7 @@ __device__ __forceinline__ f8 load8(const bf16* p) {
   }
   return r;
 }
+__device__ __forceinline__ f8 load8(const bf16* p) { return unpack8(*reinterpret_cast<const uint4*>(p)); }
 __device__ __forceinline__ f8 load8(const float* p) {
   float4 a = *reinterpret_cast<const float4*>(p);
   float4 b = *reinterpret_cast<const float4*>(p + 4);
@@ -79,28 +79,82 @@ __device__ __forceinline__ void store8(float* p, const f8& r) {
   *reinterpret_cast<float4*>(p + 4) = make_float4(r.v[4], r.v[5], r.v[6], r.v[7]);
 }
 
+// MUFU approximations without the denormal / range fix-up code the CUDA intrinsics carry (3-4 extra
+// instructions each): inputs here are O(1), flush-to-zero is harmless.
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // erf-GELU and derivative in fp32 (ofasys/module/gelu.py:18-19 -> F.gelu(x.float())).
-// erf via Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below the bf16 rounding of the result): one
-// exp + 5 FMA + 1 rcp instead of erff's long path; the exp is shared with the pdf term of the gradient.
+// q = 0.5 erfc(|x|/sqrt2) via Abramowitz-Stegun 7.1.26 (|err| <= 0.75e-7 on q, far below the bf16 rounding of
+// the result): one rcp + one ex2 + 6 FMA instead of erff's long path; the exponential is shared with the pdf
+// term of the gradient.  cdf = 1 - q for x >= 0, q otherwise.
 __device__ __forceinline__ void gelu_parts(float x, float& cdf, float& pdf_x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));  // MUFU.RCP
-  const float e = __expf(-z * z);  // = exp(-x^2/2)
-  const float poly = t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 1.061405429f, -1.453152027f), 1.421413741f), -0.284496736f), 0.254829592f);
-  const float erf_abs = fmaf(-poly, e, 1.0f);
-  cdf = 0.5f * (1.0f + copysignf(erf_abs, x));
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  const float e = fast_ex2(x * x * (-0.5f * 1.4426950408889634f));  // exp(-x^2/2)
+  const float poly =
+      t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f), 0.5f * 1.421413741f), 0.5f * -0.284496736f),
+               0.5f * 0.254829592f);
+  const float q = poly * e;
+  cdf = x >= 0.f ? 1.0f - q : q;
   pdf_x = 0.39894228040143268f * e * x;
 }
 __device__ __forceinline__ float gelu_f(float x) {
-  float cdf, px;
-  gelu_parts(x, cdf, px);
-  return x * cdf;
+  const float t = fast_rcp(fmaf(0.3275911f * 0.70710678118654752f, fabsf(x), 1.0f));
+  const float e = fast_ex2(x * x * (-0.5f * 1.4426950408889634f));
+  const float poly =
+      t * fmaf(t, fmaf(t, fmaf(t, fmaf(t, 0.5f * 1.061405429f, 0.5f * -1.453152027f), 0.5f * 1.421413741f), 0.5f * -0.284496736f),
+               0.5f * 0.254829592f);
+  return fmaf(-fabsf(x), poly * e, fmaxf(x, 0.f));  // x * cdf = max(x,0) - |x| q
 }
 __device__ __forceinline__ float gelu_grad_f(float x) {
   float cdf, px;
   gelu_parts(x, cdf, px);
   return cdf + px;
 }
+
+// ---- async row pipeline: cp.async.bulk (TMA engine, 1-D) global -> shared ring, mbarrier completion ----------
+// HBM-bound row kernels (LayerNorm family) keep several rows per CTA in flight without holding them in registers:
+// one elected thread issues a bulk copy per input and stage, all threads wait on the stage's mbarrier and read
+// their 16/32 bytes from shared memory.
+namespace rowpipe {
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void init(uint64_t* bars, int n) {  // call from one thread, then __syncthreads()
+  for (int i = 0; i < n; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s32(bars + i)), "r"(1));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void expect(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s32(bar)), "r"(bytes) : "memory");
+}
+// bytes % 16 == 0, src and dst 16-byte aligned
+__device__ __forceinline__ void load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(s32(dst)), "l"(src),
+               "r"(bytes), "r"(s32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t a = s32(bar);
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(a), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+}  // namespace rowpipe
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   bf162 h = __floats2bfloat162_rn(a, b);

@@ -5,7 +5,7 @@
 
 namespace {
 
-constexpr int PARTIAL_ROWS = 888;  // == ofab_ln_partial_rows()
+constexpr int PARTIAL_ROWS = 296;  // == ofab_ln_partial_rows()
 
 __device__ __forceinline__ float block_sum128(float v, float* red) {
   v = warp_sum(v);

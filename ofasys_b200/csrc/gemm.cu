@@ -156,6 +156,10 @@ struct GemmParams {
   int64_t ldd;
   int d_bf16;
   int tma_store;  // epilogue writes bf16 tiles through swizzled smem + TMA (coalesced); else direct st.global
+  // split-K: the K loop is cut into `splits` ranges of kb_per_split k-blocks; range s of output tile t is its own
+  // work item and writes a partial result into slab s of D (slabs are split_stride elements apart; fp32, direct path)
+  int splits, kb_per_split;
+  int64_t split_stride;
   int dbg;        // development: 1 = no global stores, 2 = no TMEM reads, 4 = no MMA issue, 8 = no TMA loads
 };
 
@@ -180,7 +184,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   constexpr uint32_t B_BYTES = BNL * BK * 2;
   constexpr uint32_t TMEM_COLS = 2 * BN;  // double-buffered accumulator (256 or 512 columns)
   constexpr uint32_t STG_BYTES = BLOCK_M * 128;  // one 128-row x 64-col bf16 store tile
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "tmem columns must be a power of two");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512, "tmem columns must be a power of two");
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment; do not rely on the dynamic-smem base
@@ -198,7 +202,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);  // tiles of 128*CG rows
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int num_tiles = m_tiles * n_tiles;
+  const int mn_tiles = m_tiles * n_tiles;
+  const int num_tiles = mn_tiles * p.splits;
   const int num_k_blocks = (p.K + BK - 1) / BK;
   const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
   const bool leader = rank == 0;
@@ -240,9 +245,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
-        const int m0 = (t % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;  // this CTA's 128 rows
-        const int n0 = (t / m_tiles) * BN + (int)rank * BNL;                   // this CTA's slice of the B tile
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int tt = t % mn_tiles, sp = t / mn_tiles;
+        const int m0 = (tt % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;  // this CTA's 128 rows
+        const int n0 = (tt / m_tiles) * BN + (int)rank * BNL;                   // this CTA's slice of the B tile
+        const int kb_begin = sp * p.kb_per_split, kb_end = min(num_k_blocks, kb_begin + p.kb_per_split);
+        for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (leader) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
           else mbar_arrive_remote(full_bar + stage, 0);
@@ -291,7 +298,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         mbar_wait(tmem_empty + as, aphase ^ 1);
         tcgen05_fence_after();
         const uint32_t tmem_d = tmem_base + as * BN;
-        for (int kb = 0; kb < num_k_blocks; ++kb) {
+        const int kb_count = min(num_k_blocks, (t / mn_tiles + 1) * p.kb_per_split) - (t / mn_tiles) * p.kb_per_split;
+        for (int kb = 0; kb < kb_count; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tcgen05_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES);
@@ -310,7 +318,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           }
           // frees the smem slot (in both CTAs when paired) once these MMAs retire
           if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage);
-          if (kb == num_k_blocks - 1) {
+          if (kb == kb_count - 1) {
             if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as);
           }
           if (++stage == STAGES) {
@@ -330,8 +338,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     for (int t = tile0; t < num_tiles; t += tile_step, ++iter) {
       const int as = iter & 1;
       const uint32_t aphase = (iter >> 1) & 1;
-      const int m0 = (t % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
-      const int n0 = (t / m_tiles) * BN;
+      const int tt = t % mn_tiles, sp = t / mn_tiles;
+      const int m0 = (tt % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
+      const int n0 = (tt / m_tiles) * BN;
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
       const int row = m0 + rloc;
@@ -446,7 +455,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
                   if (n + j < p.N) dp[j] = __float2bfloat16(v[j]);
               }
             } else {
-              float* dp = reinterpret_cast<float*>(p.D) + (int64_t)row * p.ldd + n;
+              float* dp = reinterpret_cast<float*>(p.D) + (int64_t)sp * p.split_stride + (int64_t)row * p.ldd + n;
               if (n + 32 <= p.N) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dp + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
@@ -485,6 +494,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 EncodeTiledFn get_encode_fn() {
+  // The driver entry point needs a current context on the CALLING thread.  A thread that has only ever used cached
+  // allocations (e.g. a fresh autograd worker whose first CUDA work is this GEMM) has none bound yet:
+  // cuTensorMapEncodeTiled then fails with CUDA_ERROR_INVALID_CONTEXT.  cudaFree(0) binds the primary context.
+  static thread_local bool ctx_bound = false;
+  if (!ctx_bound) {
+    cudaFree(0);
+    ctx_bound = true;
+  }
   static EncodeTiledFn fn = nullptr;
   if (fn) return fn;
   void* p = nullptr;
@@ -532,7 +549,7 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
     configured = true;
   }
   const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG), n_tiles = (p.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles;
+  const int tiles = m_tiles * n_tiles * p.splits;
   const int units = ofab_sm_count() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
   const int grid = (tiles < units ? tiles : units) * CG;
   cudaLaunchConfig_t cfg = {};
@@ -552,11 +569,10 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   return OFAB_OK;
 }
 
-}  // namespace
-
-extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major, const void* B,
-                              int64_t ldb, int b_mn_major, const void* bias, const float* residual, int64_t ldr, void* D,
-                              int64_t ldd, int d_dt, ofab_stream_t stream) {
+// splits > 1: split-K into `splits` fp32 partial slabs at D (see GemmParams); forces the 256 x 128 pair tile.
+int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major, const void* B, int64_t ldb, int b_mn_major,
+             const void* bias, const float* residual, int64_t ldr, void* D, int64_t ldd, int d_dt, int splits, int64_t split_stride,
+             ofab_stream_t stream) {
   OFAB_REQUIRE(M > 0 && N > 0 && K > 0, "ofab_gemm_bf16: empty problem M=%lld N=%lld K=%lld", (long long)M, (long long)N, (long long)K);
   OFAB_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "ofab_gemm_bf16: dimension overflow");
   OFAB_REQUIRE(lda % 8 == 0 && ldb % 8 == 0, "ofab_gemm_bf16: lda=%lld ldb=%lld must be multiples of 8 (16-byte TMA strides)", (long long)lda, (long long)ldb);
@@ -577,28 +593,35 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
     const int64_t units = sms / cg;
     const double waves = (double)((tiles + units - 1) / units);
     // per-tile efficiency factors fitted to the measured sweep (profiles/r01_gemm_sweep_v4.json)
-    const double eff = cg == 2 ? (bn == 256 ? 1.0 : 1.25) : (bn == 256 ? 1.1 : 1.3);
+    // (128 x 64 tiles exist for completeness and tests: measured slower than 256 x 128 pair tiles even on the
+    // 768 x 768 wgrads they spread over 2x the SMs -- the K loop, not the SM count, bounds those; see split-K)
+    const double eff = cg == 2 ? (bn == 256 ? 1.0 : 1.25) : (bn == 256 ? 1.1 : bn == 128 ? 1.3 : 4.0);
     return waves * bn * eff;
   };
   int BN = 256, CG = 2;
   double best = 1e30;
-  const int bns[2] = {256, 128};
+  const int bns[3] = {256, 128, 64};
   for (int cg = 2; cg >= 1; --cg)
-    for (int bi = 0; bi < 2; ++bi) {
+    for (int bi = 0; bi < 3; ++bi) {
       const int bn = bns[bi];
+      if (bn == 64 && cg == 2) continue;                // 64-wide tiles only in the 1-CTA form
       if (b_mn_major && (bn / cg) % 64 != 0) continue;  // MN-major B is staged in 64-wide atoms
       const double c = cost(bn, cg);
       if (c < best - 1e-9) { best = c; BN = bn; CG = cg; }
     }
   if (const char* ov = getenv("OFAB_GEMM_BN")) {  // development overrides for tile-shape experiments
     const int v = atoi(ov);
-    if (v == 128 || v == 256) BN = v;
+    if (v == 64 || v == 128 || v == 256) BN = v;
   }
   if (const char* ov = getenv("OFAB_GEMM_CG")) {
     const int v = atoi(ov);
     if (v == 1 || v == 2) CG = v;
   }
-  if (b_mn_major && (BN / CG) % 64 != 0) CG = 1;
+  if (splits > 1) {
+    BN = 128;
+    CG = 2;
+  }
+  if (BN == 64 || (b_mn_major && (BN / CG) % 64 != 0)) CG = 1;
 
   CUtensorMap ta, tb;
   int rc;
@@ -612,7 +635,7 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   if (rc) return rc;
   // bf16 outputs without a residual leave through swizzled smem + TMA stores of 128 x 64 tiles (coalesced 128 B rows)
   // (N % 8: only whole 16-byte chunks are sent through the bulk-tensor store; ragged N takes the direct path)
-  const int tma_store = (d_dt == OFAB_BF16 && residual == nullptr && N % 8 == 0) ? 1 : 0;
+  const int tma_store = (d_dt == OFAB_BF16 && residual == nullptr && N % 8 == 0 && splits <= 1) ? 1 : 0;
   int tma_store_f = tma_store;
   if (getenv("OFAB_GEMM_FORCE_TMA_STORE") && d_dt == OFAB_BF16 && residual == nullptr) tma_store_f = 1;  // development probe
   CUtensorMap td;
@@ -632,6 +655,13 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
   p.ldd = ldd;
   p.d_bf16 = d_dt == OFAB_BF16;
   p.tma_store = tma_store_f;
+  {
+    const int nkb = (int)((K + BK - 1) / BK);
+    p.splits = splits > 1 ? splits : 1;
+    p.kb_per_split = (nkb + p.splits - 1) / p.splits;
+    p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // no empty K range
+    p.split_stride = split_stride;
+  }
   p.dbg = 0;
   if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
   cudaStream_t st = (cudaStream_t)stream;
@@ -645,11 +675,100 @@ extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, in
     if (!a_mn_major && b_mn_major) GO(256, false, true);
     if (a_mn_major && !b_mn_major) GO(256, true, false);
     GO(256, true, true);
-  } else {
+  } else if (BN == 128) {
     if (!a_mn_major && !b_mn_major) GO(128, false, false);
     if (!a_mn_major && b_mn_major) GO(128, false, true);
     if (a_mn_major && !b_mn_major) GO(128, true, false);
     GO(128, true, true);
+  } else {
+    if (!a_mn_major && !b_mn_major) return launch<64, false, false, 1>(ta, tb, td, p, st);
+    if (!a_mn_major && b_mn_major) return launch<64, false, true, 1>(ta, tb, td, p, st);
+    if (a_mn_major && !b_mn_major) return launch<64, true, false, 1>(ta, tb, td, p, st);
+    return launch<64, true, true, 1>(ta, tb, td, p, st);
   }
 #undef GO
+}
+
+// out[r, c] = sum_s ws[s, r, c]  (fp32 slabs [M, N]) -> D (bf16 or fp32, leading dimension ldd)
+template <typename TO>
+__global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t slab, int64_t M, int64_t N, TO* __restrict__ D,
+                                     int64_t ldd) {
+  const int64_t nvec = M * (N / 4);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (N / 4), c = (i % (N / 4)) * 4;
+    float4 acc = *reinterpret_cast<const float4*>(ws + r * N + c);
+    for (int sp = 1; sp < splits; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)sp * slab + r * N + c);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (sizeof(TO) == 4) {
+      *reinterpret_cast<float4*>(reinterpret_cast<float*>(D) + r * ldd + c) = acc;
+    } else {
+      uint2 u;
+      u.x = pack_bf16(acc.x, acc.y);
+      u.y = pack_bf16(acc.z, acc.w);
+      *reinterpret_cast<uint2*>(reinterpret_cast<bf16*>(D) + r * ldd + c) = u;
+    }
+  }
+}
+
+// Split-K plan for a GEMM whose output has too few 256 x 128 tiles to fill the chip (wgrads of narrow layers: the
+// tile count does not grow with the batch, the K loop does).  Model: one k-block (128 deep) of a pair tile takes
+// ~0.68 us; the reduction reads `splits` fp32 slabs at ~4 TB/s.  Returns 1 when splitting does not pay.
+int splitk_plan(int64_t M, int64_t N, int64_t K) {
+  if (N % 8 != 0 || K < 16 * 128) return 1;  // short contractions: nothing to win
+  const int64_t tiles = ((M + 255) / 256) * ((N + 127) / 128);
+  const int64_t units = ofab_sm_count() / 2;
+  const int64_t nkb = (K + 127) / 128;
+  int best = 1;
+  double best_t = 1e30;
+  const int cand[6] = {1, 2, 3, 4, 6, 8};
+  for (int ci = 0; ci < 6; ++ci) {
+    const int sp = cand[ci];
+    if (sp > 1 && nkb / sp < 4) break;
+    const double waves = (double)((tiles * sp + units - 1) / units);
+    const double t_gemm = waves * (double)((nkb + sp - 1) / sp) * 0.68 + 4.0;
+    const double t_red = sp > 1 ? 2.5 + (sp + 0.5) * (double)M * (double)N * 4.0 / 4e6 : 0.0;
+    if (t_gemm + t_red < best_t - 1e-9) {
+      best_t = t_gemm + t_red;
+      best = sp;
+    }
+  }
+  return best;
+}
+
+}  // namespace
+
+extern "C" int ofab_gemm_bf16(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major, const void* B,
+                              int64_t ldb, int b_mn_major, const void* bias, const float* residual, int64_t ldr, void* D,
+                              int64_t ldd, int d_dt, ofab_stream_t stream) {
+  return gemm_run(M, N, K, A, lda, a_mn_major, B, ldb, b_mn_major, bias, residual, ldr, D, ldd, d_dt, 1, 0, stream);
+}
+
+extern "C" int64_t ofab_gemm_splitk_workspace_elems(int64_t M, int64_t N, int64_t K) {
+  const int sp = (M > 0 && N > 0 && K > 0) ? splitk_plan(M, N, K) : 1;
+  return sp > 1 ? (int64_t)sp * M * N : 0;
+}
+
+extern "C" int ofab_gemm_bf16_splitk(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_mn_major, const void* B,
+                                     int64_t ldb, int b_mn_major, void* D, int64_t ldd, int d_dt, float* workspace,
+                                     int64_t workspace_elems, ofab_stream_t stream) {
+  OFAB_REQUIRE(M > 0 && N > 0 && K > 0, "ofab_gemm_bf16_splitk: empty problem");
+  const int sp = splitk_plan(M, N, K);
+  if (sp <= 1) return gemm_run(M, N, K, A, lda, a_mn_major, B, ldb, b_mn_major, nullptr, nullptr, 0, D, ldd, d_dt, 1, 0, stream);
+  OFAB_REQUIRE(workspace != nullptr && workspace_elems >= (int64_t)sp * M * N && ((uintptr_t)workspace & 15) == 0,
+               "ofab_gemm_bf16_splitk: workspace too small (need ofab_gemm_splitk_workspace_elems = %lld fp32) or unaligned",
+               (long long)((int64_t)sp * M * N));
+  OFAB_REQUIRE(d_dt == OFAB_BF16 || d_dt == OFAB_F32, "ofab_gemm_bf16_splitk: bad d_dt");
+  OFAB_REQUIRE(ldd >= N && ldd % 4 == 0 && ((uintptr_t)D & 15) == 0, "ofab_gemm_bf16_splitk: D must be 16-byte aligned with ldd %% 4 == 0");
+  int rc = gemm_run(M, N, K, A, lda, a_mn_major, B, ldb, b_mn_major, nullptr, nullptr, 0, workspace, N, OFAB_F32, sp, M * N, stream);
+  if (rc) return rc;
+  const int64_t nvec = M * (N / 4);
+  const int grid = (int)((nvec + 255) / 256 < (int64_t)ofab_sm_count() * 8 ? (nvec + 255) / 256 : (int64_t)ofab_sm_count() * 8);
+  if (d_dt == OFAB_F32)
+    splitk_reduce_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, sp, M * N, M, N, (float*)D, ldd);
+  else
+    splitk_reduce_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, sp, M * N, M, N, (bf16*)D, ldd);
+  OFAB_LAUNCH_CHECK("ofab_gemm_bf16_splitk reduce");
+  return OFAB_OK;
 }

@@ -1,21 +1,27 @@
 // LayerNorm family (HBM-bound): plain / GELU-fused LN, the fused LN -> +residual -> LN junction,
 // and the column reductions that finish dgamma/dbeta and bias gradients.
 //
-// Layout: one row is owned by cols/8 threads (rounded up to whole warps), one 8-column vector per thread, so a
-// row is read from HBM exactly once and written once and register use stays low enough for ~36 resident warps
-// per SM.  Backward kernels are persistent over rows (fixed grid of OFAB_LN_PARTIAL_ROWS blocks) so per-column
-// dgamma/dbeta partial sums stay in registers and leave as one row per block.
+// Layout: one row is owned by cols/8 threads (rounded up to whole warps), one 8-column vector per thread; a CTA of
+// ~384 threads works on a GROUP of blockDim/tpr consecutive rows per iteration.  Every kernel is persistent (grid =
+// 2 CTAs per SM) and reads its inputs through an ASYNC ROW PIPELINE: the contiguous bytes of the next row groups are
+// fetched by the TMA engine (cp.async.bulk, 1-D) into a shared-memory ring while the current group is being
+// reduced, so the bytes in flight per SM (3-4 groups x 6-36 KB per CTA) do not depend on register-held loads or on
+// occupancy.  Threads take their 16/32 bytes from shared memory, results leave with plain vector stores.
+// Backward kernels keep per-column dgamma/dbeta partial sums in registers over their whole row range and emit one
+// partial row per CTA (OFAB_LN_PARTIAL_ROWS rows, finished by reduce_partials).
+#include <mutex>
+#include <unordered_set>
+
 #include "common.cuh"
 
-#define OFAB_LN_PARTIAL_ROWS 888  // 6 x 148 SMs: persistent backward grid
+#define OFAB_LN_PARTIAL_ROWS 296  // 2 x 148 SMs: persistent backward grid = resident CTAs
 
 extern "C" int ofab_ln_partial_rows(void) { return OFAB_LN_PARTIAL_ROWS; }
 
 namespace {
 
 // Thread layout of every LayerNorm kernel: a row is owned by `tpr` threads (a multiple of 32), each holding ONE
-// vector of 8 consecutive columns, so per-thread state is tiny and many warps stay resident to cover HBM
-// latency; a block of 384 (512 for cols > 3072) threads works on blockDim/tpr rows at a time.
+// vector of 8 consecutive columns; a block of rpb * tpr threads works on rpb rows at a time.
 struct RowCtx {
   int tpr, rpb, rib, lane_in_row, wir, wpr, c;
   bool col_ok;
@@ -32,34 +38,85 @@ __device__ __forceinline__ RowCtx row_ctx(int tpr, int cols) {
   r.col_ok = r.c < cols && r.rib < r.rpb;
   return r;
 }
-// sum over the threads of one row group; all row groups of the block call this together
-__device__ __forceinline__ float group_sum(float v, float* red /* [16][16] */, const RowCtx& r) {
+
+// Sums over the threads of one row group; all threads of the block call these together.  Cross-warp step: one
+// partial per warp goes to shared memory, then every thread reads the partial of warp (lane & 15) of its row and
+// finishes with a 16-lane butterfly (wpr <= 16).  `red` is double-buffered ([2][256] values) so ONE __syncthreads per
+// call suffices: a buffer is rewritten two calls later, after every thread has passed the barrier in between.
+// `sync_always`: barrier even when rows are one warp wide (callers use it to release a pipeline stage).
+__device__ __forceinline__ float group_sum(float v, float* red, int& flip, const RowCtx& r, bool sync_always) {
   v = warp_sum(v);
-  if (r.wpr == 1) return v;
+  if (r.wpr == 1) {
+    if (sync_always) __syncthreads();
+    return v;
+  }
+  float* buf = red + flip * 256;
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) buf[r.rib * 16 + r.wir] = v;
   __syncthreads();
-  if ((threadIdx.x & 31) == 0 && r.rib < 16) red[r.rib * 16 + r.wir] = v;
-  __syncthreads();
-  float s = 0.f;
-  for (int w = 0; w < r.wpr; ++w) s += red[(r.rib < 16 ? r.rib : 0) * 16 + w];
+  const int l = threadIdx.x & 15;
+  float s = l < r.wpr ? buf[r.rib * 16 + l] : 0.f;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
 }
-__device__ __forceinline__ void group_sum2(float& a, float& b, float* red /* [2][16][16] */, const RowCtx& r) {
+__device__ __forceinline__ void group_sum2(float& a, float& b, float2* red, int& flip, const RowCtx& r, bool sync_always) {
   a = warp_sum(a);
   b = warp_sum(b);
-  if (r.wpr == 1) return;
-  __syncthreads();
-  if ((threadIdx.x & 31) == 0 && r.rib < 16) {
-    red[r.rib * 16 + r.wir] = a;
-    red[256 + r.rib * 16 + r.wir] = b;
+  if (r.wpr == 1) {
+    if (sync_always) __syncthreads();
+    return;
   }
+  float2* buf = red + flip * 256;
+  flip ^= 1;
+  if ((threadIdx.x & 31) == 0) buf[r.rib * 16 + r.wir] = make_float2(a, b);
   __syncthreads();
-  float sa = 0.f, sb = 0.f;
-  for (int w = 0; w < r.wpr; ++w) {
-    sa += red[(r.rib < 16 ? r.rib : 0) * 16 + w];
-    sb += red[256 + (r.rib < 16 ? r.rib : 0) * 16 + w];
+  const int l = threadIdx.x & 15;
+  float2 s = l < r.wpr ? buf[r.rib * 16 + l] : make_float2(0.f, 0.f);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
   }
-  a = sa;
-  b = sb;
+  a = s.x;
+  b = s.y;
+}
+
+// ---- persistent schedule + async input ring --------------------------------------------------------------
+// Iteration `it` of a CTA works on row group g = blockIdx.x + it * gridDim.x (rows g*rpb .. g*rpb+rpb-1, contiguous
+// in memory).  Dynamic shared memory: [128 B of mbarriers][NST stages]; a stage holds, for each of the NIN inputs,
+// the rpb rows of the group back to back.
+constexpr int kLnBarBytes = 128;
+template <int NIN>
+struct RowInputs {
+  const uint8_t* p[NIN];
+  uint32_t row_bytes[NIN];  // cols * sizeof(element)
+  uint32_t off[NIN];        // byte offset of input k inside a stage (rpb * sum of earlier row_bytes)
+  uint32_t stage_bytes;
+};
+template <int NIN>
+__device__ __forceinline__ void ring_issue(const RowInputs<NIN>& in, uint8_t* ring, uint64_t* bars, int stage, int64_t it, int64_t rows, int rpb) {
+  const int64_t row0 = ((int64_t)blockIdx.x + it * gridDim.x) * rpb;
+  const int64_t left = rows - row0;
+  const uint32_t nr = (uint32_t)(left < rpb ? left : rpb);
+  uint32_t total = 0;
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) total += nr * in.row_bytes[k];
+  rowpipe::expect(bars + stage, total);
+  uint8_t* dst = ring + (size_t)stage * in.stage_bytes;
+#pragma unroll
+  for (int k = 0; k < NIN; ++k) rowpipe::load(dst + in.off[k], in.p[k] + row0 * in.row_bytes[k], nr * in.row_bytes[k], bars + stage);
+}
+// common prologue: barrier init + first NST groups in flight.  Returns this CTA's iteration count.
+template <int NIN, int NST>
+__device__ __forceinline__ int64_t ring_start(const RowInputs<NIN>& in, uint8_t* ring, uint64_t* bars, int64_t rows, int rpb) {
+  const int64_t ngroups = (rows + rpb - 1) / rpb;
+  const int64_t my_n = (int64_t)blockIdx.x < ngroups ? (ngroups - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  if (threadIdx.x == 0) rowpipe::init(bars, NST);
+  __syncthreads();
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NST && i < my_n; ++i) ring_issue<NIN>(in, ring, bars, i, i, rows, rpb);
+  return my_n;
 }
 
 // Write this block's per-column partial sums (one f8 per thread and slab) as row blockIdx.x of every slab,
@@ -84,43 +141,58 @@ __device__ __forceinline__ void flush_partials(f8 (&acc)[NS], float* __restrict_
   }
 }
 
+#define LN_BOUNDS(MAXT) __launch_bounds__(MAXT, (MAXT) > 384 ? 1 : 2)  // MAXT = 288 / 384: two CTAs per SM; 512: one
+
 // ------------------------------------------------------------------------------------ forward
-template <typename TX, typename TY, bool GELU>
-__global__ void __launch_bounds__(512) ln_fwd_kernel(const TX* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
-                                                     TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows,
-                                                     int cols, float eps, int tpr) {
-  __shared__ float red[256];
+template <typename TX, typename TY, bool GELU, int MAXT>
+__global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
+                                              TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int cols,
+                                              float eps, int tpr) {
+  constexpr int NST = 6;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ float red[512];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+  uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
+  RowInputs<1> in;
+  in.p[0] = reinterpret_cast<const uint8_t*>(x);
+  in.row_bytes[0] = (uint32_t)cols * sizeof(TX);
+  in.off[0] = 0;
+  in.stage_bytes = (uint32_t)r.rpb * in.row_bytes[0];
+  const int64_t my_n = ring_start<1, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
   f8 g, b;
   if (r.col_ok) {
     g = load8(gamma + r.c);
     b = load8(beta + r.c);
   }
-  const int64_t ngroups = (rows + r.rpb - 1) / r.rpb;
-  for (int64_t rb = blockIdx.x; rb < ngroups; rb += gridDim.x) {
-    const int64_t row = rb * r.rpb + r.rib;
+  int stage = 0, flip = 0;
+  uint32_t phase = 0;
+  for (int64_t it = 0; it < my_n; ++it) {
+    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
     const bool live = r.col_ok && row < rows;
+    rowpipe::wait(bars + stage, phase);
     f8 v;
     float s = 0.f;
     if (live) {
-      v = load8(x + row * cols + r.c);
+      v = load8(reinterpret_cast<const TX*>(ring + (size_t)stage * in.stage_bytes) + r.rib * cols + r.c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (GELU) v.v[j] = gelu_f(v.v[j]);
         s += v.v[j];
       }
     }
-    const float mu = group_sum(s, red, r) * inv_n;
+    const float mu = group_sum(s, red, flip, r, true) * inv_n;  // barrier: every thread has consumed the stage
+    if (threadIdx.x == 0 && it + NST < my_n) ring_issue<1>(in, ring, bars, stage, it + NST, rows, r.rpb);
     float q = 0.f;
     if (live) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v.v[j] - mu;
-        q += d * d;
+        v.v[j] -= mu;
+        q = fmaf(v.v[j], v.v[j], q);
       }
     }
-    const float rs = rsqrtf(group_sum(q, red, r) * inv_n + eps);
+    const float rs = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
     if (live) {
       if (r.lane_in_row == 0) {
         mean[row] = mu;
@@ -128,20 +200,36 @@ __global__ void __launch_bounds__(512) ln_fwd_kernel(const TX* __restrict__ x, c
       }
       f8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = (v.v[j] - mu) * rs * g.v[j] + b.v[j];
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(v.v[j] * rs, g.v[j], b.v[j]);
       store8(y + row * cols + r.c, o);
+    }
+    if (++stage == NST) {
+      stage = 0;
+      phase ^= 1;
     }
   }
 }
 
 // ----------------------------------------------------------------------------------- backward
-template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM>
-__global__ void __launch_bounds__(512) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const bf16* __restrict__ gamma,
-                                                     const float* __restrict__ mean, const float* __restrict__ rstd, TDX* __restrict__ dx,
-                                                     float* __restrict__ partial, int64_t rows, int cols, int tpr) {
-  __shared__ float red[512];
-  extern __shared__ float fbuf[];
+template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM, int MAXT>
+__global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const bf16* __restrict__ gamma,
+                                              const float* __restrict__ mean, const float* __restrict__ rstd, TDX* __restrict__ dx,
+                                              float* __restrict__ partial, int64_t rows, int cols, int tpr) {
+  constexpr int NST = 4;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ float2 red[512];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+  uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
+  RowInputs<2> in;
+  in.p[0] = reinterpret_cast<const uint8_t*>(x);
+  in.p[1] = reinterpret_cast<const uint8_t*>(dy);
+  in.row_bytes[0] = (uint32_t)cols * sizeof(TX);
+  in.row_bytes[1] = (uint32_t)cols * sizeof(TDY);
+  in.off[0] = 0;
+  in.off[1] = (uint32_t)r.rpb * in.row_bytes[0];
+  in.stage_bytes = (uint32_t)r.rpb * (in.row_bytes[0] + in.row_bytes[1]);
+  const int64_t my_n = ring_start<2, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
   f8 g;
   if (r.col_ok) g = load8(gamma + r.c);
@@ -150,18 +238,21 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const TDY* __restrict__ dy,
   for (int s = 0; s < 3; ++s)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
-  const int64_t ngroups = (rows + r.rpb - 1) / r.rpb;
-  for (int64_t rb = blockIdx.x; rb < ngroups; rb += gridDim.x) {
-    const int64_t row = rb * r.rpb + r.rib;
+  int stage = 0, flip = 0;
+  uint32_t phase = 0;
+  for (int64_t it = 0; it < my_n; ++it) {
+    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
     const bool live = r.col_ok && row < rows;
-    float mu = 0.f, rs = 0.f;
+    rowpipe::wait(bars + stage, phase);
+    float rs = 0.f;
     f8 xh, d, gp;
     float s1 = 0.f, s2 = 0.f;
     if (live) {
-      mu = mean[row];
+      const uint8_t* st = ring + (size_t)stage * in.stage_bytes;
+      const f8 pre = load8(reinterpret_cast<const TX*>(st) + r.rib * cols + r.c);
+      d = load8(reinterpret_cast<const TDY*>(st + in.off[1]) + r.rib * cols + r.c);
       rs = rstd[row];
-      const f8 pre = load8(x + row * cols + r.c);
-      d = load8(dy + row * cols + r.c);
+      const float nmr = -mean[row] * rs;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float a = pre.v[j];
@@ -171,43 +262,61 @@ __global__ void __launch_bounds__(512) ln_bwd_kernel(const TDY* __restrict__ dy,
           gp.v[j] = cdf + px;
           a *= cdf;
         }
-        xh.v[j] = (a - mu) * rs;
-        acc[0].v[j] += d.v[j] * xh.v[j];
+        xh.v[j] = fmaf(a, rs, nmr);
+        acc[0].v[j] = fmaf(d.v[j], xh.v[j], acc[0].v[j]);
         acc[1].v[j] += d.v[j];
         const float gg = d.v[j] * g.v[j];
         d.v[j] = gg;
-        s1 += gg * xh.v[j];
+        s1 = fmaf(gg, xh.v[j], s1);
         s2 += gg;
       }
     }
-    group_sum2(s1, s2, red, r);
-    const float c1 = s1 * inv_n, c2 = s2 * inv_n;
+    group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
+    if (threadIdx.x == 0 && it + NST < my_n) ring_issue<2>(in, ring, bars, stage, it + NST, rows, r.rpb);
     if (live) {
+      const float c1 = -s1 * inv_n * rs, c2 = -s2 * inv_n * rs;
       f8 o;
       if (ACCUM) o = load8(reinterpret_cast<const TDX*>(dx) + row * cols + r.c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        float t = rs * (d.v[j] - c2 - xh.v[j] * c1);
+        float t = fmaf(xh.v[j], c1, fmaf(d.v[j], rs, c2));  // rs * (d - mean(d) - xh * mean(d xh))
         if (GELU) t *= gp.v[j];
         acc[2].v[j] += t;
         o.v[j] = ACCUM ? o.v[j] + t : t;
       }
       store8(dx + row * cols + r.c, o);
     }
+    if (++stage == NST) {
+      stage = 0;
+      phase ^= 1;
+    }
   }
-  flush_partials<3>(acc, partial, cols, r, fbuf);
+  flush_partials<3>(acc, partial, cols, r, reinterpret_cast<float*>(ring));
 }
 
 // ---------------------------------------------------------------- fused LN -> +res -> LN
 // HAS_LN1 = false: x_new = x + a (no first LayerNorm): the deferred residual add of an FFN output fused
 // with the next block's pre-LayerNorm.
-template <bool HAS_LN1>
-__global__ void __launch_bounds__(512) ln_res_ln_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ x, const bf16* __restrict__ g1,
-                                                            const bf16* __restrict__ b1, const bf16* __restrict__ g2, const bf16* __restrict__ b2,
-                                                            float* __restrict__ x_new, bf16* __restrict__ y, float* __restrict__ stats,
-                                                            int64_t rows, int cols, float eps, int tpr) {
-  __shared__ float red[256];
+template <bool HAS_LN1, int MAXT>
+__global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ x, const bf16* __restrict__ g1,
+                                                     const bf16* __restrict__ b1, const bf16* __restrict__ g2, const bf16* __restrict__ b2,
+                                                     float* __restrict__ x_new, bf16* __restrict__ y, float* __restrict__ stats,
+                                                     int64_t rows, int cols, float eps, int tpr) {
+  constexpr int NST = 3;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ float red[512];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+  uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
+  RowInputs<2> in;
+  in.p[0] = reinterpret_cast<const uint8_t*>(x);
+  in.p[1] = reinterpret_cast<const uint8_t*>(a);
+  in.row_bytes[0] = (uint32_t)cols * 4u;
+  in.row_bytes[1] = (uint32_t)cols * 2u;
+  in.off[0] = 0;
+  in.off[1] = (uint32_t)r.rpb * in.row_bytes[0];
+  in.stage_bytes = (uint32_t)r.rpb * (in.row_bytes[0] + in.row_bytes[1]);
+  const int64_t my_n = ring_start<2, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
   f8 gg1, bb1, gg2, bb2;
   if (r.col_ok) {
@@ -218,50 +327,59 @@ __global__ void __launch_bounds__(512) ln_res_ln_fwd_kernel(const bf16* __restri
     gg2 = load8(g2 + r.c);
     bb2 = load8(b2 + r.c);
   }
-  const int64_t ngroups = (rows + r.rpb - 1) / r.rpb;
-  for (int64_t rb = blockIdx.x; rb < ngroups; rb += gridDim.x) {
-    const int64_t row = rb * r.rpb + r.rib;
+  int stage = 0, flip = 0;
+  uint32_t phase = 0;
+  for (int64_t it = 0; it < my_n; ++it) {
+    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
     const bool live = r.col_ok && row < rows;
+    rowpipe::wait(bars + stage, phase);
     f8 v, xx;
     float s = 0.f;
     if (live) {
-      v = load8(a + row * cols + r.c);
-      xx = load8(x + row * cols + r.c);
+      const uint8_t* st = ring + (size_t)stage * in.stage_bytes;
+      xx = load8(reinterpret_cast<const float*>(st) + r.rib * cols + r.c);
+      v = load8(reinterpret_cast<const bf16*>(st + in.off[1]) + r.rib * cols + r.c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) s += v.v[j];
     }
+    // (first) barrier of the iteration: every thread has consumed the stage -> refill it
     float m1 = 0.f, r1 = 1.f;
     if (HAS_LN1) {
-      m1 = group_sum(s, red, r) * inv_n;
+      m1 = group_sum(s, red, flip, r, true) * inv_n;
+    } else {
+      __syncthreads();
+    }
+    if (threadIdx.x == 0 && it + NST < my_n) ring_issue<2>(in, ring, bars, stage, it + NST, rows, r.rpb);
+    if (HAS_LN1) {
       float q = 0.f;
       if (live) {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float d = v.v[j] - m1;
-          q += d * d;
+          v.v[j] -= m1;
+          q = fmaf(v.v[j], v.v[j], q);
         }
       }
-      r1 = rsqrtf(group_sum(q, red, r) * inv_n + eps);
+      r1 = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
     }
     s = 0.f;
     if (live) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v.v[j] = HAS_LN1 ? xx.v[j] + ((v.v[j] - m1) * r1 * gg1.v[j] + bb1.v[j]) : xx.v[j] + v.v[j];
+        v.v[j] = HAS_LN1 ? xx.v[j] + fmaf(v.v[j] * r1, gg1.v[j], bb1.v[j]) : xx.v[j] + v.v[j];
         s += v.v[j];
       }
       store8(x_new + row * cols + r.c, v);
     }
-    const float m2 = group_sum(s, red, r) * inv_n;
+    const float m2 = group_sum(s, red, flip, r, false) * inv_n;
     float q = 0.f;
     if (live) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float d = v.v[j] - m2;
-        q += d * d;
+        v.v[j] -= m2;
+        q = fmaf(v.v[j], v.v[j], q);
       }
     }
-    const float r2 = rsqrtf(group_sum(q, red, r) * inv_n + eps);
+    const float r2 = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
     if (live) {
       if (r.lane_in_row == 0) {
         stats[row] = m1;
@@ -271,21 +389,45 @@ __global__ void __launch_bounds__(512) ln_res_ln_fwd_kernel(const bf16* __restri
       }
       f8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = (v.v[j] - m2) * r2 * gg2.v[j] + bb2.v[j];
+      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(v.v[j] * r2, gg2.v[j], bb2.v[j]);
       store8(y + row * cols + r.c, o);
+    }
+    if (++stage == NST) {
+      stage = 0;
+      phase ^= 1;
     }
   }
 }
 
-template <bool HAS_LN1>
-__global__ void __launch_bounds__(512) ln_res_ln_bwd_kernel(const float* __restrict__ dxn, const bf16* __restrict__ dy, const bf16* __restrict__ a,
-                                                            const float* __restrict__ x_new, const bf16* __restrict__ g1,
-                                                            const bf16* __restrict__ g2, const float* __restrict__ stats,
-                                                            float* __restrict__ dxt, bf16* __restrict__ da, float* __restrict__ partial,
-                                                            int64_t rows, int cols, int tpr) {
-  __shared__ float red[512];
-  extern __shared__ float fbuf[];
+template <bool HAS_LN1, int MAXT>
+__global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ dxn, const bf16* __restrict__ dy, const bf16* __restrict__ a,
+                                                     const float* __restrict__ x_new, const bf16* __restrict__ g1,
+                                                     const bf16* __restrict__ g2, const float* __restrict__ stats,
+                                                     float* __restrict__ dxt, bf16* __restrict__ da, float* __restrict__ partial,
+                                                     int64_t rows, int cols, int tpr) {
+  constexpr int NST = 2;
+  constexpr int NIN = HAS_LN1 ? 4 : 3;
+  extern __shared__ __align__(128) uint8_t dsm[];
+  __shared__ float2 red[512];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
+  uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
+  RowInputs<NIN> in;
+  in.p[0] = reinterpret_cast<const uint8_t*>(x_new);
+  in.p[1] = reinterpret_cast<const uint8_t*>(dxn);
+  in.p[2] = reinterpret_cast<const uint8_t*>(dy);
+  in.row_bytes[0] = in.row_bytes[1] = (uint32_t)cols * 4u;
+  in.row_bytes[2] = (uint32_t)cols * 2u;
+  in.off[0] = 0;
+  in.off[1] = (uint32_t)r.rpb * (uint32_t)cols * 4u;
+  in.off[2] = (uint32_t)r.rpb * (uint32_t)cols * 8u;
+  if (HAS_LN1) {
+    in.p[NIN - 1] = reinterpret_cast<const uint8_t*>(a);
+    in.row_bytes[NIN - 1] = (uint32_t)cols * 2u;
+    in.off[NIN - 1] = (uint32_t)r.rpb * (uint32_t)cols * 10u;
+  }
+  in.stage_bytes = (uint32_t)r.rpb * (uint32_t)cols * (HAS_LN1 ? 12u : 10u);
+  const int64_t my_n = ring_start<NIN, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
   f8 gg1, gg2;
   if (r.col_ok) {
@@ -297,48 +439,58 @@ __global__ void __launch_bounds__(512) ln_res_ln_bwd_kernel(const float* __restr
   for (int s = 0; s < 5; ++s)
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
-  const int64_t ngroups = (rows + r.rpb - 1) / r.rpb;
-  for (int64_t rb = blockIdx.x; rb < ngroups; rb += gridDim.x) {
-    const int64_t row = rb * r.rpb + r.rib;
+  int stage = 0, flip = 0;
+  uint32_t phase = 0;
+  for (int64_t it = 0; it < my_n; ++it) {
+    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
     const bool live = r.col_ok && row < rows;
-    float m1 = 0.f, r1 = 0.f, m2 = 0.f, r2 = 0.f;
-    f8 xh, d, up, aa;
+    rowpipe::wait(bars + stage, phase);
+    float m1 = 0.f, r1 = 0.f, r2 = 0.f;
+    f8 xh, d, tot;
+    uint4 a_raw = make_uint4(0u, 0u, 0u, 0u);  // the bf16 row of `a` stays packed until LN1's backward needs it
     float s1 = 0.f, s2 = 0.f;
     if (live) {
-      m1 = stats[row]; r1 = stats[rows + row]; m2 = stats[2 * rows + row]; r2 = stats[3 * rows + row];
-      const f8 xx = load8(x_new + row * cols + r.c);
-      d = load8(dy + row * cols + r.c);
-      up = load8(dxn + row * cols + r.c);
-      if (HAS_LN1) aa = load8(a + row * cols + r.c);
+      const uint8_t* st = ring + (size_t)stage * in.stage_bytes;
+      const int e = r.rib * cols + r.c;
+      const f8 xx = load8(reinterpret_cast<const float*>(st) + e);
+      tot = load8(reinterpret_cast<const float*>(st + in.off[1]) + e);  // upstream d x_new
+      d = load8(reinterpret_cast<const bf16*>(st + in.off[2]) + e);
+      if (HAS_LN1) a_raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(st + in.off[NIN - 1]) + e);
+      m1 = stats[row];
+      r1 = stats[rows + row];
+      r2 = stats[3 * rows + row];
+      const float nmr = -stats[2 * rows + row] * r2;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        xh.v[j] = (xx.v[j] - m2) * r2;
-        acc[2].v[j] += d.v[j] * xh.v[j];
+        xh.v[j] = fmaf(xx.v[j], r2, nmr);
+        acc[2].v[j] = fmaf(d.v[j], xh.v[j], acc[2].v[j]);
         acc[3].v[j] += d.v[j];
         const float t = d.v[j] * gg2.v[j];
         d.v[j] = t;
-        s1 += t * xh.v[j];
+        s1 = fmaf(t, xh.v[j], s1);
         s2 += t;
       }
     }
-    group_sum2(s1, s2, red, r);
-    float c1 = s1 * inv_n, c2 = s2 * inv_n;
-    s1 = s2 = 0.f;
-    f8 tot;
+    group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
+    if (threadIdx.x == 0 && it + NST < my_n) ring_issue<NIN>(in, ring, bars, stage, it + NST, rows, r.rpb);
+    float t1 = 0.f, t2 = 0.f;
     if (live) {
+      const float c1 = -s1 * inv_n * r2, c2 = -s2 * inv_n * r2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tot.v[j] = up.v[j] + r2 * (d.v[j] - c2 - xh.v[j] * c1);
+      for (int j = 0; j < 8; ++j) tot.v[j] += fmaf(xh.v[j], c1, fmaf(d.v[j], r2, c2));  // + LN2'(dy)
       store8(dxt + row * cols + r.c, tot);
       if (HAS_LN1) {
+        const f8 aa = unpack8(a_raw);
+        const float nm1 = -m1 * r1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh.v[j] = (aa.v[j] - m1) * r1;
-          acc[0].v[j] += tot.v[j] * xh.v[j];
+          xh.v[j] = fmaf(aa.v[j], r1, nm1);
+          acc[0].v[j] = fmaf(tot.v[j], xh.v[j], acc[0].v[j]);
           acc[1].v[j] += tot.v[j];
           const float t = tot.v[j] * gg1.v[j];
           d.v[j] = t;
-          s1 += t * xh.v[j];
-          s2 += t;
+          t1 = fmaf(t, xh.v[j], t1);
+          t2 += t;
         }
       } else {
         store8(da + row * cols + r.c, tot);  // d a = d x_new
@@ -347,21 +499,24 @@ __global__ void __launch_bounds__(512) ln_res_ln_bwd_kernel(const float* __restr
       }
     }
     if (HAS_LN1) {
-      group_sum2(s1, s2, red, r);
-      c1 = s1 * inv_n;
-      c2 = s2 * inv_n;
+      group_sum2(t1, t2, red, flip, r, false);
       if (live) {
+        const float c1 = -t1 * inv_n * r1, c2 = -t2 * inv_n * r1;
         f8 o;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o.v[j] = r1 * (d.v[j] - c2 - xh.v[j] * c1);
+          o.v[j] = fmaf(xh.v[j], c1, fmaf(d.v[j], r1, c2));
           acc[4].v[j] += o.v[j];
         }
         store8(da + row * cols + r.c, o);
       }
     }
+    if (++stage == NST) {
+      stage = 0;
+      phase ^= 1;
+    }
   }
-  flush_partials<5>(acc, partial, cols, r, fbuf);
+  flush_partials<5>(acc, partial, cols, r, reinterpret_cast<float*>(ring));
 }
 
 // ------------------------------------------------------------------------------------ colsum
@@ -417,40 +572,72 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int co
 
 // ---------------------------------------------------------------------------------- dispatch
 struct LnLaunch {
-  int tpr, block, smem;
+  int tpr, rpb, block, grid;
 };
-static inline LnLaunch ln_launch(int cols) {
+// `target`: threads per block the kernel was compiled for at 2 CTAs / SM (384: <= 80 registers; 288: <= 112)
+static inline LnLaunch ln_launch(int cols, int target = 384) {
   LnLaunch l;
-  l.tpr = ((cols / 8) + 31) / 32 * 32;           // threads per row: one 8-column vector each
-  l.block = l.tpr >= 96 ? l.tpr : 384;           // one row per block (3..16 warps); narrow rows share a block
-  l.smem = l.block * 8 * (int)sizeof(float);     // row-group combine buffer of the backward kernels
+  l.tpr = ((cols / 8) + 31) / 32 * 32;             // threads per row: one 8-column vector each
+  l.rpb = l.tpr >= target ? 1 : target / l.tpr;    // rows per block iteration (wider rows: one row, up to 512 threads, 1 CTA / SM)
+  l.block = l.rpb * l.tpr;
+  l.grid = ofab_sm_count() * (l.block > target ? 1 : 2);  // persistent: resident CTAs (see LN_BOUNDS)
+  if (l.grid > OFAB_LN_PARTIAL_ROWS) l.grid = OFAB_LN_PARTIAL_ROWS;
   return l;
 }
-static inline int ln_fwd_grid(int64_t rows, const LnLaunch& l) {
-  const int rpb = l.block / l.tpr;
-  int64_t nb = (rows + rpb - 1) / rpb;
-  const int64_t cap = (int64_t)ofab_sm_count() * 16;
-  return (int)(nb < cap ? (nb > 0 ? nb : 1) : cap);
+// dynamic shared memory: mbarriers + `nst` stages of rpb rows of all staged inputs (`bytes_per_col` = sum of their
+// element sizes); backward kernels reuse the ring to combine the row groups' partial sums (block * 8 floats)
+static inline int ln_smem(const LnLaunch& l, int cols, int bytes_per_col, int nst, bool bwd) {
+  const int ring = nst * l.rpb * cols * bytes_per_col;
+  const int fb = bwd ? l.block * 8 * (int)sizeof(float) : 0;
+  return kLnBarBytes + (ring > fb ? ring : fb);
 }
+constexpr int kLnMaxSmem = 200 * 1024;
+static int ln_configure(const void* kern) {  // opt in to > 48 KB dynamic shared memory, once per kernel
+  static std::mutex mu;
+  static std::unordered_set<const void*> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count(kern)) return OFAB_OK;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kLnMaxSmem);
+  if (e != cudaSuccess) return ofab_cuda_fail(e, "LayerNorm: cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+  done.insert(kern);
+  return OFAB_OK;
+}
+#define LN_ALIGNED16(p) ((((uintptr_t)(p)) & 15) == 0)
+// launch kernel template K<..., 384> or K<..., 512> by block size
+#define LN_GO(GRID, SMEM, TARGET, K384, K512, ...)                              \
+  do {                                                                          \
+    auto k384 = K384;                                                           \
+    auto k512 = K512;                                                           \
+    const void* kp = l.block > (TARGET) ? (const void*)k512 : (const void*)k384; \
+    int rc_ = ln_configure(kp);                                                 \
+    if (rc_) return rc_;                                                        \
+    if (l.block > (TARGET)) k512<<<GRID, l.block, SMEM, st>>>(__VA_ARGS__);     \
+    else k384<<<GRID, l.block, SMEM, st>>>(__VA_ARGS__);                        \
+  } while (0)
 
 extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const void* beta, void* y, int y_dt, float* mean,
                            float* rstd, int64_t rows, int cols, float eps, int gelu, ofab_stream_t stream) {
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_fwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(rows >= 0, "ofab_ln_fwd: rows < 0");
+  OFAB_REQUIRE(LN_ALIGNED16(x) && LN_ALIGNED16(y) && LN_ALIGNED16(gamma) && LN_ALIGNED16(beta), "ofab_ln_fwd: x / y / gamma / beta must be 16-byte aligned");
   if (rows == 0) return OFAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const LnLaunch l = ln_launch(cols);
-  const int grid = ln_fwd_grid(rows, l);
+  const int64_t ngroups = (rows + l.rpb - 1) / l.rpb;
+  const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
+  const int smem = ln_smem(l, cols, x_dt == OFAB_F32 ? 4 : 2, 6, false);
 #define ARGS(TX, TY) (const TX*)x, (const bf16*)gamma, (const bf16*)beta, (TY*)y, mean, rstd, rows, cols, eps, l.tpr
-  if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) ln_fwd_kernel<float, bf16, false><<<grid, l.block, 0, st>>>(ARGS(float, bf16));
-  else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && !gelu) ln_fwd_kernel<bf16, bf16, false><<<grid, l.block, 0, st>>>(ARGS(bf16, bf16));
-  else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && gelu) ln_fwd_kernel<bf16, bf16, true><<<grid, l.block, 0, st>>>(ARGS(bf16, bf16));
-  else if (x_dt == OFAB_F32 && y_dt == OFAB_F32 && !gelu) ln_fwd_kernel<float, float, false><<<grid, l.block, 0, st>>>(ARGS(float, float));
-  else if (x_dt == OFAB_BF16 && y_dt == OFAB_F32 && !gelu) ln_fwd_kernel<bf16, float, false><<<grid, l.block, 0, st>>>(ARGS(bf16, float));
+#define FWD(TX, TY, G) LN_GO(grid, smem, 384, (ln_fwd_kernel<TX, TY, G, 384>), (ln_fwd_kernel<TX, TY, G, 512>), ARGS(TX, TY))
+  if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) FWD(float, bf16, false);
+  else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && !gelu) FWD(bf16, bf16, false);
+  else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && gelu) FWD(bf16, bf16, true);
+  else if (x_dt == OFAB_F32 && y_dt == OFAB_F32 && !gelu) FWD(float, float, false);
+  else if (x_dt == OFAB_BF16 && y_dt == OFAB_F32 && !gelu) FWD(bf16, float, false);
   else {
     ofab_set_error("ofab_ln_fwd: unsupported dtype combination x=%d y=%d gelu=%d", x_dt, y_dt, gelu);
     return OFAB_ERR_ARG;
   }
+#undef FWD
 #undef ARGS
   OFAB_LAUNCH_CHECK("ofab_ln_fwd");
   return OFAB_OK;
@@ -461,26 +648,25 @@ extern "C" int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
                            int cols, int gelu, ofab_stream_t stream) {
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_bwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(!dx_accum || dx_dt == OFAB_F32, "ofab_ln_bwd: dx_accum needs fp32 dx");
+  OFAB_REQUIRE(LN_ALIGNED16(x) && LN_ALIGNED16(dy) && LN_ALIGNED16(dx) && LN_ALIGNED16(gamma) && LN_ALIGNED16(dgb_partial),
+               "ofab_ln_bwd: x / dy / dx / gamma / dgb_partial must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   const LnLaunch l = ln_launch(cols);
-  const int grid = OFAB_LN_PARTIAL_ROWS;
+  const int grid = OFAB_LN_PARTIAL_ROWS;  // every partial row is written (idle CTAs write zeros)
+  const int smem = ln_smem(l, cols, (x_dt == OFAB_F32 ? 4 : 2) + (dy_dt == OFAB_F32 ? 4 : 2), 4, true);
 #define ARGS(TDY, TX, TDX) (const TDY*)dy, (const TX*)x, (const bf16*)gamma, mean, rstd, (TDX*)dx, dgb_partial, rows, cols, l.tpr
-  if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && dx_accum)
-    ln_bwd_kernel<bf16, float, float, false, true><<<grid, l.block, l.smem, st>>>(ARGS(bf16, float, float));
-  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum)
-    ln_bwd_kernel<bf16, float, float, false, false><<<grid, l.block, l.smem, st>>>(ARGS(bf16, float, float));
-  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && gelu)
-    ln_bwd_kernel<bf16, bf16, bf16, true, false><<<grid, l.block, l.smem, st>>>(ARGS(bf16, bf16, bf16));
-  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && !gelu)
-    ln_bwd_kernel<bf16, bf16, bf16, false, false><<<grid, l.block, l.smem, st>>>(ARGS(bf16, bf16, bf16));
-  else if (dy_dt == OFAB_F32 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum)
-    ln_bwd_kernel<float, float, float, false, false><<<grid, l.block, l.smem, st>>>(ARGS(float, float, float));
-  else if (dy_dt == OFAB_F32 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && !gelu)
-    ln_bwd_kernel<float, bf16, bf16, false, false><<<grid, l.block, l.smem, st>>>(ARGS(float, bf16, bf16));
+#define BWD(TDY, TX, TDX, G, A) LN_GO(grid, smem, 384, (ln_bwd_kernel<TDY, TX, TDX, G, A, 384>), (ln_bwd_kernel<TDY, TX, TDX, G, A, 512>), ARGS(TDY, TX, TDX))
+  if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && dx_accum) BWD(bf16, float, float, false, true);
+  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum) BWD(bf16, float, float, false, false);
+  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && gelu) BWD(bf16, bf16, bf16, true, false);
+  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && !gelu) BWD(bf16, bf16, bf16, false, false);
+  else if (dy_dt == OFAB_F32 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum) BWD(float, float, float, false, false);
+  else if (dy_dt == OFAB_F32 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && !gelu) BWD(float, bf16, bf16, false, false);
   else {
     ofab_set_error("ofab_ln_bwd: unsupported dtype combination dy=%d x=%d dx=%d gelu=%d accum=%d", dy_dt, x_dt, dx_dt, gelu, dx_accum);
     return OFAB_ERR_ARG;
   }
+#undef BWD
 #undef ARGS
   OFAB_LAUNCH_CHECK("ofab_ln_bwd");
   return OFAB_OK;
@@ -490,14 +676,19 @@ extern "C" int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1,
                                   const void* b2, float* x_new, void* y, float* stats, int64_t rows, int cols,
                                   float eps, ofab_stream_t stream) {
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_res_ln_fwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
+  OFAB_REQUIRE(LN_ALIGNED16(a) && LN_ALIGNED16(x) && LN_ALIGNED16(x_new) && LN_ALIGNED16(y), "ofab_ln_res_ln_fwd: a / x / x_new / y must be 16-byte aligned");
   if (rows == 0) return OFAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
   const LnLaunch l = ln_launch(cols);
-  const int grid = ln_fwd_grid(rows, l);
+  const int64_t ngroups = (rows + l.rpb - 1) / l.rpb;
+  const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
+  const int smem = ln_smem(l, cols, 6, 3, false);
   if (g1 != nullptr)
-    ln_res_ln_fwd_kernel<true><<<grid, l.block, 0, st>>>((const bf16*)a, x, (const bf16*)g1, (const bf16*)b1, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
+    LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<true, 384>), (ln_res_ln_fwd_kernel<true, 512>), (const bf16*)a, x, (const bf16*)g1, (const bf16*)b1,
+          (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
   else
-    ln_res_ln_fwd_kernel<false><<<grid, l.block, 0, st>>>((const bf16*)a, x, nullptr, nullptr, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
+    LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<false, 384>), (ln_res_ln_fwd_kernel<false, 512>), (const bf16*)a, x, (const bf16*)nullptr,
+          (const bf16*)nullptr, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_fwd");
   return OFAB_OK;
 }
@@ -506,12 +697,22 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
                                   const void* g2, const float* stats, float* dx_tot, void* da, float* dgb_partial,
                                   int64_t rows, int cols, ofab_stream_t stream) {
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_res_ln_bwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
+  OFAB_REQUIRE(LN_ALIGNED16(dx_new) && LN_ALIGNED16(dy) && LN_ALIGNED16(x_new) && LN_ALIGNED16(dx_tot) && LN_ALIGNED16(da) &&
+                   LN_ALIGNED16(dgb_partial) && (g1 == nullptr || LN_ALIGNED16(a)),
+               "ofab_ln_res_ln_bwd: tensors must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  const LnLaunch l = ln_launch(cols);
-  if (g1 != nullptr)
-    ln_res_ln_bwd_kernel<true><<<OFAB_LN_PARTIAL_ROWS, l.block, l.smem, st>>>(dx_new, (const bf16*)dy, (const bf16*)a, x_new, (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
-  else
-    ln_res_ln_bwd_kernel<false><<<OFAB_LN_PARTIAL_ROWS, l.block, l.smem, st>>>(dx_new, (const bf16*)dy, nullptr, x_new, nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
+  const int grid = OFAB_LN_PARTIAL_ROWS;
+  if (g1 != nullptr) {
+    const LnLaunch l = ln_launch(cols, 288);  // 5 accumulator slabs: ~110 registers -> 288-thread CTAs, still two per SM
+    const int smem = ln_smem(l, cols, 12, 2, true);
+    LN_GO(grid, smem, 288, (ln_res_ln_bwd_kernel<true, 288>), (ln_res_ln_bwd_kernel<true, 512>), dx_new, (const bf16*)dy, (const bf16*)a, x_new,
+          (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
+  } else {
+    const LnLaunch l = ln_launch(cols);
+    const int smem = ln_smem(l, cols, 10, 2, true);
+    LN_GO(grid, smem, 384, (ln_res_ln_bwd_kernel<false, 384>), (ln_res_ln_bwd_kernel<false, 512>), dx_new, (const bf16*)dy, (const bf16*)nullptr, x_new,
+          (const bf16*)nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
+  }
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_bwd");
   return OFAB_OK;
 }

@@ -209,6 +209,15 @@ def gemm(M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldd, bias=None, residual=None
     return out
 
 
+def gemm_splitk(M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldd):
+    """out[M,N] = A * B^T for few-tile / long-K problems (weight gradients): split-K partial slabs + one reduction
+    when that pays, the plain kernel otherwise (see include/ofab.h)."""
+    n_ws = _lib.lib().ofab_gemm_splitk_workspace_elems(M, N, K)
+    ws = torch.empty(n_ws, dtype=torch.float32, device=out.device) if n_ws > 0 else None
+    _lib.call("ofab_gemm_bf16_splitk", M, N, K, _p(A), lda, int(a_mn), _p(B), ldb, int(b_mn), _p(out), ldd, _DT[out.dtype], _p(ws), n_ws, _s())
+    return out
+
+
 def _as2d(x):
     if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0:
         return x
@@ -258,7 +267,7 @@ class _LinearFn(torch.autograd.Function):
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
             dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
-            gemm(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
+            gemm_splitk(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _take_bias_hint(dy, N)  # produced for free by the LayerNorm backward that emitted dy
             if db is None:

@@ -119,7 +119,7 @@ def test_cabi_exports_every_declared_symbol():
     assert declared == set(_lib.EXPORTS), (declared ^ set(_lib.EXPORTS))
     lib = _lib.lib()
     assert lib.ofab_version() >= 100
-    assert lib.ofab_ln_partial_rows() == 888
+    assert lib.ofab_ln_partial_rows() == 296
 
 
 def test_no_cpu_fallback():

@@ -19,7 +19,7 @@ from oracle import oracle_model as om
 from util import bf16_round_state_dict, build_product, load_golden, rel_l2, to_product_slots
 
 pytestmark = pytest.mark.gpu
-SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A"]
+SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A", "large_A"]
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.json")
 
 
@@ -155,10 +155,12 @@ def test_golden_logits_from_reference():
     assert rel_l2(logits.float(), g["logits"]) <= 1.5e-2
 
 
-def test_cfg1_tiny_text_infilling_gpu():
-    """BASELINE.json configs[0] on the CUDA path: loss / lse / sampled logits vs the reference dump."""
+@pytest.mark.parametrize("name", ["cfg1_tiny", "cfg2_base", "cfg3_asr_base"])
+def test_full_size_configs_gpu(name):
+    """BASELINE.json configs[0..2] at their full model sizes on the CUDA path (cfg1 tiny text_infilling; cfg2 OFA-base
+    image_caption = bench.py's workload; cfg3 OFA-base ASR with ragged fbank lengths): loss / lse / sampled logits /
+    per-parameter gradient norms vs the dump of the reference itself (tests/golden, fp32 weights)."""
     dev = torch.device("cuda:0")
-    name = "cfg1_tiny"
     g = load_golden(name)
     sd = cases.synth_state_dict(g["spec"], seed=0)
     m = build_product(name)

@@ -158,9 +158,8 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn)
 
 
-@pytest.mark.parametrize("cg", [1, 2])
-@pytest.mark.parametrize("bn", [128, 256])
-@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+@pytest.mark.parametrize("bn,cg", [(64, 1), (128, 1), (128, 2), (256, 1), (256, 2)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
 def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg):
     """Every (BN, cta_group) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles and
     CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair)."""
@@ -182,6 +181,10 @@ def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg):
         ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, N, bias=bias)
         ref = A.float() @ B.float().t() + bias.float()
         assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn, bn, cg)
+        if N % 8 == 0:  # bf16 output through the swizzled-smem + TMA-store epilogue
+            outb = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+            ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, outb, N, bias=bias)
+            assert rel_l2(outb.float(), ref) <= 4e-3, (M, N, K, a_mn, b_mn, bn, cg)
 
 
 def test_gemm_epilogues():
@@ -216,6 +219,59 @@ def test_gemm_many_tiles_persistent():
     out = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
     ops.gemm(M, N, K, A, K, 0, B, K, 0, out, N)
     assert rel_l2(out, A.float() @ B.float().t()) <= TOL16
+
+
+@pytest.mark.parametrize("M,N,K,expect_split", [(768, 768, 8480, True), (1536, 768, 8480, True), (2304, 768, 16960, True),
+                                                 (768, 768, 2048, True), (3072, 768, 8480, False), (136, 72, 1000, False),
+                                                 (768, 776, 4100, True)])
+@pytest.mark.parametrize("a_mn,b_mn", [(1, 1), (0, 0)])
+def test_gemm_splitk(M, N, K, expect_split, a_mn, b_mn):
+    """Split-K weight-gradient GEMM (few output tiles, long contraction): partial fp32 slabs + reduction must equal the
+    plain product; ragged K tails and K ranges of unequal length included."""
+    from ofasys_b200 import _lib, ops
+
+    gen = g()
+    A, B = rnd(M, K, gen=gen, scale=0.5), rnd(N, K, gen=gen, scale=0.5)
+    Am = A.t().contiguous() if a_mn else A
+    Bm = B.t().contiguous() if b_mn else B
+    n_ws = _lib.lib().ofab_gemm_splitk_workspace_elems(M, N, K)
+    assert (n_ws > 0) == expect_split, (M, N, K, n_ws)
+    assert n_ws % (M * N) == 0
+    ref = A.float() @ B.float().t()
+    out32 = torch.full((M, N), 7.0, dtype=torch.float32, device=dev())
+    ops.gemm_splitk(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out32, N)
+    assert rel_l2(out32, ref) <= TOL32, (M, N, K)
+    out16 = torch.empty(M, N, dtype=torch.bfloat16, device=dev())
+    ops.gemm_splitk(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out16, N)
+    assert rel_l2(out16, ref) <= 4e-3, (M, N, K)
+
+
+def test_gemm_first_cuda_call_of_a_fresh_thread():
+    """The tensor-map encoder is a driver entry point: a thread that has not bound the primary context yet (a fresh
+    autograd worker whose first CUDA work is a GEMM) must still be able to launch."""
+    import threading
+
+    from ofasys_b200 import ops
+
+    gen = g()
+    M, N, K = 588, 576, 48
+    A, B = rnd(M, K, gen=gen), rnd(N, K, gen=gen)
+    out = torch.empty(M, N, dtype=torch.float32, device=dev())
+    torch.cuda.synchronize()
+    err = []
+
+    def work():
+        try:
+            ops.gemm(M, N, K, A, K, 0, B, K, 0, out, N)
+            torch.cuda.synchronize()
+        except Exception as ex:  # noqa: BLE001
+            err.append(ex)
+
+    th = threading.Thread(target=work)
+    th.start()
+    th.join()
+    assert not err, err
+    assert rel_l2(out, A.float() @ B.float().t()) <= TOL32
 
 
 @pytest.mark.parametrize("with_res", [False, True])

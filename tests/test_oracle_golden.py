@@ -10,7 +10,7 @@ from oracle import cases
 from oracle import oracle_model as om
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
-SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A"]
+SMALL = ["text_A", "text_B", "patch_B", "audio_A", "resnet_A", "video_A", "large_A"]
 
 
 def rel_l2(a, b):
@@ -76,12 +76,15 @@ def test_box_quantisation():
     assert om.quantize_box(x).tolist() == [0, 499, 997, 999]
 
 
-def test_cfg1_tiny_text_infilling():
-    """BASELINE.json configs[0]: OFA-tiny 4L/4L d=256, S=T=128, bs=2, V=50265 (checksummed)."""
-    g = load("cfg1_tiny")
+@pytest.mark.parametrize("name", ["cfg1_tiny", "cfg2_base", "cfg3_asr_base"])
+def test_full_size_configs(name):
+    """BASELINE.json configs[0..2] at their full model sizes (checksummed: V=50265 logits do not fit a fixture):
+    cfg1 OFA-tiny 4L/4L d=256 text_infilling S=T=128; cfg2 OFA-base 12L/12L image_caption (patch-embed, 257+8 -> 64);
+    cfg3 OFA-base ASR (fbank 998x80 ragged + 12-token prompt -> 128), batch 2 each."""
+    g = load(name)
     sd = cases.synth_state_dict(g["spec"], seed=0)
-    cfg = cases.oracle_cfg("cfg1_tiny")
-    slots, target = cases.make_inputs("cfg1_tiny")
+    cfg = cases.oracle_cfg(name)
+    slots, target = cases.make_inputs(name)
     torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
     loss, logits, grads = om.loss_and_grads(sd, cfg, slots, target)
     assert abs(loss.item() - g["loss"].item()) <= 1e-5 * abs(g["loss"].item())
