@@ -90,9 +90,21 @@ __device__ __forceinline__ void tma_load_2d_2sm(void* dst, const CUtensorMap* ma
       "l"(map), "r"(mbar), "r"(c0), "r"(c1)
       : "memory");
 }
-__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar) {
+// same, delivered to the same smem offset in every CTA of `cta_mask` (cluster ranks); each destination signals the
+// barrier of ITS pair's leader.  Used by 4-CTA clusters: two CTA pairs that work on adjacent N tiles of one M tile
+// share the A operand -- each CTA fetches half of its A rows' K range and multicasts it to its twin in the other pair.
+__device__ __forceinline__ void tma_load_2d_2sm_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t cta_mask) {
+  const uint32_t mbar = smem_u32(bar) & 0xFEFFFFFFu;
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(mbar), "h"(cta_mask), "r"(c0), "r"(c1)
+      : "memory");
+}
+// arrive (once the MMAs issued so far retire) on the barrier at this smem offset in every CTA of `cta_mask`
+__device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-               "h"((uint16_t)3)
+               "h"(cta_mask)
                : "memory");
 }
 __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -174,7 +186,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void*
 // both CTAs' shared memory, so per-SM smem traffic per MMA is halved.
 // BK = K elements per pipeline stage (64 or 128): one mbarrier hand-shake per BK/16 MMAs; with BK = 128 a
 // K-major operand stage holds two 64-wide swizzle atoms.
-template <int BN, bool A_MN, bool B_MN, int CG, int BK, int STAGES>
+// CL = cluster size: CG for the plain forms; 4 = two CTA pairs per cluster (CG = 2) on N-adjacent tiles of the same
+// M tile with the A operand multicast between them: A traffic from L2 is halved (the kernel is fed at ~70 B/ns per SM
+// whatever the tile shape, so bytes per FLOP, not MMA issue, bound it).
+template <int BN, bool A_MN, bool B_MN, int CG, int BK, int STAGES, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
                  const __grid_constant__ CUtensorMap tma_d, const GemmParams p) {
@@ -202,13 +217,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);  // tiles of 128*CG rows
   const int n_tiles = (p.N + BN - 1) / BN;
-  const int mn_tiles = m_tiles * n_tiles;
+  constexpr int NP = CL / CG;              // CTA pairs (CG = 2) per cluster: 1, or 2 with A multicast
+  static_assert(CL == CG || (CG == 2 && CL == 4 && BK == 128), "cluster forms: CG, or 4 = two pairs");
+  const int mn_tiles = m_tiles * (n_tiles / NP);  // work items: NP N-adjacent tiles each (host guarantees n_tiles % NP == 0)
   const int num_tiles = mn_tiles * p.splits;
   const int num_k_blocks = (p.K + BK - 1) / BK;
-  const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;  // rank in the cluster
+  const uint32_t rank = crank & 1u;                          // rank in the CTA pair
+  const uint32_t pair = crank >> 1;                          // which pair of the cluster
+  const uint32_t pair_leader = crank & ~1u;                  // cluster rank of this pair's leader CTA
   const bool leader = rank == 0;
-  const int tile0 = CG == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int tile_step = CG == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile0 = (int)(blockIdx.x / CL);
+  const int tile_step = (int)(gridDim.x / CL);
+  const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));   // both CTAs of this pair
+  const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);     // every CTA of the cluster
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
@@ -216,7 +238,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_d) : "memory");
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full_bar + i, CG);  // leader's barrier: one producer arrival per CTA of the pair
-      mbar_init(empty_bar + i, 1);
+      mbar_init(empty_bar + i, NP);  // one commit per pair whose MMAs read this CTA's stage (own pair; + the twin pair's A multicast target)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(tmem_full + i, 1);
@@ -247,12 +269,12 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       for (int t = tile0; t < num_tiles; t += tile_step) {
         const int tt = t % mn_tiles, sp = t / mn_tiles;
         const int m0 = (tt % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;  // this CTA's 128 rows
-        const int n0 = (tt / m_tiles) * BN + (int)rank * BNL;                   // this CTA's slice of the B tile
+        const int n0 = ((tt / m_tiles) * NP + (int)pair) * BN + (int)rank * BNL;  // this CTA's slice of its pair's B tile
         const int kb_begin = sp * p.kb_per_split, kb_end = min(num_k_blocks, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
           if (leader) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
-          else mbar_arrive_remote(full_bar + stage, 0);
+          else mbar_arrive_remote(full_bar + stage, pair_leader);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
           const int k0 = kb * BK;
@@ -261,7 +283,14 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             if (CG == 1) tma_load_2d(dst, map, full_bar + stage, c0, c1);
             else tma_load_2d_2sm(dst, map, full_bar + stage, c0, c1);
           };
-          if (!A_MN) {
+          if (NP == 2) {
+            // A is shared with the twin CTA (same rank, other pair): fetch ONE of the two boxes, multicast to both
+            const uint16_t twins = (uint16_t)((1u << rank) | (1u << (rank + 2)));
+            if (!(p.dbg & 8)) {
+              if (!A_MN) tma_load_2d_2sm_mc(sa + pair * (BLOCK_M * 128), &tma_a, full_bar + stage, k0 + (int)pair * 64, m0, twins);
+              else tma_load_2d_2sm_mc(sa + pair * (BK * 128), &tma_a, full_bar + stage, m0 + (int)pair * 64, k0, twins);
+            }
+          } else if (!A_MN) {
 #pragma unroll
             for (int a = 0; a < KA; ++a) load(sa + a * (BLOCK_M * 128), &tma_a, k0 + a * 64, m0);
           } else {
@@ -317,9 +346,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
             else umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
           }
           // frees the smem slot (in both CTAs when paired) once these MMAs retire
-          if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage);
+          if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage, all_mask);
           if (kb == kb_count - 1) {
-            if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as);
+            if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as, pair_mask);
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -340,7 +369,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       const uint32_t aphase = (iter >> 1) & 1;
       const int tt = t % mn_tiles, sp = t / mn_tiles;
       const int m0 = (tt % m_tiles) * (BLOCK_M * CG) + (int)rank * BLOCK_M;
-      const int n0 = (tt / m_tiles) * BN;
+      const int n0 = ((tt / m_tiles) * NP + (int)pair) * BN;
       mbar_wait(tmem_full + as, aphase);
       tcgen05_fence_after();
       const int row = m0 + rloc;
@@ -473,7 +502,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
       __syncwarp();
       if (lane == 0) {
         if (CG == 1) mbar_arrive(tmem_empty + as);
-        else mbar_arrive_remote(tmem_empty + as, 0);  // the MMA issuer waits on the leader's barrier
+        else mbar_arrive_remote(tmem_empty + as, pair_leader);  // the MMA issuer waits on its pair leader's barrier
       }
     }
     if (p.tma_store && etid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // stores landed before smem dies
@@ -533,37 +562,50 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, 
   return OFAB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG>
+template <int BN, bool A_MN, bool B_MN, int CG, int CL>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
   constexpr int BK = CG == 2 ? 128 : 64;
+  constexpr int NP = CL / CG;
   constexpr int stage_bytes = BLOCK_M * BK * 2 + (BN / CG) * BK * 2;
   constexpr int kFixed = 2 * BLOCK_M * 128 /*store staging*/ + 1024 /*barriers*/ + 1024 /*alignment slack*/;
   constexpr int STAGES = ((kSmemMax - kFixed) / stage_bytes) > 8 ? 8 : ((kSmemMax - kFixed) / stage_bytes);
   static_assert(STAGES >= 2, "pipeline needs at least two stages");
   constexpr int smem_bytes = STAGES * stage_bytes + kFixed;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CG, BK, STAGES>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, CG, BK, STAGES, CL>;
   static bool configured = false;
-  if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
-    if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaFuncSetAttribute");
-    configured = true;
-  }
-  const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG), n_tiles = (p.N + BN - 1) / BN;
-  const int tiles = m_tiles * n_tiles * p.splits;
-  const int units = ofab_sm_count() / CG;  // CTAs (CG = 1) or CTA pairs (CG = 2) resident at once
-  const int grid = (tiles < units ? tiles : units) * CG;
+  static int max_clusters = 0;  // co-resident clusters of this shape (4-CTA clusters must fit inside a GPC)
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaFuncSetAttribute");
+    max_clusters = ofab_sm_count() / CL;
+    if (CL > 2) {
+      cfg.gridDim = dim3(max_clusters * CL);
+      int n = 0;
+      e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+      if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaOccupancyMaxActiveClusters");
+      if (n < 1) {
+        ofab_set_error("ofab_gemm_bf16: no %d-CTA cluster of this kernel fits on the device", CL);
+        return OFAB_ERR_CUDA;
+      }
+      if (n < max_clusters) max_clusters = n;
+    }
+    configured = true;
+  }
+  const int m_tiles = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG), n_tiles = (p.N + BN - 1) / BN;
+  const int tiles = m_tiles * (n_tiles / NP) * p.splits;  // work items of one cluster: NP N-adjacent tiles
+  const int grid = (tiles < max_clusters ? tiles : max_clusters) * CL;
+  cfg.gridDim = dim3(grid);
   cudaError_t e = cudaLaunchKernelEx(&cfg, kern, ta, tb, td, p);
   if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16 launch");
   return OFAB_OK;
@@ -665,10 +707,17 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
   p.dbg = 0;
   if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
   cudaStream_t st = (cudaStream_t)stream;
-#define GO(BNV, AM, BM)                                   \
-  do {                                                    \
-    if (CG == 2) return launch<BNV, AM, BM, 2>(ta, tb, td, p, st); \
-    return launch<BNV, AM, BM, 1>(ta, tb, td, p, st);          \
+  // CTA pairs on an even number of N tiles run as 4-CTA clusters (two pairs share A by TMA multicast)
+  int CL = CG;
+  if (CG == 2 && ((N + BN - 1) / BN) % 2 == 0) CL = 4;
+  if (const char* ov = getenv("OFAB_GEMM_CL")) {  // development override: 2 = never multicast
+    if (atoi(ov) == 2 && CL == 4) CL = 2;
+  }
+#define GO(BNV, AM, BM)                                                      \
+  do {                                                                       \
+    if (CL == 4) return launch<BNV, AM, BM, 2, 4>(ta, tb, td, p, st);        \
+    if (CG == 2) return launch<BNV, AM, BM, 2, 2>(ta, tb, td, p, st);        \
+    return launch<BNV, AM, BM, 1, 1>(ta, tb, td, p, st);                     \
   } while (0)
   if (BN == 256) {
     if (!a_mn_major && !b_mn_major) GO(256, false, false);
@@ -681,10 +730,10 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
     if (a_mn_major && !b_mn_major) GO(128, true, false);
     GO(128, true, true);
   } else {
-    if (!a_mn_major && !b_mn_major) return launch<64, false, false, 1>(ta, tb, td, p, st);
-    if (!a_mn_major && b_mn_major) return launch<64, false, true, 1>(ta, tb, td, p, st);
-    if (a_mn_major && !b_mn_major) return launch<64, true, false, 1>(ta, tb, td, p, st);
-    return launch<64, true, true, 1>(ta, tb, td, p, st);
+    if (!a_mn_major && !b_mn_major) return launch<64, false, false, 1, 1>(ta, tb, td, p, st);
+    if (!a_mn_major && b_mn_major) return launch<64, false, true, 1, 1>(ta, tb, td, p, st);
+    if (a_mn_major && !b_mn_major) return launch<64, true, false, 1, 1>(ta, tb, td, p, st);
+    return launch<64, true, true, 1, 1>(ta, tb, td, p, st);
   }
 #undef GO
 }

@@ -158,17 +158,19 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn)
 
 
-@pytest.mark.parametrize("bn,cg", [(64, 1), (128, 1), (128, 2), (256, 1), (256, 2)])
+@pytest.mark.parametrize("bn,cg,cl", [(64, 1, 1), (128, 1, 1), (128, 2, 2), (128, 2, 4), (256, 1, 1), (256, 2, 2), (256, 2, 4)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
-def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg):
-    """Every (BN, cta_group) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles and
-    CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair)."""
+def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl):
+    """Every (BN, cta_group, cluster) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles,
+    CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair) and 4-CTA clusters of two pairs that
+    share A by TMA multicast (taken when the N-tile count is even; cl=2 forbids them)."""
     from ofasys_b200 import ops
 
     monkeypatch.setenv("OFAB_GEMM_BN", str(bn))
     monkeypatch.setenv("OFAB_GEMM_CG", str(cg))
+    monkeypatch.setenv("OFAB_GEMM_CL", str(cl))
     gen = g()
-    for (M, N, K) in [(1000, 776, 200), (8480 // 4, 2304, 768), (300, 136, 3072)]:
+    for (M, N, K) in [(1000, 776, 200), (8480 // 4, 2304, 768), (300, 136, 3072), (2048 + 24, 1024, 520)]:
         if a_mn:
             M = (M + 7) // 8 * 8
         if b_mn:
@@ -231,6 +233,8 @@ def test_gemm_splitk(M, N, K, expect_split, a_mn, b_mn):
     from ofasys_b200 import _lib, ops
 
     gen = g()
+    if not a_mn:
+        K = (K + 7) // 8 * 8  # K-major operands need 16-byte rows
     A, B = rnd(M, K, gen=gen, scale=0.5), rnd(N, K, gen=gen, scale=0.5)
     Am = A.t().contiguous() if a_mn else A
     Bm = B.t().contiguous() if b_mn else B

@@ -37,7 +37,7 @@ def bench(name, M, N, K, a_mn, b_mn, out_dtype=torch.bfloat16):
     Bm = B.t().contiguous() if b_mn else B
     Np = (N + 7) // 8 * 8
     out = torch.empty(M, Np, dtype=out_dtype, device=dev)
-    t = time_it(lambda: ops.gemm(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, Np))
+    t = time_it(lambda: (ops.gemm_splitk if (a_mn and b_mn and out_dtype == torch.bfloat16) else ops.gemm)(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out, Np))
     tc = time_it(lambda: torch.matmul(A, B.t()))
     fl = 2.0 * M * N * K
     return {"name": name, "M": M, "N": N, "K": K, "a_mn": a_mn, "b_mn": b_mn, "us": t * 1e6, "tflops": fl / t / 1e12,
