@@ -707,11 +707,13 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
   p.dbg = 0;
   if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
   cudaStream_t st = (cudaStream_t)stream;
-  // CTA pairs on an even number of N tiles run as 4-CTA clusters (two pairs share A by TMA multicast)
+  // 4-CTA clusters (two CTA pairs on N-adjacent tiles share A by TMA multicast) are correct but MEASURED SLOWER than
+  // independent pairs on every shape of the benchmark step (profiles/r01_gemm_cluster4_vs_pairs.txt: +5..20 %, wgrads
+  // up to +70 %): the two pairs advance in lock-step through shared empty barriers and fewer clusters are co-resident.
+  // They stay available (OFAB_GEMM_CL=4, even N-tile counts) for experiments and are covered by the tests.
   int CL = CG;
-  if (CG == 2 && ((N + BN - 1) / BN) % 2 == 0) CL = 4;
-  if (const char* ov = getenv("OFAB_GEMM_CL")) {  // development override: 2 = never multicast
-    if (atoi(ov) == 2 && CL == 4) CL = 2;
+  if (const char* ov = getenv("OFAB_GEMM_CL")) {
+    if (atoi(ov) == 4 && CG == 2 && ((N + BN - 1) / BN) % 2 == 0) CL = 4;
   }
 #define GO(BNV, AM, BM)                                                      \
   do {                                                                       \
@@ -762,13 +764,19 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 }
 
 // Split-K plan for a GEMM whose output has too few 256 x 128 tiles to fill the chip (wgrads of narrow layers: the
-// tile count does not grow with the batch, the K loop does).  Model: one k-block (128 deep) of a pair tile takes
-// ~0.68 us; the reduction reads `splits` fp32 slabs at ~4 TB/s.  Returns 1 when splitting does not pay.
+// tile count does not grow with the batch, the K loop does).  Model fitted to measurements on B200: one k-block
+// (128 deep) of a pair tile takes ~0.58 us (+4 us per launch); splitting costs ~8 us (second launch, partial-slab
+// round trip) plus the reduction's read of `splits` fp32 slabs at ~4 TB/s.  Returns 1 when splitting does not pay.
 int splitk_plan(int64_t M, int64_t N, int64_t K) {
-  if (N % 8 != 0 || K < 16 * 128) return 1;  // short contractions: nothing to win
+  if (N % 8 != 0) return 1;
+  const int64_t nkb = (K + 127) / 128;
+  if (const char* ov = getenv("OFAB_GEMM_SPLITS")) {  // development / test override
+    const int v = atoi(ov);
+    if (v >= 1 && v <= 16) return (int)(v < nkb ? v : nkb);
+  }
+  if (nkb < 16) return 1;  // short contractions: nothing to win
   const int64_t tiles = ((M + 255) / 256) * ((N + 127) / 128);
   const int64_t units = ofab_sm_count() / 2;
-  const int64_t nkb = (K + 127) / 128;
   int best = 1;
   double best_t = 1e30;
   const int cand[6] = {1, 2, 3, 4, 6, 8};
@@ -776,8 +784,8 @@ int splitk_plan(int64_t M, int64_t N, int64_t K) {
     const int sp = cand[ci];
     if (sp > 1 && nkb / sp < 4) break;
     const double waves = (double)((tiles * sp + units - 1) / units);
-    const double t_gemm = waves * (double)((nkb + sp - 1) / sp) * 0.68 + 4.0;
-    const double t_red = sp > 1 ? 2.5 + (sp + 0.5) * (double)M * (double)N * 4.0 / 4e6 : 0.0;
+    const double t_gemm = waves * (double)((nkb + sp - 1) / sp) * 0.58 + 4.0;
+    const double t_red = sp > 1 ? 8.0 + (sp + 0.5) * (double)M * (double)N * 4.0 / 4e6 : 0.0;
     if (t_gemm + t_red < best_t - 1e-9) {
       best_t = t_gemm + t_red;
       best = sp;

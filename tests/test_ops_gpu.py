@@ -163,7 +163,7 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
 def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl):
     """Every (BN, cta_group, cluster) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles,
     CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair) and 4-CTA clusters of two pairs that
-    share A by TMA multicast (taken when the N-tile count is even; cl=2 forbids them)."""
+    share A by TMA multicast (opt-in through OFAB_GEMM_CL=4, taken when the N-tile count is even)."""
     from ofasys_b200 import ops
 
     monkeypatch.setenv("OFAB_GEMM_BN", str(bn))
@@ -223,15 +223,17 @@ def test_gemm_many_tiles_persistent():
     assert rel_l2(out, A.float() @ B.float().t()) <= TOL16
 
 
-@pytest.mark.parametrize("M,N,K,expect_split", [(768, 768, 8480, True), (1536, 768, 8480, True), (2304, 768, 16960, True),
-                                                 (768, 768, 2048, True), (3072, 768, 8480, False), (136, 72, 1000, False),
-                                                 (768, 776, 4100, True)])
+@pytest.mark.parametrize("M,N,K,splits", [(768, 768, 8480, 0), (1536, 768, 8480, 0), (3072, 768, 8480, 0), (136, 72, 1000, 0),
+                                           (768, 776, 4100, 3), (2304, 768, 2048, 4), (300, 136, 1100, 8), (768, 768, 8480, 6)])
 @pytest.mark.parametrize("a_mn,b_mn", [(1, 1), (0, 0)])
-def test_gemm_splitk(M, N, K, expect_split, a_mn, b_mn):
+def test_gemm_splitk(monkeypatch, M, N, K, splits, a_mn, b_mn):
     """Split-K weight-gradient GEMM (few output tiles, long contraction): partial fp32 slabs + reduction must equal the
-    plain product; ragged K tails and K ranges of unequal length included."""
+    plain product; ragged K tails and K ranges of unequal length included.  splits = 0: the library's own plan
+    (768x768 and 1536x768 wgrads of the benchmark step split, 3072x768 and tiny problems do not); > 0: forced."""
     from ofasys_b200 import _lib, ops
 
+    if splits:
+        monkeypatch.setenv("OFAB_GEMM_SPLITS", str(splits))
     gen = g()
     if not a_mn:
         K = (K + 7) // 8 * 8  # K-major operands need 16-byte rows
@@ -239,8 +241,11 @@ def test_gemm_splitk(M, N, K, expect_split, a_mn, b_mn):
     Am = A.t().contiguous() if a_mn else A
     Bm = B.t().contiguous() if b_mn else B
     n_ws = _lib.lib().ofab_gemm_splitk_workspace_elems(M, N, K)
-    assert (n_ws > 0) == expect_split, (M, N, K, n_ws)
     assert n_ws % (M * N) == 0
+    if not splits:
+        assert (n_ws > 0) == ((M, N) in ((768, 768), (1536, 768))), (M, N, K, n_ws)
+    elif splits > 1:
+        assert n_ws == min(splits, (K + 127) // 128) * M * N
     ref = A.float() @ B.float().t()
     out32 = torch.full((M, N), 7.0, dtype=torch.float32, device=dev())
     ops.gemm_splitk(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out32, N)
