@@ -237,7 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
     if (p.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_d) : "memory");
     for (int i = 0; i < STAGES; ++i) {
-      mbar_init(full_bar + i, CG);  // leader's barrier: one producer arrival per CTA of the pair
+      mbar_init(full_bar + i, 1);  // leader's barrier: ONE arrival (its own expect_tx, which counts the bytes of both CTAs of the pair)
       mbar_init(empty_bar + i, NP);  // one commit per pair whose MMAs read this CTA's stage (own pair; + the twin pair's A multicast target)
     }
     for (int i = 0; i < 2; ++i) {
@@ -273,8 +273,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         const int kb_begin = sp * p.kb_per_split, kb_end = min(num_k_blocks, kb_begin + p.kb_per_split);
         for (int kb = kb_begin; kb < kb_end; ++kb) {
           mbar_wait(empty_bar + stage, phase ^ 1);
+          // the non-leader's loads signal the leader's barrier directly (complete_tx); bytes that land before the
+          // leader's expect_tx only drive the transaction count negative for a moment
           if (leader) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
-          else mbar_arrive_remote(full_bar + stage, pair_leader);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
           const int k0 = kb * BK;
@@ -562,9 +563,8 @@ int make_map(CUtensorMap* map, const void* ptr, uint64_t inner, uint64_t outer, 
   return OFAB_OK;
 }
 
-template <int BN, bool A_MN, bool B_MN, int CG, int CL>
+template <int BN, bool A_MN, bool B_MN, int CG, int CL, int BK = (CG == 2 ? 128 : 64)>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, const GemmParams& p, cudaStream_t st) {
-  constexpr int BK = CG == 2 ? 128 : 64;
   constexpr int NP = CL / CG;
   constexpr int stage_bytes = BLOCK_M * BK * 2 + (BN / CG) * BK * 2;
   constexpr int kFixed = 2 * BLOCK_M * 128 /*store staging*/ + 1024 /*barriers*/ + 1024 /*alignment slack*/;
@@ -668,7 +668,10 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
   CUtensorMap ta, tb;
   int rc;
   // K-major operands are loaded as 64-wide (128 B) K atoms x rows; MN-major operands as 64-wide MN atoms x BK rows
-  const uint32_t BK = CG == 2 ? 128 : 64;
+  uint32_t BK = CG == 2 ? 128 : 64;
+  if (const char* ov = getenv("OFAB_GEMM_BK")) {  // development: 64-deep stages (twice as many) for CTA pairs
+    if (atoi(ov) == 64 && CG == 2 && splits <= 1) BK = 64;
+  }
   if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BLOCK_M);
   else rc = make_map(&ta, A, (uint64_t)M, (uint64_t)K, (uint64_t)lda, 64, BK);
   if (rc) return rc;
@@ -703,6 +706,7 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
     p.kb_per_split = (nkb + p.splits - 1) / p.splits;
     p.splits = (nkb + p.kb_per_split - 1) / p.kb_per_split;  // no empty K range
     p.split_stride = split_stride;
+    OFAB_REQUIRE(splits <= 1 || p.splits == splits, "ofab_gemm_bf16: split-K plan (%d ranges) does not tile %d k-blocks", splits, nkb);
   }
   p.dbg = 0;
   if (const char* ov = getenv("OFAB_GEMM_DBG")) p.dbg = atoi(ov);
@@ -713,11 +717,12 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
   // They stay available (OFAB_GEMM_CL=4, even N-tile counts) for experiments and are covered by the tests.
   int CL = CG;
   if (const char* ov = getenv("OFAB_GEMM_CL")) {
-    if (atoi(ov) == 4 && CG == 2 && ((N + BN - 1) / BN) % 2 == 0) CL = 4;
+    if (atoi(ov) == 4 && CG == 2 && BK == 128 && ((N + BN - 1) / BN) % 2 == 0) CL = 4;
   }
 #define GO(BNV, AM, BM)                                                      \
   do {                                                                       \
     if (CL == 4) return launch<BNV, AM, BM, 2, 4>(ta, tb, td, p, st);        \
+    if (CG == 2 && BK == 64) return launch<BNV, AM, BM, 2, 2, 64>(ta, tb, td, p, st); \
     if (CG == 2) return launch<BNV, AM, BM, 2, 2>(ta, tb, td, p, st);        \
     return launch<BNV, AM, BM, 1, 1>(ta, tb, td, p, st);                     \
   } while (0)
@@ -770,9 +775,14 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
 int splitk_plan(int64_t M, int64_t N, int64_t K) {
   if (N % 8 != 0) return 1;
   const int64_t nkb = (K + 127) / 128;
+  // ranges of equal k-block count with no empty range: `want` ranges -> ceil(nkb / ceil(nkb / want)) ranges
+  auto effective = [nkb](int64_t want) {
+    const int64_t per = (nkb + want - 1) / want;
+    return (int)((nkb + per - 1) / per);
+  };
   if (const char* ov = getenv("OFAB_GEMM_SPLITS")) {  // development / test override
     const int v = atoi(ov);
-    if (v >= 1 && v <= 16) return (int)(v < nkb ? v : nkb);
+    if (v >= 1 && v <= 16) return effective(v < nkb ? v : nkb);
   }
   if (nkb < 16) return 1;  // short contractions: nothing to win
   const int64_t tiles = ((M + 255) / 256) * ((N + 127) / 128);
@@ -791,7 +801,7 @@ int splitk_plan(int64_t M, int64_t N, int64_t K) {
       best = sp;
     }
   }
-  return best;
+  return effective(best);
 }
 
 }  // namespace

@@ -158,9 +158,10 @@ def test_gemm_layouts(M, N, K, a_mn, b_mn):
     assert rel_l2(out, ref) <= TOL32, (M, N, K, a_mn, b_mn)
 
 
-@pytest.mark.parametrize("bn,cg,cl", [(64, 1, 1), (128, 1, 1), (128, 2, 2), (128, 2, 4), (256, 1, 1), (256, 2, 2), (256, 2, 4)])
+@pytest.mark.parametrize("bn,cg,cl,bk", [(64, 1, 1, 64), (128, 1, 1, 64), (128, 2, 2, 128), (128, 2, 4, 128), (256, 1, 1, 64), (256, 2, 2, 128),
+                                         (256, 2, 4, 128), (128, 2, 2, 64), (256, 2, 2, 64)])
 @pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
-def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl):
+def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl, bk):
     """Every (BN, cta_group, cluster) instantiation, not only the one the cost model picks: 1-CTA 128xBN tiles,
     CTA-pair 256xBN tiles (tcgen05 cta_group::2, B tile split across the pair) and 4-CTA clusters of two pairs that
     share A by TMA multicast (opt-in through OFAB_GEMM_CL=4, taken when the N-tile count is even)."""
@@ -169,6 +170,7 @@ def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl):
     monkeypatch.setenv("OFAB_GEMM_BN", str(bn))
     monkeypatch.setenv("OFAB_GEMM_CG", str(cg))
     monkeypatch.setenv("OFAB_GEMM_CL", str(cl))
+    monkeypatch.setenv("OFAB_GEMM_BK", str(bk))  # CTA pairs: 128-deep stages (default) or twice as many 64-deep ones
     gen = g()
     for (M, N, K) in [(1000, 776, 200), (8480 // 4, 2304, 768), (300, 136, 3072), (2048 + 24, 1024, 520)]:
         if a_mn:
