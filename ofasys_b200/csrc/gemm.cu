@@ -117,6 +117,18 @@ __device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, u
       "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
@@ -145,19 +157,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2 at bits [61,64)), version 1 at [46,48).
+// UMMA shared-memory descriptor, SWIZZLE_128B (layout_type 2 at bits [61,64)), version 1 at [46,48):
+//   bits [0,14) address >> 4, [16,30) LBO >> 4, [32,46) SBO >> 4.
 //  K-major : rows of 128 B; 8-row groups are 1024 B apart (SBO); one swizzle atom along K (LBO unused).
 //  MN-major: 64-element (128 B) MN atoms of BK rows each; SBO = 8 K-rows (1024 B),
 //            LBO = stride between MN atoms (BK * 128 B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;  // descriptor version for sm_100
-  d |= (uint64_t)2 << 61;  // SWIZZLE_128B
-  return d;
-}
+// (built in the MMA issuer: constant high word, low word advanced per K step)
 
 struct GemmParams {
   int M, N, K;
@@ -263,7 +268,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    if (lane == 0) {
+    // (whole warp, warp-uniform control flow; one elected lane issues -- see the MMA issuer)
+    {
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -275,19 +282,19 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
           mbar_wait(empty_bar + stage, phase ^ 1);
           // the non-leader's loads signal the leader's barrier directly (complete_tx); bytes that land before the
           // leader's expect_tx only drive the transaction count negative for a moment
-          if (leader) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
+          if (leader && issuer) mbar_expect_tx(full_bar + stage, (p.dbg & 8) ? 0u : (A_BYTES + B_BYTES) * CG);
           uint8_t* sa = smem_a + stage * A_BYTES;
           uint8_t* sb = smem_b + stage * B_BYTES;
           const int k0 = kb * BK;
           auto load = [&](void* dst, const CUtensorMap* map, int c0, int c1) {
-            if (p.dbg & 8) return;
+            if ((p.dbg & 8) || !issuer) return;
             if (CG == 1) tma_load_2d(dst, map, full_bar + stage, c0, c1);
             else tma_load_2d_2sm(dst, map, full_bar + stage, c0, c1);
           };
           if (NP == 2) {
             // A is shared with the twin CTA (same rank, other pair): fetch ONE of the two boxes, multicast to both
             const uint16_t twins = (uint16_t)((1u << rank) | (1u << (rank + 2)));
-            if (!(p.dbg & 8)) {
+            if (!(p.dbg & 8) && issuer) {
               if (!A_MN) tma_load_2d_2sm_mc(sa + pair * (BLOCK_M * 128), &tma_a, full_bar + stage, k0 + (int)pair * 64, m0, twins);
               else tma_load_2d_2sm_mc(sa + pair * (BK * 128), &tma_a, full_bar + stage, m0 + (int)pair * 64, k0, twins);
             }
@@ -305,6 +312,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
 #pragma unroll
             for (int i = 0; i < BNL / 64; ++i) load(sb + i * (BK * 128), &tma_b, n0 + i * 64, k0);
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -314,11 +322,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (leader CTA only)
-    if (lane == 0 && leader) {
+    // The WHOLE warp runs this loop with warp-uniform values (tile, stage, descriptors) and one elected lane issues
+    // the tcgen05 instructions: the operands then live in uniform registers.  (Issued from a `lane == 0` branch the
+    // same code needed an ELECT / R2UR waterfall around every MMA -- ~19 dependent instructions per 64-clock MMA,
+    // which made instruction issue, not the tensor core, the pace of the main loop.)
+    if (leader) {
       // instruction descriptor: D=f32 [4,6)=1, A=bf16 [7,10)=1, B=bf16 [10,13)=1, a_major bit15, b_major bit16,
       // N>>3 at [17,23), M>>4 at [24,29)
       constexpr uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                  ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BLOCK_M * CG) >> 4) << 24);
+      // shared-memory descriptors (see make_smem_desc): the high word is constant, the low word is
+      // (address >> 4) | (LBO >> 4) << 16 and advances by a compile-time constant per K step
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      constexpr uint32_t a_lbo = A_MN ? (((uint32_t)(BK * 128) >> 4) << 16) : 0u;
+      constexpr uint32_t b_lbo = B_MN ? (((uint32_t)(BK * 128) >> 4) << 16) : 0u;
+      // (& 0x3FFF: inside a cluster the shared-window address carries the CTA rank above bit 24)
+      const uint32_t a_lo0 = ((smem_u32(smem_a) >> 4) & 0x3FFFu) | a_lbo;
+      const uint32_t b_lo0 = ((smem_u32(smem_b) >> 4) & 0x3FFFu) | b_lbo;
+      const bool issuer = elect_one();
       int stage = 0;
       uint32_t phase = 0;
       int iter = 0;
@@ -332,25 +353,29 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
         for (int kb = 0; kb < kb_count; ++kb) {
           mbar_wait(full_bar + stage, phase);
           tcgen05_fence_after();
-          const uint32_t a_addr = smem_u32(smem_a + stage * A_BYTES);
-          const uint32_t b_addr = smem_u32(smem_b + stage * B_BYTES);
+          const uint32_t a_lo = a_lo0 + (uint32_t)stage * (A_BYTES >> 4);
+          const uint32_t b_lo = b_lo0 + (uint32_t)stage * (B_BYTES >> 4);
+          if (issuer && !(p.dbg & 4)) {
 #pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k) {
-            // K-major: 64-wide atom (k / 4), then 16 elements (32 B) inside the 128 B swizzle row.
-            // MN-major: 16 K-rows of 128 B (2048 B) per step; atoms along MN are BK*128 B apart (LBO).
-            const uint64_t adesc = A_MN ? make_smem_desc(a_addr + k * (UMMA_K * 128), BK * 128, 1024)
-                                        : make_smem_desc(a_addr + (k >> 2) * (BLOCK_M * 128) + (k & 3) * (UMMA_K * 2), 0, 1024);
-            const uint64_t bdesc = B_MN ? make_smem_desc(b_addr + k * (UMMA_K * 128), BK * 128, 1024)
-                                        : make_smem_desc(b_addr + (k >> 2) * (BNL * 128) + (k & 3) * (UMMA_K * 2), 0, 1024);
-            if (p.dbg & 4) continue;
-            if (CG == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
-            else umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              // K-major: 64-wide atom (k / 4), then 16 elements (32 B) inside the 128 B swizzle row.
+              // MN-major: 16 K-rows of 128 B (2048 B) per step; atoms along MN are BK*128 B apart (LBO).
+              const uint32_t a_off = A_MN ? (uint32_t)(k * (UMMA_K * 128)) >> 4 : (uint32_t)((k >> 2) * (BLOCK_M * 128) + (k & 3) * (UMMA_K * 2)) >> 4;
+              const uint32_t b_off = B_MN ? (uint32_t)(k * (UMMA_K * 128)) >> 4 : (uint32_t)((k >> 2) * (BNL * 128) + (k & 3) * (UMMA_K * 2)) >> 4;
+              const uint64_t adesc = ((uint64_t)desc_hi << 32) | (uint64_t)(a_lo + a_off);
+              const uint64_t bdesc = ((uint64_t)desc_hi << 32) | (uint64_t)(b_lo + b_off);
+              if (CG == 1) umma_bf16(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+              else umma_bf16_2sm(tmem_d, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
-          // frees the smem slot (in both CTAs when paired) once these MMAs retire
-          if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage, all_mask);
-          if (kb == kb_count - 1) {
-            if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as, pair_mask);
+          if (issuer) {
+            // frees the smem slot (in both CTAs when paired) once these MMAs retire
+            if (CG == 1) umma_commit(empty_bar + stage); else umma_commit_2sm(empty_bar + stage, all_mask);
+            if (kb == kb_count - 1) {
+              if (CG == 1) umma_commit(tmem_full + as); else umma_commit_2sm(tmem_full + as, pair_mask);
+            }
           }
+          __syncwarp();
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;

@@ -33,18 +33,6 @@ def _c(t):
 
 
 # ------------------------------------------------------------------------------------ reductions
-_SIDE_STREAMS = {}
-
-
-def _side_stream(device):
-    """One helper stream per device for HBM-bound reductions that run next to the tensor-bound GEMMs of the same
-    backward node (fork / join inside that node, so CUDA-graph capture sees a closed diamond)."""
-    s = _SIDE_STREAMS.get(device.index)
-    if s is None:
-        s = _SIDE_STREAMS[device.index] = torch.cuda.Stream(device=device)
-    return s
-
-
 def colsum(x2d, out_dtype=torch.bfloat16, out=None, accumulate=False, scratch=None):
     """out[c] (+)= sum_r x2d[r, c]; x2d may have a row stride (last dim contiguous)."""
     assert x2d.dim() == 2 and x2d.stride(1) == 1
@@ -274,19 +262,6 @@ class _LinearFn(torch.autograd.Function):
         dy2 = dyb.reshape(M, N) if dyb.is_contiguous() else _as2d(dyb.reshape(M, N))
         ld = dy2.stride(0)
         dx = dw = db = None
-        fork = None
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = _take_bias_hint(dy, N)  # produced for free by the LayerNorm backward that emitted dy
-            if db is None:
-                # bias gradient = column sums of dy: HBM-bound, so it runs on the side stream next to the two
-                # tensor-bound GEMMs below (buffers are allocated on the main stream, the side stream only borrows them)
-                db = torch.empty(N, dtype=torch.bfloat16, device=dy.device)
-                scratch = torch.empty(_lib.lib().ofab_colsum_scratch_elems(N), dtype=torch.float32, device=dy.device)
-                cur, side = torch.cuda.current_stream(), _side_stream(dy.device)
-                side.wait_stream(cur)
-                with torch.cuda.stream(side):
-                    colsum(dy2, out=db, scratch=scratch)
-                fork = (cur, side)
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.bfloat16, device=dy.device)
             gemm(M, K, N, dy2, ld, 0, w, K, 1, dx, K)  # dX = dY * W   (W read MN-major in place)
@@ -294,8 +269,12 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
             gemm_splitk(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
-        if fork is not None:
-            fork[0].wait_stream(fork[1])
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = _take_bias_hint(dy, N)  # produced for free by the LayerNorm backward that emitted dy
+            if db is None:
+                # (measured: running this HBM-bound reduction on a side stream next to the two GEMMs above gains nothing --
+                # the persistent GEMM CTAs leave no SM idle and the reduction's traffic slows them by as much)
+                db = colsum(dy2, torch.bfloat16)
         return dx, dw, db, d_res
 
 

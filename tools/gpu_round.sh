@@ -2,10 +2,10 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 400 python -m pytest tests/test_ops_gpu.py -x -q -k "gemm" > gpurun_out/pytest_gemm.log 2>&1; echo "pytest gemm rc=$?"; tail -5 gpurun_out/pytest_gemm.log
+timeout 400 python -m pytest tests/test_ops_gpu.py -x -q -k "gemm" > gpurun_out/pytest_gemm.log 2>&1; G_RC=$?; echo "pytest gemm rc=$G_RC"; tail -5 gpurun_out/pytest_gemm.log
+if [ $G_RC -ne 0 ]; then exit 1; fi
 timeout 300 python tools/gemm_bench.py > gpurun_out/gemm_bench.log 2>&1; cat gpurun_out/gemm_bench.log
-OFAB_GEMM_BK=64 timeout 300 python tools/gemm_bench.py > gpurun_out/gemm_bench_bk64.log 2>&1; cat gpurun_out/gemm_bench_bk64.log
-timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_b64.json 2> gpurun_out/bench_b64.err; echo "bench rc=$?"
+( time timeout 1200 python -m pytest tests -m gpu -q ) > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"
+tail -8 gpurun_out/pytest_gpu.log
+timeout 600 python bench.py --steps 20 --warmup 5 --kprofile --no-cpu > gpurun_out/bench_b64.json 2> gpurun_out/bench_b64.err; echo "bench rc=$?"
 cat gpurun_out/bench_b64.json; tail -3 gpurun_out/bench_b64.err
-OFAB_GEMM_BK=64 timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu > gpurun_out/bench_b64_bk64.json 2> gpurun_out/bench_b64_bk64.err; echo "bench bk64 rc=$?"
-cat gpurun_out/bench_b64_bk64.json
