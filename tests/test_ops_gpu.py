@@ -247,7 +247,9 @@ def test_gemm_splitk(monkeypatch, M, N, K, splits, a_mn, b_mn):
     if not splits:
         assert (n_ws > 0) == ((M, N) in ((768, 768), (1536, 768))), (M, N, K, n_ws)
     elif splits > 1:
-        assert n_ws == min(splits, (K + 127) // 128) * M * N
+        nkb = (K + 127) // 128
+        per = -(-nkb // min(splits, nkb))  # k-blocks per range; ranges = ceil(nkb / per): no empty range
+        assert n_ws == -(-nkb // per) * M * N
     ref = A.float() @ B.float().t()
     out32 = torch.full((M, N), 7.0, dtype=torch.float32, device=dev())
     ops.gemm_splitk(M, N, K, Am, Am.stride(0), a_mn, Bm, Bm.stride(0), b_mn, out32, N)
