@@ -367,9 +367,10 @@ def run_gpu(args, rank, world, local_rank):
             orig(name, *a)
             e.record()
             if name == "ofab_gemm_bf16":  # M N K A lda a_mn B ldb b_mn bias residual ldr D ldd d_dt stream
-                spec = (a[0], a[1], a[2], a[5], a[8], a[9] is not None and a[9].value is not None, a[10] is not None and a[10].value is not None, a[14], False)
+                spec = (a[0], a[1], a[2], a[4], a[5], a[7], a[8], a[9] is not None and a[9].value is not None,
+                        a[10] is not None and a[10].value is not None, a[11], a[13], a[14], False)
             else:  # M N K A lda a_mn B ldb b_mn D ldd d_dt ws ws_elems stream
-                spec = (a[0], a[1], a[2], a[5], a[8], False, False, a[11], True)
+                spec = (a[0], a[1], a[2], a[4], a[5], a[7], a[8], False, False, 0, a[10], a[11], True)
             recs.append((2.0 * a[0] * a[1] * a[2], s, e, spec))
 
         _lib.call = call
@@ -399,20 +400,19 @@ def run_gpu(args, rank, world, local_rank):
             return pool[k]
 
         def replay_list():
-            for i, (M, N, K, a_mn, b_mn, has_bias, has_res, d_dt, split) in enumerate(launch_list):
-                A = scratch("A", (K, M) if a_mn else (M, K), torch.bfloat16, i)
-                Bm = scratch("B", (K, N) if b_mn else (N, K), torch.bfloat16, i)
+            for i, (M, N, K, lda, a_mn, ldb, b_mn, has_bias, has_res, ldr, ldd, d_dt, split) in enumerate(launch_list):
+                A = scratch("A", (K if a_mn else M, lda), torch.bfloat16, i)    # same leading dimensions as the real call
+                Bm = scratch("B", (K if b_mn else N, ldb), torch.bfloat16, i)
                 odt = torch.float32 if d_dt == 0 else torch.bfloat16
-                Np = (N + 7) // 8 * 8
-                D = scratch("D", (M, Np), odt, i)
+                D = scratch("D", (M, ldd), odt, i)
                 if split:
-                    _ops.gemm_splitk(M, N, K, A, A.stride(0), a_mn, Bm, Bm.stride(0), b_mn, D, Np)
+                    _ops.gemm_splitk(M, N, K, A, lda, a_mn, Bm, ldb, b_mn, D, ldd)
                 else:
-                    bias = scratch("bias", (Np,), torch.bfloat16, i) if has_bias else None
-                    res = scratch("res", (M, Np), torch.float32, i) if has_res else None
-                    _ops.gemm(M, N, K, A, A.stride(0), a_mn, Bm, Bm.stride(0), b_mn, D, Np, bias=bias, residual=res, ldr=Np)
+                    bias = scratch("bias", ((N + 7) // 8 * 8,), torch.bfloat16, i) if has_bias else None
+                    res = scratch("res", (M, ldr), torch.float32, i) if has_res else None
+                    _ops.gemm(M, N, K, A, lda, a_mn, Bm, ldb, b_mn, D, ldd, bias=bias, residual=res, ldr=ldr)
 
-        fl_list = sum(2.0 * sp[0] * sp[1] * sp[2] for sp in launch_list)
+        fl_list = sum(2.0 * sp[0] * sp[1] * sp[2] for sp in launch_list)  # (the padded tied-logits width is counted as launched)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             replay_list()

@@ -239,6 +239,8 @@ def test_gemm_splitk(monkeypatch, M, N, K, splits, a_mn, b_mn):
     gen = g()
     if not a_mn:
         K = (K + 7) // 8 * 8  # K-major operands need 16-byte rows
+    else:
+        M = (M + 7) // 8 * 8  # ... MN-major ones 16-byte columns
     A, B = rnd(M, K, gen=gen, scale=0.5), rnd(N, K, gen=gen, scale=0.5)
     Am = A.t().contiguous() if a_mn else A
     Bm = B.t().contiguous() if b_mn else B
