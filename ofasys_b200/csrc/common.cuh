@@ -120,6 +120,62 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + px;
 }
 
+// ---- dropout / drop-path masks: counter-based RNG (Philox4x32, 7 rounds), no mask tensor in HBM --------------------
+// The mask of the 8-column vector starting at column c of row r is a pure function of (seed, step, site, r, c / 8),
+// so forward and backward kernels regenerate the same bits whatever their thread layout.  `state` lives in device
+// memory ([0] seed, [1] step counter) so a CUDA-graph replay draws fresh masks: the host only bumps the counter.
+// Semantics: ofasys/module/dropout.py:14-25 (F.dropout: zero with probability p, scale kept values by 1/(1-p)) and
+// ofasys/module/droppath.py:13-63 (per-sample keep mask scaled by 1/keep on the residual branch).
+struct DropArgs {
+  const unsigned long long* state;  // device [2]: seed, step
+  uint32_t site;                     // call site within the step (host counter, same order every step)
+  uint32_t thresh16;                 // an element is dropped when its 16 random bits < thresh16  (= round(p * 65536))
+  float inv_keep;                    // 1 / (1 - p)
+  uint32_t dp_thresh32;              // drop-path: a sample is dropped when its 32 random bits < dp_thresh32; 0 = off
+  float dp_inv_keep;                 // 1 / (1 - drop_path_rate)
+  int rows_per_sample;               // rows are [B * T]: sample of row r = r / rows_per_sample
+};
+__device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
+#pragma unroll
+  for (int r = 0; r < 7; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u;
+    k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+struct DropCtx {  // per-kernel constants
+  uint2 key;
+  uint32_t step_lo;
+};
+__device__ __forceinline__ DropCtx drop_ctx(const DropArgs& d) {
+  const unsigned long long seed = d.state[0], step = d.state[1];
+  DropCtx c;
+  c.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32));
+  c.step_lo = (uint32_t)step;
+  return c;
+}
+// multipliers (0 or inv_keep [* drop-path scale]) of the 8 columns [c, c+8) of row `row`
+__device__ __forceinline__ f8 drop_mask8(const DropArgs& d, const DropCtx& k, int64_t row, int c) {
+  float scale = d.inv_keep;
+  if (d.dp_thresh32 != 0u) {
+    const uint32_t b = (uint32_t)(row / d.rows_per_sample);
+    const uint4 r = philox4x32_7(make_uint4(b, 0x0D509A7Fu, d.site, k.step_lo), k.key);
+    scale = r.x < d.dp_thresh32 ? 0.f : scale * d.dp_inv_keep;
+  }
+  const uint4 r = philox4x32_7(make_uint4((uint32_t)row, (uint32_t)((unsigned long long)row >> 32) ^ (d.site * 0x9E3779B9u), (uint32_t)(c >> 3), k.step_lo), k.key);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+  f8 m;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint32_t bits = (w[j >> 1] >> (16 * (j & 1))) & 0xFFFFu;
+    m.v[j] = bits < d.thresh16 ? 0.f : scale;
+  }
+  return m;
+}
+
 // ---- async row pipeline: cp.async.bulk (TMA engine, 1-D) global -> shared ring, mbarrier completion ----------
 // HBM-bound row kernels (LayerNorm family) keep several rows per CTA in flight without holding them in registers:
 // one elected thread issues a bulk copy per input and stage, all threads wait on the stage's mbarrier and read

@@ -96,12 +96,25 @@ __global__ void __launch_bounds__(128) embed_ln_fwd_kernel(const EmbedArgs a, fl
   }
 }
 
-__global__ void __launch_bounds__(128) embed_ln_bwd_kernel(const EmbedArgs a, const float* __restrict__ mean, const float* __restrict__ rstd,
+// 512 threads = 4 row slots of 128 threads: each slot walks its own rows (named barrier per slot), so the persistent
+// grid of PARTIAL_ROWS CTAs keeps 16 warps per CTA in flight; the slots' partial sums are combined at the end.
+__device__ __forceinline__ float slot_sum128(float v, float* red /* [4] of this slot */, int slot) {
+  v = warp_sum(v);
+  asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory");
+  if ((threadIdx.x & 31) == 0) red[(threadIdx.x >> 5) & 3] = v;
+  asm volatile("bar.sync %0, 128;" ::"r"(slot + 1) : "memory");
+  return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(512) embed_ln_bwd_kernel(const EmbedArgs a, const float* __restrict__ mean, const float* __restrict__ rstd,
                                                            const float* __restrict__ dout, int64_t dout_bs, float* __restrict__ dE,
                                                            int64_t padding_idx, bf16* __restrict__ ddense, float* __restrict__ dpos,
                                                            float* __restrict__ partial) {
-  __shared__ float red[4];
-  const int c = threadIdx.x * 8;
+  __shared__ float red_all[4][4];
+  __shared__ float comb[3][1024];  // slots 1..3 hand their per-column partial sums to slot 0
+  const int slot = threadIdx.x >> 7;
+  float* red = red_all[slot];
+  const int c = (threadIdx.x & 127) * 8;
   const bool col_ok = c < a.d;
   const float inv_n = 1.0f / (float)a.d;
   f8 g, acc[4];  // dgamma, dbeta, dtype, dcls
@@ -111,7 +124,7 @@ __global__ void __launch_bounds__(128) embed_ln_bwd_kernel(const EmbedArgs a, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
   const int64_t rows = (int64_t)a.B * a.T;
-  for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
+  for (int64_t row = (int64_t)blockIdx.x * 4 + slot; row < rows; row += (int64_t)gridDim.x * 4) {
     const int b = (int)(row / a.T), t = (int)(row % a.T);
     const bool zero = a.zero_mask != nullptr && a.zero_mask[row];
     const float mu = mean[row], rs = rstd[row];
@@ -136,8 +149,8 @@ __global__ void __launch_bounds__(128) embed_ln_bwd_kernel(const EmbedArgs a, co
         s2 += dy.v[j];
       }
     }
-    const float c1 = block_sum128(s1, red) * inv_n;
-    const float c2 = block_sum128(s2, red) * inv_n;
+    const float c1 = slot_sum128(s1, red, slot) * inv_n;
+    const float c2 = slot_sum128(s2, red, slot) * inv_n;
     if (col_ok) {
       f8 dp;
 #pragma unroll
@@ -163,9 +176,20 @@ __global__ void __launch_bounds__(128) embed_ln_bwd_kernel(const EmbedArgs a, co
       }
     }
   }
-  if (col_ok) {
 #pragma unroll
-    for (int s = 0; s < 4; ++s) store8(partial + ((int64_t)s * PARTIAL_ROWS + blockIdx.x) * a.d + c, acc[s]);
+  for (int s = 0; s < 4; ++s) {
+    __syncthreads();
+    if (slot > 0 && col_ok) store8(comb[slot - 1] + c, acc[s]);
+    __syncthreads();
+    if (slot == 0 && col_ok) {
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const f8 o = load8(comb[k] + c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[s].v[j] += o.v[j];
+      }
+      store8(partial + ((int64_t)s * PARTIAL_ROWS + blockIdx.x) * a.d + c, acc[s]);
+    }
   }
 }
 
@@ -278,7 +302,7 @@ extern "C" int ofab_embed_ln_bwd(const ofab_embed_ln_bwd_args* a, ofab_stream_t 
   int rc = to_args(&a->f, e, "ofab_embed_ln_bwd");
   if (rc) return rc;
   OFAB_REQUIRE(a->dout != nullptr && a->dgb_partial != nullptr, "ofab_embed_ln_bwd: dout / dgb_partial NULL");
-  embed_ln_bwd_kernel<<<PARTIAL_ROWS, 128, 0, (cudaStream_t)stream>>>(e, a->f.mean, a->f.rstd, a->dout, a->dout_bs, a->dE, a->padding_idx,
+  embed_ln_bwd_kernel<<<PARTIAL_ROWS, 512, 0, (cudaStream_t)stream>>>(e, a->f.mean, a->f.rstd, a->dout, a->dout_bs, a->dE, a->padding_idx,
                                                                       (bf16*)a->ddense, a->dpos, a->dgb_partial);
   OFAB_LAUNCH_CHECK("ofab_embed_ln_bwd");
   return OFAB_OK;

@@ -2,10 +2,9 @@
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-timeout 400 python -m pytest tests/test_ops_gpu.py -q -k "splitk" > gpurun_out/pytest_gemm.log 2>&1; echo "pytest splitk rc=$?"; tail -3 gpurun_out/pytest_gemm.log
-timeout 600 python bench.py --steps 20 --warmup 5 --kprofile > gpurun_out/bench_b64.json 2> gpurun_out/bench_b64.err; echo "bench rc=$?"
-cat gpurun_out/bench_b64.json; tail -3 gpurun_out/bench_b64.err
-timeout 600 python bench.py --steps 20 --warmup 5 --batch 32 --no-cpu > gpurun_out/bench_b32.json 2> gpurun_out/bench_b32.err; echo "bench b32 rc=$?"
-cat gpurun_out/bench_b32.json
-timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; echo "bench ref rc=$?"
-cat gpurun_out/bench_ref.json
+timeout 400 python tools/gemm_sweep.py > gpurun_out/gemm_sweep.log 2>&1; cat gpurun_out/gemm_sweep.log
+for k in gemm ln attn; do
+  timeout 300 ncu --set full --clock-control none --import-source on -k regex:"gemm_bf16|ln_bwd|ln_fwd|attn_" -c 9 -o gpurun_out/prof_$k -f python tools/one_kernel.py $k > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?"
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 3000 -c 1000 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 1 --no-graph --no-cpu --batch 64 > gpurun_out/bench_under_ncu.log 2>&1; echo "ncu launches rc=$?"
+tail -3 gpurun_out/launches.csv | cut -c1-300
