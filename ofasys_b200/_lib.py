@@ -2,7 +2,7 @@
 or a call fails, the product path raises."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libofab.so")
@@ -12,6 +12,11 @@ F32, BF16 = 0, 1
 
 class OfabError(RuntimeError):
     pass
+
+
+class Dropout(Structure):
+    """ofab_dropout (include/ofab.h): counter-based keep mask, no mask tensor."""
+    _fields_ = [("state", c_void_p), ("site", c_uint32), ("p", c_float), ("drop_path", c_float), ("rows_per_sample", c_int)]
 
 
 class AttnFwdArgs(Structure):
@@ -44,6 +49,7 @@ class EmbedLnArgs(Structure):
         ("pos", c_void_p), ("type", c_void_p), ("gamma", c_void_p), ("beta", c_void_p),
         ("zero_mask", c_void_p), ("eps", c_float),
         ("out", c_void_p), ("out_bs", c_int64), ("mean", c_void_p), ("rstd", c_void_p),
+        ("drop", POINTER(Dropout)),
     ]
 
 
@@ -60,11 +66,12 @@ _SIGS = {
     "ofab_last_error": (c_char_p, []),
     "ofab_device_check": (c_int, [c_int]),
     "ofab_num_sms": (c_int, []),
-    "ofab_ln_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
-    "ofab_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int, c_void_p]),
+    "ofab_dropout_apply": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, POINTER(Dropout), c_void_p]),
+    "ofab_ln_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, POINTER(Dropout), c_void_p]),
+    "ofab_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int, POINTER(Dropout), c_void_p]),
     "ofab_ln_partial_rows": (c_int, []),
-    "ofab_ln_res_ln_fwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_void_p]),
-    "ofab_ln_res_ln_bwd": (c_int, [c_void_p] * 10 + [c_int64, c_int, c_void_p]),
+    "ofab_ln_res_ln_fwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, POINTER(Dropout), c_void_p]),
+    "ofab_ln_res_ln_bwd": (c_int, [c_void_p] * 10 + [c_int64, c_int, POINTER(Dropout), c_void_p]),
     "ofab_colsum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ofab_colsum_scratch_elems": (c_int64, [c_int64]),
     "ofab_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),

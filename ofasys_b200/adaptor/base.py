@@ -116,8 +116,7 @@ class BaseAdaptor(nn.Module):
     def hook(self, slot, pos_table, tokens=None, dense=None, cls=None, zero_mask=None):
         """Fused forward_hook_fn (base.py:152-191) -> (embed fp32 [B,T,d], pos_embed bf16 [1,T,d] or None).
         pos_table: bf16 rows [>=T, d] indexed by position t."""
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("adaptor dropout > 0: parity and headline runs use p=0 (SURVEY 8d)")
+        drop = ops.dropout_state(self.layernorm_embedding.weight.device).spec(self.dropout_p) if self.training else None
         entangle = bool(self.cfg.entangle_position_embedding)
         type_vec = self.type_embedding.weight if (slot.is_src and self.type_embedding is not None) else None
         pad = self.dictionary.pad() if tokens is not None and self.dictionary is not None else None
@@ -125,7 +124,7 @@ class BaseAdaptor(nn.Module):
             self.layernorm_embedding.weight, self.layernorm_embedding.bias, tokens=tokens,
             E=self.embed_weight if tokens is not None else None, dense=dense, cls=cls,
             pos=pos_table if entangle else None, type_vec=type_vec, zero_mask=zero_mask,
-            eps=self.layernorm_embedding.eps, padding_idx=pad,
+            eps=self.layernorm_embedding.eps, padding_idx=pad, drop=drop,
         )
         T = embed.shape[1]
         pos = None

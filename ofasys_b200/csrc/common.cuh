@@ -135,6 +135,24 @@ struct DropArgs {
   float dp_inv_keep;                 // 1 / (1 - drop_path_rate)
   int rows_per_sample;               // rows are [B * T]: sample of row r = r / rows_per_sample
 };
+// public descriptor -> kernel form.  Returns false (message set) on a bad descriptor.
+static inline bool ofab_drop_args(const ofab_dropout* d, DropArgs& a, const char* who) {
+  if (d->state == nullptr || !(d->p >= 0.f && d->p < 1.f) || !(d->drop_path >= 0.f && d->drop_path < 1.f) ||
+      (d->drop_path > 0.f && d->rows_per_sample <= 0)) {
+    ofab_set_error("%s: bad ofab_dropout (state=%p p=%g drop_path=%g rows_per_sample=%d)", who, (const void*)d->state, (double)d->p,
+                   (double)d->drop_path, d->rows_per_sample);
+    return false;
+  }
+  a.state = reinterpret_cast<const unsigned long long*>(d->state);
+  a.site = d->site;
+  a.thresh16 = (uint32_t)(d->p * 65536.0f + 0.5f);
+  a.inv_keep = 1.0f / (1.0f - d->p);
+  const double t = (double)d->drop_path * 4294967296.0;
+  a.dp_thresh32 = d->drop_path > 0.f ? (uint32_t)(t > 4294967295.0 ? 4294967295.0 : (t < 1.0 ? 1.0 : t)) : 0u;
+  a.dp_inv_keep = 1.0f / (1.0f - d->drop_path);
+  a.rows_per_sample = d->rows_per_sample > 0 ? d->rows_per_sample : 1;
+  return true;
+}
 __device__ __forceinline__ uint4 philox4x32_7(uint4 c, uint2 k) {
 #pragma unroll
   for (int r = 0; r < 7; ++r) {

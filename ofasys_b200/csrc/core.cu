@@ -230,3 +230,44 @@ extern "C" int ofab_relu_inplace(void* y, int64_t n, ofab_stream_t stream) {
   OFAB_LAUNCH_CHECK("ofab_relu_inplace");
   return OFAB_OK;
 }
+
+// ---- standalone dropout (un-fused call sites: the reference-layout API path, tests) ------------------------------
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, const DropArgs da) {
+  const DropCtx dk = drop_ctx(da);
+  const int vpr = cols >> 3;  // 8-column vectors per row
+  const int64_t nvec = rows * vpr;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t row = i / vpr;
+    const int c = (int)(i % vpr) * 8;
+    f8 v = load8(x + row * cols + c);
+    const f8 m = drop_mask8(da, dk, row, c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v.v[j] *= m.v[j];
+    store8(y + row * cols + c, v);
+  }
+}
+}  // namespace
+
+extern "C" int ofab_dropout_apply(const void* x, void* y, int dt, int64_t rows, int cols, const ofab_dropout* drop, ofab_stream_t stream) {
+  OFAB_REQUIRE(x != nullptr && y != nullptr && drop != nullptr, "ofab_dropout_apply: NULL argument");
+  OFAB_REQUIRE(rows >= 0 && cols > 0 && cols % 8 == 0, "ofab_dropout_apply: cols=%d must be a positive multiple of 8", cols);
+  OFAB_REQUIRE((((uintptr_t)x) & 15) == 0 && (((uintptr_t)y) & 15) == 0, "ofab_dropout_apply: x / y must be 16-byte aligned");
+  DropArgs da{};
+  if (!ofab_drop_args(drop, da, "ofab_dropout_apply")) return OFAB_ERR_ARG;
+  if (rows == 0) return OFAB_OK;
+  const int64_t nvec = rows * (cols >> 3);
+  const int64_t want = (nvec + 255) / 256, cap = (int64_t)ofab_sm_count() * 8;
+  const unsigned grid = (unsigned)(want < cap ? want : cap);
+  if (dt == OFAB_F32)
+    dropout_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rows, cols, da);
+  else if (dt == OFAB_BF16)
+    dropout_apply_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, cols, da);
+  else {
+    ofab_set_error("ofab_dropout_apply: dt=%d", dt);
+    return OFAB_ERR_ARG;
+  }
+  OFAB_LAUNCH_CHECK("ofab_dropout_apply");
+  return OFAB_OK;
+}

@@ -22,6 +22,8 @@ struct EmbedArgs {
   int has_cls;
   const uint8_t* zero_mask;
   float eps;
+  int drop_on;   // adaptor dropout on the LayerNorm output (adaptor/base.py:181)
+  DropArgs drop;
 };
 
 // pre-LN value of this thread's 8 columns of row (b, t)
@@ -62,6 +64,8 @@ __global__ void __launch_bounds__(128) embed_ln_fwd_kernel(const EmbedArgs a, fl
     be = load8(a.beta + c);
   }
   const int64_t rows = (int64_t)a.B * a.T;
+  DropCtx dk;
+  if (a.drop_on) dk = drop_ctx(a.drop);
   for (int64_t row = blockIdx.x; row < rows; row += gridDim.x) {
     const int b = (int)(row / a.T), t = (int)(row % a.T);
     f8 v;
@@ -91,6 +95,11 @@ __global__ void __launch_bounds__(128) embed_ln_fwd_kernel(const EmbedArgs a, fl
       f8 o;
 #pragma unroll
       for (int j = 0; j < 8; ++j) o.v[j] = zero ? 0.f : (v.v[j] - mu) * rs * g.v[j] + be.v[j];
+      if (a.drop_on) {
+        const f8 m = drop_mask8(a.drop, dk, row, c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o.v[j] *= m.v[j];
+      }
       store8(out + (int64_t)b * out_bs + (int64_t)t * a.d + c, o);
     }
   }
@@ -124,6 +133,8 @@ __global__ void __launch_bounds__(512) embed_ln_bwd_kernel(const EmbedArgs a, co
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
   const int64_t rows = (int64_t)a.B * a.T;
+  DropCtx dk;
+  if (a.drop_on) dk = drop_ctx(a.drop);
   for (int64_t row = (int64_t)blockIdx.x * 4 + slot; row < rows; row += (int64_t)gridDim.x * 4) {
     const int b = (int)(row / a.T), t = (int)(row % a.T);
     const bool zero = a.zero_mask != nullptr && a.zero_mask[row];
@@ -138,6 +149,11 @@ __global__ void __launch_bounds__(512) embed_ln_bwd_kernel(const EmbedArgs a, co
         for (int j = 0; j < 8; ++j) dy.v[j] = 0.f;
       } else {
         dy = load8(dout + (int64_t)b * dout_bs + (int64_t)t * a.d + c);
+        if (a.drop_on) {
+          const f8 m = drop_mask8(a.drop, dk, row, c);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) dy.v[j] *= m.v[j];
+        }
       }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -280,6 +296,9 @@ int to_args(const ofab_embed_ln_args* a, EmbedArgs& e, const char* who) {
   e.has_cls = a->has_cls ? 1 : 0;
   e.zero_mask = a->zero_mask;
   e.eps = a->eps;
+  e.drop_on = a->drop != nullptr && (a->drop->p > 0.f || a->drop->drop_path > 0.f);
+  e.drop = DropArgs{};
+  if (e.drop_on && !ofab_drop_args(a->drop, e.drop, who)) return OFAB_ERR_ARG;
   return OFAB_OK;
 }
 

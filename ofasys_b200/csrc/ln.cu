@@ -144,10 +144,11 @@ __device__ __forceinline__ void flush_partials(f8 (&acc)[NS], float* __restrict_
 #define LN_BOUNDS(MAXT) __launch_bounds__(MAXT, (MAXT) > 384 ? 1 : 2)  // MAXT = 288 / 384: two CTAs per SM; 512: one
 
 // ------------------------------------------------------------------------------------ forward
-template <typename TX, typename TY, bool GELU, int MAXT>
+// DROP (GELU form only): activation dropout between GELU and the LayerNorm (transformer_layer.py:195).
+template <typename TX, typename TY, bool GELU, int MAXT, bool DROP = false>
 __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                               TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int cols,
-                                              float eps, int tpr) {
+                                              float eps, int tpr, const DropArgs da) {
   constexpr int NST = 6;
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ float red[512];
@@ -161,6 +162,8 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
   in.stage_bytes = (uint32_t)r.rpb * in.row_bytes[0];
   const int64_t my_n = ring_start<1, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
+  DropCtx dk;
+  if (DROP) dk = drop_ctx(da);
   f8 g, b;
   if (r.col_ok) {
     g = load8(gamma + r.c);
@@ -177,10 +180,15 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
     if (live) {
       v = load8(reinterpret_cast<const TX*>(ring + (size_t)stage * in.stage_bytes) + r.rib * cols + r.c);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 8; ++j)
         if (GELU) v.v[j] = gelu_f(v.v[j]);
-        s += v.v[j];
+      if (DROP) {
+        const f8 m = drop_mask8(da, dk, row, r.c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] *= m.v[j];
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s += v.v[j];
     }
     const float mu = group_sum(s, red, flip, r, true) * inv_n;  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<1>(in, ring, bars, stage, it + NST, rows, r.rpb);
@@ -211,10 +219,10 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
 }
 
 // ----------------------------------------------------------------------------------- backward
-template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM, int MAXT>
+template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM, int MAXT, bool DROP = false>
 __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const bf16* __restrict__ gamma,
                                               const float* __restrict__ mean, const float* __restrict__ rstd, TDX* __restrict__ dx,
-                                              float* __restrict__ partial, int64_t rows, int cols, int tpr) {
+                                              float* __restrict__ partial, int64_t rows, int cols, int tpr, const DropArgs da) {
   constexpr int NST = 4;
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ float2 red[512];
@@ -231,6 +239,8 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
   in.stage_bytes = (uint32_t)r.rpb * (in.row_bytes[0] + in.row_bytes[1]);
   const int64_t my_n = ring_start<2, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
+  DropCtx dk;
+  if (DROP) dk = drop_ctx(da);
   f8 g;
   if (r.col_ok) g = load8(gamma + r.c);
   f8 acc[3];  // dgamma, dbeta, column sums of dx (= bias gradient of the Linear that produced x)
@@ -253,6 +263,8 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
       d = load8(reinterpret_cast<const TDY*>(st + in.off[1]) + r.rib * cols + r.c);
       rs = rstd[row];
       const float nmr = -mean[row] * rs;
+      f8 m;
+      if (DROP) m = drop_mask8(da, dk, row, r.c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float a = pre.v[j];
@@ -261,6 +273,10 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
           gelu_parts(a, cdf, px);
           gp.v[j] = cdf + px;
           a *= cdf;
+          if (DROP) {  // LN input = m * gelu(x): the mask scales the value and the chain-rule factor alike
+            a *= m.v[j];
+            gp.v[j] *= m.v[j];
+          }
         }
         xh.v[j] = fmaf(a, rs, nmr);
         acc[0].v[j] = fmaf(d.v[j], xh.v[j], acc[0].v[j]);
@@ -297,11 +313,12 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
 // ---------------------------------------------------------------- fused LN -> +res -> LN
 // HAS_LN1 = false: x_new = x + a (no first LayerNorm): the deferred residual add of an FFN output fused
 // with the next block's pre-LayerNorm.
-template <bool HAS_LN1, int MAXT>
+// DROP: x_new = x + mask * branch  (residual dropout + drop-path of the block, transformer_layer.py:181,87)
+template <bool HAS_LN1, int MAXT, bool DROP = false>
 __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ x, const bf16* __restrict__ g1,
                                                      const bf16* __restrict__ b1, const bf16* __restrict__ g2, const bf16* __restrict__ b2,
                                                      float* __restrict__ x_new, bf16* __restrict__ y, float* __restrict__ stats,
-                                                     int64_t rows, int cols, float eps, int tpr) {
+                                                     int64_t rows, int cols, float eps, int tpr, const DropArgs da) {
   constexpr int NST = 3;
   extern __shared__ __align__(128) uint8_t dsm[];
   __shared__ float red[512];
@@ -318,6 +335,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
   in.stage_bytes = (uint32_t)r.rpb * (in.row_bytes[0] + in.row_bytes[1]);
   const int64_t my_n = ring_start<2, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
+  DropCtx dk;
+  if (DROP) dk = drop_ctx(da);
   f8 gg1, bb1, gg2, bb2;
   if (r.col_ok) {
     if (HAS_LN1) {
@@ -363,9 +382,13 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
     }
     s = 0.f;
     if (live) {
+      f8 m;
+      if (DROP) m = drop_mask8(da, dk, row, r.c);
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        v.v[j] = HAS_LN1 ? xx.v[j] + fmaf(v.v[j] * r1, gg1.v[j], bb1.v[j]) : xx.v[j] + v.v[j];
+        float br = HAS_LN1 ? fmaf(v.v[j] * r1, gg1.v[j], bb1.v[j]) : v.v[j];
+        if (DROP) br *= m.v[j];
+        v.v[j] = xx.v[j] + br;
         s += v.v[j];
       }
       store8(x_new + row * cols + r.c, v);
@@ -399,12 +422,12 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
   }
 }
 
-template <bool HAS_LN1, int MAXT>
+template <bool HAS_LN1, int MAXT, bool DROP = false>
 __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ dxn, const bf16* __restrict__ dy, const bf16* __restrict__ a,
                                                      const float* __restrict__ x_new, const bf16* __restrict__ g1,
                                                      const bf16* __restrict__ g2, const float* __restrict__ stats,
                                                      float* __restrict__ dxt, bf16* __restrict__ da, float* __restrict__ partial,
-                                                     int64_t rows, int cols, int tpr) {
+                                                     int64_t rows, int cols, int tpr, const DropArgs dra) {
   constexpr int NST = 2;
   constexpr int NIN = HAS_LN1 ? 4 : 3;
   extern __shared__ __align__(128) uint8_t dsm[];
@@ -429,6 +452,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
   in.stage_bytes = (uint32_t)r.rpb * (uint32_t)cols * (HAS_LN1 ? 12u : 10u);
   const int64_t my_n = ring_start<NIN, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
+  DropCtx dk;
+  if (DROP) dk = drop_ctx(dra);
   f8 gg1, gg2;
   if (r.col_ok) {
     if (HAS_LN1) gg1 = load8(g1 + r.c);
@@ -479,6 +504,11 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
 #pragma unroll
       for (int j = 0; j < 8; ++j) tot.v[j] += fmaf(xh.v[j], c1, fmaf(d.v[j], r2, c2));  // + LN2'(dy)
       store8(dxt + row * cols + r.c, tot);
+      if (DROP) {  // gradient of the residual branch = mask * d x_new
+        const f8 m = drop_mask8(dra, dk, row, r.c);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) tot.v[j] *= m.v[j];
+      }
       if (HAS_LN1) {
         const f8 aa = unpack8(a_raw);
         const float nm1 = -m1 * r1;
@@ -603,6 +633,11 @@ static int ln_configure(const void* kern) {  // opt in to > 48 KB dynamic shared
   return OFAB_OK;
 }
 #define LN_ALIGNED16(p) ((((uintptr_t)(p)) & 15) == 0)
+// optional dropout descriptor -> kernel form (`has` = descriptor given and not a no-op)
+#define LN_DROP(who)                                                             \
+  DropArgs da{};                                                                 \
+  const bool has_drop = drop != nullptr && (drop->p > 0.f || drop->drop_path > 0.f); \
+  if (has_drop && !ofab_drop_args(drop, da, who)) return OFAB_ERR_ARG
 // launch kernel template K<..., 384> or K<..., 512> by block size
 #define LN_GO(GRID, SMEM, TARGET, K384, K512, ...)                              \
   do {                                                                          \
@@ -616,7 +651,9 @@ static int ln_configure(const void* kern) {  // opt in to > 48 KB dynamic shared
   } while (0)
 
 extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const void* beta, void* y, int y_dt, float* mean,
-                           float* rstd, int64_t rows, int cols, float eps, int gelu, ofab_stream_t stream) {
+                           float* rstd, int64_t rows, int cols, float eps, int gelu, const ofab_dropout* drop, ofab_stream_t stream) {
+  LN_DROP("ofab_ln_fwd");
+  OFAB_REQUIRE(!has_drop || (gelu && x_dt == OFAB_BF16 && y_dt == OFAB_BF16), "ofab_ln_fwd: dropout is fused only into the bf16 GELU form");
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_fwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(rows >= 0, "ofab_ln_fwd: rows < 0");
   OFAB_REQUIRE(LN_ALIGNED16(x) && LN_ALIGNED16(y) && LN_ALIGNED16(gamma) && LN_ALIGNED16(beta), "ofab_ln_fwd: x / y / gamma / beta must be 16-byte aligned");
@@ -626,9 +663,10 @@ extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const voi
   const int64_t ngroups = (rows + l.rpb - 1) / l.rpb;
   const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
   const int smem = ln_smem(l, cols, x_dt == OFAB_F32 ? 4 : 2, 6, false);
-#define ARGS(TX, TY) (const TX*)x, (const bf16*)gamma, (const bf16*)beta, (TY*)y, mean, rstd, rows, cols, eps, l.tpr
+#define ARGS(TX, TY) (const TX*)x, (const bf16*)gamma, (const bf16*)beta, (TY*)y, mean, rstd, rows, cols, eps, l.tpr, da
 #define FWD(TX, TY, G) LN_GO(grid, smem, 384, (ln_fwd_kernel<TX, TY, G, 384>), (ln_fwd_kernel<TX, TY, G, 512>), ARGS(TX, TY))
-  if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) FWD(float, bf16, false);
+  if (has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
+  else if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) FWD(float, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && !gelu) FWD(bf16, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && gelu) FWD(bf16, bf16, true);
   else if (x_dt == OFAB_F32 && y_dt == OFAB_F32 && !gelu) FWD(float, float, false);
@@ -645,7 +683,9 @@ extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const voi
 
 extern "C" int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, const void* gamma, const float* mean,
                            const float* rstd, void* dx, int dx_dt, int dx_accum, float* dgb_partial, int64_t rows,
-                           int cols, int gelu, ofab_stream_t stream) {
+                           int cols, int gelu, const ofab_dropout* drop, ofab_stream_t stream) {
+  LN_DROP("ofab_ln_bwd");
+  OFAB_REQUIRE(!has_drop || (gelu && dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16), "ofab_ln_bwd: dropout is fused only into the bf16 GELU form");
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_bwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(!dx_accum || dx_dt == OFAB_F32, "ofab_ln_bwd: dx_accum needs fp32 dx");
   OFAB_REQUIRE(LN_ALIGNED16(x) && LN_ALIGNED16(dy) && LN_ALIGNED16(dx) && LN_ALIGNED16(gamma) && LN_ALIGNED16(dgb_partial),
@@ -654,9 +694,10 @@ extern "C" int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
   const LnLaunch l = ln_launch(cols);
   const int grid = OFAB_LN_PARTIAL_ROWS;  // every partial row is written (idle CTAs write zeros)
   const int smem = ln_smem(l, cols, (x_dt == OFAB_F32 ? 4 : 2) + (dy_dt == OFAB_F32 ? 4 : 2), 4, true);
-#define ARGS(TDY, TX, TDX) (const TDY*)dy, (const TX*)x, (const bf16*)gamma, mean, rstd, (TDX*)dx, dgb_partial, rows, cols, l.tpr
+#define ARGS(TDY, TX, TDX) (const TDY*)dy, (const TX*)x, (const bf16*)gamma, mean, rstd, (TDX*)dx, dgb_partial, rows, cols, l.tpr, da
 #define BWD(TDY, TX, TDX, G, A) LN_GO(grid, smem, 384, (ln_bwd_kernel<TDY, TX, TDX, G, A, 384>), (ln_bwd_kernel<TDY, TX, TDX, G, A, 512>), ARGS(TDY, TX, TDX))
-  if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && dx_accum) BWD(bf16, float, float, false, true);
+  if (has_drop) LN_GO(grid, smem, 384, (ln_bwd_kernel<bf16, bf16, bf16, true, false, 384, true>), (ln_bwd_kernel<bf16, bf16, bf16, true, false, 512, true>), ARGS(bf16, bf16, bf16));
+  else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && dx_accum) BWD(bf16, float, float, false, true);
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum) BWD(bf16, float, float, false, false);
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && gelu) BWD(bf16, bf16, bf16, true, false);
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && !gelu) BWD(bf16, bf16, bf16, false, false);
@@ -674,7 +715,8 @@ extern "C" int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
 
 extern "C" int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1, const void* b1, const void* g2,
                                   const void* b2, float* x_new, void* y, float* stats, int64_t rows, int cols,
-                                  float eps, ofab_stream_t stream) {
+                                  float eps, const ofab_dropout* drop, ofab_stream_t stream) {
+  LN_DROP("ofab_ln_res_ln_fwd");
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_res_ln_fwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(LN_ALIGNED16(a) && LN_ALIGNED16(x) && LN_ALIGNED16(x_new) && LN_ALIGNED16(y), "ofab_ln_res_ln_fwd: a / x / x_new / y must be 16-byte aligned");
   if (rows == 0) return OFAB_OK;
@@ -683,19 +725,26 @@ extern "C" int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1,
   const int64_t ngroups = (rows + l.rpb - 1) / l.rpb;
   const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
   const int smem = ln_smem(l, cols, 6, 3, false);
-  if (g1 != nullptr)
-    LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<true, 384>), (ln_res_ln_fwd_kernel<true, 512>), (const bf16*)a, x, (const bf16*)g1, (const bf16*)b1,
-          (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
-  else
-    LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<false, 384>), (ln_res_ln_fwd_kernel<false, 512>), (const bf16*)a, x, (const bf16*)nullptr,
-          (const bf16*)nullptr, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr);
+#define RFWD(L1, D)                                                                                                                     \
+  LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<L1, 384, D>), (ln_res_ln_fwd_kernel<L1, 512, D>), (const bf16*)a, x, (const bf16*)g1, \
+        (const bf16*)b1, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr, da)
+  if (g1 != nullptr) {
+    if (has_drop) RFWD(true, true); else RFWD(true, false);
+  } else {
+    if (has_drop) RFWD(false, true); else RFWD(false, false);
+  }
+#undef RFWD
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_fwd");
   return OFAB_OK;
 }
 
 extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const void* a, const float* x_new, const void* g1,
-                                  const void* g2, const float* stats, float* dx_tot, void* da, float* dgb_partial,
-                                  int64_t rows, int cols, ofab_stream_t stream) {
+                                  const void* g2, const float* stats, float* dx_tot, void* da_out, float* dgb_partial,
+                                  int64_t rows, int cols, const ofab_dropout* drop, ofab_stream_t stream) {
+  void* da = da_out;
+  DropArgs dra{};
+  const bool has_drop = drop != nullptr && (drop->p > 0.f || drop->drop_path > 0.f);
+  if (has_drop && !ofab_drop_args(drop, dra, "ofab_ln_res_ln_bwd")) return OFAB_ERR_ARG;
   OFAB_REQUIRE(cols % 8 == 0 && cols >= 8 && cols <= 4096, "ofab_ln_res_ln_bwd: cols=%d must be a multiple of 8 in [8,4096]", cols);
   OFAB_REQUIRE(LN_ALIGNED16(dx_new) && LN_ALIGNED16(dy) && LN_ALIGNED16(x_new) && LN_ALIGNED16(dx_tot) && LN_ALIGNED16(da) &&
                    LN_ALIGNED16(dgb_partial) && (g1 == nullptr || LN_ALIGNED16(a)),
@@ -705,13 +754,19 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
   if (g1 != nullptr) {
     const LnLaunch l = ln_launch(cols, 288);  // 5 accumulator slabs: ~110 registers -> 288-thread CTAs, still two per SM
     const int smem = ln_smem(l, cols, 12, 2, true);
-    LN_GO(grid, smem, 288, (ln_res_ln_bwd_kernel<true, 288>), (ln_res_ln_bwd_kernel<true, 512>), dx_new, (const bf16*)dy, (const bf16*)a, x_new,
-          (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
+#define RBWD(D)                                                                                                                          \
+  LN_GO(grid, smem, 288, (ln_res_ln_bwd_kernel<true, 288, D>), (ln_res_ln_bwd_kernel<true, 512, D>), dx_new, (const bf16*)dy, (const bf16*)a, \
+        x_new, (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr, dra)
+    if (has_drop) RBWD(true); else RBWD(false);
+#undef RBWD
   } else {
     const LnLaunch l = ln_launch(cols);
     const int smem = ln_smem(l, cols, 10, 2, true);
-    LN_GO(grid, smem, 384, (ln_res_ln_bwd_kernel<false, 384>), (ln_res_ln_bwd_kernel<false, 512>), dx_new, (const bf16*)dy, (const bf16*)nullptr, x_new,
-          (const bf16*)nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr);
+#define RBWD(D)                                                                                                                       \
+  LN_GO(grid, smem, 384, (ln_res_ln_bwd_kernel<false, 384, D>), (ln_res_ln_bwd_kernel<false, 512, D>), dx_new, (const bf16*)dy,           \
+        (const bf16*)nullptr, x_new, (const bf16*)nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr, dra)
+    if (has_drop) RBWD(true); else RBWD(false);
+#undef RBWD
   }
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_bwd");
   return OFAB_OK;

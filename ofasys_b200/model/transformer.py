@@ -26,12 +26,16 @@ class TransformerEncoder(nn.Module):
         dpr = torch.linspace(0, cfg.encode_drop_path_rate, cfg.encoder.layers)
         self.layers = nn.ModuleList([TransformerEncoderLayer(cfg, drop_path_rate=float(dpr[i])) for i in range(cfg.encoder.layers)])
         self.layer_norm = LayerNorm(cfg.encoder.embed_dim) if cfg.encoder.normalize_before else None
+        self._uses_dropout = any(float(getattr(cfg, k, 0.0) or 0.0) > 0 for k in
+                                 ("dropout", "attention_dropout", "activation_dropout", "relu_dropout", "encode_drop_path_rate"))
 
     def forward(self, slots: List[Slot], return_all_hiddens: bool = False, return_all_attention_weights: bool = False):
         if len(slots) == 0:
             return None
         if return_all_attention_weights:
             raise NotImplementedError("attention maps are never materialised by the fused kernel")
+        if self.training and self._uses_dropout:
+            ops.dropout_state().next_step()  # the encoder opens a step: fresh masks, call-site counter restarted
         embed, masks, pos, biases, _ = self.adaptor(slots)
         x = embed  # padded rows already zeroed by the adaptor kernels (transformer.py:109-112)
         states = [x.transpose(0, 1)] if return_all_hiddens else []
@@ -49,7 +53,7 @@ class TransformerEncoder(nn.Module):
                 x = out
                 states.append(x.transpose(0, 1))
         if pending is not None:
-            x, xb = ops.ln_res_ln(pending, x, None, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+            x, xb = ops.ln_res_ln(pending[0], x, None, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, drop=pending[1])
         else:
             xb = self.layer_norm(x) if self.layer_norm is not None else ops.to_bf16(x)  # bf16 [B, S, C]
         return {
@@ -154,7 +158,7 @@ class TransformerDecoder(nn.Module):
                 x = out
                 inner.append(x.transpose(0, 1))
         if pending is not None:
-            _, x = ops.ln_res_ln(pending, x, None, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps)
+            _, x = ops.ln_res_ln(pending[0], x, None, None, self.layer_norm.weight, self.layer_norm.bias, self.layer_norm.eps, drop=pending[1])
         else:
             x = self.layer_norm(x) if self.layer_norm is not None else ops.to_bf16(x)  # bf16 B x T x C
         return x, {"attn": [None], "inner_states": inner, "decoder_attentions": [], "cross_attentions": []}

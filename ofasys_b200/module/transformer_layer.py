@@ -24,30 +24,51 @@ def _check(cfg, side):
         raise NotImplementedError("modal_ffn / scale_resids are off in every BASELINE config and not implemented")
 
 
+def _branch_drop(layer, x):
+    """Descriptor of the block's residual-branch masks: `dropout_module` then `drop_path` on the branch before it is
+    added to the residual (transformer_layer.py:181,87,203 / :433,466,489,333).  None in eval mode or when both are 0.
+    x: [B, T, C] (drop-path drops whole samples = groups of T rows)."""
+    if not layer.training:
+        return None
+    return ops.dropout_state(x.device).spec(layer.dropout_p, layer.drop_path_rate, x.shape[1])
+
+
 def _ffn(layer, x2):
-    """x2 = final_layer_norm(x) bf16 -> fc2(ffn_ln(gelu(fc1 x2))) bf16.  The residual add is deferred: it is
+    """x2 = final_layer_norm(x) bf16 -> fc2(ffn_ln(act_drop(gelu(fc1 x2)))) bf16.  The residual add is deferred: it is
     fused with the next block's pre-LayerNorm (ops.ln_res_ln with no first LN), so the GEMM epilogue stays a
-    plain coalesced bf16 TMA store."""
+    plain coalesced bf16 TMA store.  Returns (y, descriptor of the dropout / drop-path still owed to y)."""
     h = ops.linear(x2, layer.fc1.weight, layer.fc1.bias)
     if layer.ffn_layernorm is not None:
-        h = ops.layer_norm(h, layer.ffn_layernorm.weight, layer.ffn_layernorm.bias, layer.ffn_layernorm.eps, gelu=True)
+        act_drop = ops.dropout_state(h.device).spec(layer.activation_dropout_p) if layer.training else None
+        h = ops.layer_norm(h, layer.ffn_layernorm.weight, layer.ffn_layernorm.bias, layer.ffn_layernorm.eps, gelu=True, drop=act_drop)
     else:
         raise NotImplementedError("scale_fc=False")
-    return ops.linear(h, layer.fc2.weight, layer.fc2.bias)
+    y = ops.linear(h, layer.fc2.weight, layer.fc2.bias)
+    return y, _branch_drop(layer, y)
 
 
 def _enter(x, pending, ln):
-    """(x, pending FFN output of the previous layer) -> (x + pending, ln(x + pending))."""
+    """(x, pending = (FFN output of the previous layer, its dropout descriptor)) -> (x + drop(y), ln(x + drop(y)))."""
     if pending is None:
         return x, ln(x)
-    return ops.ln_res_ln(pending, x, None, None, ln.weight, ln.bias, ln.eps)
+    y, drop = pending
+    return ops.ln_res_ln(y, x, None, None, ln.weight, ln.bias, ln.eps, drop=drop)
 
 
-def _junction(attn_out, x_res, ln_attn, ln_next):
-    """x_new = x_res + ln_attn(attn_out); y = ln_next(x_new)."""
+def _junction(layer, attn_out, x_res, ln_attn, ln_next):
+    """x_new = x_res + drop(ln_attn(attn_out)); y = ln_next(x_new)."""
     if ln_attn is None:
         raise NotImplementedError("scale_attn=False")
-    return ops.ln_res_ln(attn_out, x_res, ln_attn.weight, ln_attn.bias, ln_next.weight, ln_next.bias, ln_next.eps)
+    return ops.ln_res_ln(attn_out, x_res, ln_attn.weight, ln_attn.bias, ln_next.weight, ln_next.bias, ln_next.eps,
+                         drop=_branch_drop(layer, attn_out))
+
+
+def _act_dropout_p(cfg):
+    """transformer_layer.py:42-46: activation_dropout, falling back to the legacy relu_dropout."""
+    p = float(getattr(cfg, "activation_dropout", 0.0) or 0.0)
+    if p == 0:
+        p = float(getattr(cfg, "relu_dropout", 0.0) or 0.0)
+    return p
 
 
 class TransformerEncoderLayer(nn.Module):
@@ -60,7 +81,8 @@ class TransformerEncoderLayer(nn.Module):
         self.self_attn = MultiheadAttention(self.embed_dim, cfg.encoder.attention_heads, dropout=cfg.attention_dropout,
                                             self_attention=True, scale_factor=cfg.attn_scale_factor, scale_heads=cfg.scale_heads)
         self.self_attn_layer_norm = LayerNorm(self.embed_dim)
-        self.dropout_p = cfg.dropout
+        self.dropout_p = float(cfg.dropout)
+        self.activation_dropout_p = _act_dropout_p(cfg)
         self.normalize_before = True
         self.fc1 = nn.Linear(self.embed_dim, cfg.encoder.ffn_embed_dim)
         self.fc2 = nn.Linear(cfg.encoder.ffn_embed_dim, self.embed_dim)
@@ -75,20 +97,19 @@ class TransformerEncoderLayer(nn.Module):
     def forward(self, x, encoder_padding_mask=None, attn_mask=None, self_attn_bias=None, need_attn=False, modal_mask=None,
                 batch_first=False, pending=None, defer=False):
         """x: T x B x C (reference layout) or B x T x C with batch_first=True; fp32 residual stream.
-        Internal fast path (used by TransformerEncoder): `pending` = previous layer's FFN output whose residual add
-        is still owed; with defer=True this layer returns ((x, pending'), None) instead of adding its own."""
-        if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError("dropout / drop-path > 0: parity and headline runs use p=0 (SURVEY 8d)")
+        Internal fast path (used by TransformerEncoder): `pending` = (previous layer's FFN output whose residual add
+        is still owed, its dropout descriptor); with defer=True this layer returns ((x, pending'), None) instead of
+        adding its own."""
         if not batch_first:
             x = x.transpose(0, 1).contiguous()
         x = ops.to_f32(x)
         x, x1 = _enter(x, pending, self.self_attn_layer_norm)
         a, _ = self.self_attn(x1, key_padding_mask=encoder_padding_mask, attn_bias=self_attn_bias, batch_first=True, causal=attn_mask is not None)
-        x, x2 = _junction(a, x, self.attn_ln, self.final_layer_norm)
-        y = _ffn(self, x2)
+        x, x2 = _junction(self, a, x, self.attn_ln, self.final_layer_norm)
+        y, ydrop = _ffn(self, x2)
         if defer:
-            return (x, y), None
-        x = ops.add_residual(x, y)
+            return (x, (y, ydrop)), None
+        x = ops.add_residual(x, ops.dropout(y, ydrop))
         if not batch_first:
             x = x.transpose(0, 1)
         return x, None
@@ -102,7 +123,8 @@ class TransformerDecoderLayer(nn.Module):
         _check(cfg, "decoder")
         assert not no_encoder_attn and not cfg.cross_self_attention
         self.embed_dim = cfg.decoder.embed_dim
-        self.dropout_p = cfg.dropout
+        self.dropout_p = float(cfg.dropout)
+        self.activation_dropout_p = _act_dropout_p(cfg)
         self.self_attn = MultiheadAttention(self.embed_dim, cfg.decoder.attention_heads, dropout=cfg.attention_dropout,
                                             self_attention=True, scale_factor=cfg.attn_scale_factor, scale_heads=cfg.scale_heads)
         self.self_attn_ln = LayerNorm(self.embed_dim) if cfg.scale_attn else None
@@ -129,8 +151,6 @@ class TransformerDecoderLayer(nn.Module):
                 self_attn_bias=None, cross_attn_bias=None, modal_mask=None, batch_first=False, pending=None, defer=False):
         if incremental_state is not None or prev_self_attn_state is not None or prev_attn_state is not None:
             raise NotImplementedError("incremental decoding is outside the fwd+bwd hot path")
-        if self.training and (self.dropout_p > 0 or self.drop_path_rate > 0):
-            raise NotImplementedError("dropout / drop-path > 0: parity and headline runs use p=0 (SURVEY 8d)")
         if not batch_first:
             x = x.transpose(0, 1).contiguous()
             encoder_out = encoder_out.transpose(0, 1).contiguous()
@@ -139,14 +159,14 @@ class TransformerDecoderLayer(nn.Module):
         # the decoder passes False (not None) when biases are off -> manual path (transformer.py:476-477)
         a, _ = self.self_attn(x1, key_padding_mask=self_attn_padding_mask, attn_bias=self_attn_bias if self_attn_bias is not None else False,
                               batch_first=True, causal=self_attn_mask is not None)
-        x, x2 = _junction(a, x, self.self_attn_ln, self.encoder_attn_layer_norm)
+        x, x2 = _junction(self, a, x, self.self_attn_ln, self.encoder_attn_layer_norm)
         c, _ = self.encoder_attn(x2, key=encoder_out, value=encoder_out, key_padding_mask=encoder_padding_mask, static_kv=True,
                                  attn_bias=cross_attn_bias, batch_first=True, causal=False)
-        x, x3 = _junction(c, x, self.cross_attn_ln, self.final_layer_norm)
-        y = _ffn(self, x3)
+        x, x3 = _junction(self, c, x, self.cross_attn_ln, self.final_layer_norm)
+        y, ydrop = _ffn(self, x3)
         if defer:
-            return (x, y), None, None
-        x = ops.add_residual(x, y)
+            return (x, (y, ydrop)), None, None
+        x = ops.add_residual(x, ops.dropout(y, ydrop))
         if not batch_first:
             x = x.transpose(0, 1)
         return x, None, None

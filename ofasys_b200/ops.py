@@ -32,6 +32,91 @@ def _c(t):
     return t if t.is_contiguous() else t.contiguous()
 
 
+# ------------------------------------------------------------------------------------ dropout state
+class DropoutState:
+    """Seed + step counter of the counter-based dropout masks (include/ofab.h `ofab_dropout`), one per device.
+
+    The two int64 words live in DEVICE memory and are read by the kernels when they run, so a captured CUDA graph
+    draws fresh masks on every replay: `next_step()` is a device-side increment that is part of the captured work.
+    Call sites of one step are told apart by `site`, a host counter restarted by next_step(); backward kernels get
+    the descriptor their forward used and regenerate the same mask (no mask tensor is ever stored).
+    """
+
+    def __init__(self, device, seed=None):
+        seed = torch.initial_seed() if seed is None else seed
+        self.state = torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64, device=device)
+        self._one = torch.ones(1, dtype=torch.int64, device=device)
+        self.site = 0
+
+    def reseed(self, seed, step=0):
+        self.state.copy_(torch.tensor([seed & 0x7FFFFFFFFFFFFFFF, step], dtype=torch.int64))
+        self.site = 0
+
+    def next_step(self):
+        self.state[1:2].add_(self._one)
+        self.site = 0
+
+    def spec(self, p=0.0, drop_path=0.0, rows_per_sample=0):
+        """A fresh call-site descriptor, or None when nothing would be dropped."""
+        if p <= 0.0 and drop_path <= 0.0:
+            return None
+        self.site += 1
+        d = _lib.Dropout()
+        d.state, d.site, d.p, d.drop_path, d.rows_per_sample = self.state.data_ptr(), self.site, float(p), float(drop_path), int(rows_per_sample)
+        d._keep = self.state  # the descriptor holds a raw pointer into it
+        return d
+
+
+_DROPOUT_STATES = {}
+
+
+def dropout_state(device=None) -> DropoutState:
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    st = _DROPOUT_STATES.get(device)
+    if st is None:
+        st = _DROPOUT_STATES[device] = DropoutState(device)
+    return st
+
+
+def _dp(drop):
+    return None if drop is None else ctypes.byref(drop)
+
+
+class _DropoutFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, drop):
+        _need_cuda(x)
+        x = _c(x)
+        cols = x.shape[-1]
+        y = torch.empty_like(x)
+        _lib.call("ofab_dropout_apply", _p(x), _p(y), _DT[x.dtype], x.numel() // cols, cols, _dp(drop), _s())
+        ctx.drop = drop
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dy = _c(dy)
+        cols = dy.shape[-1]
+        dx = torch.empty_like(dy)
+        _lib.call("ofab_dropout_apply", _p(dy), _p(dx), _DT[dy.dtype], dy.numel() // cols, cols, _dp(ctx.drop), _s())
+        return dx, None
+
+
+def dropout(x, drop):
+    """x * keep-mask of descriptor `drop` (DropoutState.spec); identity when drop is None.  Rows = all leading dims."""
+    return x if drop is None else _DropoutFn.apply(x, drop)
+
+
+def dropout_mask(drop, rows, cols, device=None):
+    """The fp32 multipliers [rows, cols] descriptor `drop` applies (0 or 1/keep): what tests hand to the oracle."""
+    ones = torch.ones((rows, cols), dtype=torch.float32, device=device or "cuda")
+    out = torch.empty_like(ones)
+    _lib.call("ofab_dropout_apply", _p(ones), _p(out), F32, rows, cols, _dp(drop), _s())
+    return out
+
+
 # ------------------------------------------------------------------------------------ reductions
 def colsum(x2d, out_dtype=torch.bfloat16, out=None, accumulate=False, scratch=None):
     """out[c] (+)= sum_r x2d[r, c]; x2d may have a row stride (last dim contiguous)."""
@@ -112,7 +197,7 @@ def _partial_rows():
 
 class _LayerNormFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, eps, gelu, out_dtype):
+    def forward(ctx, x, weight, bias, eps, gelu, out_dtype, drop=None):
         _need_cuda(x, weight, bias)
         x = _c(x)
         cols = x.shape[-1]
@@ -120,9 +205,10 @@ class _LayerNormFn(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         mean = torch.empty(rows, dtype=torch.float32, device=x.device)
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
-        _lib.call("ofab_ln_fwd", _p(x), _DT[x.dtype], _p(weight), _p(bias), _p(y), _DT[out_dtype], _p(mean), _p(rstd), rows, cols, eps, int(gelu), _s())
+        _lib.call("ofab_ln_fwd", _p(x), _DT[x.dtype], _p(weight), _p(bias), _p(y), _DT[out_dtype], _p(mean), _p(rstd), rows, cols, eps, int(gelu), _dp(drop), _s())
         ctx.save_for_backward(x, weight, mean, rstd)
         ctx.gelu = gelu
+        ctx.drop = drop
         return y
 
     @staticmethod
@@ -134,21 +220,22 @@ class _LayerNormFn(torch.autograd.Function):
         dx = torch.empty_like(x)
         partial = torch.empty((3, _partial_rows(), cols), dtype=torch.float32, device=x.device)
         _lib.call("ofab_ln_bwd", _p(dy), _DT[dy.dtype], _p(x), _DT[x.dtype], _p(weight), _p(mean), _p(rstd), _p(dx), _DT[dx.dtype], 0,
-                  _p(partial), rows, cols, int(ctx.gelu), _s())
+                  _p(partial), rows, cols, int(ctx.gelu), _dp(ctx.drop), _s())
         g = _reduce_partials(partial, weight.dtype)
         if dx.dtype == torch.bfloat16:
             _hint_bias_grad(dx, g[2])
-        return dx, g[0], g[1], None, None, None
+        return dx, g[0], g[1], None, None, None, None
 
 
-def layer_norm(x, weight, bias, eps=1e-5, gelu=False, out_dtype=torch.bfloat16):
-    """LN(gelu?(x)).  x fp32 -> bf16/fp32, or bf16 -> bf16/fp32 (gelu only bf16 -> bf16)."""
-    return _LayerNormFn.apply(x, weight, bias, eps, gelu, out_dtype)
+def layer_norm(x, weight, bias, eps=1e-5, gelu=False, out_dtype=torch.bfloat16, drop=None):
+    """LN(drop?(gelu?(x))).  x fp32 -> bf16/fp32, or bf16 -> bf16/fp32 (gelu only bf16 -> bf16; `drop` = activation
+    dropout descriptor, gelu form only)."""
+    return _LayerNormFn.apply(x, weight, bias, eps, gelu, out_dtype, drop)
 
 
 class _LnResLnFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, a, x, w1, b1, w2, b2, eps):
+    def forward(ctx, a, x, w1, b1, w2, b2, eps, drop=None):
         _need_cuda(a, x)
         a, x = _c(a), _c(x)
         assert a.dtype == torch.bfloat16 and x.dtype == torch.float32
@@ -157,9 +244,10 @@ class _LnResLnFn(torch.autograd.Function):
         x_new = torch.empty_like(x)
         y = torch.empty_like(a)
         stats = torch.empty((4, rows), dtype=torch.float32, device=a.device)
-        _lib.call("ofab_ln_res_ln_fwd", _p(a), _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(x_new), _p(y), _p(stats), rows, cols, eps, _s())
+        _lib.call("ofab_ln_res_ln_fwd", _p(a), _p(x), _p(w1), _p(b1), _p(w2), _p(b2), _p(x_new), _p(y), _p(stats), rows, cols, eps, _dp(drop), _s())
         ctx.save_for_backward(a if w1 is not None else None, x_new, w1, w2, stats)
         ctx.shape_a = a.shape
+        ctx.drop = drop
         return x_new, y
 
     @staticmethod
@@ -172,17 +260,18 @@ class _LnResLnFn(torch.autograd.Function):
         dx_tot = torch.empty_like(x_new)
         da = torch.empty(ctx.shape_a, dtype=torch.bfloat16, device=x_new.device)
         partial = torch.empty((5, _partial_rows(), cols), dtype=torch.float32, device=x_new.device)
-        _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _s())
+        _lib.call("ofab_ln_res_ln_bwd", _p(dx_new), _p(dy), _p(a), _p(x_new), _p(w1), _p(w2), _p(stats), _p(dx_tot), _p(da), _p(partial), rows, cols, _dp(ctx.drop), _s())
         g = _reduce_partials(partial, w2.dtype)
         _hint_bias_grad(da, g[4])
         if w1 is None:
-            return da, dx_tot, None, None, g[2], g[3], None
-        return da, dx_tot, g[0], g[1], g[2], g[3], None
+            return da, dx_tot, None, None, g[2], g[3], None, None
+        return da, dx_tot, g[0], g[1], g[2], g[3], None, None
 
 
-def ln_res_ln(a, x, w1, b1, w2, b2, eps=1e-5):
-    """x_new = x + LN1(a); y = LN2(x_new).  Returns (x_new fp32, y bf16).  w1 = b1 = None: x_new = x + a."""
-    return _LnResLnFn.apply(a, x, w1, b1, w2, b2, eps)
+def ln_res_ln(a, x, w1, b1, w2, b2, eps=1e-5, drop=None):
+    """x_new = x + drop(LN1(a)); y = LN2(x_new).  Returns (x_new fp32, y bf16).  w1 = b1 = None: x_new = x + drop(a).
+    `drop`: residual dropout / drop-path descriptor of the block (DropoutState.spec) or None."""
+    return _LnResLnFn.apply(a, x, w1, b1, w2, b2, eps, drop)
 
 
 class _AddFn(torch.autograd.Function):
@@ -440,7 +529,7 @@ class _EmbedLnFn(torch.autograd.Function):
     """out = LN(src + pos + type) (fp32 [B, T, d]); src = E[tokens] or [cls; dense]."""
 
     @staticmethod
-    def forward(ctx, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx):
+    def forward(ctx, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx, drop=None):
         dev = gamma.device
         _need_cuda(gamma)
         if tokens is not None:
@@ -461,15 +550,17 @@ class _EmbedLnFn(torch.autograd.Function):
         mean = torch.empty(B * T, dtype=torch.float32, device=dev)
         rstd = torch.empty(B * T, dtype=torch.float32, device=dev)
         a = _lib.EmbedLnArgs()
-        _EmbedLnFn._fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd)
+        _EmbedLnFn._fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd, drop)
         _lib.call("ofab_embed_ln_fwd", ctypes.byref(a), _s())
         ctx.save_for_backward(tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, mean, rstd)
         ctx.meta = (B, T, d, eps, padding_idx)
+        ctx.drop = drop
         return out
 
     @staticmethod
-    def _fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd):
+    def _fill(a, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, out, mean, rstd, drop=None):
         a.B, a.T, a.d = B, T, d
+        a.drop = None if drop is None else ctypes.pointer(drop)
         a.tokens = None if tokens is None else tokens.data_ptr()
         a.E = None if E is None or tokens is None else E.data_ptr()
         a.dense = None if dense is None else dense.data_ptr()
@@ -491,7 +582,7 @@ class _EmbedLnFn(torch.autograd.Function):
         dev = gamma.device
         dout = _c(dout)
         a = _lib.EmbedLnBwdArgs()
-        _EmbedLnFn._fill(a.f, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, None, mean, rstd)
+        _EmbedLnFn._fill(a.f, B, T, d, tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, None, mean, rstd, ctx.drop)
         a.dout, a.dout_bs = dout.data_ptr(), T * d
         dE = ddense = dpos = None
         if tokens is not None and ctx.needs_input_grad[1]:
@@ -521,11 +612,11 @@ class _EmbedLnFn(torch.autograd.Function):
             dE = cast_bf16(dE)
         if dpos is not None:
             dpos = cast_bf16(dpos).view(pos.shape)
-        return None, dE, ddense, dcls, dpos, dtype_vec, dgamma, dbeta, None, None, None
+        return None, dE, ddense, dcls, dpos, dtype_vec, dgamma, dbeta, None, None, None, None
 
 
-def embed_ln(gamma, beta, tokens=None, E=None, dense=None, cls=None, pos=None, type_vec=None, zero_mask=None, eps=1e-5, padding_idx=None):
-    return _EmbedLnFn.apply(tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx)
+def embed_ln(gamma, beta, tokens=None, E=None, dense=None, cls=None, pos=None, type_vec=None, zero_mask=None, eps=1e-5, padding_idx=None, drop=None):
+    return _EmbedLnFn.apply(tokens, E, dense, cls, pos, type_vec, gamma, beta, zero_mask, eps, padding_idx, drop)
 
 
 # ------------------------------------------------------------------------------------ criterion

@@ -108,6 +108,21 @@ def audio_out_lengths(in_lens: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# ------------------------------------------------------------------ dropout sites
+# The reference draws its masks from torch's RNG (module/dropout.py:14-25 -> F.dropout; module/droppath.py:13-63),
+# the CUDA path from a counter-based hash, so the two can only be compared with the SAME masks: a parity test
+# installs DROP_HOOK(kind, x) -> multiplier tensor broadcastable to x (0 or 1/keep, drop-path folded in) and the
+# oracle multiplies it in at exactly the places the reference calls its Dropout / DropPath modules.  kind:
+#   "embed" (adaptor/base.py:181, x is B x T x C), "attn_probs" (multihead_attention.py:335, B*H x T x S),
+#   "branch" (transformer_layer.py:181,203 / :433,466,489 followed by drop_path :87,:333, x is T x B x C),
+#   "act" (transformer_layer.py:195,481, T x B x 4C).  None = eval mode / p = 0 (every golden fixture).
+DROP_HOOK = None
+
+
+def _drop(kind, x):
+    return x if DROP_HOOK is None else x * DROP_HOOK(kind, x)
+
+
 # ------------------------------------------------------------------ small modules
 def layer_norm(x, sd, prefix, eps=1e-5):
     """module/layer_norm.py:27-32 -> torch.nn.LayerNorm."""
@@ -153,6 +168,7 @@ def mha(sd, prefix, cfg: OracleConfig, query, key, kpm, attn_mask, attn_bias, fa
         w = w.view(B, H, T, S).masked_fill(kpm.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
         w = w.view(B * H, T, S)  # :319-326
     p = F.softmax(w.float(), dim=-1).type_as(w)  # :333-334 (module/utils.py:451)
+    p = _drop("attn_probs", p)  # :335
     a = torch.bmm(p, v)  # :338
     a = a.transpose(0, 1).contiguous().view(T, B, C)
     if not fast_path and (prefix + ".c_attn") in sd:
@@ -165,6 +181,7 @@ def mha(sd, prefix, cfg: OracleConfig, query, key, kpm, attn_mask, attn_bias, fa
 def ffn(sd, prefix, x):
     """transformer_layer.py:188-207: fc1 -> gelu(fp32) -> ffn_layernorm (scale_fc) -> fc2."""
     x = gelu(linear(x, sd, prefix + ".fc1"))
+    x = _drop("act", x)  # :195 / :481
     if (prefix + ".ffn_layernorm.weight") in sd:
         x = layer_norm(x, sd, prefix + ".ffn_layernorm")
     return linear(x, sd, prefix + ".fc2")
@@ -177,11 +194,11 @@ def encoder_layer(sd, prefix, cfg, x, kpm, self_attn_bias):
     x = mha(sd, prefix + ".self_attn", cfg, x, x, kpm, None, self_attn_bias, fast_path=self_attn_bias is None)
     if (prefix + ".attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".attn_ln")
-    x = residual + x
+    x = residual + _drop("branch", x)  # :181, :87
     residual = x
     x = layer_norm(x, sd, prefix + ".final_layer_norm")
     x = ffn(sd, prefix, x)
-    return residual + x
+    return residual + _drop("branch", x)  # :203, :87
 
 
 def decoder_layer(sd, prefix, cfg, x, enc, enc_kpm, self_mask, self_kpm, self_bias, cross_bias):
@@ -192,17 +209,17 @@ def decoder_layer(sd, prefix, cfg, x, enc, enc_kpm, self_mask, self_kpm, self_bi
     x = mha(sd, prefix + ".self_attn", cfg, x, x, self_kpm, self_mask, self_bias, fast_path=False)
     if (prefix + ".self_attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".self_attn_ln")
-    x = residual + x
+    x = residual + _drop("branch", x)  # :433, :333
     residual = x
     x = layer_norm(x, sd, prefix + ".encoder_attn_layer_norm")
     x = mha(sd, prefix + ".encoder_attn", cfg, x, enc, enc_kpm, None, cross_bias, fast_path=False)
     if (prefix + ".cross_attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".cross_attn_ln")
-    x = residual + x
+    x = residual + _drop("branch", x)  # :466, :333
     residual = x
     x = layer_norm(x, sd, prefix + ".final_layer_norm")
     x = ffn(sd, prefix, x)
-    return residual + x
+    return residual + _drop("branch", x)  # :489, :333
 
 
 # ------------------------------------------------------------------ adaptors
@@ -226,7 +243,7 @@ def _hook(sd, ap, cfg: OracleConfig, slot: OSlot, out: AOut, num_layers: int, re
     embed = layer_norm(embed, sd, ap + ".layernorm_embedding")
     if out.pos_embed is not None:
         out.pos_embed = layer_norm(out.pos_embed, sd, ap + ".layernorm_position")
-    out.embed = embed
+    out.embed = _drop("embed", embed)  # :181
     if not out.self_attn_bias and cfg.mode == "A":
         B, T = embed.shape[:2]
         out.self_attn_bias = []
