@@ -29,6 +29,7 @@ class AttnFwdArgs(Structure):
         ("rp_idx", c_void_p), ("table", c_void_p), ("n_buckets", c_int),
         ("kpm", c_void_p), ("causal", c_int), ("scale", c_float),
         ("o", c_void_p), ("o_bs", c_int64), ("o_rs", c_int64), ("lse", c_void_p),
+        ("drop", POINTER(Dropout)),
     ]
 
 

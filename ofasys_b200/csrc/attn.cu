@@ -83,6 +83,36 @@ struct AttnCommon {
   float scale;
 };
 
+// ---- attention dropout (multihead_attention.py:335: attn_probs = dropout(softmax(scores))) ------------------------
+// The keep bit of probability (b, h, i, j) is a keyed 32-bit hash of i * Tk + j; the two key words come from one
+// Philox4x32-7 call per thread on (seed, step, site, b * H + h), so the forward kernel and both backward kernels --
+// whose accumulator layouts differ (queries x keys vs keys x queries) -- regenerate the same bits element by element.
+// The softmax denominator and the saved log-sum-exp stay those of the undropped scores; backward keeps
+// delta = rowsum(dO * O) unchanged because rowsum(P * dP) = rowsum(P_drop * dP_drop).
+struct AttnDrop {
+  const unsigned long long* state;  // device [2]: seed, step (see DropArgs)
+  uint32_t site;
+  uint32_t thresh32;  // dropped when hash < thresh32  (= p * 2^32)
+  float inv_keep;     // 1 / (1 - p)
+};
+__device__ __forceinline__ uint2 attn_drop_key(const AttnDrop& d, int bh) {
+  const unsigned long long seed = d.state[0], step = d.state[1];
+  const uint4 r = philox4x32_7(make_uint4((uint32_t)bh, d.site, (uint32_t)step, 0x6A09E667u),
+                               make_uint2((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32)));
+  return make_uint2(r.x, r.y | 1u);
+}
+__device__ __forceinline__ bool attn_keep(const uint2 key, uint32_t ij, uint32_t thresh32) {
+  uint32_t x = (ij ^ key.x) * 0x9E3779B1u;
+  x ^= x >> 15;
+  x *= 0x85EBCA77u;
+  x ^= x >> 13;
+  x *= key.y;  // odd
+  x ^= x >> 16;
+  x *= 0xC2B2AE3Du;
+  x ^= x >> 15;
+  return x >= thresh32;
+}
+
 // Key-validity mask of one 64-key tile (bit jl set <=> key k0+jl is in range and not padding), built
 // cooperatively by warps 0 and 1 while the tile's cp.async copies are in flight.
 __device__ __forceinline__ void build_kmask(const AttnCommon& p, int b, int k0, uint32_t* dst /* smem [2] */) {
@@ -154,9 +184,9 @@ __device__ __forceinline__ float finish_tile(const AttnCommon& p, float (&s)[8][
 // ===================================================================================== forward
 // smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | key-validity bitmap (Tk bits) | table column (n_buckets floats)
 // K/V ring: 2 stages, one __syncthreads per key tile: tile kv+1 is fetched (cp.async) while tile kv is consumed.
-template <bool HAS_POS, bool HAS_TAB>
+template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
 __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
-                                                                        float* __restrict__ lse) {
+                                                                        float* __restrict__ lse, const AttnDrop ad) {
   constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
   constexpr int NST = 2;
   extern __shared__ __align__(128) uint8_t smem[];
@@ -200,6 +230,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
     for (int j = 0; j < 4; ++j) oacc[i][j] = 0.f;
   float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};  // running max (log2 domain) and sum per query row
   const int row_g[2] = {q0 + warp * 16 + g, q0 + warp * 16 + g + 8};
+  uint2 dkey = make_uint2(0u, 1u);
+  if (DROP) dkey = attn_drop_key(ad, b * p.H + h);
 
   for (int kv = 0; kv < n_kv; ++kv) {
     const int st = kv % NST;
@@ -265,6 +297,15 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
         }
 #pragma unroll
       for (int r = 0; r < 2; ++r) l_run[r] += ps[r];
+      if (DROP) {  // the row sums above are those of the undropped probabilities; only the P V product sees the mask
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const uint32_t ij = (uint32_t)row_g[e >> 1] * (uint32_t)p.Tk + (uint32_t)(k0 + nt * 8 + 2 * t + (e & 1));
+            s[nt][e] = attn_keep(dkey, ij, ad.thresh32) ? s[nt][e] * ad.inv_keep : 0.f;
+          }
+      }
 #pragma unroll
       for (int dt = 0; dt < 8; ++dt) {
         oacc[dt][0] *= corr[0]; oacc[dt][1] *= corr[0];
@@ -329,13 +370,14 @@ struct AttnBwdExtra {
   bf16 *dq, *dk, *dv, *dpq, *dpk;
   int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   float* dtable;
+  AttnDrop drop;
 };
 
 // ---- dK / dV: one CTA per 64-key tile, loops over query tiles.  Works on transposed scores
 // S^T[key, query] so every accumulator row belongs to this CTA's keys.
 // Query-side operands (Q, dO, lse, delta) are double-buffered when no table column competes for shared memory
 // (NSB = 2: tile qt+1 is fetched while tile qt is consumed, one barrier per tile).
-template <bool HAS_POS, bool HAS_TAB>
+template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
 __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   constexpr int NSB = HAS_TAB ? 1 : 2;
@@ -397,6 +439,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
 #pragma unroll
     for (int j = 0; j < 4; ++j) dv[i][j] = 0.f;
   const int key_g[2] = {k0 + warp * 16 + g, k0 + warp * 16 + g + 8};
+  uint2 dkey = make_uint2(0u, 1u);
+  if (DROP) dkey = attn_drop_key(e.drop, b * p.H + h);
 
   for (int qt = q_start; qt < n_q; ++qt) {
     const int q0 = qt * TILE;
@@ -452,15 +496,32 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
       for (int el = 0; el < 4; ++el) s[nt][el] = fast_ex2(fmaf(s[nt][el], mult, -lse2[nt * 8 + 2 * t + (el & 1)]));
-    // dV += P^T dO
+    if (DROP) {  // dropped probabilities are kept with a NEGATIVE sign: |s| = P, sign = keep bit
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int el = 0; el < 4; ++el) {
+          const uint32_t ij = (uint32_t)(q0 + nt * 8 + 2 * t + (el & 1)) * (uint32_t)p.Tk + (uint32_t)key_g[el >> 1];
+          if (!attn_keep(dkey, ij, e.drop.thresh32)) s[nt][el] = -s[nt][el];
+        }
+    }
+    const float ik = DROP ? e.drop.inv_keep : 1.0f;
+    // dV += P_drop^T dO
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
       if (kb2 < np_n) {
         uint32_t pa[4];
-        pa[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
-        pa[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
-        pa[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
-        pa[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+        if (DROP) {
+          pa[0] = pack_bf16(fmaxf(s[2 * kb2][0], 0.f) * ik, fmaxf(s[2 * kb2][1], 0.f) * ik);
+          pa[1] = pack_bf16(fmaxf(s[2 * kb2][2], 0.f) * ik, fmaxf(s[2 * kb2][3], 0.f) * ik);
+          pa[2] = pack_bf16(fmaxf(s[2 * kb2 + 1][0], 0.f) * ik, fmaxf(s[2 * kb2 + 1][1], 0.f) * ik);
+          pa[3] = pack_bf16(fmaxf(s[2 * kb2 + 1][2], 0.f) * ik, fmaxf(s[2 * kb2 + 1][3], 0.f) * ik);
+        } else {
+          pa[0] = pack_bf16(s[2 * kb2][0], s[2 * kb2][1]);
+          pa[1] = pack_bf16(s[2 * kb2][2], s[2 * kb2][3]);
+          pa[2] = pack_bf16(s[2 * kb2 + 1][0], s[2 * kb2 + 1][1]);
+          pa[3] = pack_bf16(s[2 * kb2 + 1][2], s[2 * kb2 + 1][3]);
+        }
 #pragma unroll
         for (int dp = 0; dp < 4; ++dp) {
           uint32_t bb[4];
@@ -494,7 +555,14 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int el = 0; el < 4; ++el) s[nt][el] *= fmaf(dp_[nt][el], p.scale, -dls[nt * 8 + 2 * t + (el & 1)]);
+      for (int el = 0; el < 4; ++el) {
+        if (DROP) {  // dP = keep / (1 - p) * dP_drop
+          const float dpm = s[nt][el] > 0.f ? dp_[nt][el] * ik : 0.f;
+          s[nt][el] = fabsf(s[nt][el]) * fmaf(dpm, p.scale, -dls[nt * 8 + 2 * t + (el & 1)]);
+        } else {
+          s[nt][el] *= fmaf(dp_[nt][el], p.scale, -dls[nt * 8 + 2 * t + (el & 1)]);
+        }
+      }
     // dK' += dS^T Q'
 #pragma unroll
     for (int kb2 = 0; kb2 < 4; ++kb2) {
@@ -540,7 +608,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
 
 // ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles (K / V double-buffered when no
 // table column competes for shared memory).
-template <bool HAS_POS, bool HAS_TAB>
+template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
 __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   constexpr int NSB = HAS_TAB ? 1 : 2;
@@ -615,6 +683,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
   for (int i = 0; i < NH * 8; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) dq[i][j] = 0.f;
+  uint2 dkey = make_uint2(0u, 1u);
+  if (DROP) dkey = attn_drop_key(e.drop, b * p.H + h);
 
   const int n_kv = p.causal ? min((p.Tk + TILE - 1) / TILE, (q0 + TILE + TILE - 1) / TILE) : (p.Tk + TILE - 1) / TILE;
   for (int kv = 0; kv < n_kv; ++kv) {
@@ -696,6 +766,10 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
 #pragma unroll
       for (int el = 0; el < 4; ++el) {
         const float pe = fast_ex2(fmaf(s[nt][el], mult, -lse2_r[el >> 1]));  // masked scores are -inf -> 0
+        if (DROP) {  // dP = keep / (1 - p) * dP_drop
+          const uint32_t ij = (uint32_t)row_g[el >> 1] * (uint32_t)p.Tk + (uint32_t)(k0 + nt * 8 + 2 * t + (el & 1));
+          dp_[nt][el] = attn_keep(dkey, ij, e.drop.thresh32) ? dp_[nt][el] * e.drop.inv_keep : 0.f;
+        }
         if (has_tab) {
           const float ds = pe * (dp_[nt][el] - dl_r[el >> 1]);
           const int ix = idxs[has_tab ? nt : 0][el];
@@ -772,6 +846,21 @@ int fill_common(const ofab_attn_fwd_args* a, AttnCommon& c) {
   return OFAB_OK;
 }
 
+// optional attention dropout -> kernel form; `on` = descriptor given and p > 0
+int fill_drop(const ofab_dropout* d, AttnDrop& ad, bool& on, int Tq, int Tk) {
+  ad = AttnDrop{nullptr, 0u, 0u, 1.0f};
+  on = d != nullptr && d->p > 0.f;
+  if (!on) return OFAB_OK;
+  OFAB_REQUIRE(d->state != nullptr && d->p < 1.f && d->drop_path == 0.f, "ofab_attn: bad attention dropout descriptor (p=%g drop_path=%g)", (double)d->p, (double)d->drop_path);
+  OFAB_REQUIRE((int64_t)Tq * Tk < (1ll << 32), "ofab_attn: Tq * Tk must fit 32 bits with dropout");
+  ad.state = reinterpret_cast<const unsigned long long*>(d->state);
+  ad.site = d->site;
+  const double t = (double)d->p * 4294967296.0;
+  ad.thresh32 = (uint32_t)(t > 4294967295.0 ? 4294967295.0 : t);
+  ad.inv_keep = 1.0f / (1.0f - d->p);
+  return OFAB_OK;
+}
+
 template <typename K>
 int set_smem(K kern, int bytes, const char* what) {
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
@@ -793,13 +882,18 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
   const int smem = (3 * nh + 2) * TILE_BYTES + kwords * 4 + c.n_buckets * 4;
   dim3 grid((a->Tq + TILE - 1) / TILE, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
-#define FWD(P, T)                                                                                  \
-  {                                                                                                \
-    if ((rc = set_smem(attn_fwd_kernel<P, T>, smem, "ofab_attn_fwd smem"))) return rc;             \
-    attn_fwd_kernel<P, T><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse);      \
+  AttnDrop ad;
+  bool drop_on;
+  if ((rc = fill_drop(a->drop, ad, drop_on, a->Tq, a->Tk))) return rc;
+#define FWD_(P, T, D)                                                                                     \
+  {                                                                                                       \
+    if ((rc = set_smem(attn_fwd_kernel<P, T, D>, smem, "ofab_attn_fwd smem"))) return rc;                 \
+    attn_fwd_kernel<P, T, D><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse, ad);      \
   }
+#define FWD(P, T) { if (drop_on) FWD_(P, T, true) else FWD_(P, T, false) }
   if (pos && tab) FWD(true, true) else if (pos) FWD(true, false) else if (tab) FWD(false, true) else FWD(false, false)
 #undef FWD
+#undef FWD_
   OFAB_LAUNCH_CHECK("ofab_attn_fwd");
   return OFAB_OK;
 }
@@ -821,6 +915,8 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   e.dq = (bf16*)a->dq; e.dk = (bf16*)a->dk; e.dv = (bf16*)a->dv; e.dpq = (bf16*)a->dpq; e.dpk = (bf16*)a->dpk;
   e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
   e.dtable = a->dtable;
+  bool drop_on;
+  if ((rc = fill_drop(a->f.drop, e.drop, drop_on, a->f.Tq, a->f.Tk))) return rc;
   const int nh = pos ? 2 : 1;
   const int nsb = tab ? 1 : 2;  // query- / key-side stages (double-buffered unless a table column needs the space)
   const int kwords = ((a->f.Tk + 63) / 64) * 2;
@@ -828,16 +924,18 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   const int smem_q = (nh + 1) * (1 + nsb) * TILE_BYTES + kwords * 4 + 2 * c.n_buckets * 4;
   dim3 gkv((a->f.Tk + TILE - 1) / TILE, a->f.H, a->f.B), gq((a->f.Tq + TILE - 1) / TILE, a->f.H, a->f.B);
   // dQ first: it also computes delta = rowsum(dO * O) that the dK/dV kernel needs
-#define BWD(P, T)                                                                                   \
-  {                                                                                                 \
-    if ((rc = set_smem(attn_bwd_dq_kernel<P, T>, smem_q, "ofab_attn_bwd smem"))) return rc;         \
-    if ((rc = set_smem(attn_bwd_dkv_kernel<P, T>, smem_kv, "ofab_attn_bwd smem"))) return rc;       \
-    attn_bwd_dq_kernel<P, T><<<gq, 128, smem_q, st>>>(c, e);                                        \
-    OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");                                                          \
-    attn_bwd_dkv_kernel<P, T><<<gkv, 128, smem_kv, st>>>(c, e);                                     \
+#define BWD_(P, T, D)                                                                                  \
+  {                                                                                                    \
+    if ((rc = set_smem(attn_bwd_dq_kernel<P, T, D>, smem_q, "ofab_attn_bwd smem"))) return rc;         \
+    if ((rc = set_smem(attn_bwd_dkv_kernel<P, T, D>, smem_kv, "ofab_attn_bwd smem"))) return rc;       \
+    attn_bwd_dq_kernel<P, T, D><<<gq, 128, smem_q, st>>>(c, e);                                        \
+    OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");                                                             \
+    attn_bwd_dkv_kernel<P, T, D><<<gkv, 128, smem_kv, st>>>(c, e);                                     \
   }
+#define BWD(P, T) { if (drop_on) BWD_(P, T, true) else BWD_(P, T, false) }
   if (pos && tab) BWD(true, true) else if (pos) BWD(true, false) else if (tab) BWD(false, true) else BWD(false, false)
 #undef BWD
+#undef BWD_
   OFAB_LAUNCH_CHECK("ofab_attn_bwd dkv");
   return OFAB_OK;
 }

@@ -63,8 +63,6 @@ class MultiheadAttention(nn.Module):
         pass causal=True (a non-None attn_mask is taken to be that mask).  Returns (out bf16, None)."""
         if incremental_state is not None or need_weights or need_head_weights:
             raise NotImplementedError("incremental decoding / returned attention maps are outside the fwd+bwd hot path")
-        if self.training and self.dropout_p > 0:
-            raise NotImplementedError("attention dropout > 0 is not supported by the fused kernel (reference default is 0.0)")
         if isinstance(attn_bias, torch.Tensor):
             raise NotImplementedError("dense attn_bias tensors are replaced by ofasys_b200.ops.PositionBias")
         if causal is None:
@@ -77,14 +75,15 @@ class MultiheadAttention(nn.Module):
         scale = float(self.head_dim) ** -0.5 if fast else self.scaling
         bias = attn_bias if isinstance(attn_bias, ops.PositionBias) else None
         H = self.num_heads
+        drop = ops.dropout_state(x.device).spec(self.dropout_p) if self.training else None  # on the probabilities (:335)
         if self.self_attention or key is None or key is query:
             qkv = ops.linear(x, self._cat(("q_proj", "k_proj", "v_proj"), "weight"), self._cat(("q_proj", "k_proj", "v_proj"), "bias"))
-            ctx = ops.attention(qkv, None, H, scale, bias, key_padding_mask, causal)
+            ctx = ops.attention(qkv, None, H, scale, bias, key_padding_mask, causal, drop=drop)
         else:
             mem = ops.to_bf16(key)
             q = ops.linear(x, self.q_proj.weight, self.q_proj.bias)
             kv = ops.linear(mem, self._cat(("k_proj", "v_proj"), "weight"), self._cat(("k_proj", "v_proj"), "bias"))
-            ctx = ops.attention(q, kv, H, scale, bias, key_padding_mask, causal)
+            ctx = ops.attention(q, kv, H, scale, bias, key_padding_mask, causal, drop=drop)
         w_out = self.out_proj.weight
         if self.c_attn is not None and not fast:
             w_out = ops.scale_cols(w_out, self.c_attn, self.head_dim)  # einsum('tbhd,h->tbhd') folded into out_proj (:342-346)

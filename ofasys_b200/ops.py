@@ -409,8 +409,9 @@ class PositionBias:
         self.pq, self.pk, self.rp_idx, self.table = pq, pk, rp_idx, table
 
 
-def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse):
+def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse, drop=None):
     args.B, args.H, args.Tq, args.Tk = B, H, Tq, Tk
+    args.drop = None if drop is None else ctypes.pointer(drop)
     args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     args.q_bs, args.q_rs = q.stride(0), q.stride(1)
     args.k_bs, args.k_rs = k.stride(0), k.stride(1)
@@ -439,7 +440,7 @@ class _AttentionFn(torch.autograd.Function):
     """q_src: self-attention -> packed qkv [B, T, 3d]; cross-attention -> q [B, Tq, d] with kv_src [B, Tk, 2d]."""
 
     @staticmethod
-    def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H):
+    def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H, drop=None):
         _need_cuda(q_src)
         q_src = _c(q_src)
         d = H * 64
@@ -463,10 +464,11 @@ class _AttentionFn(torch.autograd.Function):
         o = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=q_src.device)
         lse = torch.empty((B, H, Tq), dtype=torch.float32, device=q_src.device)
         a = _lib.AttnFwdArgs()
-        _fill_attn(a, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse)
+        _fill_attn(a, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse, drop)
         _lib.call("ofab_attn_fwd", ctypes.byref(a), _s())
         ctx.save_for_backward(q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse)
         ctx.meta = (causal, scale, H, None if table is None else table.dtype)
+        ctx.drop = drop
         return o
 
     @staticmethod
@@ -488,7 +490,7 @@ class _AttentionFn(torch.autograd.Function):
             dq, dk, dv = dq_src, dkv_src[..., :d], dkv_src[..., d:]
         Tq, Tk = q.shape[1], k.shape[1]
         a = _lib.AttnBwdArgs()
-        _fill_attn(a.f, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse)
+        _fill_attn(a.f, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse, ctx.drop)
         a.d_o, a.do_bs, a.do_rs = d_o.data_ptr(), d_o.stride(0), d_o.stride(1)
         a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
         a.dq_bs, a.dq_rs = dq.stride(0), dq.stride(1)
@@ -516,12 +518,30 @@ class _AttentionFn(torch.autograd.Function):
                 dpk = colsum(dpk.view(B, Tk * d), torch.bfloat16).view(1, Tk, d)
         if dtab is not None:
             dtab = cast_bf16(dtab) if table_dtype == torch.bfloat16 else dtab
-        return dq_src, dkv_src, dpq, dpk, dtab, None, None, None, None, None
+        return dq_src, dkv_src, dpq, dpk, dtab, None, None, None, None, None, None
 
 
-def attention(q_src, kv_src, H, scale, bias: PositionBias = None, key_padding_mask=None, causal=False):
+def attention(q_src, kv_src, H, scale, bias: PositionBias = None, key_padding_mask=None, causal=False, drop=None):
+    """`drop`: dropout descriptor for the attention probabilities (DropoutState.spec(p)) or None."""
     b = bias or PositionBias()
-    return _AttentionFn.apply(q_src, kv_src, b.pq, b.pk, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H)
+    return _AttentionFn.apply(q_src, kv_src, b.pq, b.pk, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H, drop)
+
+
+def attention_dropout_mask(drop, B, H, Tq, Tk, device=None):
+    """The fp32 multipliers [B, H, Tq, Tk] an attention dropout descriptor applies to the probabilities (tests):
+    recovered exactly by running the kernel on zero scores (uniform P = 1/Tk) against V = identity columns."""
+    dev = device or "cuda"
+    out = torch.empty((B, H, Tq, Tk), dtype=torch.float32, device=dev)
+    q = torch.zeros((B, Tq, H * 64), dtype=torch.bfloat16, device=dev)
+    for j0 in range(0, Tk, 64):
+        n = min(64, Tk - j0)
+        kv = torch.zeros((B, Tk, 2 * H * 64), dtype=torch.bfloat16, device=dev)
+        v = kv[..., H * 64:].view(B, Tk, H, 64)
+        for jj in range(n):
+            v[:, j0 + jj, :, jj] = 1.0
+        o = _AttentionFn.apply(q, kv, None, None, None, None, None, False, 1.0, H, drop)  # o[b,i,h,jj] = mask / Tk
+        out[..., j0:j0 + n] = (o.view(B, Tq, H, 64)[..., :n].permute(0, 2, 1, 3) > 0).float() * (1.0 / (1.0 - drop.p))
+    return out
 
 
 # ------------------------------------------------------------------------------------ adaptor hook

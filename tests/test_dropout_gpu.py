@@ -168,6 +168,63 @@ def test_embed_ln_dropout():
     assert rel_l2(g.grad.float(), g_.grad) < 1.5e-2
 
 
+def _attn_ref(q, k, v, kpm, causal, scale, H, mask):
+    """multihead_attention.py:308-338 in fp32 with the dropout multipliers applied to the probabilities (:335)."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    sp = lambda t: t.view(t.shape[0], t.shape[1], H, 64).transpose(1, 2)
+    s = torch.matmul(sp(q), sp(k).transpose(2, 3)) * scale
+    if causal:
+        s = s + torch.triu(torch.full((Tq, Tk), float("-inf"), device=s.device), 1)
+    if kpm is not None:
+        s = s.masked_fill(kpm[:, None, None, :].bool(), float("-inf"))
+    p = torch.softmax(s, dim=-1) * mask
+    return torch.matmul(p, sp(v)).transpose(1, 2).reshape(B, Tq, d)
+
+
+@pytest.mark.parametrize("mode,Tq,Tk,causal,use_kpm", [("self", 130, 130, False, True), ("self", 64, 64, True, False),
+                                                      ("cross", 24, 265, False, True), ("self", 257, 257, True, True)])
+def test_attention_dropout(mode, Tq, Tk, causal, use_kpm):
+    ops = _ops()
+    torch.manual_seed(4)
+    st = ops.DropoutState("cuda:0", seed=17)
+    st.next_step()
+    B, H = 2, 3
+    d = H * 64
+    scale = 128 ** -0.5
+    if mode == "self":
+        qkv = torch.randn(B, Tq, 3 * d, device="cuda").bfloat16().requires_grad_(True)
+        kv = None
+    else:
+        qkv = torch.randn(B, Tq, d, device="cuda").bfloat16().requires_grad_(True)
+        kv = torch.randn(B, Tk, 2 * d, device="cuda").bfloat16().requires_grad_(True)
+    kpm = None
+    if use_kpm:
+        kpm = torch.zeros(B, Tk, dtype=torch.bool, device="cuda")
+        kpm[1, Tk - Tk // 4:] = True
+        kpm[0, 3] = True
+    drop = st.spec(0.25)
+    o = ops.attention(qkv, kv, H, scale, None, kpm, causal, drop=drop)
+    do = torch.randn_like(o)
+    o.backward(do)
+    mask = ops.attention_dropout_mask(drop, B, H, Tq, Tk)
+    frac = (mask == 0).float().mean().item()
+    assert abs(frac - 0.25) < 0.02, frac
+    # no structure along either axis (the hash is of i * Tk + j)
+    assert ((mask == 0).float().mean(dim=(0, 1, 2)) - 0.25).abs().max().item() < 0.12
+    assert ((mask == 0).float().mean(dim=(0, 1, 3)) - 0.25).abs().max().item() < 0.12
+    refs = [t.detach().float().requires_grad_(True) for t in (qkv, kv) if t is not None]
+    if mode == "self":
+        q_, k_, v_ = refs[0][..., :d], refs[0][..., d:2 * d], refs[0][..., 2 * d:]
+    else:
+        q_, k_, v_ = refs[0], refs[1][..., :d], refs[1][..., d:]
+    orf = _attn_ref(q_, k_, v_, kpm, causal, scale, H, mask)
+    orf.backward(do.float())
+    assert rel_l2(o, orf) <= 1e-2
+    for t, r in zip([t for t in (qkv, kv) if t is not None], refs):
+        assert rel_l2(t.grad, r.grad) <= 2e-2, tuple(t.shape)
+
+
 def test_graph_replay_draws_fresh_masks():
     """state lives in device memory and next_step() is device work: every replay of a captured step sees a new mask."""
     ops = _ops()
@@ -198,8 +255,8 @@ def test_graph_replay_draws_fresh_masks():
 class _Recorder:
     """Records the descriptors a product forward creates and replays them, in order, as the oracle's masks."""
 
-    def __init__(self, ops, active):
-        self.ops, self.active, self.specs, self.i = ops, active, [], 0
+    def __init__(self, ops, active, heads=1):
+        self.ops, self.active, self.specs, self.i, self.heads = ops, active, [], 0, heads
         self._orig = ops.DropoutState.spec
 
     def __enter__(self):
@@ -228,6 +285,9 @@ class _Recorder:
         if kind in ("branch", "act"):  # T x B x C in the reference layout; kernel rows are b * T + t
             T, B, C = x.shape
             return self.ops.dropout_mask(d, B * T, C).view(B, T, C).transpose(0, 1).cpu().to(x.dtype)
+        if kind == "attn_probs":  # B*H x T x S
+            BH, T, S = x.shape
+            return self.ops.attention_dropout_mask(d, BH // self.heads, self.heads, T, S).view(BH, T, S).cpu().to(x.dtype)
         raise AssertionError(kind)
 
 
@@ -246,11 +306,14 @@ def test_model_parity_with_dropout(name):
     m = build_product(name)
     m.load_state_dict(sd, strict=False)
     m = m.to(torch.bfloat16).to(dev).train()
-    p_res, p_act, p_path = 0.1, 0.1, 0.2
+    p_res, p_act, p_path, p_attn = 0.1, 0.1, 0.2, 0.1
     L = len(m.encoder.layers)
     for i, layer in enumerate(list(m.encoder.layers) + list(m.decoder.layers)):
         layer.dropout_p, layer.activation_dropout_p = p_res, p_act
         layer.drop_path_rate = p_path * (i % L) / max(L - 1, 1)  # transformer.py:58,249 linspace(0, rate, L) schedule
+        for att in (layer.self_attn, getattr(layer, "encoder_attn", None)):
+            if att is not None:
+                att.dropout_p = p_attn
     for mod in m.modules():
         if hasattr(mod, "hook") and hasattr(mod, "dropout_p"):
             mod.dropout_p = p_res
@@ -258,10 +321,11 @@ def test_model_parity_with_dropout(name):
     ops.dropout_state(dev).reseed(2024)
     pslots = to_product_slots(slots, dev)
     tgt = target.to(dev)
-    active = {"embed": True, "branch": True, "act": True, "attn_probs": False}
+    active = {"embed": True, "branch": True, "act": True, "attn_probs": True}
+    H = cfg.heads
 
     # (1) logits through the reference-facing API
-    with _Recorder(ops, active) as rec:
+    with _Recorder(ops, active, H) as rec:
         logits, _ = m(pslots)
         torch.cuda.synchronize()
         om.DROP_HOOK = rec.hook
@@ -279,7 +343,7 @@ def test_model_parity_with_dropout(name):
     assert rel_l2(logits_ref, logits_eval) > 0.05
 
     # (2) measured path: fused projection + criterion + backward (a new step -> new masks)
-    with _Recorder(ops, active) as rec:
+    with _Recorder(ops, active, H) as rec:
         m.zero_grad(set_to_none=True)
         loss = m.forward_loss(pslots, tgt)
         loss.backward()
