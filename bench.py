@@ -209,6 +209,8 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     _lib.check(_lib.lib().ofab_device_check(local_rank), "device check")
+    if args.no_pdl:
+        _lib.lib().ofab_set_pdl(0)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
@@ -253,7 +255,8 @@ def run_gpu(args, rank, world, local_rank):
                     fwd_bwd()
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
-        try:
+
+        def capture():
             c0 = _lib.launch_count
             g = torch.cuda.CUDAGraph()
             for p in params:
@@ -270,10 +273,23 @@ def run_gpu(args, rank, world, local_rank):
                     state["loss"] = fwd_bwd()
             state["graph"] = g
             state["launches"] = _lib.launch_count - c0
-        except Exception as ex:  # stay correct: fall back to eager launches and say so
-            print(f"[bench] CUDA graph capture failed ({type(ex).__name__}: {ex}); running eagerly", file=sys.stderr)
-            use_graph = False
+
+        try:
+            capture()
+        except Exception as ex:
+            print(f"[bench] CUDA graph capture failed ({type(ex).__name__}: {ex})", file=sys.stderr)
             torch.cuda.synchronize()
+            use_graph = False
+            if not args.no_pdl:  # programmatic edges are the newest piece of the capture: retry once without them
+                _lib.lib().ofab_set_pdl(0)
+                args.no_pdl = True
+                try:
+                    capture()
+                    use_graph = True
+                    print("[bench] captured without PDL", file=sys.stderr)
+                except Exception as ex2:
+                    print(f"[bench] capture without PDL failed too ({type(ex2).__name__}: {ex2}); running eagerly", file=sys.stderr)
+                    torch.cuda.synchronize()
 
     buckets = early_b = late_b = None
 
@@ -528,7 +544,7 @@ def run_gpu(args, rank, world, local_rank):
             "metric": METRIC, "value": value, "unit": "seq/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "src_len": 257 + PROMPT, "tgt_len": TGT,
-                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph),
+                       "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "pdl": not args.no_pdl,
                        "grad_exchange": (None if world == 1 else "NCCL all-reduce(avg) of flat 64 MB buckets" + ("; decoder-side buckets overlap the encoder backward" if split else "")), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "algorithmic_gflop_per_seq": 3 * FWD_GFLOP_PER_SEQ, "ntokens_per_rank": ntok},
             "clocks": clocks,
@@ -556,6 +572,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: average all gradients after the whole backward (no split)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B of the kernel-boundary overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

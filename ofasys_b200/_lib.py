@@ -67,6 +67,7 @@ _SIGS = {
     "ofab_last_error": (c_char_p, []),
     "ofab_device_check": (c_int, [c_int]),
     "ofab_num_sms": (c_int, []),
+    "ofab_set_pdl": (c_int, [c_int]),
     "ofab_dropout_apply": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int, POINTER(Dropout), c_void_p]),
     "ofab_ln_fwd": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, POINTER(Dropout), c_void_p]),
     "ofab_ln_bwd": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_int64, c_int, c_int, POINTER(Dropout), c_void_p]),

@@ -200,6 +200,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qb * TILE;
   const bool warp_live = q0 + warp * 16 < p.Tq;  // tail tile: warps without valid query rows only help loading
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
 
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
@@ -395,6 +397,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int k0 = kb * TILE;
   const bool warp_live = k0 + warp * 16 < p.Tk;
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above (this kernel reads the delta written by the dQ kernel before it)
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
   const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
@@ -625,6 +629,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int q0 = qb * TILE;
   const bool warp_live = q0 + warp * 16 < p.Tq;
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const bf16* qg = p.q + (int64_t)b * p.q_bs + h * 64;
   const bf16* kg = p.k + (int64_t)b * p.k_bs + h * 64;
   const bf16* vg = p.v + (int64_t)b * p.v_bs + h * 64;
@@ -888,7 +894,7 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
 #define FWD_(P, T, D)                                                                                     \
   {                                                                                                       \
     if ((rc = set_smem(attn_fwd_kernel<P, T, D>, smem, "ofab_attn_fwd smem"))) return rc;                 \
-    attn_fwd_kernel<P, T, D><<<grid, 128, smem, st>>>(c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse, ad);      \
+    ofab_launch(attn_fwd_kernel<P, T, D>, grid, dim3(128), smem, st, c, (bf16*)a->o, a->o_bs, a->o_rs, a->lse, ad); \
   }
 #define FWD(P, T) { if (drop_on) FWD_(P, T, true) else FWD_(P, T, false) }
   if (pos && tab) FWD(true, true) else if (pos) FWD(true, false) else if (tab) FWD(false, true) else FWD(false, false)
@@ -928,9 +934,9 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   {                                                                                                    \
     if ((rc = set_smem(attn_bwd_dq_kernel<P, T, D>, smem_q, "ofab_attn_bwd smem"))) return rc;         \
     if ((rc = set_smem(attn_bwd_dkv_kernel<P, T, D>, smem_kv, "ofab_attn_bwd smem"))) return rc;       \
-    attn_bwd_dq_kernel<P, T, D><<<gq, 128, smem_q, st>>>(c, e);                                        \
+    ofab_launch(attn_bwd_dq_kernel<P, T, D>, gq, dim3(128), smem_q, st, c, e);                         \
     OFAB_LAUNCH_CHECK("ofab_attn_bwd dq");                                                             \
-    attn_bwd_dkv_kernel<P, T, D><<<gkv, 128, smem_kv, st>>>(c, e);                                     \
+    ofab_launch(attn_bwd_dkv_kernel<P, T, D>, gkv, dim3(128), smem_kv, st, c, e);                      \
   }
 #define BWD(P, T) { if (drop_on) BWD_(P, T, true) else BWD_(P, T, false) }
   if (pos && tab) BWD(true, true) else if (pos) BWD(true, false) else if (tab) BWD(false, true) else BWD(false, false)

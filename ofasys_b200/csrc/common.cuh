@@ -30,6 +30,33 @@ int ofab_cuda_fail(cudaError_t e, const char* what);
 
 int ofab_sm_count();  // cached
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
+// A step is ~950 short kernels back to back on one stream (CUDA graph): with plain stream order each boundary costs a
+// full drain + launch + ramp.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, kernel N+1's CTAs
+// become resident as soon as every CTA of kernel N has started (N calls pdl_launch() first thing), run their
+// prologue (barrier init, TMEM allocation, descriptor prefetch, index math) and park in pdl_wait() until kernel N has
+// COMPLETED and its writes are visible.  Rule for every kernel launched through ofab_launch(): no global-memory read
+// or write before pdl_wait().  Ordering stays transitive (a kernel cannot complete before its own wait returns).
+bool ofab_pdl_enabled();  // OFAB_PDL=0 in the environment or ofab_set_pdl(0) turns the attribute off
+__device__ __forceinline__ void pdl_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline cudaError_t ofab_launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = ofab_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#endif
+
 // ---- device helpers ------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

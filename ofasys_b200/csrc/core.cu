@@ -1,5 +1,6 @@
 // libofab core: error plumbing, device checks, small data-movement kernels.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -28,6 +29,20 @@ int ofab_sm_count() {
   return cached[dev];
 }
 
+static int g_pdl = -1;  // -1: read OFAB_PDL from the environment on first use
+bool ofab_pdl_enabled() {
+  if (g_pdl < 0) {
+    const char* e = getenv("OFAB_PDL");
+    g_pdl = (e != nullptr && e[0] == '0') ? 0 : 1;
+  }
+  return g_pdl != 0;
+}
+extern "C" int ofab_set_pdl(int on) {
+  const int prev = ofab_pdl_enabled() ? 1 : 0;
+  g_pdl = on ? 1 : 0;
+  return prev;
+}
+
 extern "C" int ofab_version(void) { return 100; }
 extern "C" const char* ofab_last_error(void) { return g_err; }
 extern "C" int ofab_num_sms(void) { return ofab_sm_count(); }
@@ -45,6 +60,8 @@ extern "C" int ofab_device_check(int device) {
 
 namespace {
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restrict__ y, int64_t n8, int64_t n) {
+  pdl_launch();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x)
     store8(y + i * 8, load8(x + i * 8));
   if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
@@ -53,6 +70,8 @@ __global__ void cast_f32_bf16_kernel(const float* __restrict__ x, bf16* __restri
   }
 }
 __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restrict__ y, int64_t n8, int64_t n) {
+  pdl_launch();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x)
     store8(y + i * 8, load8(x + i * 8));
   if (blockIdx.x == 0 && threadIdx.x < (n & 7)) {
@@ -61,6 +80,8 @@ __global__ void cast_bf16_f32_kernel(const bf16* __restrict__ x, float* __restri
   }
 }
 __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ o, int64_t n4, int64_t n) {
+  pdl_launch();
+  pdl_wait();
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 x = reinterpret_cast<const float4*>(a)[i], y = reinterpret_cast<const float4*>(b)[i];
     reinterpret_cast<float4*>(o)[i] = make_float4(x.x + y.x, x.y + y.y, x.z + y.z, x.w + y.w);
@@ -72,6 +93,8 @@ __global__ void add_f32_kernel(const float* __restrict__ a, const float* __restr
 }
 __global__ void scale_cols_kernel(const bf16* __restrict__ W, const bf16* __restrict__ c, bf16* __restrict__ out,
                                   int64_t rows, int64_t cols, int group) {
+  pdl_launch();
+  pdl_wait();
   const int64_t n = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t k = i % cols;
@@ -81,6 +104,8 @@ __global__ void scale_cols_kernel(const bf16* __restrict__ W, const bf16* __rest
 // one block per (row-chunk, head): dW = dWe * c; dc[h] += sum dWe * W
 __global__ void scale_cols_bwd_kernel(const bf16* __restrict__ dWe, const bf16* __restrict__ W, const bf16* __restrict__ c,
                                       bf16* __restrict__ dW, float* __restrict__ dc, int64_t rows, int64_t cols, int group) {
+  pdl_launch();
+  pdl_wait();
   const int h = blockIdx.y;
   const float ch = __bfloat162float(c[h]);
   float s = 0.f;
@@ -145,13 +170,13 @@ inline int ew_grid(int64_t work, int threads) {
 
 extern "C" int ofab_cast_f32_bf16(const float* x, void* y, int64_t n, ofab_stream_t stream) {
   if (n <= 0) return OFAB_OK;
-  cast_f32_bf16_kernel<<<ew_grid(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>(x, (bf16*)y, n / 8, n);
+  ofab_launch(cast_f32_bf16_kernel, dim3(ew_grid(n / 8 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, x, (bf16*)y, n / 8, n);
   OFAB_LAUNCH_CHECK("ofab_cast_f32_bf16");
   return OFAB_OK;
 }
 extern "C" int ofab_cast_bf16_f32(const void* x, float* y, int64_t n, ofab_stream_t stream) {
   if (n <= 0) return OFAB_OK;
-  cast_bf16_f32_kernel<<<ew_grid(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, y, n / 8, n);
+  ofab_launch(cast_bf16_f32_kernel, dim3(ew_grid(n / 8 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, y, n / 8, n);
   OFAB_LAUNCH_CHECK("ofab_cast_bf16_f32");
   return OFAB_OK;
 }
@@ -188,13 +213,13 @@ extern "C" int ofab_multi_copy(const void* chunks, int64_t n_chunks, ofab_stream
 }
 extern "C" int ofab_add_f32(const float* a, const float* b, float* out, int64_t n, ofab_stream_t stream) {
   if (n <= 0) return OFAB_OK;
-  add_f32_kernel<<<ew_grid(n / 4 + 1, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4, n);
+  ofab_launch(add_f32_kernel, dim3(ew_grid(n / 4 + 1, 256)), dim3(256), 0, (cudaStream_t)stream, a, b, out, n / 4, n);
   OFAB_LAUNCH_CHECK("ofab_add_f32");
   return OFAB_OK;
 }
 extern "C" int ofab_scale_cols(const void* W, const void* c, void* out, int64_t rows, int64_t cols, int group, ofab_stream_t stream) {
   OFAB_REQUIRE(group > 0 && cols % group == 0, "ofab_scale_cols: cols %% group != 0");
-  scale_cols_kernel<<<ew_grid(rows * cols, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)W, (const bf16*)c, (bf16*)out, rows, cols, group);
+  ofab_launch(scale_cols_kernel, dim3(ew_grid(rows * cols, 256)), dim3(256), 0, (cudaStream_t)stream, (const bf16*)W, (const bf16*)c, (bf16*)out, rows, cols, group);
   OFAB_LAUNCH_CHECK("ofab_scale_cols");
   return OFAB_OK;
 }
@@ -202,7 +227,7 @@ extern "C" int ofab_scale_cols_bwd(const void* dW_eff, const void* W, const void
                                    int64_t cols, int group, ofab_stream_t stream) {
   OFAB_REQUIRE(group > 0 && cols % group == 0, "ofab_scale_cols_bwd: cols %% group != 0");
   dim3 grid((unsigned)ew_grid(rows * group, 256 * 8), (unsigned)(cols / group));
-  scale_cols_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)dW_eff, (const bf16*)W, (const bf16*)c, (bf16*)dW, dc, rows, cols, group);
+  ofab_launch(scale_cols_bwd_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)dW_eff, (const bf16*)W, (const bf16*)c, (bf16*)dW, dc, rows, cols, group);
   OFAB_LAUNCH_CHECK("ofab_scale_cols_bwd");
   return OFAB_OK;
 }
@@ -235,6 +260,8 @@ extern "C" int ofab_relu_inplace(void* y, int64_t n, ofab_stream_t stream) {
 namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_apply_kernel(const T* __restrict__ x, T* __restrict__ y, int64_t rows, int cols, const DropArgs da) {
+  pdl_launch();
+  pdl_wait();
   const DropCtx dk = drop_ctx(da);
   const int vpr = cols >> 3;  // 8-column vectors per row
   const int64_t nvec = rows * vpr;
@@ -261,9 +288,9 @@ extern "C" int ofab_dropout_apply(const void* x, void* y, int dt, int64_t rows, 
   const int64_t want = (nvec + 255) / 256, cap = (int64_t)ofab_sm_count() * 8;
   const unsigned grid = (unsigned)(want < cap ? want : cap);
   if (dt == OFAB_F32)
-    dropout_apply_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)x, (float*)y, rows, cols, da);
+    ofab_launch((dropout_apply_kernel<float>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)x, (float*)y, rows, cols, da);
   else if (dt == OFAB_BF16)
-    dropout_apply_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>((const bf16*)x, (bf16*)y, rows, cols, da);
+    ofab_launch((dropout_apply_kernel<bf16>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const bf16*)x, (bf16*)y, rows, cols, da);
   else {
     ofab_set_error("ofab_dropout_apply: dt=%d", dt);
     return OFAB_ERR_ARG;

@@ -237,6 +237,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   const uint16_t pair_mask = (uint16_t)(3u << (2 * pair));   // both CTAs of this pair
   const uint16_t all_mask = (uint16_t)((1u << CL) - 1u);     // every CTA of the cluster
 
+  pdl_launch();  // PDL: the next kernel's CTAs may become resident as ours retire
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_a) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tma_b) : "memory");
@@ -265,6 +266,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constan
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  // PDL: everything above (descriptor prefetch, barrier init, cluster handshake, TMEM allocation) overlaps the tail
+  // of the previous kernel; global memory (TMA loads, bias / residual reads, stores) is touched only below.
+  pdl_wait();
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -603,13 +607,15 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& td, 
   cfg.blockDim = dim3(kNumThreads);
   cfg.dynamicSmemBytes = smem_bytes;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = ofab_pdl_enabled() ? 2 : 1;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return ofab_cuda_fail(e, "ofab_gemm_bf16: cudaFuncSetAttribute");
@@ -774,6 +780,8 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
 template <typename TO>
 __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, int64_t slab, int64_t M, int64_t N, TO* __restrict__ D,
                                      int64_t ldd) {
+  pdl_launch();
+  pdl_wait();
   const int64_t nvec = M * (N / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (N / 4), c = (i % (N / 4)) * 4;
@@ -858,9 +866,9 @@ extern "C" int ofab_gemm_bf16_splitk(int64_t M, int64_t N, int64_t K, const void
   const int64_t nvec = M * (N / 4);
   const int grid = (int)((nvec + 255) / 256 < (int64_t)ofab_sm_count() * 8 ? (nvec + 255) / 256 : (int64_t)ofab_sm_count() * 8);
   if (d_dt == OFAB_F32)
-    splitk_reduce_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, sp, M * N, M, N, (float*)D, ldd);
+    ofab_launch((splitk_reduce_kernel<float>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, workspace, sp, M * N, M, N, (float*)D, ldd);
   else
-    splitk_reduce_kernel<bf16><<<grid, 256, 0, (cudaStream_t)stream>>>(workspace, sp, M * N, M, N, (bf16*)D, ldd);
+    ofab_launch((splitk_reduce_kernel<bf16>), dim3(grid), dim3(256), 0, (cudaStream_t)stream, workspace, sp, M * N, M, N, (bf16*)D, ldd);
   OFAB_LAUNCH_CHECK("ofab_gemm_bf16_splitk reduce");
   return OFAB_OK;
 }

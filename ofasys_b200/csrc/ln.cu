@@ -151,6 +151,8 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
                                               float eps, int tpr, const DropArgs da) {
   constexpr int NST = 6;
   extern __shared__ __align__(128) uint8_t dsm[];
+  pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
+  pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
   __shared__ float red[512];
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
@@ -225,6 +227,8 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
                                               float* __restrict__ partial, int64_t rows, int cols, int tpr, const DropArgs da) {
   constexpr int NST = 4;
   extern __shared__ __align__(128) uint8_t dsm[];
+  pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
+  pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
   __shared__ float2 red[512];
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
@@ -321,6 +325,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
                                                      int64_t rows, int cols, float eps, int tpr, const DropArgs da) {
   constexpr int NST = 3;
   extern __shared__ __align__(128) uint8_t dsm[];
+  pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
+  pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
   __shared__ float red[512];
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
@@ -431,6 +437,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
   constexpr int NST = 2;
   constexpr int NIN = HAS_LN1 ? 4 : 3;
   extern __shared__ __align__(128) uint8_t dsm[];
+  pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
+  pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
   __shared__ float2 red[512];
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
@@ -556,6 +564,8 @@ template <typename T>
 __global__ void colsum_stage1(const T* __restrict__ in, int64_t rows, int64_t cols, int64_t ld,
                               float* __restrict__ partial) {
   __shared__ float sm[4][64];
+  pdl_launch();
+  pdl_wait();
   const int64_t c = (int64_t)blockIdx.x * 64 + threadIdx.x;
   const int64_t per = (rows + COLSUM_CHUNKS - 1) / COLSUM_CHUNKS;
   const int64_t r0 = (int64_t)blockIdx.y * per;
@@ -570,6 +580,8 @@ __global__ void colsum_stage1(const T* __restrict__ in, int64_t rows, int64_t co
 }
 template <typename TO>
 __global__ void colsum_stage2(const float* __restrict__ partial, int64_t cols, TO* __restrict__ out, int accumulate) {
+  pdl_launch();
+  pdl_wait();
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= cols) return;
   float s = 0.f;
@@ -585,6 +597,8 @@ __global__ void colsum_stage2(const float* __restrict__ partial, int64_t cols, T
 template <typename TO>
 __global__ void reduce_partials_kernel(const float* __restrict__ partial, int cols, TO* __restrict__ out) {
   __shared__ float sm[32][33];
+  pdl_launch();
+  pdl_wait();
   const int c = blockIdx.x * 32 + threadIdx.x;
   const float* base = partial + (int64_t)blockIdx.y * OFAB_LN_PARTIAL_ROWS * cols;
   float s = 0.f;
@@ -646,8 +660,8 @@ static int ln_configure(const void* kern) {  // opt in to > 48 KB dynamic shared
     const void* kp = l.block > (TARGET) ? (const void*)k512 : (const void*)k384; \
     int rc_ = ln_configure(kp);                                                 \
     if (rc_) return rc_;                                                        \
-    if (l.block > (TARGET)) k512<<<GRID, l.block, SMEM, st>>>(__VA_ARGS__);     \
-    else k384<<<GRID, l.block, SMEM, st>>>(__VA_ARGS__);                        \
+    if (l.block > (TARGET)) ofab_launch(k512, dim3(GRID), dim3(l.block), SMEM, st, __VA_ARGS__); \
+    else ofab_launch(k384, dim3(GRID), dim3(l.block), SMEM, st, __VA_ARGS__);   \
   } while (0)
 
 extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const void* beta, void* y, int y_dt, float* mean,
@@ -782,15 +796,15 @@ extern "C" int ofab_colsum(const void* in, int in_dt, int64_t rows, int64_t cols
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((unsigned)((cols + 63) / 64), COLSUM_CHUNKS), block(64, 4);
   if (in_dt == OFAB_F32)
-    colsum_stage1<float><<<grid, block, 0, st>>>((const float*)in, rows, cols, ld, scratch);
+    ofab_launch((colsum_stage1<float>), dim3(grid), dim3(block), 0, st, (const float*)in, rows, cols, ld, scratch);
   else
-    colsum_stage1<bf16><<<grid, block, 0, st>>>((const bf16*)in, rows, cols, ld, scratch);
+    ofab_launch((colsum_stage1<bf16>), dim3(grid), dim3(block), 0, st, (const bf16*)in, rows, cols, ld, scratch);
   OFAB_LAUNCH_CHECK("ofab_colsum stage1");
   const int g2 = (int)((cols + 255) / 256);
   if (out_dt == OFAB_F32)
-    colsum_stage2<float><<<g2, 256, 0, st>>>(scratch, cols, (float*)out, accumulate);
+    ofab_launch((colsum_stage2<float>), dim3(g2), dim3(256), 0, st, scratch, cols, (float*)out, accumulate);
   else
-    colsum_stage2<bf16><<<g2, 256, 0, st>>>(scratch, cols, (bf16*)out, accumulate);
+    ofab_launch((colsum_stage2<bf16>), dim3(g2), dim3(256), 0, st, scratch, cols, (bf16*)out, accumulate);
   OFAB_LAUNCH_CHECK("ofab_colsum stage2");
   return OFAB_OK;
 }
@@ -799,9 +813,9 @@ extern "C" int ofab_reduce_partials(const float* partial, int nslabs, int cols, 
   OFAB_REQUIRE(nslabs > 0 && cols > 0, "ofab_reduce_partials: bad shape");
   dim3 grid((cols + 31) / 32, nslabs), block(32, 32);
   if (out_dt == OFAB_F32)
-    reduce_partials_kernel<float><<<grid, block, 0, (cudaStream_t)stream>>>(partial, cols, (float*)out);
+    ofab_launch((reduce_partials_kernel<float>), dim3(grid), dim3(block), 0, (cudaStream_t)stream, partial, cols, (float*)out);
   else
-    reduce_partials_kernel<bf16><<<grid, block, 0, (cudaStream_t)stream>>>(partial, cols, (bf16*)out);
+    ofab_launch((reduce_partials_kernel<bf16>), dim3(grid), dim3(block), 0, (cudaStream_t)stream, partial, cols, (bf16*)out);
   OFAB_LAUNCH_CHECK("ofab_reduce_partials");
   return OFAB_OK;
 }
