@@ -459,6 +459,43 @@ def run_gpu(args, rank, world, local_rank):
                 "avg_launch_us": t_list * 1e6 / max(1, len(launch_list)),
                 "achieved_eager_events": ach_eager, "gemm_ms_per_step_eager_events": tm * 1e3 / n_eager}
 
+    # ---- the step that follows the measured path every update: gradient norm + clip + fp32-master
+    # Adam over all parameters (csrc/optim.cu), timed on the gradients the last replay left in p.grad.  HBM-bound:
+    # 2 B (norm pass) + 2 + 12 B read, 12 + 2 B written per element.  Reported next to the headline, not inside it
+    # (the metric is fwd+bwd, optimizer step excluded: SURVEY 8d).
+    optim_rec = None
+    if rank == 0:
+        try:
+            from ofasys_b200 import FusedAdam
+
+            gparams = [p for p in params if p.grad is not None]
+            n_el = sum(p.numel() for p in gparams)
+            opt = FusedAdam(gparams, lr=1e-12, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+
+            def opt_step():
+                opt._table_ready = False
+                opt.multiply_grads(1.0 / max(1, ntok))
+                opt.clip_grad_norm(1.0)
+                opt.step()
+
+            for _ in range(3):
+                opt_step()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                opt_step()
+            e1.record()
+            torch.cuda.synchronize()
+            t_opt = e0.elapsed_time(e1) / 10
+            pk = peaks()
+            gbs = n_el * 30.0 / (t_opt * 1e-3) / 1e9
+            optim_rec = {"kernels": "adam_sqnorm_kernel + adam_norm_final_kernel + adam_step_kernel", "ms_per_update": t_opt, "elements": n_el,
+                         "algorithmic_bytes_per_element": 30, "achieved_gbs": gbs, "peak_gbs": pk["hbm"], "frac": gbs / pk["hbm"], "bound": "hbm"}
+            del opt
+        except Exception as ex:
+            optim_rec = {"error": f"{type(ex).__name__}: {ex}"}
+
     if args.kprofile:  # every rank runs the steps (collectives), rank 0 writes
         # kernel-level timeline of the replayed step (CUPTI via torch.profiler): hot caches, real back-to-back execution
         from torch.profiler import ProfilerActivity, profile
@@ -553,6 +590,7 @@ def run_gpu(args, rank, world, local_rank):
             "model_tflops": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world,
             "model_frac_of_bf16_peak": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world / pk["tf_sustained"],
             "roofline": roof,
+            "optimizer_step": optim_rec,
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -4,5 +4,6 @@ See DESIGN.md (scope, kernels, rooflines) and INTEGRATION.md (how it drops under
 from .configure import BaseDataclass, ConfigStore, register_config
 from .preprocessor import Dictionary, ModalityType, Slot
 from .model import GeneralistModel, GeneralistModelConfig
+from .optim import FusedAdam
 
-__all__ = ["ModalityType", "Slot", "Dictionary", "GeneralistModel", "GeneralistModelConfig", "BaseDataclass", "ConfigStore", "register_config"]
+__all__ = ["ModalityType", "Slot", "Dictionary", "GeneralistModel", "GeneralistModelConfig", "BaseDataclass", "ConfigStore", "register_config", "FusedAdam"]

@@ -2,7 +2,7 @@
 or a call fails, the product path raises."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libofab.so")
@@ -17,6 +17,17 @@ class OfabError(RuntimeError):
 class Dropout(Structure):
     """ofab_dropout (include/ofab.h): counter-based keep mask, no mask tensor."""
     _fields_ = [("state", c_void_p), ("site", c_uint32), ("p", c_float), ("drop_path", c_float), ("rows_per_sample", c_int)]
+
+
+class AdamTensor(Structure):
+    """ofab_adam_tensor (56 bytes; the host builds an array of these and copies it to the device)."""
+    _fields_ = [("p", c_void_p), ("g", c_void_p), ("master", c_void_p), ("m", c_void_p), ("v", c_void_p), ("n", c_int64), ("first_block", c_int64)]
+
+
+class AdamHyper(Structure):
+    _fields_ = [("lr", c_double), ("weight_decay", c_double), ("beta1_d", c_double), ("beta2_d", c_double),
+                ("beta1", c_float), ("beta2", c_float), ("eps", c_float), ("grad_scale", c_float), ("max_norm", c_float),
+                ("step", c_int64), ("norm", c_void_p)]
 
 
 class AttnFwdArgs(Structure):
@@ -111,6 +122,9 @@ _SIGS = {
     "ofab_bn_stats": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "ofab_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "ofab_bn_bwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "ofab_adam_chunk_elems": (c_int, []),
+    "ofab_grad_norm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
+    "ofab_adam_step": (c_int, [c_void_p, c_int, c_int64, POINTER(AdamHyper), c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -144,7 +158,7 @@ def check(rc, what=""):
         raise OfabError(f"libofab call failed ({rc}) {what}: {msg}")
 
 
-_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2, "ofab_bn_stats": 2, "ofab_bn_bwd": 3}
+_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2, "ofab_bn_stats": 2, "ofab_bn_bwd": 3, "ofab_grad_norm": 2}
 
 
 def call(name, *args):

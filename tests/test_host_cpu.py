@@ -143,3 +143,13 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dp, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
+
+
+def test_fused_adam_refuses_cpu_parameters():
+    """The optimizer step has no CPU fallback either."""
+    import ofasys_b200 as ob
+    from ofasys_b200._lib import OfabError
+
+    p = torch.nn.Parameter(torch.zeros(8, dtype=torch.bfloat16))
+    with pytest.raises(OfabError):
+        ob.FusedAdam([p])

@@ -93,3 +93,25 @@ def test_full_size_configs(name):
     for k, st in g["grad_stats"].items():
         if st is not None:
             assert abs(grads[k].double().norm().item() - st[2].item()) <= 2e-4 * st[2].item() + 1e-6, k
+
+
+def test_optimizer_oracle_matches_reference_adam():
+    """oracle_optim.update (restatement of multiply_grads -> clip_grad_norm -> fp32 Adam -> bf16 copy) against the
+    outputs of the reference's own Adam.step / clip_grad_norm_ (tests/golden/optim_adam.pt, oracle/make_golden_optim.py)."""
+    from oracle import oracle_optim as oo
+
+    fx = torch.load(os.path.join(GOLD, "optim_adam.pt"), weights_only=False)
+    params, steps, hyper, scales = oo.make_case()
+    masters = [p.float() for p in params]
+    ms = [torch.zeros_like(m) for m in masters]
+    vs = [torch.zeros_like(m) for m in masters]
+    for k, (gs, c) in enumerate(zip(steps, scales)):
+        norm, p16 = oo.update(masters, gs, ms, vs, k + 1, hyper["lr"], hyper["betas"], hyper["eps"], hyper["weight_decay"], c, hyper["max_norm"])
+        assert abs(float(norm) - float(fx["norms"][k])) <= 1e-6 * float(fx["norms"][k])
+        for name, cur in (("masters", masters), ("exp_avg", ms), ("exp_avg_sq", vs), ("params_bf16", p16)):
+            for i in fx["small"]:
+                assert torch.equal(cur[i], fx[name][k][i]), (name, k, i)  # same torch ops in the same order: bit-exact
+            for i, t in enumerate(cur):
+                s, a = t.double().sum(), t.double().abs().sum()
+                assert abs(s - fx[name + "_sum"][k][i]) <= 1e-9 * max(1.0, float(a)), (name, k, i)
+                assert abs(a - fx[name + "_abs"][k][i]) <= 1e-9 * max(1.0, float(a)), (name, k, i)

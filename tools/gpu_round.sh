@@ -1,11 +1,6 @@
 #!/bin/bash
 set -x
 mkdir -p gpurun_out
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv
-nvidia-smi topo -m | head -12
-timeout 300 python -m pytest tests/test_cotrain_gpu.py tests/test_model_gpu.py -m gpu -x -q -k "cotrain or box or text_only or split" > gpurun_out/pytest_cotrain.log 2>&1; echo "pytest rc=$?"; tail -5 gpurun_out/pytest_cotrain.log
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 20 --warmup 5 --kprofile --no-cpu > gpurun_out/bench_n2.json 2> gpurun_out/bench_n2.err; echo "bench n2 rc=$?"
-cat gpurun_out/bench_n2.json; tail -3 gpurun_out/bench_n2.err
-cp gpurun_out/kprofile.json gpurun_out/kprofile_n2.json
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu --no-overlap > gpurun_out/bench_n2_noov.json 2> gpurun_out/bench_n2_noov.err; echo "bench n2 noov rc=$?"
-cat gpurun_out/bench_n2_noov.json
+timeout 300 python -m pytest tests/test_optim_gpu.py -m gpu -x -q > gpurun_out/pytest_optim.log 2>&1; echo "pytest optim rc=$?"; tail -12 gpurun_out/pytest_optim.log
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:"adam_" -c 6 -o gpurun_out/prof_adam -f python tools/one_kernel.py adam > gpurun_out/ncu_adam.log 2>&1; echo "ncu adam rc=$?"
+timeout 200 ncu -i gpurun_out/prof_adam.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,launch__grid_size,launch__block_size,sm__throughput.avg.pct_of_peak_sustained_elapsed > gpurun_out/ncu_adam_raw.csv 2>/dev/null; head -c 1500 gpurun_out/ncu_adam_raw.csv

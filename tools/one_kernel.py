@@ -31,4 +31,17 @@ elif which == "ln":  # GELU + ffn_layernorm of the benchmark step: rows 8480 x 3
     for _ in range(3):
         y = ops.layer_norm(x, w, b, gelu=True)
         y.backward(torch.randn_like(y))
+elif which == "adam":  # optimizer step over 200 M elements in 300 tensors (OFA-base sized)
+    from ofasys_b200 import FusedAdam
+
+    ps = [torch.nn.Parameter((torch.randn(768, 3072, device=dev) * 0.02).bfloat16()) for _ in range(80)] + \
+         [torch.nn.Parameter((torch.randn(768, device=dev) * 0.02).bfloat16()) for _ in range(220)]
+    for p in ps:
+        p.grad = (torch.randn_like(p.float()) * 0.01).bfloat16()
+    opt = FusedAdam(ps, lr=1e-4, weight_decay=0.01)
+    for _ in range(3):
+        opt._table_ready = False
+        opt.multiply_grads(1.0 / 3000)
+        opt.clip_grad_norm(1.0)
+        opt.step()
 torch.cuda.synchronize()
