@@ -95,8 +95,8 @@ _SIGS = {
     "ofab_attn_bwd": (c_int, [POINTER(AttnBwdArgs), c_void_p]),
     "ofab_embed_ln_fwd": (c_int, [POINTER(EmbedLnArgs), c_void_p]),
     "ofab_embed_ln_bwd": (c_int, [POINTER(EmbedLnBwdArgs), c_void_p]),
-    "ofab_ce_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
-    "ofab_ce_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "ofab_ce_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
+    "ofab_ce_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "ofab_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_cast_bf16_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_video_frames": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),

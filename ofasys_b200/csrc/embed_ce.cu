@@ -217,12 +217,16 @@ __device__ __forceinline__ void online_merge(float& m, float& s, float m2, float
   m = mn;
 }
 
+// eps > 0: label smoothing (label_smoothed_cross_entropy.py:62-92): the row loss becomes
+//   (1 - eps - eps_i) * (lse - x_t) + eps_i * (V * lse - sum_c x_c),  eps_i = eps / (V - 1)
+// which needs the plain sum of the row's logits next to the online log-sum-exp.
 __global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ target,
-                                                     int64_t ignore_index, float* __restrict__ lse, float* __restrict__ loss_sum) {
-  __shared__ float sm_m[8], sm_s[8];
+                                                     int64_t ignore_index, float* __restrict__ lse, float* __restrict__ loss_sum, float eps,
+                                                     float* __restrict__ nll_sum) {
+  __shared__ float sm_m[8], sm_s[8], sm_x[8];
   const int64_t r = blockIdx.x;
   const bf16* row = logits + r * ld;
-  float m = -INFINITY, s = 0.f;
+  float m = -INFINITY, s = 0.f, xs = 0.f;
   const int64_t V8 = V / 8;
   for (int64_t i = threadIdx.x; i < V8; i += 256) {
     const f8 x = load8(row + i * 8);
@@ -232,11 +236,19 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ lo
     const float mn = fmaxf(m, mx);
     float acc = s * __expf(m - mn);
 #pragma unroll
-    for (int j = 0; j < 8; ++j) acc += __expf(x.v[j] - mn);
+    for (int j = 0; j < 8; ++j) {
+      acc += __expf(x.v[j] - mn);
+      xs += x.v[j];
+    }
     m = mn;
     s = acc;
   }
-  for (int64_t i = V8 * 8 + threadIdx.x; i < V; i += 256) online_merge(m, s, __bfloat162float(row[i]), 1.f);
+  for (int64_t i = V8 * 8 + threadIdx.x; i < V; i += 256) {
+    const float x = __bfloat162float(row[i]);
+    online_merge(m, s, x, 1.f);
+    xs += x;
+  }
+  xs = warp_sum(xs);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
@@ -245,21 +257,37 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(const bf16* __restrict__ lo
   if ((threadIdx.x & 31) == 0) {
     sm_m[threadIdx.x >> 5] = m;
     sm_s[threadIdx.x >> 5] = s;
+    sm_x[threadIdx.x >> 5] = xs;
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float M = sm_m[0], S = sm_s[0];
-    for (int w = 1; w < 8; ++w) online_merge(M, S, sm_m[w], sm_s[w]);
+    float M = sm_m[0], S = sm_s[0], X = sm_x[0];
+    for (int w = 1; w < 8; ++w) {
+      online_merge(M, S, sm_m[w], sm_s[w]);
+      X += sm_x[w];
+    }
     const float l = M + logf(S);
     lse[r] = l;
     const int64_t tg = target[r];
-    if (tg != ignore_index) atomicAdd(loss_sum, l - __bfloat162float(row[tg]));
+    if (tg != ignore_index) {
+      const float nll = l - __bfloat162float(row[tg]);
+      float loss = nll;
+      if (eps > 0.f) {
+        const float eps_i = eps / (float)(V - 1);
+        loss = (1.0f - eps - eps_i) * nll + eps_i * ((float)V * l - X);
+      }
+      atomicAdd(loss_sum, loss);
+      if (nll_sum != nullptr) atomicAdd(nll_sum, nll);
+    }
   }
 }
 
 __global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ logits, int64_t V, int64_t ld, const int64_t* __restrict__ target,
                                                      int64_t ignore_index, const float* __restrict__ lse, const float* __restrict__ gscale,
-                                                     bf16* __restrict__ dlogits) {
+                                                     bf16* __restrict__ dlogits, float eps) {
+  // d loss_row / d x_c = softmax_c - (1 - eps - eps_i) * [c == target] - eps_i      (eps = 0: softmax - onehot)
+  const float eps_i = eps > 0.f ? eps / (float)(V - 1) : 0.f;
+  const float w_t = 1.0f - eps - eps_i;
   const int64_t r = blockIdx.x;
   const bf16* row = logits + r * ld;
   bf16* drow = dlogits + r * ld;
@@ -273,13 +301,13 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ lo
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const float pr = counted ? __expf(x.v[j] - l) : 0.f;
-      x.v[j] = g * (pr - ((i * 8 + j) == tg ? 1.f : 0.f));
+      x.v[j] = g * (pr - ((i * 8 + j) == tg ? w_t : 0.f) - eps_i);
     }
     store8(drow + i * 8, x);
   }
   for (int64_t i = V8 * 8 + threadIdx.x; i < V; i += 256) {
     const float pr = counted ? __expf(__bfloat162float(row[i]) - l) : 0.f;
-    drow[i] = __float2bfloat16(g * (pr - (i == tg ? 1.f : 0.f)));
+    drow[i] = __float2bfloat16(g * (pr - (i == tg ? w_t : 0.f) - eps_i));
   }
 }
 
@@ -328,17 +356,20 @@ extern "C" int ofab_embed_ln_bwd(const ofab_embed_ln_bwd_args* a, ofab_stream_t 
 }
 
 extern "C" int ofab_ce_fwd(const void* logits, int64_t rows, int64_t V, int64_t ld, const int64_t* target, int64_t ignore_index,
-                           float* lse, float* loss_sum, ofab_stream_t stream) {
-  OFAB_REQUIRE(rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "ofab_ce_fwd: bad shape rows=%lld V=%lld ld=%lld (ld multiple of 8)", (long long)rows, (long long)V, (long long)ld);
-  ce_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, loss_sum);
+                           float* lse, float* loss_sum, float label_smoothing, float* nll_sum, ofab_stream_t stream) {
+  OFAB_REQUIRE(rows > 0 && V > 1 && ld >= V && ld % 8 == 0, "ofab_ce_fwd: bad shape rows=%lld V=%lld ld=%lld (ld multiple of 8)", (long long)rows, (long long)V, (long long)ld);
+  OFAB_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, "ofab_ce_fwd: label_smoothing=%g out of [0, 1)", (double)label_smoothing);
+  ce_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, loss_sum, label_smoothing, nll_sum);
   OFAB_LAUNCH_CHECK("ofab_ce_fwd");
   return OFAB_OK;
 }
 
 extern "C" int ofab_ce_bwd(const void* logits, int64_t rows, int64_t V, int64_t ld, const int64_t* target, int64_t ignore_index,
-                           const float* lse, const float* gscale, void* dlogits, ofab_stream_t stream) {
-  OFAB_REQUIRE(rows > 0 && V > 0 && ld >= V && ld % 8 == 0, "ofab_ce_bwd: bad shape");
-  ce_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, gscale, (bf16*)dlogits);
+                           const float* lse, const float* gscale, void* dlogits, float label_smoothing, ofab_stream_t stream) {
+  OFAB_REQUIRE(rows > 0 && V > 1 && ld >= V && ld % 8 == 0, "ofab_ce_bwd: bad shape");
+  OFAB_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, "ofab_ce_bwd: label_smoothing=%g out of [0, 1)", (double)label_smoothing);
+  ce_bwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, gscale, (bf16*)dlogits,
+                                                                  label_smoothing);
   OFAB_LAUNCH_CHECK("ofab_ce_bwd");
   return OFAB_OK;
 }

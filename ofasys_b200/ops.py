@@ -644,7 +644,7 @@ class _CrossEntropyFn(torch.autograd.Function):
     """sum-reduced CE over rows whose target != ignore_index; logits bf16 [..., V] (row stride % 8 == 0)."""
 
     @staticmethod
-    def forward(ctx, logits, target, ignore_index):
+    def forward(ctx, logits, target, ignore_index, label_smoothing=0.0):
         _need_cuda(logits, target)
         V = logits.shape[-1]
         l2 = logits.reshape(-1, V) if logits.dim() != 2 else logits
@@ -657,25 +657,26 @@ class _CrossEntropyFn(torch.autograd.Function):
         tgt = _c(target.reshape(-1))
         lse = torch.empty(rows, dtype=torch.float32, device=logits.device)
         loss = torch.zeros(1, dtype=torch.float32, device=logits.device)
-        _lib.call("ofab_ce_fwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(loss), _s())
+        _lib.call("ofab_ce_fwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(loss), float(label_smoothing), None, _s())
         ctx.save_for_backward(l2, tgt, lse)
-        ctx.meta = (ignore_index, logits.shape)
+        ctx.meta = (ignore_index, logits.shape, float(label_smoothing))
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         l2, tgt, lse = ctx.saved_tensors
-        ignore_index, shape = ctx.meta
+        ignore_index, shape, eps = ctx.meta
         rows, V = l2.shape
         ld = l2.stride(0)
         dl = torch.empty((rows, ld), dtype=torch.bfloat16, device=l2.device)
         gs = _c(g.reshape(1).to(torch.float32))
-        _lib.call("ofab_ce_bwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(gs), _p(dl), _s())
-        return dl[:, :V].view(shape) if ld == V else dl[:, :V].unflatten(0, shape[:-1]), None, None
+        _lib.call("ofab_ce_bwd", _p(l2), rows, V, ld, _p(tgt), ignore_index, _p(lse), _p(gs), _p(dl), eps, _s())
+        return dl[:, :V].view(shape) if ld == V else dl[:, :V].unflatten(0, shape[:-1]), None, None, None
 
 
-def cross_entropy_sum(logits, target, ignore_index=1):
-    return _CrossEntropyFn.apply(logits, target, ignore_index)
+def cross_entropy_sum(logits, target, ignore_index=1, label_smoothing=0.0):
+    """sum-reduced (label-smoothed) cross entropy over the rows whose target != ignore_index."""
+    return _CrossEntropyFn.apply(logits, target, ignore_index, label_smoothing)
 
 
 class _LinearCrossEntropyFn(torch.autograd.Function):
@@ -683,7 +684,7 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
     criterion (cross_entropy.py:62-67) so the [rows, V] logits live only as one bf16 scratch."""
 
     @staticmethod
-    def forward(ctx, x, E, target, ignore_index):
+    def forward(ctx, x, E, target, ignore_index, label_smoothing=0.0, nll_out=None):
         _need_cuda(x, E, target)
         x2 = _as2d(x)
         M, K = x2.shape
@@ -695,20 +696,20 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
         tgt = _c(target.reshape(-1))
         lse = torch.empty(M, dtype=torch.float32, device=x.device)
         loss = torch.zeros(1, dtype=torch.float32, device=x.device)
-        _lib.call("ofab_ce_fwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(loss), _s())
+        _lib.call("ofab_ce_fwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(loss), float(label_smoothing), _p(nll_out), _s())
         ctx.save_for_backward(x2, E, tgt, lse, logits)
-        ctx.meta = (ignore_index, x.shape)
+        ctx.meta = (ignore_index, x.shape, float(label_smoothing))
         return loss[0]
 
     @staticmethod
     def backward(ctx, g):
         x2, E, tgt, lse, logits = ctx.saved_tensors
-        ignore_index, xshape = ctx.meta
+        ignore_index, xshape, eps = ctx.meta
         M, K = x2.shape
         V = E.shape[0]
         Vp = logits.shape[1]
         gs = _c(g.reshape(1).to(torch.float32))
-        _lib.call("ofab_ce_bwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(gs), _p(logits), _s())  # in place
+        _lib.call("ofab_ce_bwd", _p(logits), M, V, Vp, _p(tgt), ignore_index, _p(lse), _p(gs), _p(logits), eps, _s())  # in place
         dx = dE = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=torch.bfloat16, device=x2.device)
@@ -717,11 +718,13 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             dE = torch.empty((V, K), dtype=torch.bfloat16, device=x2.device)
             gemm(V, K, M, logits, Vp, 1, x2, x2.stride(0), 1, dE, K)
-        return dx, dE, None, None
+        return dx, dE, None, None, None, None
 
 
-def linear_cross_entropy(x, E, target, ignore_index=1):
-    return _LinearCrossEntropyFn.apply(x, E, target, ignore_index)
+def linear_cross_entropy(x, E, target, ignore_index=1, label_smoothing=0.0, nll_out=None):
+    """loss = sum-CE(x E^T, target), optionally label-smoothed (label_smoothed_cross_entropy.py:62-92).  nll_out: optional
+    zeroed fp32 [1] tensor that receives the plain nll sum (the reference logs it next to the loss)."""
+    return _LinearCrossEntropyFn.apply(x, E, target, ignore_index, label_smoothing, nll_out)
 
 
 # ------------------------------------------------------------------------------------ adaptors' convs

@@ -522,6 +522,30 @@ def cross_entropy_sum(logits, target, pad=PAD):
     return F.nll_loss(lprobs, target.view(-1), ignore_index=pad, reduction="sum")
 
 
+def label_smoothed_cross_entropy_sum(logits, target, epsilon, pad=PAD):
+    """engine/criterion/label_smoothed_cross_entropy.py:62-92,175-191 (no constraint masks, no drop-worst): fp32
+    log-softmax; over non-pad targets  loss = (1 - eps - eps_i) * nll + eps_i * smooth  with smooth = -sum_c lprobs,
+    eps_i = eps / (V - 1).  Returns (loss_sum, nll_sum, ntokens)."""
+    lprobs = F.log_softmax(logits.float(), dim=-1).view(-1, logits.size(-1))
+    tgt = target.view(-1)
+    keep = tgt != pad
+    lprobs, tgt = lprobs[keep], tgt[keep]
+    nll = -lprobs.gather(dim=-1, index=tgt.unsqueeze(-1)).squeeze(-1)
+    smooth = -lprobs.sum(dim=-1)
+    eps_i = epsilon / (lprobs.size(-1) - 1)
+    loss = (1.0 - epsilon - eps_i) * nll + eps_i * smooth
+    return loss.sum(), nll.sum(), loss.numel()
+
+
+def make_ls_case(seed=7, rows=37, V=1003, eps=0.1):
+    """Seeded logits (bf16 values) / targets with padding for the label-smoothed criterion fixtures."""
+    g = torch.Generator().manual_seed(seed)
+    logits = (torch.randn(rows, V, generator=g) * 2.0).to(torch.bfloat16)
+    target = torch.randint(4, V, (rows,), generator=g)
+    target[::5] = PAD
+    return logits, target, eps
+
+
 # ------------------------------------------------------------------ helpers for tests / bench
 def make_cfg_from_state_dict(sd, mode, **kw) -> OracleConfig:
     d = sd["encoder.adaptor.embed_tokens.weight"].shape[1]

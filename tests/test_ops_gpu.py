@@ -804,3 +804,52 @@ def test_pdl_chain_matches_plain_stream_order():
                 assert torch.equal(r, t)
     finally:
         lib.ofab_set_pdl(prev)
+
+
+# ------------------------------------------------------------------------------ label-smoothed criterion
+def test_label_smoothed_cross_entropy_vs_oracle_and_reference_fixture():
+    """ofab_ce_fwd / _bwd with label_smoothing > 0 against the oracle restatement and the reference's
+    own label_smoothed_nll_loss outputs (tests/golden/ls_ce.pt); V = 1003 exercises the ragged tail (ld padded to 1008).
+    Loss in fp32 -> 2e-5 relative; dlogits are stored in bf16 -> 6e-3 rel-L2."""
+    import os
+
+    from ofasys_b200 import ops
+    from oracle import oracle_model as om
+
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ls_ce.pt"), weights_only=False)
+    logits, target, eps = om.make_ls_case()
+    x = logits.to(dev()).requires_grad_(True)
+    loss = ops.cross_entropy_sum(x, target.to(dev()), ignore_index=1, label_smoothing=eps)
+    loss.backward()
+    xr = logits.float().requires_grad_(True)
+    lr, nr, _ = om.label_smoothed_cross_entropy_sum(xr, target, eps)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) <= 2e-5 * abs(lr.item())
+    assert abs(loss.item() - float(fx["loss"])) <= 2e-5 * abs(float(fx["loss"]))
+    assert rel_l2(x.grad, xr.grad) <= 6e-3
+    assert rel_l2(x.grad, fx["dlogits"]) <= 6e-3
+    pad_rows = (target == 1).nonzero().flatten()
+    assert not x.grad[pad_rows.to(dev())].any()  # padding rows: exactly zero gradient
+
+
+def test_linear_label_smoothed_cross_entropy_fused():
+    """The tied projection fused with the label-smoothed criterion, plus the plain nll for logging."""
+    from ofasys_b200 import ops
+    from oracle import oracle_model as om
+
+    gen = g()
+    M, K, V, eps = 48, 128, 515, 0.1
+    x = rnd(M, K, gen=gen, scale=0.5).requires_grad_(True)
+    E = rnd(V, K, gen=gen, scale=0.2).requires_grad_(True)
+    tgt = torch.randint(2, V, (M,), generator=gen)
+    tgt[::7] = 1
+    nll = torch.zeros(1, dtype=torch.float32, device=dev())
+    loss = ops.linear_cross_entropy(x, E, tgt.to(dev()), 1, eps, nll)
+    loss.backward()
+    xr, Er = x.detach().float().cpu().requires_grad_(True), E.detach().float().cpu().requires_grad_(True)
+    logits_r = (xr @ Er.t()).to(torch.bfloat16).float()  # the kernel's logits are one bf16 scratch
+    lr, nr, _ = om.label_smoothed_cross_entropy_sum(xr @ Er.t(), tgt, eps)
+    lr.backward()
+    assert abs(loss.item() - lr.item()) <= 3e-3 * abs(lr.item())
+    assert abs(nll.item() - nr.item()) <= 3e-3 * abs(nr.item())
+    assert rel_l2(x.grad, xr.grad) <= TOL16 and rel_l2(E.grad, Er.grad) <= TOL16

@@ -71,7 +71,9 @@ def test_fused_adam_matches_oracle_and_reference_fixture():
             _close_bf16(gp[i].data, p16[i], ("param", k, i))
         for i in fx["small"]:  # the reference's own outputs
             _close32(opt.master(i), fx["masters"][k][i], ("master vs reference", k, i), rel=5e-5, atol=1e-7)
-            _close32(opt.exp_avg(i), fx["exp_avg"][k][i], ("exp_avg vs reference", k, i), rel=5e-5)
+            # exp_avg sums terms of both signs: the 1.5e-5 relative clip-factor difference of step 1 (terms ~1.5e-4) is an
+            # absolute ~2e-9 that a later, nearly cancelled element cannot express as a relative error
+            _close32(opt.exp_avg(i), fx["exp_avg"][k][i], ("exp_avg vs reference", k, i), rel=5e-5, atol=1e-8)
             _close32(opt.exp_avg_sq(i), fx["exp_avg_sq"][k][i], ("exp_avg_sq vs reference", k, i), rel=1e-4)
             _close_bf16(gp[i].data, fx["params_bf16"][k][i], ("param vs reference", k, i), frac=5e-3)
         opt.zero_grad()

@@ -115,3 +115,20 @@ def test_optimizer_oracle_matches_reference_adam():
                 s, a = t.double().sum(), t.double().abs().sum()
                 assert abs(s - fx[name + "_sum"][k][i]) <= 1e-9 * max(1.0, float(a)), (name, k, i)
                 assert abs(a - fx[name + "_abs"][k][i]) <= 1e-9 * max(1.0, float(a)), (name, k, i)
+
+
+def test_label_smoothed_criterion_oracle_matches_reference():
+    """oracle_model.label_smoothed_cross_entropy_sum against the reference's own label_smoothed_nll_loss
+    (tests/golden/ls_ce.pt, oracle/make_golden_criterion.py)."""
+    fx = torch.load(os.path.join(GOLD, "ls_ce.pt"), weights_only=False)
+    logits, target, eps = om.make_ls_case()
+    x = logits.float().requires_grad_(True)
+    loss, nll, ntok = om.label_smoothed_cross_entropy_sum(x, target, eps)
+    loss.backward()
+    assert ntok == fx["ntokens"]
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-6 * abs(float(fx["loss"]))
+    assert abs(float(nll) - float(fx["nll_loss"])) <= 1e-6 * abs(float(fx["nll_loss"]))
+    assert ((x.grad - fx["dlogits"]).norm() / fx["dlogits"].norm()).item() <= 1e-6
+    # eps = 0 is the plain criterion
+    l0, n0, _ = om.label_smoothed_cross_entropy_sum(logits.float(), target, 0.0)
+    assert abs(float(l0) - float(om.cross_entropy_sum(logits.float(), target))) <= 1e-6 * abs(float(l0)) and float(l0) == float(n0)
