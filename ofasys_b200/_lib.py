@@ -5,7 +5,7 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libofab.so")
+LIB_PATH = os.environ.get("OFAB_LIB") or os.path.join(_HERE, "libofab.so")  # OFAB_LIB: an alternative build (kernel A/B runs)
 
 F32, BF16 = 0, 1
 

@@ -16,6 +16,14 @@
 
 namespace {
 
+// resident CTAs per SM the register allocator is asked for (no position columns / with): the forward kernel fits 4
+// (<= 128 registers) or 3 (<= 168), the backward kernels 3 or 2
+#ifndef ATTN_FWD_MINB
+#define ATTN_FWD_MINB 3  // measured (tools/build_attn_variants.sh, B=32 S=265 / 1040): 102 / 177 us at 3 vs 110 / 186 us at 4 (spills)
+#endif
+#ifndef ATTN_BWD_MINB
+#define ATTN_BWD_MINB 3
+#endif
 constexpr int TILE = 64;
 constexpr int TILE_BYTES = TILE * 128;  // 64 rows x 64 bf16
 
@@ -69,6 +77,34 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// acc[16 x 64] += A[rows row0 .. row0+16 of tile ta] * B^T[all 64 rows of tile tb], both tiles 64 bf16 deep.
+// For every 16-deep k step the A fragment and ALL B fragments are loaded first and the eight MMAs follow: the
+// ldmatrix latencies overlap each other instead of stalling each MMA pair on the load issued right before it (the
+// per-pair `np < np_n` predicate of the ragged-tail form kept the compiler from grouping them: the SASS had
+// LDSM -> 2 x HMMA -> LDSM -> ... and the profile ~1.3 short-scoreboard stall cycles per issued instruction).
+// FULL: all four 16-row groups of the B tile hold valid rows (np_n == 4), no predicates at all.
+template <bool FULL>
+__device__ __forceinline__ void mma_tile_ab(float (&acc)[8][4], uint32_t ta, uint32_t tb, int row0, int np_n) {
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    uint32_t a[4], bb[4][4];
+    frag_a(ta, row0, kk, a);
+#pragma unroll
+    for (int np = 0; np < 4; ++np)
+      if (FULL || np < np_n) frag_b(tb, np * 16, kk, bb[np]);
+#pragma unroll
+    for (int np = 0; np < 4; ++np)
+      if (FULL || np < np_n) {
+        mma16816(acc[2 * np], a, bb[np][0], bb[np][1]);
+        mma16816(acc[2 * np + 1], a, bb[np][2], bb[np][3]);
+      }
+  }
+}
+__device__ __forceinline__ void mma_tile_ab(float (&acc)[8][4], uint32_t ta, uint32_t tb, int row0, int np_n) {
+  if (np_n == 4) mma_tile_ab<true>(acc, ta, tb, row0, 4);
+  else mma_tile_ab<false>(acc, ta, tb, row0, np_n);
 }
 
 struct AttnCommon {
@@ -185,7 +221,7 @@ __device__ __forceinline__ float finish_tile(const AttnCommon& p, float (&s)[8][
 // smem: Q (NH tiles) | K 2 stages x NH | V 2 stages | key-validity bitmap (Tk bits) | table column (n_buckets floats)
 // K/V ring: 2 stages, one __syncthreads per key tile: tile kv+1 is fetched (cp.async) while tile kv is consumed.
 template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
-__global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
+__global__ void __launch_bounds__(128, HAS_POS ? ATTN_FWD_MINB - 1 : ATTN_FWD_MINB) attn_fwd_kernel(const AttnCommon p, bf16* __restrict__ o, int64_t o_bs, int64_t o_rs,
                                                                         float* __restrict__ lse, const AttnDrop ad) {
   constexpr int NH = HAS_POS ? 2 : 1;  // 64-wide halves of the QK contraction
   constexpr int NST = 2;
@@ -253,23 +289,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 3 : 4) attn_fwd_kernel(const At
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-      for (int hf = 0; hf < NH; ++hf) {
-        const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + (st * NH + hf) * TILE_BYTES;
-#pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
-          uint32_t a[4];
-          frag_a(tq, warp * 16, kk, a);
-#pragma unroll
-          for (int np = 0; np < 4; ++np) {
-            if (np < np_n) {
-              uint32_t bb[4];
-              frag_b(tk, np * 16, kk, bb);
-              mma16816(s[2 * np], a, bb[0], bb[1]);
-              mma16816(s[2 * np + 1], a, bb[2], bb[3]);
-            }
-          }
-        }
-      }
+      for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sQ + hf * TILE_BYTES, sK + (st * NH + hf) * TILE_BYTES, warp * 16, np_n);
       // ---- bias / mask / online softmax (log2 domain: p = ex2(s * mult - m), one FFMA + one MUFU per score)
       const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
       float mx[2] = {-INFINITY, -INFINITY};
@@ -380,7 +400,7 @@ struct AttnBwdExtra {
 // Query-side operands (Q, dO, lse, delta) are double-buffered when no table column competes for shared memory
 // (NSB = 2: tile qt+1 is fetched while tile qt is consumed, one barrier per tile).
 template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
-__global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
+__global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MINB) attn_bwd_dkv_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   constexpr int NSB = HAS_TAB ? 1 : 2;
   constexpr int QST = (NH + 1) * TILE_BYTES;      // one query-side stage: Q (NH tiles) | dO
@@ -477,23 +497,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-    for (int hf = 0; hf < NH; ++hf) {
-      const uint32_t tk = sK + hf * TILE_BYTES, tq = sQ + hf * TILE_BYTES;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t a[4];
-        frag_a(tk, warp * 16, kk, a);
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          if (np < np_n) {
-            uint32_t bb[4];
-            frag_b(tq, np * 16, kk, bb);
-            mma16816(s[2 * np], a, bb[0], bb[1]);
-            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
-          }
-        }
-      }
-    }
+    for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sK + hf * TILE_BYTES, sQ + hf * TILE_BYTES, warp * 16, np_n);
     // P^T = ex2(S^T * mult - lse2[query])   (masked scores are -inf -> 0)
     const float mult = finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
 #pragma unroll
@@ -541,20 +545,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t a[4];
-      frag_a(sV, warp * 16, kk, a);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (np < np_n) {
-          uint32_t bb[4];
-          frag_b(sDO, np * 16, kk, bb);
-          mma16816(dp_[2 * np], a, bb[0], bb[1]);
-          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
+    mma_tile_ab(dp_, sV, sDO, warp * 16, np_n);
     // scale * dS^T = P^T * (scale * dP^T - scale * delta[query])
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -613,7 +604,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dkv_kernel(cons
 // ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles (K / V double-buffered when no
 // table column competes for shared memory).
 template <bool HAS_POS, bool HAS_TAB, bool DROP = false>
-__global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
+__global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MINB) attn_bwd_dq_kernel(const AttnCommon p, const AttnBwdExtra e) {
   constexpr int NH = HAS_POS ? 2 : 1;
   constexpr int NSB = HAS_TAB ? 1 : 2;
   constexpr int KST = (NH + 1) * TILE_BYTES;      // one key-side stage: K (NH tiles) | V
@@ -721,43 +712,14 @@ __global__ void __launch_bounds__(128, HAS_POS ? 2 : 3) attn_bwd_dq_kernel(const
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-    for (int hf = 0; hf < NH; ++hf) {
-      const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + hf * TILE_BYTES;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        uint32_t a[4];
-        frag_a(tq, warp * 16, kk, a);
-#pragma unroll
-        for (int np = 0; np < 4; ++np) {
-          if (np < np_n) {
-            uint32_t bb[4];
-            frag_b(tk, np * 16, kk, bb);
-            mma16816(s[2 * np], a, bb[0], bb[1]);
-            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
-          }
-        }
-      }
-    }
+    for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sQ + hf * TILE_BYTES, sK + hf * TILE_BYTES, warp * 16, np_n);
     // dP = dO V^T
     float dp_[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t a[4];
-      frag_a(sDO, warp * 16, kk, a);
-#pragma unroll
-      for (int np = 0; np < 4; ++np) {
-        if (np < np_n) {
-          uint32_t bb[4];
-          frag_b(sV, np * 16, kk, bb);
-          mma16816(dp_[2 * np], a, bb[0], bb[1]);
-          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
-        }
-      }
-    }
+    mma_tile_ab(dp_, sDO, sV, warp * 16, np_n);
     // P, dS ; relative-position table gradient
     int idxs[has_tab ? 8 : 1][4];
     if (has_tab) {

@@ -28,10 +28,12 @@ def _close32(a, b, what, rel=2e-6, atol=1e-10):
 
 
 def _close_bf16(a, b, what, frac=1e-3):
-    a, b = a.detach().cpu(), b
-    diff = (a.view(torch.int16).int() - b.view(torch.int16).int()).abs()
-    assert int(diff.max()) <= 1, (what, int(diff.max()))
-    assert float((diff != 0).float().mean()) <= frac, (what, float((diff != 0).float().mean()))
+    """bf16 copies of masters that agree to ~1e-6: identical except for rare rounding ties (one bf16 ulp = 2^-8 relative;
+    near zero, where a master is itself only an update's rounding noise, an absolute 1e-7)."""
+    a, b = a.detach().cpu().float(), b.float()
+    err = (a - b).abs()
+    assert bool((err <= 2.0 ** -7 * b.abs() + 1e-7).all()), (what, float(err.max()))
+    assert float((err != 0).float().mean()) <= frac, (what, float((err != 0).float().mean()))
 
 
 def test_fused_adam_matches_oracle_and_reference_fixture():
