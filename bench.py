@@ -452,8 +452,19 @@ def run_gpu(args, rank, world, local_rank):
         ach = fl_list / t_list / 1e12
         del gg
         pool.clear()
+        # DRAM traffic of the dominant kernel: measured once under ncu (dram__bytes_read.sum + dram__bytes_write.sum over the
+        # GEMM launches of one step, tools/launch_list_summary.py -> profiles/r01_gemm_traffic.json), per launch like `achieved`
+        traffic = traffic_note = None
+        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tp):
+            try:
+                tj = json.load(open(tp))
+                if int(tj.get("per_gpu_batch", -1)) == B:
+                    traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("note")
+            except Exception:
+                pass
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                "frac": ach / pk["tf_sustained"], "traffic": None, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
+                "frac": ach / pk["tf_sustained"], "traffic": traffic, "traffic_unit": "bytes/launch (ncu)", "traffic_note": traffic_note, "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({pk['src']})",
                 "how": "the step's GEMM launch list replayed back to back as one CUDA graph, CUDA events around the replay",
                 "gemm_launches_per_step": len(launch_list), "gemm_ms_per_step": t_list * 1e3,
                 "avg_launch_us": t_list * 1e6 / max(1, len(launch_list)),

@@ -16,10 +16,12 @@
 
 namespace {
 
-// resident CTAs per SM the register allocator is asked for (no position columns / with): the forward kernel fits 4
-// (<= 128 registers) or 3 (<= 168), the backward kernels 3 or 2
+// resident CTAs per SM the register allocator is asked for (no position columns / with): tools/build_attn_variants.sh
+// builds alternatives for A/B runs.  Measured in the whole step (B=64): forward 4 / backward 3 is the best of
+// {4,3} x {3,2}; grouping all ldmatrix loads of a k step ahead of its MMAs (profiles/r01_attn_variants.txt) cost
+// 120-244 B of spills in the backward kernels and +8 % of their in-step time.
 #ifndef ATTN_FWD_MINB
-#define ATTN_FWD_MINB 3  // measured (tools/build_attn_variants.sh, B=32 S=265 / 1040): 102 / 177 us at 3 vs 110 / 186 us at 4 (spills)
+#define ATTN_FWD_MINB 4
 #endif
 #ifndef ATTN_BWD_MINB
 #define ATTN_BWD_MINB 3
@@ -77,34 +79,6 @@ __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], 
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
-// acc[16 x 64] += A[rows row0 .. row0+16 of tile ta] * B^T[all 64 rows of tile tb], both tiles 64 bf16 deep.
-// For every 16-deep k step the A fragment and ALL B fragments are loaded first and the eight MMAs follow: the
-// ldmatrix latencies overlap each other instead of stalling each MMA pair on the load issued right before it (the
-// per-pair `np < np_n` predicate of the ragged-tail form kept the compiler from grouping them: the SASS had
-// LDSM -> 2 x HMMA -> LDSM -> ... and the profile ~1.3 short-scoreboard stall cycles per issued instruction).
-// FULL: all four 16-row groups of the B tile hold valid rows (np_n == 4), no predicates at all.
-template <bool FULL>
-__device__ __forceinline__ void mma_tile_ab(float (&acc)[8][4], uint32_t ta, uint32_t tb, int row0, int np_n) {
-#pragma unroll
-  for (int kk = 0; kk < 4; ++kk) {
-    uint32_t a[4], bb[4][4];
-    frag_a(ta, row0, kk, a);
-#pragma unroll
-    for (int np = 0; np < 4; ++np)
-      if (FULL || np < np_n) frag_b(tb, np * 16, kk, bb[np]);
-#pragma unroll
-    for (int np = 0; np < 4; ++np)
-      if (FULL || np < np_n) {
-        mma16816(acc[2 * np], a, bb[np][0], bb[np][1]);
-        mma16816(acc[2 * np + 1], a, bb[np][2], bb[np][3]);
-      }
-  }
-}
-__device__ __forceinline__ void mma_tile_ab(float (&acc)[8][4], uint32_t ta, uint32_t tb, int row0, int np_n) {
-  if (np_n == 4) mma_tile_ab<true>(acc, ta, tb, row0, 4);
-  else mma_tile_ab<false>(acc, ta, tb, row0, np_n);
 }
 
 struct AttnCommon {
@@ -289,7 +263,23 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_FWD_MINB - 1 : ATTN_FWD_MI
 #pragma unroll
         for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-      for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sQ + hf * TILE_BYTES, sK + (st * NH + hf) * TILE_BYTES, warp * 16, np_n);
+      for (int hf = 0; hf < NH; ++hf) {
+        const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + (st * NH + hf) * TILE_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          uint32_t a[4];
+          frag_a(tq, warp * 16, kk, a);
+#pragma unroll
+          for (int np = 0; np < 4; ++np) {
+            if (np < np_n) {
+              uint32_t bb[4];
+              frag_b(tk, np * 16, kk, bb);
+              mma16816(s[2 * np], a, bb[0], bb[1]);
+              mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+            }
+          }
+        }
+      }
       // ---- bias / mask / online softmax (log2 domain: p = ex2(s * mult - m), one FFMA + one MUFU per score)
       const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
       float mx[2] = {-INFINITY, -INFINITY};
@@ -497,7 +487,23 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-    for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sK + hf * TILE_BYTES, sQ + hf * TILE_BYTES, warp * 16, np_n);
+    for (int hf = 0; hf < NH; ++hf) {
+      const uint32_t tk = sK + hf * TILE_BYTES, tq = sQ + hf * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        frag_a(tk, warp * 16, kk, a);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (np < np_n) {
+            uint32_t bb[4];
+            frag_b(tq, np * 16, kk, bb);
+            mma16816(s[2 * np], a, bb[0], bb[1]);
+            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          }
+        }
+      }
+    }
     // P^T = ex2(S^T * mult - lse2[query])   (masked scores are -inf -> 0)
     const float mult = finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
 #pragma unroll
@@ -545,7 +551,20 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
-    mma_tile_ab(dp_, sV, sDO, warp * 16, np_n);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      frag_a(sV, warp * 16, kk, a);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < np_n) {
+          uint32_t bb[4];
+          frag_b(sDO, np * 16, kk, bb);
+          mma16816(dp_[2 * np], a, bb[0], bb[1]);
+          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
     // scale * dS^T = P^T * (scale * dP^T - scale * delta[query])
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
@@ -712,14 +731,43 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
 #pragma unroll
       for (int j = 0; j < 4; ++j) s[i][j] = 0.f;
 #pragma unroll
-    for (int hf = 0; hf < NH; ++hf) mma_tile_ab(s, sQ + hf * TILE_BYTES, sK + hf * TILE_BYTES, warp * 16, np_n);
+    for (int hf = 0; hf < NH; ++hf) {
+      const uint32_t tq = sQ + hf * TILE_BYTES, tk = sK + hf * TILE_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint32_t a[4];
+        frag_a(tq, warp * 16, kk, a);
+#pragma unroll
+        for (int np = 0; np < 4; ++np) {
+          if (np < np_n) {
+            uint32_t bb[4];
+            frag_b(tk, np * 16, kk, bb);
+            mma16816(s[2 * np], a, bb[0], bb[1]);
+            mma16816(s[2 * np + 1], a, bb[2], bb[3]);
+          }
+        }
+      }
+    }
     // dP = dO V^T
     float dp_[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) dp_[i][j] = 0.f;
-    mma_tile_ab(dp_, sDO, sV, warp * 16, np_n);
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t a[4];
+      frag_a(sDO, warp * 16, kk, a);
+#pragma unroll
+      for (int np = 0; np < 4; ++np) {
+        if (np < np_n) {
+          uint32_t bb[4];
+          frag_b(sV, np * 16, kk, bb);
+          mma16816(dp_[2 * np], a, bb[0], bb[1]);
+          mma16816(dp_[2 * np + 1], a, bb[2], bb[3]);
+        }
+      }
+    }
     // P, dS ; relative-position table gradient
     int idxs[has_tab ? 8 : 1][4];
     if (has_tab) {

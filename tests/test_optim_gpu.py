@@ -148,6 +148,8 @@ def test_model_step_with_fused_adam_changes_every_used_parameter():
         if grads[k] is None:
             assert torch.equal(p.data, before[k]), k
             continue
-        big = grads[k].float().abs() > 1e-3 * grads[k].float().abs().max()
+        # elements whose gradient is not small against eps * sqrt(1 - beta2) / (grad scale): there the first update is a
+        # full -lr * sign(g) (smaller gradients give a fraction of lr that may round to no bf16 movement at all)
+        big = grads[k].float().abs() > 0.1 * grads[k].float().abs().max()
         moved = (p.data.float() - before[k].float())
         assert bool((torch.sign(moved[big]) == -torch.sign(grads[k].float()[big])).float().mean() > 0.98), k
