@@ -122,6 +122,8 @@ _SIGS = {
     "ofab_bn_stats": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "ofab_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "ofab_bn_bwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "ofab_fbank": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
+    "ofab_utterance_cmvn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ofab_adam_chunk_elems": (c_int, []),
     "ofab_grad_norm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "ofab_adam_step": (c_int, [c_void_p, c_int, c_int64, POINTER(AdamHyper), c_void_p]),

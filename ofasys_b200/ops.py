@@ -5,6 +5,7 @@ walk; every kernel that runs is ours.  All functions require CUDA tensors and ra
 there is no CPU or eager fallback.
 """
 import ctypes
+import weakref
 
 import torch
 
@@ -140,19 +141,23 @@ def _reduce_partials(partial, dtype):
 
 # Bias-gradient side channel: the LayerNorm backward kernels already hold every element of the gradient they
 # emit (dx / da) in registers, so they also accumulate its column sums -- which is exactly the bias gradient of the
-# Linear layer that consumes that gradient next in backward.  The hint is keyed by the gradient's storage.
+# Linear layer that consumes that gradient next in backward.  The hint is looked up by the gradient's address and is
+# valid only for THE SAME tensor object (weak reference): the caching allocator hands a freed gradient's address to
+# later tensors of the same size, and an unconsumed hint must never be taken for one of those.
 _BIAS_HINTS = {}
 
 
 def _hint_bias_grad(grad_tensor, colsum_vec):
     if len(_BIAS_HINTS) > 64:
         _BIAS_HINTS.clear()
-    _BIAS_HINTS[(grad_tensor.data_ptr(), grad_tensor.numel())] = colsum_vec
+    _BIAS_HINTS[(grad_tensor.data_ptr(), grad_tensor.numel())] = (weakref.ref(grad_tensor), colsum_vec)
 
 
 def _take_bias_hint(grad_tensor, n):
-    v = _BIAS_HINTS.pop((grad_tensor.data_ptr(), grad_tensor.numel()), None)
-    return v if v is not None and v.numel() == n else None
+    ent = _BIAS_HINTS.pop((grad_tensor.data_ptr(), grad_tensor.numel()), None)
+    if ent is None or ent[0]() is not grad_tensor:
+        return None
+    return ent[1] if ent[1].numel() == n else None
 
 
 def cast_bf16(x):

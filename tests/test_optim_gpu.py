@@ -153,3 +153,59 @@ def test_model_step_with_fused_adam_changes_every_used_parameter():
         big = grads[k].float().abs() > 0.1 * grads[k].float().abs().max()
         moved = (p.data.float() - before[k].float())
         assert bool((torch.sign(moved[big]) == -torch.sign(grads[k].float()[big])).float().mean() > 0.98), k
+
+
+def test_training_trajectory_matches_oracle_training():
+    """Five updates of the tiny text model -- forward_loss + backward + multiply_grads(1/ntokens) + clip_grad_norm(1.0) +
+    FusedAdam.step -- against the same loop run by the oracle on CPU in fp32 (oracle_model.loss_and_grads +
+    oracle_optim.update, bf16 parameters with fp32 masters as the reference's bf16 mode keeps them).  The loss must fall
+    and stay on the oracle's trajectory (bf16 gradients: 1 % on the loss after five compounding updates)."""
+    import ofasys_b200 as ob
+    from oracle import cases
+    from oracle import oracle_model as om
+    from util import build_product, load_golden, to_product_slots
+
+    dev = torch.device("cuda:0")
+    g = load_golden("text_A")
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    cfg = cases.oracle_cfg("text_A")
+    m = build_product("text_A")
+    m.load_state_dict(sd, strict=False)
+    m = m.to(torch.bfloat16).to(dev).train()
+    slots, target = cases.make_inputs("text_A")
+    pslots, tgt = to_product_slots(slots, dev), target.to(dev)
+    ntok = int((target != 1).sum())
+    hyper = dict(lr=2e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01)
+    opt = ob.FusedAdam(m.parameters(), **hyper)
+
+    # oracle side: unique parameter tensors (the tied embedding is one tensor under two names)
+    names = [k for k, _ in m.named_parameters()]
+    o_params = {k: sd[k].to(torch.bfloat16) for k in names}
+    masters = [o_params[k].float() for k in names]
+    ms = [torch.zeros_like(t) for t in masters]
+    vs = [torch.zeros_like(t) for t in masters]
+
+    losses, losses_ref = [], []
+    for step in range(1, 6):
+        opt.zero_grad()
+        loss = m.forward_loss(pslots, tgt)
+        loss.backward()
+        opt.multiply_grads(1.0 / ntok)
+        opt.clip_grad_norm(1.0)
+        opt.step()
+        losses.append(loss.item() / ntok)
+
+        sd_o = dict(sd)
+        for k in names:
+            sd_o[k] = o_params[k].float()
+        sd_o["decoder.adaptor.embed_tokens.weight"] = sd_o["encoder.adaptor.embed_tokens.weight"]
+        l_ref, _, grads = om.loss_and_grads(sd_o, cfg, slots, target)
+        gb = [grads[k].to(torch.bfloat16) for k in names]
+        _, p16 = oo.update(masters, gb, ms, vs, step, hyper["lr"], hyper["betas"], hyper["eps"], hyper["weight_decay"], 1.0 / ntok, 1.0)
+        for k, p in zip(names, p16):
+            o_params[k] = p
+        losses_ref.append(l_ref.item() / ntok)
+    assert all(b < a for a, b in zip(losses, losses[1:])), losses
+    assert losses[-1] < 0.9 * losses[0], losses
+    for a, b in zip(losses, losses_ref):
+        assert abs(a - b) <= 1e-2 * abs(b), (losses, losses_ref)

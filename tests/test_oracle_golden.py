@@ -132,3 +132,33 @@ def test_label_smoothed_criterion_oracle_matches_reference():
     # eps = 0 is the plain criterion
     l0, n0, _ = om.label_smoothed_cross_entropy_sum(logits.float(), target, 0.0)
     assert abs(float(l0) - float(om.cross_entropy_sum(logits.float(), target))) <= 1e-6 * abs(float(l0)) and float(l0) == float(n0)
+
+
+def test_audio_front_end_oracle_matches_torchaudio_and_reference_cmvn():
+    """oracle_audio.fbank against tests/golden/fbank.pt (torchaudio.compliance.kaldi.fbank, the function the reference
+    calls, + the reference's own UtteranceCMVN) and, when torchaudio is importable, against torchaudio directly.
+    Same torch ops in the same order -> 1e-6."""
+    from oracle import oracle_audio as oa
+
+    fx = torch.load(os.path.join(GOLD, "fbank.pt"), weights_only=False)
+    wav, lengths = oa.make_case()
+    for b in range(wav.shape[0]):
+        f = oa.fbank(wav[b:b + 1, : int(lengths[b])])
+        assert f.shape == fx["fbank"][b].shape
+        assert (f - fx["fbank"][b]).abs().max().item() <= 1e-5
+        c = torch.from_numpy(oa.utterance_cmvn(f.numpy()))
+        assert (c - fx["cmvn"][b]).abs().max().item() <= 1e-4
+    try:
+        import torchaudio.compliance.kaldi as ta_kaldi
+    except Exception:
+        return
+    g = torch.Generator().manual_seed(3)
+    w = torch.randn(1, 16000, generator=g) * 2000
+    assert (oa.fbank(w) - ta_kaldi.fbank(w, num_mel_bins=80, sample_frequency=16000)).abs().max().item() <= 1e-5
+    # the product's host-side tables are the same numbers
+    from ofasys_b200.preprocessor.audio import Fbank, kaldi_mel_banks, kaldi_window
+
+    assert torch.equal(kaldi_window(400), torch.hann_window(400, periodic=False).pow(0.85))
+    mel = torch.nn.functional.pad(oa.mel_banks(80, 512, 16000.0).to(torch.float32), (0, 1))
+    assert torch.equal(kaldi_mel_banks(80, 512, 16000.0), mel)
+    assert Fbank().num_frames(16000) == 98 and Fbank().num_frames(399) == 0
