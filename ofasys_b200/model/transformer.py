@@ -131,10 +131,10 @@ class TransformerDecoder(nn.Module):
 
     def extract_features(self, slots, encoder_out, incremental_state=None, full_context_alignment=False, alignment_layer=None,
                          alignment_heads=None, return_all_hiddens=False, return_all_attention_weights=False):
-        if incremental_state is not None:
-            raise NotImplementedError("incremental decoding is outside the fwd+bwd hot path (SURVEY 8f next #3)")
         if return_all_attention_weights:
             raise NotImplementedError("attention maps are never materialised by the fused kernel")
+        if incremental_state is not None:
+            return self._extract_features_incremental(slots, encoder_out, incremental_state)
         embed, masks, pos, biases, _ = self.adaptor(slots)
         enc = encoder_out["_encoder_out_bt"] if "_encoder_out_bt" in encoder_out else encoder_out["encoder_out"][0].transpose(0, 1).contiguous()
         enc_mask = encoder_out["encoder_padding_mask"][0] if encoder_out["encoder_padding_mask"] else None
@@ -162,6 +162,45 @@ class TransformerDecoder(nn.Module):
         else:
             x = self.layer_norm(x) if self.layer_norm is not None else ops.to_bf16(x)  # bf16 B x T x C
         return x, {"attn": [None], "inner_states": inner, "decoder_attentions": [], "cross_attentions": []}
+
+    def _extract_features_incremental(self, slots, encoder_out, incremental_state):
+        """One generation step (transformer.py:417-522 with incremental_state).  As in the reference the
+        adaptor sees the whole prefix (embeddings / position terms of every position so far) and the last position is
+        sliced out (:444-447, :474-475); the layers then run on that single row against the caches in
+        `incremental_state` (a plain dict owned by the caller, e.g. the sequence generator)."""
+        embed, masks, pos, biases, _ = self.adaptor(slots)
+        enc = encoder_out["_encoder_out_bt"] if "_encoder_out_bt" in encoder_out else encoder_out["encoder_out"][0].transpose(0, 1).contiguous()
+        enc_mask = encoder_out["encoder_padding_mask"][0] if encoder_out["encoder_padding_mask"] else None
+        cross_bias = None
+        if not self.cfg.entangle_position_embedding:
+            cb = self.get_cross_pos_info(pos, encoder_out["position_embeddings"][0])
+            cross_bias = ops.PositionBias(cb.pq[:, -1:].contiguous(), cb.pk)
+        x = embed[:, -1:].contiguous()
+        last_mask = masks[:, -1:]
+        step_biases = None
+        if self.cfg.use_self_attn_bias:
+            step_biases = []
+            for b in biases:
+                idx = None if b.rp_idx is None else b.rp_idx[-1:, :].contiguous()
+                step_biases.append(ops.PositionBias(b.pq[:, -1:].contiguous(), b.pk, idx, b.table))
+        for idx, layer in enumerate(self.layers):
+            bias = None
+            if step_biases is not None:
+                bias = step_biases[0] if self.cfg.share_attn_bias else step_biases[idx]
+            x, _, _ = layer(x, enc, enc_mask, incremental_state=incremental_state, self_attn_padding_mask=last_mask,
+                            self_attn_bias=bias, cross_attn_bias=cross_bias, batch_first=True)
+        x = self.layer_norm(x) if self.layer_norm is not None else ops.to_bf16(x)
+        return x, {"attn": [None], "inner_states": [], "decoder_attentions": [], "cross_attentions": []}
+
+    def reorder_incremental_state(self, incremental_state, new_order):
+        """Beam search: permute every attention cache along the batch (sequence_generator.py reorder_incremental_state;
+        multihead_attention.py:393-409)."""
+        for layer in self.layers:
+            layer.self_attn.reorder_incremental_state(incremental_state, new_order)
+            layer.encoder_attn.reorder_incremental_state(incremental_state, new_order)
+        return incremental_state
+
+    reorder_incremental_state_scripting = reorder_incremental_state
 
     def max_positions(self):
         return self.cfg.max_target_positions

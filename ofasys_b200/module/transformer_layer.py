@@ -115,6 +115,27 @@ class TransformerEncoderLayer(nn.Module):
         return x, None
 
 
+def _forward_incremental_layer(layer, x, encoder_out, encoder_padding_mask, incremental_state, self_kpm, self_bias, cross_bias, batch_first):
+    """One decoding step (transformer_layer.py:351-495 with incremental_state): x holds the new position(s) only; the
+    self-attention keys / values of earlier positions and the projected encoder output live in `incremental_state`."""
+    if not batch_first:
+        x = x.transpose(0, 1).contiguous()
+        encoder_out = encoder_out.transpose(0, 1).contiguous()
+    x = ops.to_f32(x)
+    x1 = layer.self_attn_layer_norm(x)
+    a, _ = layer.self_attn(x1, key_padding_mask=self_kpm, incremental_state=incremental_state,
+                           attn_bias=self_bias if self_bias is not None else False, batch_first=True)
+    x, x2 = _junction(layer, a, x, layer.self_attn_ln, layer.encoder_attn_layer_norm)
+    c, _ = layer.encoder_attn(x2, key=encoder_out, value=encoder_out, key_padding_mask=encoder_padding_mask,
+                              incremental_state=incremental_state, static_kv=True, attn_bias=cross_bias, batch_first=True)
+    x, x3 = _junction(layer, c, x, layer.cross_attn_ln, layer.final_layer_norm)
+    y, ydrop = _ffn(layer, x3)
+    x = ops.add_residual(x, ops.dropout(y, ydrop))
+    if not batch_first:
+        x = x.transpose(0, 1)
+    return x, None, None
+
+
 class TransformerDecoderLayer(nn.Module):
     def __init__(self, args, no_encoder_attn=False, add_bias_kv=False, add_zero_attn=False, drop_path_rate=0.0):
         super().__init__()
@@ -146,11 +167,16 @@ class TransformerDecoderLayer(nn.Module):
         self.need_attn = True
         self.drop_path_rate = float(drop_path_rate)
 
+    _forward_incremental = _forward_incremental_layer
+
     def forward(self, x, encoder_out=None, encoder_padding_mask=None, incremental_state=None, prev_self_attn_state=None,
                 prev_attn_state=None, self_attn_mask=None, self_attn_padding_mask=None, need_attn=False, need_head_weights=False,
                 self_attn_bias=None, cross_attn_bias=None, modal_mask=None, batch_first=False, pending=None, defer=False):
-        if incremental_state is not None or prev_self_attn_state is not None or prev_attn_state is not None:
-            raise NotImplementedError("incremental decoding is outside the fwd+bwd hot path")
+        if prev_self_attn_state is not None or prev_attn_state is not None:
+            raise NotImplementedError("prev_*_state injection (ONNX export path) is not supported; use incremental_state")
+        if incremental_state is not None:
+            return self._forward_incremental(x, encoder_out, encoder_padding_mask, incremental_state, self_attn_padding_mask,
+                                             self_attn_bias, cross_attn_bias, batch_first)
         if not batch_first:
             x = x.transpose(0, 1).contiguous()
             encoder_out = encoder_out.transpose(0, 1).contiguous()

@@ -447,14 +447,17 @@ class _AttentionFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H, drop=None):
         _need_cuda(q_src)
-        q_src = _c(q_src)
+        # the kernels read q / k / v through (batch, row) strides: a column slice of a packed projection or a prefix of a
+        # K|V cache is used in place as long as rows are contiguous and 16-byte aligned
+        strided_ok = lambda t: t.dim() == 3 and t.stride(2) == 1 and t.stride(0) % 8 == 0 and t.stride(1) % 8 == 0 and t.data_ptr() % 16 == 0
+        q_src = q_src if strided_ok(q_src) else _c(q_src)
         d = H * 64
         B = q_src.shape[0]
         if kv_src is None:
             assert q_src.shape[-1] == 3 * d
             q, k, v = q_src[..., :d], q_src[..., d:2 * d], q_src[..., 2 * d:]
         else:
-            kv_src = _c(kv_src)
+            kv_src = kv_src if strided_ok(kv_src) else _c(kv_src)
             assert q_src.shape[-1] == d and kv_src.shape[-1] == 2 * d
             q, k, v = q_src, kv_src[..., :d], kv_src[..., d:]
         Tq, Tk = q.shape[1], k.shape[1]
@@ -485,13 +488,13 @@ class _AttentionFn(torch.autograd.Function):
         d_o = _c(d_o)
         if kv_src is None:
             q, k, v = q_src[..., :d], q_src[..., d:2 * d], q_src[..., 2 * d:]
-            dq_src = torch.empty_like(q_src)
+            dq_src = torch.empty(q_src.shape, dtype=q_src.dtype, device=q_src.device)
             dq, dk, dv = dq_src[..., :d], dq_src[..., d:2 * d], dq_src[..., 2 * d:]
             dkv_src = None
         else:
             q, k, v = q_src, kv_src[..., :d], kv_src[..., d:]
-            dq_src = torch.empty_like(q_src)
-            dkv_src = torch.empty_like(kv_src)
+            dq_src = torch.empty(q_src.shape, dtype=q_src.dtype, device=q_src.device)
+            dkv_src = torch.empty(kv_src.shape, dtype=kv_src.dtype, device=kv_src.device)
             dq, dk, dv = dq_src, dkv_src[..., :d], dkv_src[..., d:]
         Tq, Tk = q.shape[1], k.shape[1]
         a = _lib.AttnBwdArgs()
