@@ -2,7 +2,7 @@
 or a call fails, the product path raises."""
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_uint32, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("OFAB_LIB") or os.path.join(_HERE, "libofab.so")  # OFAB_LIB: an alternative build (kernel A/B runs)
@@ -51,6 +51,7 @@ class AttnBwdArgs(Structure):
         ("dq", c_void_p), ("dk", c_void_p), ("dv", c_void_p),
         ("dq_bs", c_int64), ("dq_rs", c_int64), ("dk_bs", c_int64), ("dk_rs", c_int64), ("dv_bs", c_int64), ("dv_rs", c_int64),
         ("dpq", c_void_p), ("dpk", c_void_p), ("dtable", c_void_p), ("delta", c_void_p),
+        ("dq_colsum", c_void_p), ("dk_colsum", c_void_p), ("dv_colsum", c_void_p),
     ]
 
 
@@ -87,6 +88,7 @@ _SIGS = {
     "ofab_ln_res_ln_bwd": (c_int, [c_void_p] * 10 + [c_int64, c_int, POINTER(Dropout), c_void_p]),
     "ofab_colsum": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_int, c_int, c_void_p, c_void_p]),
     "ofab_colsum_scratch_elems": (c_int64, [c_int64]),
+    "ofab_reduce_rows": (c_int, [c_void_p, c_int, c_int64, c_int, c_void_p, c_int, c_void_p]),
     "ofab_reduce_partials": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p]),
     "ofab_gemm_bf16": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int, c_void_p]),
     "ofab_gemm_splitk_workspace_elems": (c_int64, [c_int64, c_int64, c_int64]),

@@ -371,6 +371,28 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_FWD_MINB - 1 : ATTN_FWD_MI
   }
 }
 
+// Column sums of one CTA's 64 x 64 gradient tile (rows = its queries or keys, held as 8 x [16 x 8] warp accumulators):
+// the bias gradient of the projection that produced q / k / v is the column sum of dq / dk / dv, and the tile is in
+// registers here -- one partial row per CTA goes to `out` (64 floats), a small reduction over the CTAs finishes it
+// (deterministic; replaces a separate pass that re-read the whole gradient from HBM).  Rows outside the sequence
+// hold exact zeros.  Every thread of the CTA must call this.
+__device__ __forceinline__ void tile_colsum(const float (*acc)[4], float (*cs)[64], float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, t = lane & 3;
+  __syncthreads();  // cs may still be read by a previous call
+#pragma unroll
+  for (int dt = 0; dt < 8; ++dt)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float v = acc[dt][e] + acc[dt][2 + e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      if (lane < 4) cs[warp][dt * 8 + 2 * t + e] = v;
+    }
+  __syncthreads();
+  if (threadIdx.x < 64) out[threadIdx.x] = cs[0][threadIdx.x] + cs[1][threadIdx.x] + cs[2][threadIdx.x] + cs[3][threadIdx.x];
+}
+
 // ===================================================================================== backward
 struct AttnBwdExtra {
   const bf16* d_o;
@@ -382,6 +404,7 @@ struct AttnBwdExtra {
   bf16 *dq, *dk, *dv, *dpq, *dpk;
   int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
   float* dtable;
+  float *dq_colsum, *dk_colsum, *dv_colsum;  // [B * tiles, H * 64] per-CTA column sums or NULL
   AttnDrop drop;
 };
 
@@ -618,6 +641,12 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
       }
     }
   }
+  if (e.dk_colsum != nullptr) {
+    __shared__ float cs[4][64];
+    const int64_t prow = ((int64_t)b * gridDim.x + kb) * (p.H * 64) + h * 64;
+    tile_colsum(dk, cs, e.dk_colsum + prow);
+    tile_colsum(dv, cs, e.dv_colsum + prow);
+  }
 }
 
 // ---- dQ (+ dPQ, d table): one CTA per 64-query tile, loops over key tiles (K / V double-buffered when no
@@ -840,6 +869,10 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
       if (v != 0.f) atomicAdd(e.dtable + (int64_t)i * p.H + h, v);
     }
   }
+  if (e.dq_colsum != nullptr) {
+    __shared__ float cs[4][64];
+    tile_colsum(dq, cs, e.dq_colsum + ((int64_t)b * gridDim.x + qb) * (p.H * 64) + h * 64);
+  }
 }
 
 int fill_common(const ofab_attn_fwd_args* a, AttnCommon& c) {
@@ -931,6 +964,8 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   e.dq = (bf16*)a->dq; e.dk = (bf16*)a->dk; e.dv = (bf16*)a->dv; e.dpq = (bf16*)a->dpq; e.dpk = (bf16*)a->dpk;
   e.dq_bs = a->dq_bs; e.dq_rs = a->dq_rs; e.dk_bs = a->dk_bs; e.dk_rs = a->dk_rs; e.dv_bs = a->dv_bs; e.dv_rs = a->dv_rs;
   e.dtable = a->dtable;
+  OFAB_REQUIRE((a->dk_colsum == nullptr) == (a->dv_colsum == nullptr), "ofab_attn_bwd: dk_colsum and dv_colsum go together");
+  e.dq_colsum = a->dq_colsum; e.dk_colsum = a->dk_colsum; e.dv_colsum = a->dv_colsum;
   bool drop_on;
   if ((rc = fill_drop(a->f.drop, e.drop, drop_on, a->f.Tq, a->f.Tk))) return rc;
   const int nh = pos ? 2 : 1;

@@ -614,6 +614,26 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int co
   }
 }
 
+template <typename TO>
+__global__ void reduce_rows_kernel(const float* __restrict__ partial, int64_t rows, int cols, TO* __restrict__ out) {
+  __shared__ float sm[32][33];
+  pdl_launch();
+  pdl_wait();
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const float* base = partial + (int64_t)blockIdx.y * rows * cols;
+  float s = 0.f;
+  if (c < cols)
+    for (int64_t r = threadIdx.y; r < rows; r += 32) s += base[r * cols + c];
+  sm[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 32; ++k) t += sm[k][threadIdx.x];
+    out[(int64_t)blockIdx.y * cols + c] = (TO)t;
+  }
+}
+
 // ---------------------------------------------------------------------------------- dispatch
 struct LnLaunch {
   int tpr, rpb, block, grid;
@@ -817,5 +837,16 @@ extern "C" int ofab_reduce_partials(const float* partial, int nslabs, int cols, 
   else
     ofab_launch((reduce_partials_kernel<bf16>), dim3(grid), dim3(block), 0, (cudaStream_t)stream, partial, cols, (bf16*)out);
   OFAB_LAUNCH_CHECK("ofab_reduce_partials");
+  return OFAB_OK;
+}
+
+extern "C" int ofab_reduce_rows(const float* partial, int nslabs, int64_t rows, int cols, void* out, int out_dt, ofab_stream_t stream) {
+  OFAB_REQUIRE(partial != nullptr && out != nullptr && nslabs > 0 && rows > 0 && cols > 0, "ofab_reduce_rows: bad arguments");
+  dim3 grid((cols + 31) / 32, nslabs), block(32, 32);
+  if (out_dt == OFAB_F32)
+    ofab_launch((reduce_rows_kernel<float>), grid, block, 0, (cudaStream_t)stream, partial, rows, cols, (float*)out);
+  else
+    ofab_launch((reduce_rows_kernel<bf16>), grid, block, 0, (cudaStream_t)stream, partial, rows, cols, (bf16*)out);
+  OFAB_LAUNCH_CHECK("ofab_reduce_rows");
   return OFAB_OK;
 }

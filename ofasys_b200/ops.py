@@ -518,7 +518,22 @@ class _AttentionFn(torch.autograd.Function):
             a.dtable = None
         delta = torch.empty((B, H, Tq), dtype=torch.float32, device=d_o.device)
         a.delta = delta.data_ptr()
+        # bias gradients of the q / k / v projections: the kernels leave one partial row of column sums per CTA
+        # (self-attention: Tq == Tk, one [3, B * tiles, d] buffer whose slabs reduce straight into the packed [3d] vector)
+        nq, nk = (Tq + 63) // 64, (Tk + 63) // 64
+        if kv_src is None:
+            part = torch.empty((3, B * nq, d), dtype=torch.float32, device=d_o.device)
+            a.dq_colsum, a.dk_colsum, a.dv_colsum = part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr()
+        else:
+            part_q = torch.empty((1, B * nq, d), dtype=torch.float32, device=d_o.device)
+            part_kv = torch.empty((2, B * nk, d), dtype=torch.float32, device=d_o.device)
+            a.dq_colsum, a.dk_colsum, a.dv_colsum = part_q.data_ptr(), part_kv[0].data_ptr(), part_kv[1].data_ptr()
         _lib.call("ofab_attn_bwd", ctypes.byref(a), _s())
+        for grad, partial in ((dq_src, part) if kv_src is None else (dq_src, part_q), (None, None) if kv_src is None else (dkv_src, part_kv)):
+            if grad is not None:
+                vec = torch.empty(partial.shape[0] * d, dtype=torch.bfloat16, device=d_o.device)
+                _lib.call("ofab_reduce_rows", _p(partial), partial.shape[0], partial.shape[1], d, _p(vec), BF16, _s())
+                _hint_bias_grad(grad, vec)
         if pq is not None:
             if pq.shape[0] == 1 and B > 1:  # broadcast positions: sum the per-sample grads
                 dpq = colsum(dpq.view(B, Tq * d), torch.bfloat16).view(1, Tq, d)
