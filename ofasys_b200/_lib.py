@@ -30,6 +30,13 @@ class AdamHyper(Structure):
                 ("step", c_int64), ("norm", c_void_p)]
 
 
+class CtcArgs(Structure):
+    _fields_ = [("logits", c_void_p), ("dt", c_int), ("t_stride", c_int64), ("b_stride", c_int64),
+                ("B", c_int), ("T", c_int), ("C", c_int), ("input_lengths", c_void_p), ("targets", c_void_p), ("Lmax", c_int),
+                ("target_lengths", c_void_p), ("blank", c_int), ("zero_infinity", c_int),
+                ("lse", c_void_p), ("alpha", c_void_p), ("nll", c_void_p), ("gscale", c_void_p), ("dlogits", c_void_p)]
+
+
 class AttnFwdArgs(Structure):
     _fields_ = [
         ("B", c_int), ("H", c_int), ("Tq", c_int), ("Tk", c_int),
@@ -126,6 +133,8 @@ _SIGS = {
     "ofab_bn_bwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
     "ofab_fbank": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "ofab_utterance_cmvn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ofab_ctc_fwd": (c_int, [POINTER(CtcArgs), c_void_p]),
+    "ofab_ctc_bwd": (c_int, [POINTER(CtcArgs), c_void_p]),
     "ofab_adam_chunk_elems": (c_int, []),
     "ofab_grad_norm": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
     "ofab_adam_step": (c_int, [c_void_p, c_int, c_int64, POINTER(AdamHyper), c_void_p]),

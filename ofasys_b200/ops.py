@@ -750,6 +750,56 @@ def linear_cross_entropy(x, E, target, ignore_index=1, label_smoothing=0.0, nll_
     return _LinearCrossEntropyFn.apply(x, E, target, ignore_index, label_smoothing, nll_out)
 
 
+class _CtcFn(torch.autograd.Function):
+    """sum over utterances of the CTC negative log likelihood of `logits` (fused log-softmax)."""
+
+    @staticmethod
+    def forward(ctx, logits, input_lengths, targets, target_lengths, blank, zero_infinity, time_major):
+        _need_cuda(logits, targets, target_lengths)
+        assert logits.dim() == 3 and logits.stride(2) == 1 and logits.dtype in _DT
+        T, B = (logits.shape[0], logits.shape[1]) if time_major else (logits.shape[1], logits.shape[0])
+        ts, bs = (logits.stride(0), logits.stride(1)) if time_major else (logits.stride(1), logits.stride(0))
+        C = logits.shape[2]
+        targets = _c(targets.to(torch.int64))
+        Lmax = targets.shape[1]
+        target_lengths = _c(target_lengths.to(device=logits.device, dtype=torch.int64))
+        if input_lengths is not None:
+            input_lengths = _c(input_lengths.to(device=logits.device, dtype=torch.int64))
+        dev = logits.device
+        lse = torch.empty((B, T), dtype=torch.float32, device=dev)
+        alpha = torch.empty((B, T, 2 * Lmax + 1), dtype=torch.float32, device=dev)
+        nll = torch.empty(B, dtype=torch.float32, device=dev)
+        a = _lib.CtcArgs()
+        a.logits, a.dt, a.t_stride, a.b_stride = logits.data_ptr(), _DT[logits.dtype], ts, bs
+        a.B, a.T, a.C = B, T, C
+        a.input_lengths = None if input_lengths is None else input_lengths.data_ptr()
+        a.targets, a.Lmax, a.target_lengths = targets.data_ptr(), Lmax, target_lengths.data_ptr()
+        a.blank, a.zero_infinity = int(blank), int(zero_infinity)
+        a.lse, a.alpha, a.nll = lse.data_ptr(), alpha.data_ptr(), nll.data_ptr()
+        _lib.call("ofab_ctc_fwd", ctypes.byref(a), _s())
+        ctx.save_for_backward(logits, input_lengths, targets, target_lengths, lse, alpha, nll)
+        ctx.args = a
+        ctx.mark_non_differentiable(nll)
+        per = torch.where(torch.isinf(nll), torch.zeros_like(nll), nll) if zero_infinity else nll
+        return per.sum(), nll
+
+    @staticmethod
+    def backward(ctx, g, _g_nll):
+        logits, input_lengths, targets, target_lengths, lse, alpha, nll = ctx.saved_tensors
+        a = ctx.args  # pointers of the saved tensors are unchanged
+        gs = _c(g.reshape(1).to(torch.float32))
+        dl = torch.empty_strided(logits.shape, logits.stride(), dtype=logits.dtype, device=logits.device)
+        a.gscale, a.dlogits = gs.data_ptr(), dl.data_ptr()
+        _lib.call("ofab_ctc_bwd", ctypes.byref(a), _s())
+        return dl, None, None, None, None, None, None
+
+
+def ctc_loss_sum(logits, targets, target_lengths, input_lengths=None, blank=0, zero_infinity=True, time_major=False):
+    """CTC term of the ASR criterion (speech_to_text_loss.py:339-379) on raw logits [B, T, C] (time_major: [T, B, C]);
+    targets int64 [B, Lmax] left-aligned.  Returns (loss_sum, nll_per_utterance)."""
+    return _CtcFn.apply(logits, input_lengths, targets, target_lengths, blank, zero_infinity, time_major)
+
+
 # ------------------------------------------------------------------------------------ adaptors' convs
 def patch_im2col(img, patch, ldk):
     """[B, C, H, W] (fp32/bf16) -> bf16 [B*(H/p)*(W/p), ldk]; no gradient (the image is data)."""

@@ -162,3 +162,25 @@ def test_audio_front_end_oracle_matches_torchaudio_and_reference_cmvn():
     mel = torch.nn.functional.pad(oa.mel_banks(80, 512, 16000.0).to(torch.float32), (0, 1))
     assert torch.equal(kaldi_mel_banks(80, 512, 16000.0), mel)
     assert Fbank().num_frames(16000) == 98 and Fbank().num_frames(399) == 0
+
+
+def test_ctc_oracle_matches_torch_ctc_loss():
+    """oracle_ctc (restated alpha recursion, autograd gradient) against F.ctc_loss's own outputs (tests/golden/ctc.pt) and
+    against F.ctc_loss directly, float64."""
+    import torch.nn.functional as F
+
+    from oracle import oracle_ctc as oc
+
+    fx = torch.load(os.path.join(GOLD, "ctc.pt"), weights_only=False)
+    logits, targets, in_len, tgt_len, blank = oc.make_case()
+    x = logits.double().requires_grad_(True)
+    loss, nll = oc.ctc_loss_sum(x.to(torch.float64), targets, in_len, tgt_len, blank, zero_infinity=True)
+    loss.backward()
+    per = oc.ctc_nll(torch.log_softmax(logits.double(), -1), targets, in_len, tgt_len, blank)
+    assert torch.isinf(per[3]) and torch.isinf(fx["nll"][3])  # 4 frames cannot carry 8 labels
+    assert torch.allclose(per[:3], fx["nll"][:3], rtol=1e-10, atol=1e-10)
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-9 * abs(float(fx["loss"]))
+    assert ((x.grad - fx["dlogits"]).norm() / fx["dlogits"].norm()).item() <= 1e-9
+    flat = torch.cat([targets[b, : int(tgt_len[b])] for b in range(4)])
+    direct = F.ctc_loss(torch.log_softmax(logits.double(), -1), flat, in_len, tgt_len, blank=blank, reduction="sum", zero_infinity=True)
+    assert abs(float(direct) - float(loss)) <= 1e-9 * abs(float(direct))
