@@ -48,6 +48,7 @@ class AttnFwdArgs(Structure):
         ("kpm", c_void_p), ("causal", c_int), ("scale", c_float),
         ("o", c_void_p), ("o_bs", c_int64), ("o_rs", c_int64), ("lse", c_void_p),
         ("drop", POINTER(Dropout)),
+        ("rp_ld", c_int), ("rp_idx_t", c_void_p), ("rp_ld_t", c_int),
     ]
 
 

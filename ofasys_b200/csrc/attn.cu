@@ -85,7 +85,9 @@ struct AttnCommon {
   int B, H, Tq, Tk;
   const bf16 *q, *k, *v, *pq, *pk;
   int64_t q_bs, q_rs, k_bs, k_rs, v_bs, v_rs, pq_bs, pq_rs, pk_bs, pk_rs;
-  const int32_t* rp_idx;
+  const int16_t* rp_idx;    // [Tq, rp_ld] bucket ids, -1 = none (columns >= Tk hold -1; rp_ld even)
+  const int16_t* rp_idx_t;  // the same map transposed, [Tk, rp_ld_t] (dK/dV kernel: its accumulator rows are keys)
+  int rp_ld, rp_ld_t;
   const float* table;
   int n_buckets;
   const uint8_t* kpm;
@@ -151,6 +153,25 @@ __device__ __forceinline__ void build_kmask_all(const AttnCommon& p, int b, uint
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// Bucket ids of this thread's 32 scores of a 16 x 64 warp tile as 16 packed pairs (two adjacent columns per 32-bit
+// load).  Issued BEFORE the tile's MMAs so the gather latency hides behind them: with one dependent int32 load per score
+// inside finish_tile the position-bias kernels spent ~5 of ~11 stall cycles per issued instruction on the long
+// scoreboard (profiles/r01_ncu_full_v11_attn_modeA.csv).
+template <bool TRANSPOSED>
+__device__ __forceinline__ void load_idx_pairs(const AttnCommon& p, int q0, int k0, int row0, uint32_t (&ip)[8][2]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int16_t* base = TRANSPOSED ? p.rp_idx_t : p.rp_idx;
+  const int ld = TRANSPOSED ? p.rp_ld_t : p.rp_ld, nrow = TRANSPOSED ? p.Tk : p.Tq;
+  const int a0 = (TRANSPOSED ? k0 : q0) + row0 + g, b0 = (TRANSPOSED ? q0 : k0) + 2 * t;
+#pragma unroll
+  for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      const int a = a0 + 8 * hr, b = b0 + nt * 8;
+      ip[nt][hr] = (a < nrow && b < ld) ? __ldg(reinterpret_cast<const unsigned int*>(base + (int64_t)a * ld + b)) : 0xFFFFFFFFu;
+    }
+}
+
 // Score post-processing shared by forward and both backward kernels, on one warp's 16 x 64 accumulator tile.
 // Everything downstream works in the LOG2 domain: x2 = log2(e) * (scale * acc + table[bucket(i, j)]), masked -> -inf,
 // so that a probability is ONE ffma + ONE ex2:  p = ex2(x * mult - m2).
@@ -161,9 +182,10 @@ constexpr float kLn2 = 0.6931471805599453f;
 //   TRANSPOSED = false: accumulator rows are queries (row0 = first query row of the warp), columns keys.
 //   TRANSPOSED = true : accumulator rows are keys   (row0 = first key row of the warp),   columns queries.
 //   tab_s holds the table column pre-multiplied by log2(e).
+//   ip: the tile's bucket ids from load_idx_pairs (HAS_TAB only).
 template <bool TRANSPOSED, bool HAS_TAB, typename F>
 __device__ __forceinline__ float finish_tile(const AttnCommon& p, float (&s)[8][4], int q0, int k0, int row0, uint64_t kmask,
-                                             const float* tab_s, F&& on_idx) {
+                                             const float* tab_s, const uint32_t (&ip)[8][2], F&& on_idx) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   constexpr bool has_tab = HAS_TAB;
   const float c2 = p.scale * kLog2e;
@@ -180,7 +202,7 @@ __device__ __forceinline__ float finish_tile(const AttnCommon& p, float (&s)[8][
       if (p.causal) ok = ok && (j <= i);
       float v = s[nt][e] * c2;
       if (has_tab && ok && i < p.Tq) {
-        const int idx = p.rp_idx[(int64_t)i * p.Tk + j];
+        const int idx = (int)(int16_t)(ip[nt][e >> 1] >> (16 * (e & 1)));
         if (idx >= 0) {
           v += tab_s[idx];
           on_idx(nt, e, idx);
@@ -256,6 +278,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_FWD_MINB - 1 : ATTN_FWD_MI
       const int nk = min(TILE, p.Tk - k0);          // valid keys in this tile
       const int np_n = (nk + 15) >> 4;               // 16-key groups that hold a valid key
       const uint64_t kmask = (uint64_t)kmask_s[2 * kv] | ((uint64_t)kmask_s[2 * kv + 1] << 32);
+      uint32_t ip[8][2];
+      if (HAS_TAB) load_idx_pairs<false>(p, q0, k0, warp * 16, ip);
       // ---- S = Q K^T (+ PQ PK^T)
       float s[8][4];
 #pragma unroll
@@ -281,7 +305,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_FWD_MINB - 1 : ATTN_FWD_MI
         }
       }
       // ---- bias / mask / online softmax (log2 domain: p = ex2(s * mult - m), one FFMA + one MUFU per score)
-      const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+      const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, ip, [](int, int, int) {});
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt)
@@ -503,6 +527,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
     const int np_n = (nq + 15) >> 4;  // 16-query groups holding a valid query
     const uint64_t kmask = (uint64_t)kmask_s[0] | ((uint64_t)kmask_s[1] << 32);
 
+    uint32_t ip[8][2];
+    if (HAS_TAB) load_idx_pairs<true>(p, q0, k0, warp * 16, ip);
     // S^T[key, query] = K Q^T (+ PK PQ^T)
     float s[8][4];
 #pragma unroll
@@ -528,7 +554,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
       }
     }
     // P^T = ex2(S^T * mult - lse2[query])   (masked scores are -inf -> 0)
-    const float mult = finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [](int, int, int) {});
+    const float mult = finish_tile<true, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, ip, [](int, int, int) {});
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -753,6 +779,8 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
     const int nk = min(TILE, p.Tk - k0);
     const int np_n = (nk + 15) >> 4;
     const uint64_t kmask = (uint64_t)kmask_s[2 * kv] | ((uint64_t)kmask_s[2 * kv + 1] << 32);
+    uint32_t ip[8][2];
+    if (HAS_TAB) load_idx_pairs<false>(p, q0, k0, warp * 16, ip);
 
     float s[8][4];
 #pragma unroll
@@ -805,7 +833,7 @@ __global__ void __launch_bounds__(128, HAS_POS ? ATTN_BWD_MINB - 1 : ATTN_BWD_MI
 #pragma unroll
         for (int el = 0; el < 4; ++el) idxs[nt][el] = -1;
     }
-    const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, [&](int nt, int el, int idx) { if (has_tab) idxs[has_tab ? nt : 0][el] = idx; });
+    const float mult = finish_tile<false, HAS_TAB>(p, s, q0, k0, warp * 16, kmask, tab_s, ip, [&](int nt, int el, int idx) { if (has_tab) idxs[has_tab ? nt : 0][el] = idx; });
 #pragma unroll
     for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
@@ -890,7 +918,12 @@ int fill_common(const ofab_attn_fwd_args* a, AttnCommon& c) {
   c.pq = (const bf16*)a->pq; c.pk = (const bf16*)a->pk;
   c.q_bs = a->q_bs; c.q_rs = a->q_rs; c.k_bs = a->k_bs; c.k_rs = a->k_rs; c.v_bs = a->v_bs; c.v_rs = a->v_rs;
   c.pq_bs = a->pq_bs; c.pq_rs = a->pq_rs; c.pk_bs = a->pk_bs; c.pk_rs = a->pk_rs;
-  c.rp_idx = a->rp_idx; c.table = a->table; c.n_buckets = a->rp_idx ? a->n_buckets : 0;
+  OFAB_REQUIRE(a->rp_idx == nullptr || (a->rp_ld >= a->Tk && a->rp_ld % 2 == 0 && (((uintptr_t)a->rp_idx) & 3) == 0),
+               "ofab_attn: rp_idx needs an even row length rp_ld=%d >= Tk and 4-byte alignment", a->rp_ld);
+  OFAB_REQUIRE(a->rp_idx_t == nullptr || (a->rp_ld_t >= a->Tq && a->rp_ld_t % 2 == 0 && (((uintptr_t)a->rp_idx_t) & 3) == 0),
+               "ofab_attn: rp_idx_t needs an even row length rp_ld_t=%d >= Tq and 4-byte alignment", a->rp_ld_t);
+  c.rp_idx = a->rp_idx; c.rp_idx_t = a->rp_idx_t; c.rp_ld = a->rp_ld; c.rp_ld_t = a->rp_ld_t;
+  c.table = a->table; c.n_buckets = a->rp_idx ? a->n_buckets : 0;
   c.kpm = a->kpm; c.causal = a->causal; c.scale = a->scale;
   return OFAB_OK;
 }
@@ -954,6 +987,7 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   OFAB_REQUIRE(a->d_o && a->dq && a->dk && a->dv && a->delta && a->f.o && a->f.lse, "ofab_attn_bwd: NULL tensor");
   const bool pos = a->f.pq != nullptr, tab = a->f.rp_idx != nullptr;
   OFAB_REQUIRE(!pos || (a->dpq && a->dpk), "ofab_attn_bwd: dpq/dpk required when pq/pk are given");
+  OFAB_REQUIRE(!tab || a->f.rp_idx_t != nullptr, "ofab_attn_bwd: rp_idx_t (the transposed bucket map) is required with rp_idx");
   OFAB_REQUIRE(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0, "ofab_attn_bwd: grad strides must be even");
   OFAB_REQUIRE(a->do_rs % 8 == 0 && a->do_bs % 8 == 0 && a->f.o_rs % 8 == 0 && a->f.o_bs % 8 == 0, "ofab_attn_bwd: dO / O strides must be multiples of 8");
   cudaStream_t st = (cudaStream_t)stream;

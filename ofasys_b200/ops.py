@@ -414,6 +414,27 @@ class PositionBias:
         self.pq, self.pk, self.rp_idx, self.table = pq, pk, rp_idx, table
 
 
+_IDX16 = {}
+
+
+def _idx16(rp_idx):
+    """int32 [Tq, Tk] bucket map -> (int16 [Tq, ld], int16 [Tk, ld_t]): the packed pair layout the kernels gather from
+    (row lengths padded to even with -1) and its transpose for the dK/dV kernel.  Cached per map (adaptors cache theirs)."""
+    key = (rp_idx.data_ptr(), tuple(rp_idx.shape), rp_idx._version)
+    ent = _IDX16.get(key)
+    if ent is not None and ent[0]() is rp_idx:
+        return ent[1], ent[2]
+    if len(_IDX16) > 64:
+        _IDX16.clear()
+    Tq, Tk = rp_idx.shape
+    a = torch.full((Tq, (Tk + 1) // 2 * 2), -1, dtype=torch.int16, device=rp_idx.device)
+    a[:, :Tk] = rp_idx
+    b = torch.full((Tk, (Tq + 1) // 2 * 2), -1, dtype=torch.int16, device=rp_idx.device)
+    b[:, :Tq] = rp_idx.t()
+    _IDX16[key] = (weakref.ref(rp_idx), a, b)
+    return a, b
+
+
 def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse, drop=None):
     args.B, args.H, args.Tq, args.Tk = B, H, Tq, Tk
     args.drop = None if drop is None else ctypes.pointer(drop)
@@ -430,10 +451,13 @@ def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, caus
     else:
         args.pq = args.pk = None
     if rp_idx is not None:
-        args.rp_idx, args.table, args.n_buckets = rp_idx.data_ptr(), table_f32.data_ptr(), table_f32.shape[0]
+        i16, i16t = _idx16(rp_idx)
+        args._keep_idx = (i16, i16t)
+        args.rp_idx, args.rp_ld, args.rp_idx_t, args.rp_ld_t = i16.data_ptr(), i16.shape[1], i16t.data_ptr(), i16t.shape[1]
+        args.table, args.n_buckets = table_f32.data_ptr(), table_f32.shape[0]
     else:
-        args.rp_idx = args.table = None
-        args.n_buckets = 0
+        args.rp_idx = args.rp_idx_t = args.table = None
+        args.n_buckets = args.rp_ld = args.rp_ld_t = 0
     args.kpm = None if kpm is None else kpm.data_ptr()
     args.causal = int(causal)
     args.scale = scale

@@ -24,6 +24,21 @@ elif which == "attn":  # encoder self-attention of the benchmark step: B=32 H=12
     for _ in range(3):
         o = ops.attention(qkv, None, H, 0.125, None, kpm, False)
         o.backward(torch.randn_like(o))
+elif which == "attn_modeA":  # encoder self-attention with OFA's position biases (ASR: S=260, 2047-bucket table), B=32 H=12
+    B, T, H, NB = 32, 260, 12, 2047
+    d = H * 64
+    qkv = torch.randn(B, T, 3 * d, device=dev).bfloat16().requires_grad_(True)
+    pq = torch.randn(1, T, d, device=dev).bfloat16().requires_grad_(True)
+    pk = torch.randn(1, T, d, device=dev).bfloat16().requires_grad_(True)
+    tab = torch.randn(NB, H, device=dev).bfloat16().requires_grad_(True)
+    ar = torch.arange(T, device=dev)
+    idx = ((ar[:, None] - ar[None, :]).clamp(-1023, 1023) + 1023).to(torch.int32)  # Toeplitz bucket map like the adaptors'
+    idx[-12:, :] = -1
+    idx[:, -12:] = -1  # the text prompt's block has its own ids; here: no relative bias across slots
+    kpm = torch.zeros(B, T, dtype=torch.bool, device=dev)
+    for _ in range(3):
+        o = ops.attention(qkv, None, H, 0.0884, ops.PositionBias(pq, pk, idx.contiguous(), tab), kpm, False)
+        o.backward(torch.randn_like(o))
 elif which == "ln":  # GELU + ffn_layernorm of the benchmark step: rows 8480 x 3072
     x = torch.randn(8480, 3072, device=dev).bfloat16().requires_grad_(True)
     w = torch.ones(3072, device=dev).bfloat16().requires_grad_(True)
