@@ -153,3 +153,31 @@ def test_fused_adam_refuses_cpu_parameters():
     p = torch.nn.Parameter(torch.zeros(8, dtype=torch.bfloat16))
     with pytest.raises(OfabError):
         ob.FusedAdam([p])
+
+
+def test_new_ops_refuse_cpu_tensors():
+    """Criteria, dropout and the audio front end have no CPU fallback either: they raise instead of computing."""
+    from ofasys_b200 import ops
+    from ofasys_b200._lib import OfabError
+    from ofasys_b200.preprocessor.audio import Fbank, utterance_cmvn_
+
+    x = torch.zeros(4, 3, 16, dtype=torch.float32)
+    with pytest.raises(OfabError):
+        ops.ctc_loss_sum(x, torch.zeros(4, 2, dtype=torch.long), torch.ones(4, dtype=torch.long))
+    with pytest.raises(OfabError):
+        Fbank()(torch.zeros(1, 16000))
+    with pytest.raises(OfabError):
+        utterance_cmvn_(torch.zeros(1, 10, 80))
+    with pytest.raises(OfabError):
+        ops.cross_entropy_sum(torch.zeros(4, 16, dtype=torch.bfloat16), torch.zeros(4, dtype=torch.long), label_smoothing=0.1)
+
+
+def test_incremental_state_keys_are_per_module():
+    """Two attention modules never share a cache entry in the caller's incremental_state dict."""
+    from ofasys_b200.module import MultiheadAttention
+
+    a = MultiheadAttention(128, 2, self_attention=True)
+    b = MultiheadAttention(128, 2, self_attention=True)
+    assert a._state_key != b._state_key and a._state_key == a._state_key
+    st = {}
+    assert a.reorder_incremental_state(st, torch.tensor([0])) is st  # nothing cached yet: a no-op
