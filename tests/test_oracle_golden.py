@@ -184,3 +184,24 @@ def test_ctc_oracle_matches_torch_ctc_loss():
     flat = torch.cat([targets[b, : int(tgt_len[b])] for b in range(4)])
     direct = F.ctc_loss(torch.log_softmax(logits.double(), -1), flat, in_len, tgt_len, blank=blank, reduction="sum", zero_infinity=True)
     assert abs(float(direct) - float(loss)) <= 1e-9 * abs(float(direct))
+
+
+@pytest.mark.parametrize("name", ["text_A", "patch_B"])
+def test_incremental_decoding_golden_pins_the_oracle(name):
+    """tests/golden/incr_<case>.pt holds the logits the UNMODIFIED reference produced when driven step by step with
+    incremental_state (oracle/make_golden_incremental.py).  They equal the reference's own teacher-forced forward (the
+    property the GPU test of incremental decoding relies on) and the oracle's forward on the same inputs."""
+    from util import bf16_round_state_dict
+
+    fx = torch.load(os.path.join(GOLD, f"incr_{name}.pt"), weights_only=False)
+    inc, full = fx["incremental_logits"], fx["full_logits"]
+    assert ((inc - full).norm() / full.norm()).item() <= 1e-5
+    g = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    sd = bf16_round_state_dict(cases.synth_state_dict(g["spec"], seed=0))
+    slots, _ = cases.make_inputs(name)
+    for s in slots:
+        if not s.is_src:
+            s.value = torch.where(s.value == om.PAD, torch.full_like(s.value, 5), s.value)
+    with torch.no_grad():
+        logits, _ = om.model_forward(sd, cases.oracle_cfg(name), slots)
+    assert ((logits - inc).norm() / inc.norm()).item() <= 1e-5
