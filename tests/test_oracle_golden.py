@@ -205,3 +205,49 @@ def test_incremental_decoding_golden_pins_the_oracle(name):
     with torch.no_grad():
         logits, _ = om.model_forward(sd, cases.oracle_cfg(name), slots)
     assert ((logits - inc).norm() / inc.norm()).item() <= 1e-5
+
+
+@pytest.mark.parametrize("name", ["text_A", "patch_B"])
+def test_dropout_call_sites_match_the_reference(name):
+    """Row A17: tests/golden/drop_<case>.pt is the unmodified reference in training mode with every F.dropout / DropPath
+    draw taken from one seeded stream (oracle/make_golden_dropout.py).  The oracle, given the same stream through
+    DROP_HOOK, reproduces logits and loss only if it draws masks of the same shapes in the same order -- i.e. applies
+    dropout at the reference's call sites (adaptor/base.py:181, multihead_attention.py:335, transformer_layer.py:181,195,203 /
+    :433,466,481,489 and drop-path :87,:333)."""
+    from oracle.make_golden_dropout import P_ACT, P_ATTN, P_PATH, P_RES, MaskStream
+
+    fx = torch.load(os.path.join(GOLD, f"drop_{name}.pt"), weights_only=False)
+    g = torch.load(os.path.join(GOLD, f"{name}.pt"), weights_only=False)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    cfg = cases.oracle_cfg(name)
+    slots, target = cases.make_inputs(name)
+    stream = MaskStream(fx["seed"])
+    src_len = sum((s.value.shape[1] if not isinstance(s.value, dict) and s.value.dim() == 2 else 0) for s in slots if s.is_src)
+
+    def hook(kind, x):
+        if kind == "embed":
+            return stream.dropout_mult(x.shape, P_RES)
+        if kind == "act":
+            return stream.dropout_mult(x.shape, P_ACT)
+        if kind == "attn_probs":
+            # Mode B encoder self-attention (fast path) had its dropout switched off in the fixture: the only square
+            # score matrices over the full source length
+            if cfg.mode == "B" and x.shape[1] == x.shape[2] and x.shape[1] > target.shape[1]:
+                return torch.ones((), dtype=x.dtype)
+            return stream.dropout_mult(x.shape, P_ATTN)
+        if kind == "branch":  # dropout, then drop-path per sample on T x B x C (droppath.py:41-63, batch_axis = 1)
+            m = stream.dropout_mult(x.shape, P_RES)
+            keep = torch.floor((1.0 - P_PATH) + stream.uniform((1, x.shape[1], 1)))
+            return m * keep / (1.0 - P_PATH)
+        raise AssertionError(kind)
+
+    om.DROP_HOOK = hook
+    try:
+        with torch.no_grad():
+            logits, _ = om.model_forward(sd, cfg, slots)
+    finally:
+        om.DROP_HOOK = None
+    assert stream.calls == fx["draws"], (stream.calls, fx["draws"])
+    assert ((logits - fx["logits"]).norm() / fx["logits"].norm()).item() <= 1e-5
+    loss = om.cross_entropy_sum(logits, target)
+    assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
