@@ -181,3 +181,40 @@ def test_incremental_state_keys_are_per_module():
     assert a._state_key != b._state_key and a._state_key == a._state_key
     st = {}
     assert a.reorder_incremental_state(st, torch.tensor([0])) is st  # nothing cached yet: a no-op
+
+
+def test_ctypes_binding_matches_the_header():
+    """The ctypes table (_lib._SIGS / Structures) and include/ofab.h describe the same ABI: argument counts of every
+    prototype, and sizeof of every struct as a C compiler lays it out."""
+    import shutil
+    import subprocess
+    import tempfile
+
+    hdr = open(os.path.join(ROOT, "include", "ofab.h")).read()
+    code = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    protos = re.findall(r"\b(?:int|int64_t|const char\*)\s+(ofab_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", code, flags=re.S)
+    assert len(protos) >= 50
+    for name, args in protos:
+        args = args.strip()
+        n = 0 if args in ("", "void") else args.count(",") + 1
+        assert n == len(_lib._SIGS[name][1]), (name, n, len(_lib._SIGS[name][1]))
+    cc = shutil.which("gcc") or shutil.which("cc")
+    if cc is None:
+        pytest.skip("no C compiler")
+    structs = {"ofab_dropout": _lib.Dropout, "ofab_attn_fwd_args": _lib.AttnFwdArgs, "ofab_attn_bwd_args": _lib.AttnBwdArgs,
+               "ofab_embed_ln_args": _lib.EmbedLnArgs, "ofab_embed_ln_bwd_args": _lib.EmbedLnBwdArgs, "ofab_ctc_args": _lib.CtcArgs,
+               "ofab_adam_tensor": _lib.AdamTensor, "ofab_adam_hyper": _lib.AdamHyper}
+    assert set(structs) == set(re.findall(r"}\s*(ofab_[a-z_]+)\s*;", code))  # every typedef'd struct of the header is bound
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "s.c")
+        with open(src, "w") as f:
+            f.write('#include <stdio.h>\n#include "ofab.h"\nint main(void){\n')
+            for s in structs:
+                f.write(f'printf("{s} %zu\\n", sizeof({s}));\n')
+            f.write("return 0;}\n")
+        exe = os.path.join(td, "s")
+        subprocess.run([cc, "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    sizes = dict(line.split() for line in out.strip().splitlines())
+    for s, cls in structs.items():
+        assert int(sizes[s]) == ctypes.sizeof(cls), (s, sizes[s], ctypes.sizeof(cls))
