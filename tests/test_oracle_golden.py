@@ -251,3 +251,20 @@ def test_dropout_call_sites_match_the_reference(name):
     assert ((logits - fx["logits"]).norm() / fx["logits"].norm()).item() <= 1e-5
     loss = om.cross_entropy_sum(logits, target)
     assert abs(float(loss) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+
+
+def test_box_target_golden_from_reference():
+    """Row A9 / configs[4] visual_grounding: the oracle on IMAGE + TEXT -> BOX (`<bin>` tokens, BOX slot routed to the
+    text adaptor) against the unmodified reference (tests/golden/box_A.pt, oracle/make_golden_box.py); bins bit-exact."""
+    from oracle.make_golden_box import make_box_inputs
+
+    fx = torch.load(os.path.join(GOLD, "box_A.pt"), weights_only=False)
+    g = torch.load(os.path.join(GOLD, "resnet_A.pt"), weights_only=False)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    slots, target, coords, bins = make_box_inputs()
+    assert torch.equal(bins, fx["bins"])
+    with torch.no_grad():
+        logits, _ = om.model_forward(sd, cases.oracle_cfg("resnet_A"), slots)
+    assert tuple(logits.shape) == tuple(fx["logits"].shape) == (4, 5, 512)
+    assert ((logits - fx["logits"]).norm() / fx["logits"].norm()).item() <= 1e-5
+    assert abs(float(om.cross_entropy_sum(logits, target)) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
