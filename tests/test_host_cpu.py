@@ -218,3 +218,20 @@ def test_ctypes_binding_matches_the_header():
     sizes = dict(line.split() for line in out.strip().splitlines())
     for s, cls in structs.items():
         assert int(sizes[s]) == ctypes.sizeof(cls), (s, sizes[s], ctypes.sizeof(cls))
+
+
+def test_bucket_map_packing_for_the_attention_kernels():
+    """ops._idx16: int32 [Tq, Tk] bucket map -> int16 rows padded to an even length with -1, plus the transposed copy
+    the dK/dV kernel gathers from (host logic, device-agnostic)."""
+    from ofasys_b200 import ops
+
+    g = torch.Generator().manual_seed(0)
+    for Tq, Tk in ((5, 7), (8, 8), (1, 13), (33, 64)):
+        idx = torch.randint(-1, 2047, (Tq, Tk), generator=g, dtype=torch.int32)
+        a, b = ops._idx16(idx)
+        assert a.dtype == torch.int16 and b.dtype == torch.int16
+        assert a.shape == (Tq, (Tk + 1) // 2 * 2) and b.shape == (Tk, (Tq + 1) // 2 * 2)
+        assert torch.equal(a[:, :Tk].int(), idx) and torch.equal(b[:, :Tq].int(), idx.t())
+        assert bool((a[:, Tk:] == -1).all()) and bool((b[:, Tq:] == -1).all())
+        a2, b2 = ops._idx16(idx)
+        assert a2 is a and b2 is b  # cached per map object
