@@ -1,8 +1,8 @@
 """fwd+bwd throughput of the other BASELINE.json workloads on one GPU (bench.py measures configs[1] only; these are extra
 measured lines for profiles/, same method: inputs resident, whole step replayed as one CUDA graph, CUDA events).
 
-  python tools/bench_workloads.py asr [B]              # configs[2]: OFA-base ASR, fbank [B,998,80] + 12-tok prompt -> 128 tok (Mode A)
-  python tools/bench_workloads.py caption_resnet [B]   # configs[1] variant 2b: ResNet-101 224^2 + 8-tok prompt -> 64 tok (Mode A)
+  python tests/bench_workloads.py asr [B]              # configs[2]: OFA-base ASR, fbank [B,998,80] + 12-tok prompt -> 128 tok (Mode A)
+  python tests/bench_workloads.py caption_resnet [B]   # configs[1] variant 2b: ResNet-101 224^2 + 8-tok prompt -> 64 tok (Mode A)
 """
 import json
 import os
@@ -10,7 +10,7 @@ import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))  # repo root (this file lives in tests/: it uses the oracle's case definitions)
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import ofasys_b200 as ob  # noqa: E402
