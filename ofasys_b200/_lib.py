@@ -132,6 +132,7 @@ _SIGS = {
     "ofab_bn_stats": (c_int, [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "ofab_bn_apply": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_float, c_int, c_void_p]),
     "ofab_bn_bwd": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "ofab_bn_bwd_eval": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
     "ofab_fbank": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "ofab_utterance_cmvn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
     "ofab_ctc_fwd": (c_int, [POINTER(CtcArgs), c_void_p]),
@@ -172,7 +173,7 @@ def check(rc, what=""):
         raise OfabError(f"libofab call failed ({rc}) {what}: {msg}")
 
 
-_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2, "ofab_bn_stats": 2, "ofab_bn_bwd": 3, "ofab_grad_norm": 2}
+_KERNELS_PER_CALL = {"ofab_colsum": 2, "ofab_attn_bwd": 2, "ofab_bn_stats": 2, "ofab_bn_bwd": 3, "ofab_bn_bwd_eval": 3, "ofab_grad_norm": 2}
 
 
 def call(name, *args):

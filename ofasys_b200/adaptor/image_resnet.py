@@ -45,8 +45,8 @@ class ImageResnetAdaptorConfig(BaseAdaptorConfig):
 class ImageResnetAdaptor(BaseAdaptor):
     def __init__(self, embed_tokens, dictionary, is_src, general_adaptor, cfg: ImageResnetAdaptorConfig):
         super().__init__(embed_tokens, dictionary, is_src, general_adaptor, cfg)
-        assert not cfg.sync_bn and not cfg.freeze_resnet and cfg.resnet_drop_path_rate == 0.0, \
-            "sync_bn / freeze_resnet / resnet drop-path are off in every BASELINE config and not implemented"
+        assert not cfg.sync_bn and cfg.resnet_drop_path_rate == 0.0, \
+            "sync_bn / resnet drop-path are off in every BASELINE config and not implemented"
         self.embed_image_positions = Embedding(cfg.image_bucket_size**2 + 1, cfg.embed_dim)
         backbone = {"resnet50": resnet50_backbone, "resnet101": resnet101_backbone, "resnet152": resnet152_backbone}[cfg.resnet_type]
         self.embed_images = backbone()
@@ -58,6 +58,18 @@ class ImageResnetAdaptor(BaseAdaptor):
         )
         self.register_buffer("image_rp_bucket", make_image_bucket_position(cfg.image_bucket_size, image_num_rel_dis))
         self._cache = {}
+
+    def train(self, mode=True):
+        """freeze_resnet (image_resnet.py:107-114): the backbone's BatchNorms stay in eval mode with frozen affine
+        parameters -- the fine-tuning recipe of docs/source/howto/train.rst:66-69 -- while the convolutions keep training."""
+        super().train(mode)
+        if self.cfg.freeze_resnet:
+            for m in self.embed_images.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.eval()
+                    m.weight.requires_grad = False
+                    m.bias.requires_grad = False
+        return self
 
     def position_ids(self, h, w, device):
         k = (h, w, device)

@@ -246,7 +246,7 @@ __global__ void bn_bwd_stage2(const float* __restrict__ part, int C, float* __re
 // dx = gamma * rstd * (g - sum_g/R - xhat * sum_gxhat/R);  dres = g
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
                                     const float* __restrict__ var, const bf16* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ dx,
-                                    bf16* __restrict__ dres, int64_t R, int C, float eps, int relu) {
+                                    bf16* __restrict__ dres, int64_t R, int C, float eps, int relu, int frozen_stats) {
   const int C8 = C / 8;
   const int64_t total = R * C8;
   const float invR = 1.0f / (float)R;
@@ -265,7 +265,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
     for (int j = 0; j < 8; ++j) {
       const float rs = rsqrtf(var[c + j] + eps);
       const float xh = (xv.v[j] - mean[c + j]) * rs;
-      o.v[j] = gm.v[j] * rs * (g.v[j] - sums[c + j] * invR - xh * sums[C + c + j] * invR);
+      // frozen_stats (eval-mode BatchNorm: mean / var are the running buffers, constants of the graph): dx = gamma * rstd * g
+      o.v[j] = frozen_stats ? gm.v[j] * rs * g.v[j] : gm.v[j] * rs * (g.v[j] - sums[c + j] * invR - xh * sums[C + c + j] * invR);
     }
     store8(dx + i * 8, o);
   }
@@ -393,7 +394,27 @@ extern "C" int ofab_bn_bwd(const void* dy, const void* x, const void* y, const f
   bn_bwd_stage2<<<(C + 127) / 128, 128, 0, st>>>(scratch, C, sums);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd stage2");
   bn_bwd_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
-                                                                (bf16*)dx, (bf16*)dres, R, C, eps, relu);
+                                                                (bf16*)dx, (bf16*)dres, R, C, eps, relu, 0);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd apply");
+  return OFAB_OK;
+}
+
+// eval-mode (frozen) BatchNorm backward: y = relu?((x - running_mean) * rsqrt(running_var + eps) * gamma + beta (+ residual))
+extern "C" int ofab_bn_bwd_eval(const void* dy, const void* x, const void* y, const float* mean, const float* var, const void* gamma, float* sums,
+                                void* dx, void* dres, int64_t R, int C, float eps, int relu, float* scratch, ofab_stream_t stream) {
+  OFAB_REQUIRE(C % 8 == 0 && dx != nullptr, "ofab_bn_bwd_eval: bad arguments");
+  OFAB_REQUIRE(!relu || y != nullptr, "ofab_bn_bwd_eval: relu needs the forward output");
+  OFAB_REQUIRE(sums == nullptr || scratch != nullptr, "ofab_bn_bwd_eval: parameter gradients need scratch");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (sums != nullptr) {  // dbeta / dgamma wanted (BatchNorm affine parameters not frozen)
+    dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+    bn_bwd_stage1<<<grid, block, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
+    OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage1");
+    bn_bwd_stage2<<<(C + 127) / 128, 128, 0, st>>>(scratch, C, sums);
+    OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage2");
+  }
+  bn_bwd_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
+                                                                (bf16*)dx, (bf16*)dres, R, C, eps, relu, 1);
+  OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval apply");
   return OFAB_OK;
 }

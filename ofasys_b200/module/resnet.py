@@ -1,7 +1,7 @@
 """ResNet feature extractor (conv1 .. layer3, stride 16, 1024 channels) with the reference's module tree and
 parameter names (ofasys/module/resnet.py:139-261) executed channel-last on the sm_100a kernels:
 1x1 convs -> tcgen05 GEMM, 3x3 / 7x7 convs -> im2col + GEMM, BatchNorm (training statistics) + residual + ReLU
-fused (csrc/resnet.cu).  `freeze_resnet` / eval-mode BatchNorm (running statistics) is not implemented yet."""
+fused (csrc/resnet.cu); eval-mode / frozen BatchNorm uses the running statistics (ops.batch_norm_eval)."""
 import torch
 import torch.nn as nn
 
@@ -17,8 +17,10 @@ def conv1x1(in_planes, out_planes, stride=1):
 
 
 def _bn(bn: nn.BatchNorm2d, x, residual=None, relu=False):
+    """nn.BatchNorm2d.forward: batch statistics + running-buffer update in training mode, running statistics in eval mode
+    (model.eval(), or the frozen backbone of `freeze_resnet`, adaptor/image_resnet.py:107-114)."""
     if not bn.training:
-        raise NotImplementedError("eval-mode / frozen BatchNorm (freeze_resnet) is not implemented on the CUDA path yet")
+        return ops.batch_norm_eval(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, residual, relu, bn.eps)
     return ops.batch_norm_train(x, bn.weight, bn.bias, residual, relu, bn.eps, bn.momentum, bn.running_mean, bn.running_var)
 
 
@@ -99,6 +101,10 @@ class ResNet(nn.Module):
     def forward(self, x):
         """x: [B, 3, H, W] (fp32 or bf16) -> channel-last features bf16 [B, H/16, W/16, 1024]."""
         B = x.shape[0]
+        if self.training:  # torch's _BatchNorm.forward bumps num_batches_tracked (checkpoints carry it): one multi-tensor add
+            nbt = [m.num_batches_tracked for m in self.modules() if isinstance(m, nn.BatchNorm2d) and m.training and m.num_batches_tracked is not None]
+            if nbt:
+                torch._foreach_add_(nbt, 1)
         k = 3 * 49
         kp = (k + 7) // 8 * 8
         cols, Ho, Wo = ops.im2col_nchw(x, 7, 2, 3, kp)

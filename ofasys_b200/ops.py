@@ -1072,3 +1072,46 @@ class _BatchNormFn(torch.autograd.Function):
 
 def batch_norm_train(x, gamma, beta, residual=None, relu=False, eps=1e-5, momentum=0.1, run_mean=None, run_var=None):
     return _BatchNormFn.apply(x, gamma, beta, residual, relu, eps, momentum, run_mean, run_var)
+
+
+class _BatchNormEvalFn(torch.autograd.Function):
+    """Eval-mode BatchNorm (running statistics are constants) fused with (+residual) and ReLU."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, residual, relu, eps, run_mean, run_var):
+        x = _c(x)
+        C = x.shape[-1]
+        R = x.numel() // C
+        mean = _c(run_mean) if run_mean.dtype == torch.float32 else cast_f32(run_mean)
+        var = _c(run_var) if run_var.dtype == torch.float32 else cast_f32(run_var)
+        res = None if residual is None else _c(residual)
+        y = torch.empty_like(x)
+        _lib.call("ofab_bn_apply", _p(x), _p(mean), _p(var), _p(gamma), _p(beta), _p(res), _p(y), R, C, eps, int(relu), _s())
+        ctx.save_for_backward(x, y if relu else None, gamma, mean, var)
+        ctx.meta = (relu, eps, residual is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, y, gamma, mean, var = ctx.saved_tensors
+        relu, eps, has_res = ctx.meta
+        dy = _c(dy)
+        C = x.shape[-1]
+        R = x.numel() // C
+        dev = x.device
+        want_affine = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        sums = torch.empty((2, C), dtype=torch.float32, device=dev) if want_affine else None
+        scratch = torch.empty(_lib.lib().ofab_bn_scratch_elems(C), dtype=torch.float32, device=dev) if want_affine else None
+        dx = torch.empty_like(x)
+        dres = torch.empty_like(x) if has_res else None
+        _lib.call("ofab_bn_bwd_eval", _p(dy), _p(x), _p(y), _p(mean), _p(var), _p(gamma), _p(sums), _p(dx), _p(dres), R, C, eps, int(relu), _p(scratch), _s())
+        dg = db = None
+        if want_affine:
+            g = cast_bf16(sums) if gamma.dtype == torch.bfloat16 else sums
+            dg, db = g[1], g[0]
+        return dx, dg, db, dres, None, None, None, None
+
+
+def batch_norm_eval(x, gamma, beta, run_mean, run_var, residual=None, relu=False, eps=1e-5):
+    """nn.BatchNorm2d in eval mode (model.eval() / freeze_resnet, adaptor/image_resnet.py:107-114) on channel-last x."""
+    return _BatchNormEvalFn.apply(x, gamma, beta, residual, relu, eps, run_mean, run_var)
