@@ -49,6 +49,7 @@ class AttnFwdArgs(Structure):
         ("o", c_void_p), ("o_bs", c_int64), ("o_rs", c_int64), ("lse", c_void_p),
         ("drop", POINTER(Dropout)),
         ("rp_ld", c_int), ("rp_idx_t", c_void_p), ("rp_ld_t", c_int),
+        ("bias", c_void_p), ("bias_hs", c_int64), ("bias_ld", c_int), ("bias_t", c_void_p), ("bias_t_hs", c_int64), ("bias_t_ld", c_int),
     ]
 
 
@@ -60,6 +61,7 @@ class AttnBwdArgs(Structure):
         ("dq_bs", c_int64), ("dq_rs", c_int64), ("dk_bs", c_int64), ("dk_rs", c_int64), ("dv_bs", c_int64), ("dv_rs", c_int64),
         ("dpq", c_void_p), ("dpk", c_void_p), ("dtable", c_void_p), ("delta", c_void_p),
         ("dq_colsum", c_void_p), ("dk_colsum", c_void_p), ("dv_colsum", c_void_p),
+        ("ds", c_void_p),
     ]
 
 
@@ -103,6 +105,8 @@ _SIGS = {
     "ofab_gemm_bf16_splitk": (c_int, [c_int64, c_int64, c_int64, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_int, c_void_p, c_int64, c_void_p]),
     "ofab_attn_fwd": (c_int, [POINTER(AttnFwdArgs), c_void_p]),
     "ofab_attn_bwd": (c_int, [POINTER(AttnBwdArgs), c_void_p]),
+    "ofab_attn_bias_build": (c_int, [c_void_p, c_int, c_float, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]),
+    "ofab_attn_bias_bwd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p]),
     "ofab_embed_ln_fwd": (c_int, [POINTER(EmbedLnArgs), c_void_p]),
     "ofab_embed_ln_bwd": (c_int, [POINTER(EmbedLnBwdArgs), c_void_p]),
     "ofab_ce_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),

@@ -68,6 +68,7 @@ class OFAGeneralAdaptor(nn.Module):
             self.pos_q_linear = nn.Linear(embed_dim, embed_dim)
             self.pos_k_linear = nn.Linear(embed_dim, embed_dim)
         self._idx_cache = {}
+        self.dense_bias = True  # False: structured position terms inside the mma.sync attention kernels (incremental decoding)
 
     def build_embedding(self, cfg, dictionary):
         if OFAGeneralAdaptor._embed_tokens is not None:
@@ -158,6 +159,9 @@ class OFAGeneralAdaptor(nn.Module):
         n_tables = 1 if self.cfg.share_attn_bias else num_layers
         with_rel = [o for o in outs if o.rel_idx is not None]
         idx, used = self._global_idx(outs) if with_rel else (None, None)
+        # dense abs-pos term [H, S, S], once per forward and batch-invariant (the reference expands it to [B, H, S, S] and
+        # clones it per layer, general.py:223-282); every layer's attention adds its own table gather to it in ONE tile
+        abs_t = ops.abs_pos(pq, pk, self.num_attention_heads) if self.dense_bias else None
         biases = []
         for l in range(n_tables):
             table = None
@@ -166,7 +170,7 @@ class OFAGeneralAdaptor(nn.Module):
                 table = tabs[0] if len(tabs) == 1 else torch.cat(tabs, dim=0)
                 if used is not None:
                     table = table.index_select(0, used)
-            biases.append(ops.PositionBias(pq, pk, idx, table))
+            biases.append(ops.PositionBias(pq, pk, idx, table, abs=abs_t))
         out.self_attn_bias = biases
         return out
 

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libofab.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["core.cu", "ln.cu", "gemm.cu", "attn.cu", "embed_ce.cu", "conv.cu", "resnet.cu", "optim.cu", "audio.cu", "ctc.cu"]
+SOURCES = ["core.cu", "ln.cu", "gemm.cu", "attn.cu", "attn_tc.cu", "embed_ce.cu", "conv.cu", "resnet.cu", "optim.cu", "audio.cu", "ctc.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--use_fast_math=false",

@@ -957,7 +957,12 @@ extern "C" int ofab_attn_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) 
   int rc = fill_common(a, c);
   if (rc) return rc;
   OFAB_REQUIRE(a->o && a->lse, "ofab_attn_fwd: o/lse NULL");
-  OFAB_REQUIRE(a->o_rs % 2 == 0 && a->o_bs % 2 == 0, "ofab_attn_fwd: o strides must be even");
+  OFAB_REQUIRE(a->o_rs % 8 == 0 && a->o_bs % 8 == 0 && ((uintptr_t)a->o & 15) == 0, "ofab_attn_fwd: o must have 16-byte aligned rows");
+  if (ofab_attn_tc_eligible(a)) {  // tcgen05 kernels (attn_tc.cu): everything without structured position terms
+    rc = ofab_attn_tc_fwd(a, stream);
+    if (rc <= 0) return rc;
+  }
+  OFAB_REQUIRE(a->bias == nullptr, "ofab_attn_fwd: a dense bias tile needs the tcgen05 kernels (no pq / pk / rp_idx, 16-byte aligned strides)");
   const bool pos = a->pq != nullptr, tab = a->rp_idx != nullptr;
   const int nh = pos ? 2 : 1;
   const int kwords = ((a->Tk + 63) / 64) * 2;  // key-validity bitmap
@@ -990,6 +995,11 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   OFAB_REQUIRE(!tab || a->f.rp_idx_t != nullptr, "ofab_attn_bwd: rp_idx_t (the transposed bucket map) is required with rp_idx");
   OFAB_REQUIRE(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0, "ofab_attn_bwd: grad strides must be even");
   OFAB_REQUIRE(a->do_rs % 8 == 0 && a->do_bs % 8 == 0 && a->f.o_rs % 8 == 0 && a->f.o_bs % 8 == 0, "ofab_attn_bwd: dO / O strides must be multiples of 8");
+  if (ofab_attn_tc_eligible(&a->f) && a->dq_rs % 8 == 0 && a->dk_rs % 8 == 0 && a->dv_rs % 8 == 0 && a->dq_colsum == nullptr && a->dk_colsum == nullptr) {
+    rc = ofab_attn_tc_bwd(a, stream);
+    if (rc <= 0) return rc;
+  }
+  OFAB_REQUIRE(a->f.bias == nullptr, "ofab_attn_bwd: a dense bias tile needs the tcgen05 kernels");
   cudaStream_t st = (cudaStream_t)stream;
   AttnBwdExtra e;
   e.d_o = (const bf16*)a->d_o; e.do_bs = a->do_bs; e.do_rs = a->do_rs;

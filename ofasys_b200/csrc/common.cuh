@@ -30,6 +30,12 @@ int ofab_cuda_fail(cudaError_t e, const char* what);
 
 int ofab_sm_count();  // cached
 
+// tcgen05 attention (attn_tc.cu), dispatched from ofab_attn_fwd / ofab_attn_bwd (attn.cu).  *_fwd / *_bwd return OFAB_OK,
+// a negative error, or 1 = "not taken" (the driver refused a tensor map for these strides): run the mma.sync kernels.
+int ofab_attn_tc_eligible(const ofab_attn_fwd_args* a);
+int ofab_attn_tc_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream);
+int ofab_attn_tc_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream);
+
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------
 // A step is ~950 short kernels back to back on one stream (CUDA graph): with plain stream order each boundary costs a
 // full drain + launch + ramp.  Launched with cudaLaunchAttributeProgrammaticStreamSerialization, kernel N+1's CTAs

@@ -112,11 +112,12 @@ class TransformerDecoder(nn.Module):
         self.project_out_dim = None
         self.adaptive_softmax = None
 
-    def get_cross_pos_info(self, tgt_pos_embed, src_pos_embed):
-        """abs position term of the cross-attention bias (transformer.py:280-299) as extra QK columns."""
+    def get_cross_pos_info(self, tgt_pos_embed, src_pos_embed, dense=True):
+        """abs position term of the cross-attention bias (transformer.py:280-299): one dense batch-invariant [H, T, S] term
+        shared by all decoder layers (dense=False: as extra QK columns of the mma.sync kernels, incremental decoding)."""
         pq = ops.linear(ops.to_bf16(tgt_pos_embed[:1]), self.cross_pos_q_linear.weight, self.cross_pos_q_linear.bias)
         pk = ops.linear(ops.to_bf16(src_pos_embed[:1]), self.cross_pos_k_linear.weight, self.cross_pos_k_linear.bias)
-        return ops.PositionBias(pq, pk)
+        return ops.PositionBias(pq, pk, abs=ops.abs_pos(pq, pk, self.num_attention_heads) if dense else None)
 
     def forward(self, slots: List[Slot], encoder_out: Optional[Dict[str, List[torch.Tensor]]] = None, incremental_state=None,
                 features_only: bool = False, full_context_alignment: bool = False, alignment_layer: Optional[int] = None,
@@ -173,7 +174,7 @@ class TransformerDecoder(nn.Module):
         enc_mask = encoder_out["encoder_padding_mask"][0] if encoder_out["encoder_padding_mask"] else None
         cross_bias = None
         if not self.cfg.entangle_position_embedding:
-            cb = self.get_cross_pos_info(pos, encoder_out["position_embeddings"][0])
+            cb = self.get_cross_pos_info(pos, encoder_out["position_embeddings"][0], dense=False)
             cross_bias = ops.PositionBias(cb.pq[:, -1:].contiguous(), cb.pk)
         x = embed[:, -1:].contiguous()
         last_mask = masks[:, -1:]

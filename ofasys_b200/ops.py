@@ -410,8 +410,54 @@ class PositionBias:
     table : bf16 [n_buckets, H] this layer's relative-position table(s), or None
     """
 
-    def __init__(self, pq=None, pk=None, rp_idx=None, table=None):
+    def __init__(self, pq=None, pk=None, rp_idx=None, table=None, abs=None):
         self.pq, self.pk, self.rp_idx, self.table = pq, pk, rp_idx, table
+        # dense form of the abs-pos term: fp32 [H, Tq, ld] = pq_h . pk_h per head (abs_pos()), shared by every layer of a
+        # forward.  When present the attention runs on the tcgen05 kernels with ONE additive fp16 tile per layer
+        # (abs * scale + table[rp_idx]) instead of per-score gathers; when absent (e.g. the one-row slices of incremental
+        # decoding) the structured mma.sync kernels are used.
+        self.abs = abs
+
+
+class _AbsPosFn(torch.autograd.Function):
+    """abs[h, i, j] = pq[i, h*64:(h+1)*64] . pk[j, h*64:(h+1)*64]  (fp32 [H, Tq, ld], ld = ceil8(Tk); unscaled): the
+    absolute-position term of OFAGeneralAdaptor.build_abs_pos_bias (adaptor/general.py:223-243) /
+    TransformerDecoder.get_cross_pos_info (model/transformer.py:280-299) for ONE batch element -- it does not depend on b."""
+
+    @staticmethod
+    def forward(ctx, pq, pk, H):
+        _need_cuda(pq, pk)
+        pq, pk = _c(pq), _c(pk)
+        assert pq.dtype == torch.bfloat16 and pq.shape[0] == 1 and pk.shape[0] == 1
+        Tq, Tk, d = pq.shape[1], pk.shape[1], pq.shape[2]
+        ld = (Tk + 7) // 8 * 8
+        out = torch.zeros((H, Tq, ld), dtype=torch.float32, device=pq.device)
+        q2, k2 = pq[0], pk[0]
+        for h in range(H):
+            gemm(Tq, Tk, 64, q2[:, h * 64:], d, 0, k2[:, h * 64:], d, 0, out[h], ld)
+        ctx.save_for_backward(pq, pk)
+        ctx.H = H
+        return out
+
+    @staticmethod
+    def backward(ctx, dabs):
+        pq, pk = ctx.saved_tensors
+        H = ctx.H
+        Tq, Tk, d = pq.shape[1], pk.shape[1], pq.shape[2]
+        g = cast_bf16(_c(dabs))  # [H, Tq, ld]
+        ld = g.shape[2]
+        dpq = torch.empty_like(pq)
+        dpk = torch.empty_like(pk)
+        q2, k2 = pq[0], pk[0]
+        for h in range(H):
+            gemm(Tq, 64, Tk, g[h], ld, 0, k2[:, h * 64:], d, 1, dpq[0][:, h * 64:], d)   # dpq_h = dabs_h pk_h
+            gemm(Tk, 64, Tq, g[h], ld, 1, q2[:, h * 64:], d, 1, dpk[0][:, h * 64:], d)   # dpk_h = dabs_h^T pq_h
+        return dpq, dpk, None
+
+
+def abs_pos(pq, pk, H):
+    """Dense abs-pos term for PositionBias(abs=...): fp32 [H, Tq, ceil8(Tk)]."""
+    return _AbsPosFn.apply(pq, pk, H)
 
 
 _IDX16 = {}
@@ -435,8 +481,15 @@ def _idx16(rp_idx):
     return a, b
 
 
-def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse, drop=None):
+def _fill_attn(args, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f32, kpm, causal, scale, o, lse, drop=None, bias=None, bias_t=None):
     args.B, args.H, args.Tq, args.Tk = B, H, Tq, Tk
+    if bias is not None:
+        args.bias, args.bias_hs, args.bias_ld = bias.data_ptr(), bias.stride(0), bias.shape[2]
+        args.bias_t, args.bias_t_hs, args.bias_t_ld = bias_t.data_ptr(), bias_t.stride(0), bias_t.shape[2]
+    else:
+        args.bias = args.bias_t = None
+        args.bias_hs = args.bias_t_hs = 0
+        args.bias_ld = args.bias_t_ld = 0
     args.drop = None if drop is None else ctypes.pointer(drop)
     args.q, args.k, args.v = q.data_ptr(), k.data_ptr(), v.data_ptr()
     args.q_bs, args.q_rs = q.stride(0), q.stride(1)
@@ -469,7 +522,7 @@ class _AttentionFn(torch.autograd.Function):
     """q_src: self-attention -> packed qkv [B, T, 3d]; cross-attention -> q [B, Tq, d] with kv_src [B, Tk, 2d]."""
 
     @staticmethod
-    def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H, drop=None):
+    def forward(ctx, q_src, kv_src, pq, pk, table, rp_idx, kpm, causal, scale, H, drop=None, abs_t=None):
         _need_cuda(q_src)
         # the kernels read q / k / v through (batch, row) strides: a column slice of a packed projection or a prefix of a
         # K|V cache is used in place as long as rows are contiguous and 16-byte aligned
@@ -485,10 +538,25 @@ class _AttentionFn(torch.autograd.Function):
             assert q_src.shape[-1] == d and kv_src.shape[-1] == 2 * d
             q, k, v = q_src, kv_src[..., :d], kv_src[..., d:]
         Tq, Tk = q.shape[1], k.shape[1]
-        if pq is not None:
+        dense = abs_t is not None
+        bias = bias_t = None
+        if dense:
+            # ONE additive tile per layer for all batch elements: scale * abs + table[rp_idx] (fp16) and its transpose
+            assert abs_t.dtype == torch.float32 and abs_t.shape[0] == H and abs_t.shape[1] == Tq and abs_t.shape[2] >= Tk and abs_t.is_contiguous()
+            ld, ld_t = (Tk + 7) // 8 * 8, (Tq + 7) // 8 * 8
+            bias = torch.empty((H, Tq, ld), dtype=torch.float16, device=q_src.device)
+            bias_t = torch.empty((H, Tk, ld_t), dtype=torch.float16, device=q_src.device)
+            if rp_idx is not None:
+                assert rp_idx.dtype == torch.int32 and rp_idx.shape == (Tq, Tk) and rp_idx.is_contiguous()
+                table = _c(table)
+            _lib.call("ofab_attn_bias_build", _p(abs_t), abs_t.shape[2], scale, _p(rp_idx), _p(table) if rp_idx is not None else None,
+                      _DT[table.dtype] if rp_idx is not None else F32, 0 if rp_idx is None else table.shape[0], H, Tq, Tk,
+                      _p(bias), ld, _p(bias_t), ld_t, _s())
+            pq = pk = None
+        elif pq is not None:
             pq, pk = _c(pq), _c(pk)
         table_f = None
-        if rp_idx is not None:
+        if rp_idx is not None and not dense:
             assert rp_idx.dtype == torch.int32 and rp_idx.shape == (Tq, Tk) and rp_idx.is_contiguous()
             table_f = _c(table) if table.dtype == torch.float32 else cast_f32(table)
         if kpm is not None:
@@ -496,17 +564,18 @@ class _AttentionFn(torch.autograd.Function):
         o = torch.empty((B, Tq, d), dtype=torch.bfloat16, device=q_src.device)
         lse = torch.empty((B, H, Tq), dtype=torch.float32, device=q_src.device)
         a = _lib.AttnFwdArgs()
-        _fill_attn(a, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse, drop)
+        _fill_attn(a, B, H, Tq, Tk, q, k, v, pq, pk, None if dense else rp_idx, table_f, kpm, causal, scale, o, lse, drop, bias, bias_t)
         _lib.call("ofab_attn_fwd", ctypes.byref(a), _s())
-        ctx.save_for_backward(q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse)
-        ctx.meta = (causal, scale, H, None if table is None else table.dtype)
+        ctx.save_for_backward(q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse, bias, bias_t)
+        ctx.meta = (causal, scale, H, None if table is None else table.dtype, dense,
+                    None if abs_t is None else tuple(abs_t.shape), None if (table is None or not dense) else tuple(table.shape))
         ctx.drop = drop
         return o
 
     @staticmethod
     def backward(ctx, d_o):
-        q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse = ctx.saved_tensors
-        causal, scale, H, table_dtype = ctx.meta
+        q_src, kv_src, pq, pk, table_f, rp_idx, kpm, o, lse, bias, bias_t = ctx.saved_tensors
+        causal, scale, H, table_dtype, dense, abs_shape, table_shape = ctx.meta
         d = H * 64
         B = q_src.shape[0]
         d_o = _c(d_o)
@@ -522,8 +591,12 @@ class _AttentionFn(torch.autograd.Function):
             dq, dk, dv = dq_src, dkv_src[..., :d], dkv_src[..., d:]
         Tq, Tk = q.shape[1], k.shape[1]
         a = _lib.AttnBwdArgs()
-        _fill_attn(a.f, B, H, Tq, Tk, q, k, v, pq, pk, rp_idx, table_f, kpm, causal, scale, o, lse, ctx.drop)
+        _fill_attn(a.f, B, H, Tq, Tk, q, k, v, pq, pk, None if dense else rp_idx, table_f, kpm, causal, scale, o, lse, ctx.drop, bias, bias_t)
         a.d_o, a.do_bs, a.do_rs = d_o.data_ptr(), d_o.stride(0), d_o.stride(1)
+        ds = None
+        if dense:  # dS per batch element; columns past a causal tile's last key block are never written
+            ds = (torch.zeros if causal else torch.empty)((B, H, Tq, bias.shape[2]), dtype=torch.bfloat16, device=d_o.device)
+        a.ds = None if ds is None else ds.data_ptr()
         a.dq, a.dk, a.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
         a.dq_bs, a.dq_rs = dq.stride(0), dq.stride(1)
         a.dk_bs, a.dk_rs = dk.stride(0), dk.stride(1)
@@ -535,29 +608,41 @@ class _AttentionFn(torch.autograd.Function):
             a.dpq, a.dpk = dpq.data_ptr(), dpk.data_ptr()
         else:
             a.dpq = a.dpk = None
-        if rp_idx is not None:
+        if rp_idx is not None and not dense:
             dtab = torch.zeros_like(table_f)
             a.dtable = dtab.data_ptr()
         else:
             a.dtable = None
         delta = torch.empty((B, H, Tq), dtype=torch.float32, device=d_o.device)
         a.delta = delta.data_ptr()
-        # bias gradients of the q / k / v projections: the kernels leave one partial row of column sums per CTA
-        # (self-attention: Tq == Tk, one [3, B * tiles, d] buffer whose slabs reduce straight into the packed [3d] vector)
-        nq, nk = (Tq + 63) // 64, (Tk + 63) // 64
-        if kv_src is None:
-            part = torch.empty((3, B * nq, d), dtype=torch.float32, device=d_o.device)
-            a.dq_colsum, a.dk_colsum, a.dv_colsum = part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr()
+        # bias gradients of the q / k / v projections: the mma.sync kernels (structured position terms) leave one partial row
+        # of column sums per CTA (self-attention: Tq == Tk, one [3, B * tiles, d] buffer whose slabs reduce straight into the
+        # packed [3d] vector); the tcgen05 kernels do not (the Linear backward then sums its dY)
+        legacy = pq is not None or (rp_idx is not None and not dense)
+        if legacy:
+            nq, nk = (Tq + 63) // 64, (Tk + 63) // 64
+            if kv_src is None:
+                part = torch.empty((3, B * nq, d), dtype=torch.float32, device=d_o.device)
+                a.dq_colsum, a.dk_colsum, a.dv_colsum = part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr()
+            else:
+                part_q = torch.empty((1, B * nq, d), dtype=torch.float32, device=d_o.device)
+                part_kv = torch.empty((2, B * nk, d), dtype=torch.float32, device=d_o.device)
+                a.dq_colsum, a.dk_colsum, a.dv_colsum = part_q.data_ptr(), part_kv[0].data_ptr(), part_kv[1].data_ptr()
         else:
-            part_q = torch.empty((1, B * nq, d), dtype=torch.float32, device=d_o.device)
-            part_kv = torch.empty((2, B * nk, d), dtype=torch.float32, device=d_o.device)
-            a.dq_colsum, a.dk_colsum, a.dv_colsum = part_q.data_ptr(), part_kv[0].data_ptr(), part_kv[1].data_ptr()
+            a.dq_colsum = a.dk_colsum = a.dv_colsum = None
         _lib.call("ofab_attn_bwd", ctypes.byref(a), _s())
-        for grad, partial in ((dq_src, part) if kv_src is None else (dq_src, part_q), (None, None) if kv_src is None else (dkv_src, part_kv)):
-            if grad is not None:
-                vec = torch.empty(partial.shape[0] * d, dtype=torch.bfloat16, device=d_o.device)
-                _lib.call("ofab_reduce_rows", _p(partial), partial.shape[0], partial.shape[1], d, _p(vec), BF16, _s())
-                _hint_bias_grad(grad, vec)
+        if legacy:
+            for grad, partial in ((dq_src, part) if kv_src is None else (dq_src, part_q), (None, None) if kv_src is None else (dkv_src, part_kv)):
+                if grad is not None:
+                    vec = torch.empty(partial.shape[0] * d, dtype=torch.bfloat16, device=d_o.device)
+                    _lib.call("ofab_reduce_rows", _p(partial), partial.shape[0], partial.shape[1], d, _p(vec), BF16, _s())
+                    _hint_bias_grad(grad, vec)
+        dabs = None
+        if dense:  # ONE reduction over the batch per layer: table histogram + abs-pos gradient
+            dabs = torch.zeros(abs_shape, dtype=torch.float32, device=d_o.device)
+            if rp_idx is not None:
+                dtab = torch.zeros(table_shape, dtype=torch.float32, device=d_o.device)
+            _lib.call("ofab_attn_bias_bwd", _p(ds), B, H, Tq, Tk, ds.shape[3], _p(rp_idx), _p(dtab), _p(dabs), abs_shape[2], scale, 0, _s())
         if pq is not None:
             if pq.shape[0] == 1 and B > 1:  # broadcast positions: sum the per-sample grads
                 dpq = colsum(dpq.view(B, Tq * d), torch.bfloat16).view(1, Tq, d)
@@ -565,13 +650,15 @@ class _AttentionFn(torch.autograd.Function):
                 dpk = colsum(dpk.view(B, Tk * d), torch.bfloat16).view(1, Tk, d)
         if dtab is not None:
             dtab = cast_bf16(dtab) if table_dtype == torch.bfloat16 else dtab
-        return dq_src, dkv_src, dpq, dpk, dtab, None, None, None, None, None, None
+        return dq_src, dkv_src, dpq, dpk, dtab, None, None, None, None, None, None, dabs
 
 
 def attention(q_src, kv_src, H, scale, bias: PositionBias = None, key_padding_mask=None, causal=False, drop=None):
     """`drop`: dropout descriptor for the attention probabilities (DropoutState.spec(p)) or None."""
     b = bias or PositionBias()
-    return _AttentionFn.apply(q_src, kv_src, b.pq, b.pk, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H, drop)
+    if b.abs is not None:  # dense position tile: pq / pk enter through abs (their gradients flow through abs_pos())
+        return _AttentionFn.apply(q_src, kv_src, None, None, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H, drop, b.abs)
+    return _AttentionFn.apply(q_src, kv_src, b.pq, b.pk, b.table, b.rp_idx, key_padding_mask, causal, float(scale), H, drop, None)
 
 
 def attention_dropout_mask(drop, B, H, Tq, Tk, device=None):
@@ -586,7 +673,7 @@ def attention_dropout_mask(drop, B, H, Tq, Tk, device=None):
         v = kv[..., H * 64:].view(B, Tk, H, 64)
         for jj in range(n):
             v[:, j0 + jj, :, jj] = 1.0
-        o = _AttentionFn.apply(q, kv, None, None, None, None, None, False, 1.0, H, drop)  # o[b,i,h,jj] = mask / Tk
+        o = _AttentionFn.apply(q, kv, None, None, None, None, None, False, 1.0, H, drop, None)  # o[b,i,h,jj] = mask / Tk
         out[..., j0:j0 + n] = (o.view(B, Tq, H, 64)[..., :n].permute(0, 2, 1, 3) > 0).float() * (1.0 / (1.0 - drop.p))
     return out
 
