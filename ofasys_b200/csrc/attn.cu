@@ -995,7 +995,7 @@ extern "C" int ofab_attn_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) 
   OFAB_REQUIRE(!tab || a->f.rp_idx_t != nullptr, "ofab_attn_bwd: rp_idx_t (the transposed bucket map) is required with rp_idx");
   OFAB_REQUIRE(a->dq_rs % 2 == 0 && a->dk_rs % 2 == 0 && a->dv_rs % 2 == 0, "ofab_attn_bwd: grad strides must be even");
   OFAB_REQUIRE(a->do_rs % 8 == 0 && a->do_bs % 8 == 0 && a->f.o_rs % 8 == 0 && a->f.o_bs % 8 == 0, "ofab_attn_bwd: dO / O strides must be multiples of 8");
-  if (ofab_attn_tc_eligible(&a->f) && a->dq_rs % 8 == 0 && a->dk_rs % 8 == 0 && a->dv_rs % 8 == 0 && a->dq_colsum == nullptr && a->dk_colsum == nullptr) {
+  if (ofab_attn_tc_eligible(&a->f) && a->dq_rs % 8 == 0 && a->dk_rs % 8 == 0 && a->dv_rs % 8 == 0 ) {
     rc = ofab_attn_tc_bwd(a, stream);
     if (rc <= 0) return rc;
   }

@@ -115,6 +115,14 @@ __device__ __forceinline__ void tmem_ld32_nowait(uint32_t taddr, uint32_t (&r)[3
         "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   tmem_ld32_nowait(taddr, r);
@@ -138,6 +146,11 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
       "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
       : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+               "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -197,6 +210,7 @@ struct TcParams {
   float* delta;           // [B, H, Tq]
   bf16 *dq, *dk, *dv;
   int64_t dq_bs, dq_rs, dk_bs, dk_rs, dv_bs, dv_rs;
+  float *dq_colsum, *dk_colsum, *dv_colsum;  // [B * tiles, H * 64] per-CTA column sums or NULL
   bf16* ds;               // [B, H, Tq, bias_ld] raw dS = P o (dP - delta) (the gradient of the additive bias, per batch) or NULL
   TcDrop drop;
 };
@@ -213,25 +227,58 @@ __device__ __forceinline__ void build_kmask(const TcParams& p, int b, uint32_t* 
   }
 }
 
-// 32 consecutive fp16 bias values of one row starting at column c (multiple of 32) as floats * log2(e); columns >= ld read as 0
-__device__ __forceinline__ void load_bias32(const __half* __restrict__ row, int c, int ld, bool row_ok, float (&out)[32]) {
+// N consecutive fp16 bias values of one row starting at column c (N = 16 or 32) as raw 16-byte vectors (prefetched one chunk
+// ahead and converted when used); columns >= ld read as 0
+template <int NV>
+__device__ __forceinline__ void load_bias_raw(const __half* __restrict__ row, int c, int ld, bool row_ok, uint4 (&u)[NV]) {
 #pragma unroll
-  for (int v = 0; v < 4; ++v) {
-    uint4 u = make_uint4(0u, 0u, 0u, 0u);
-    if (row_ok && c + 8 * v < ld) u = __ldg(reinterpret_cast<const uint4*>(row + c + 8 * v));
-    const __half2* h = reinterpret_cast<const __half2*>(&u);
+  for (int v = 0; v < NV; ++v) {
+    u[v] = make_uint4(0u, 0u, 0u, 0u);
+    if (row_ok && c + 8 * v < ld) u[v] = __ldg(reinterpret_cast<const uint4*>(row + c + 8 * v));
+  }
+}
+__device__ __forceinline__ float bias_at(const uint4* u, int j) {  // element j of the raw chunk, times log2(e)
+  const __half* h = reinterpret_cast<const __half*>(u);
+  return __half2float(h[j]) * kLog2e;
+}
+
+// Column sums over the warp's 32 rows of v[32] (one row per lane): a transpose-reduce of 31 shuffles; afterwards lane l
+// holds the sum of column l.
+__device__ __forceinline__ float warp_colsum32(float (&v)[32]) {
+  const int lane = threadIdx.x & 31;
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const float2 f = __half22float2(h[e]);
-      out[8 * v + 2 * e] = f.x * kLog2e;
-      out[8 * v + 2 * e + 1] = f.y * kLog2e;
+  for (int s = 16, n = 32; s >= 1; s >>= 1, n >>= 1) {
+    const bool upper = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < n / 2; ++j) {
+      const float send = upper ? v[j] : v[j + n / 2];
+      const float recv = __shfl_xor_sync(0xffffffffu, send, s);
+      v[j] = (upper ? v[j + n / 2] : v[j]) + recv;
     }
   }
+  return v[0];
+}
+// Per-CTA column sums of a 128 x 64 gradient tile held in TMEM (the bias gradient of the projection that produced q / k / v
+// is the column sum of dq / dk / dv, nn.Linear backward of multihead_attention.py:199-218): each of the 4 compute warps
+// reduces its 32 rows, the warps meet in shared memory, 64 threads write one partial row.  Called by all 128 compute threads.
+__device__ __forceinline__ void tile_colsum_out(float (&lo)[32], float (&hi)[32], float* cs /* smem [4][64] */, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, quad = (threadIdx.x >> 5) & 3;
+  const float a = warp_colsum32(lo), b = warp_colsum32(hi);
+  cs[quad * 64 + lane] = a;
+  cs[quad * 64 + 32 + lane] = b;
+  asm volatile("bar.sync 1, 128;" ::: "memory");
+  const int t = (threadIdx.x - 64);  // compute threads are 64..191
+  if (t < 64) out[t] = cs[t] + cs[64 + t] + cs[128 + t] + cs[192 + t];
+  asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
 // ===================================================================================== forward
-// TMEM columns: S (fp32 scores, later bf16 P over its first half) [0, 128) | O_blk (P V of the current key block) [128, 192)
-// Online softmax over 128-key blocks; the running output lives in registers (64 fp32 per thread = per row).
+// TMEM columns: S (fp32 scores; the bf16 probabilities are written over its first half) [0, 128) | O (fp32, accumulates P V over
+// the key blocks) [128, 192).
+// Online softmax over 128-key blocks with LAZY rescaling: probabilities are taken relative to a reference maximum m_ref that
+// is only raised -- and the O accumulator in TMEM rescaled -- when a block's maximum exceeds it by more than 2^8 (the row sum
+// and O then simply carry a common factor <= 256, exact after the final division).  With OFA's score ranges that happens in
+// the first block only, so the per-block work of a row is: one pass for the maximum, one pass of ex2, no output traffic.
 template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -246,11 +293,10 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   uint64_t* q_full = bars;                         // 1
   uint64_t* full = bars + 1;                       // STAGES
   uint64_t* empty = full + STAGES;                 // STAGES
-  uint64_t* s_full = empty + STAGES;               // S = Q K^T of the block is in TMEM
-  uint64_t* p_ready = s_full + 1;                  // the block's P is in TMEM (4 warp arrivals)
-  uint64_t* o_full = p_ready + 1;                  // O_blk = P V is in TMEM
-  uint64_t* o_free = o_full + 1;                   // O_blk has been read (4 warp arrivals)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 1);
+  uint64_t* s_full = empty + STAGES;               // S = Q K^T of the block is in TMEM (and every earlier P V has retired)
+  uint64_t* p_ready = s_full + 1;                  // the block's P is in TMEM, O rescaled if needed (4 warp arrivals)
+  uint64_t* o_done = p_ready + 1;                  // the last P V has retired
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
   uint32_t* kmask_s = tmem_ptr + 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -272,8 +318,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     }
     mbar_init(s_full, 1);
     mbar_init(p_ready, 4);
-    mbar_init(o_full, 1);
-    mbar_init(o_free, 4);
+    mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -323,22 +368,21 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
         const uint32_t idesc = make_idesc(n, false);
 #pragma unroll
         for (int k = 0; k < 4; ++k) umma_ss(tmem_S, sdesc(q_addr + k * 32), sdesc(k_addr + k * 32), idesc, k != 0);
-        umma_commit(s_full);
+        umma_commit(s_full);  // (tracks every MMA issued so far: when it fires, the previous block's P V has retired too)
       }
       __syncwarp();
       mbar_wait(p_ready, kb & 1);
-      if (kb > 0) mbar_wait(o_free, (kb - 1) & 1);
       tc_fence_after();
       if (issuer) {
         const uint32_t idesc = make_idesc(64, true);
-        for (int ks = 0; ks < n / 16; ++ks) umma_ts(tmem_O, tmem_S + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, ks != 0);
-        umma_commit(o_full);
+        for (int ks = 0; ks < n / 16; ++ks) umma_ts(tmem_O, tmem_S + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, (kb | ks) != 0);
         umma_commit(empty + st);
+        if (kb == nkb - 1) umma_commit(o_done);
       }
       __syncwarp();
     }
   } else {
-    // ------------------------------------------------------------------ softmax + running output: one thread per query row
+    // ------------------------------------------------------------------ softmax: one thread per query row
     const int quad = warp & 3;
     const int row = quad * 32 + lane;
     const int i = q0 + row;
@@ -348,95 +392,122 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const __half* brow = HAS_BIAS ? p.bias + (int64_t)h * p.bias_hs + (int64_t)(row_ok ? i : 0) * p.bias_ld : nullptr;
     uint2 dkey = make_uint2(0u, 1u);
     if (DROP) dkey = tc_drop_key(p.drop, b * p.H + h);
-    float oacc[64];
-#pragma unroll
-    for (int j = 0; j < 64; ++j) oacc[j] = 0.f;
-    float m_run = -INFINITY, l_run = 0.f;
+    float m_ref = -INFINITY, l_run = 0.f;
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kb * BN;
       const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
       const int nch = (n + 31) >> 5;
+      uint4 bu[2][HAS_BIAS ? 4 : 1];
+      if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);  // in flight while the MMAs run
       mbar_wait(s_full, kb & 1);
       tc_fence_after();
-      // pass 1: x = log2(e) * (scale * s + bias), masked -> -inf; written back over the scores; block maximum
+      uint32_t r[2][32];
+      // ---- pass 1: block maximum of x = log2(e) * (scale * s + bias) over the visible keys
       float mx = -INFINITY;
-      for (int ch = 0; ch < nch; ++ch) {
-        const int c0 = ch * 32;
-        uint32_t r[32];
-        float bz[32];
-        tmem_ld32_nowait(tmem_S + lane_addr + c0, r);
-        if (HAS_BIAS) load_bias32(brow, k0 + c0, p.bias_ld, row_ok, bz);
-        tmem_ld_wait();
-        const uint32_t km = kmask_s[(k0 + c0) >> 5];
+      tmem_ld32_nowait(tmem_S + lane_addr, r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r[j]) * c2;
-          if (HAS_BIAS) x += bz[j];
-          bool ok = (km >> j) & 1u;
-          if (p.causal) ok = ok && (k0 + c0 + j <= i);
-          x = ok ? x : -INFINITY;
-          mx = fmaxf(mx, x);
-          r[j] = __float_as_uint(x);
-        }
-        tmem_st32(tmem_S + lane_addr + c0, r);
-      }
-      const float m_new = fmaxf(m_run, mx);
-      const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float corr = fast_ex2(m_run - m_use);  // ex2(-inf) = 0 for the first block
-      m_run = m_new;
-      l_run *= corr;
-      tmem_st_wait();
-      // pass 2: probabilities -> bf16 pairs over the first half of the score columns (the A operand of P V)
-      float ls = 0.f;
-      for (int ch = 0; ch < nch; ++ch) {
-        const int c0 = ch * 32;
-        uint32_t r[32], pk[16];
-        tmem_ld32(tmem_S + lane_addr + c0, r);
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float p0 = fast_ex2(__uint_as_float(r[j]) - m_use);
-          float p1 = fast_ex2(__uint_as_float(r[j + 1]) - m_use);
-          ls += p0 + p1;
-          if (DROP) {  // the row sum is that of the undropped probabilities; only P V sees the mask
-            const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
-            p0 = tc_keep(dkey, ij, p.drop.thresh32) ? p0 * p.drop.inv_keep : 0.f;
-            p1 = tc_keep(dkey, ij + 1u, p.drop.thresh32) ? p1 * p.drop.inv_keep : 0.f;
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
+          const int c0 = ch * 32;
+          tmem_ld_wait();
+          if (ch + 1 < nch) {
+            tmem_ld32_nowait(tmem_S + lane_addr + c0 + 32, r[(ch + 1) & 1]);
+            if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0 + c0 + 32, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
           }
-          pk[j >> 1] = pack_bf16(p0, p1);
+          const uint32_t km = kmask_s[(k0 + c0) >> 5];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = __uint_as_float(r[ch & 1][j]) * c2;
+            if (HAS_BIAS) x += bias_at(bu[ch & 1], j);
+            bool ok = (km >> j) & 1u;
+            if (p.causal) ok = ok && (k0 + c0 + j <= i);
+            mx = fmaxf(mx, ok ? x : -INFINITY);
+          }
         }
-        tmem_st16(tmem_S + lane_addr + (c0 >> 1), pk);
+      }
+      // ---- reference maximum: raise it (and rescale l and the O accumulator) only when the block exceeds it by > 2^8
+      const float m_cand = fmaxf(m_ref, mx);
+      const bool raise = m_cand > m_ref + 8.0f || (m_ref == -INFINITY && m_cand != -INFINITY);
+      if (kb == 0) {
+        m_ref = m_cand;
+      } else if (__any_sync(0xffffffffu, raise)) {  // warp-uniform: the TMEM accesses below are collective
+        const float corr = raise ? fast_ex2(m_ref - m_cand) : 1.0f;  // m_ref = -inf -> 0 (its O row and l are 0 anyway)
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t o[32];
+          tmem_ld32(tmem_O + lane_addr + hf * 32, o);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+          tmem_st32(tmem_O + lane_addr + hf * 32, o);
+        }
+        l_run *= corr;
+        if (raise) m_ref = m_cand;
+      }
+      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+      // ---- pass 2: probabilities -> bf16 pairs over the first half of the score columns (the A operand of P V)
+      float ls = 0.f;
+      if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);  // (L1 / L2 hits: read in pass 1)
+      tmem_ld32_nowait(tmem_S + lane_addr, r[0]);
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
+          const int c0 = ch * 32;
+          uint32_t pk[16];
+          tmem_ld_wait();
+          if (ch + 1 < nch) {
+            tmem_ld32_nowait(tmem_S + lane_addr + c0 + 32, r[(ch + 1) & 1]);
+            if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0 + c0 + 32, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
+          }
+          const uint32_t km = kmask_s[(k0 + c0) >> 5];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float pe[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              float x = fmaf(__uint_as_float(r[ch & 1][j + e]), c2, -m_use);
+              if (HAS_BIAS) x += bias_at(bu[ch & 1], j + e);
+              bool ok = (km >> (j + e)) & 1u;
+              if (p.causal) ok = ok && (k0 + c0 + j + e <= i);
+              pe[e] = ok ? fast_ex2(x) : 0.f;
+            }
+            ls += pe[0] + pe[1];
+            if (DROP) {  // the row sum is that of the undropped probabilities; only P V sees the mask
+              const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
+              pe[0] = tc_keep(dkey, ij, p.drop.thresh32) ? pe[0] * p.drop.inv_keep : 0.f;
+              pe[1] = tc_keep(dkey, ij + 1u, p.drop.thresh32) ? pe[1] * p.drop.inv_keep : 0.f;
+            }
+            pk[j >> 1] = pack_bf16(pe[0], pe[1]);
+          }
+          // P chunk ch lands on score columns [16 ch, 16 ch + 16): chunks 0 / 1 are in registers or consumed, the chunk being
+          // prefetched (ch + 1) starts at column 32 (ch + 1) >= 16 ch + 16
+          tmem_st16(tmem_S + lane_addr + (c0 >> 1), pk);
+        }
       }
       l_run += ls;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_ready);
-      // running output: O = O * corr + P V
-      mbar_wait(o_full, kb & 1);
-      tc_fence_after();
-#pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t r[32];
-        tmem_ld32(tmem_O + lane_addr + hf * 32, r);
-#pragma unroll
-        for (int j = 0; j < 32; ++j) oacc[hf * 32 + j] = fmaf(oacc[hf * 32 + j], corr, __uint_as_float(r[j]));
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_free);
     }
-    if (row_ok) {
-      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-      bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)i * p.o_rs + h * 64;
+    mbar_wait(o_done, 0);
+    tc_fence_after();
+    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
 #pragma unroll
-      for (int j = 0; j < 64; j += 8) {
-        f8 v;
+    for (int hf = 0; hf < 2; ++hf) {
+      uint32_t r[32];
+      tmem_ld32(tmem_O + lane_addr + hf * 32, r);
+      if (row_ok) {
+        bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)i * p.o_rs + h * 64 + hf * 32;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v.v[e] = oacc[j + e] * inv;
-        store8(op + j, v);
+        for (int j = 0; j < 32; j += 8) {
+          f8 v;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v.v[e] = __uint_as_float(r[j + e]) * inv;
+          store8(op + j, v);
+        }
       }
-      p.lse[((int64_t)b * p.H + h) * p.Tq + i] = l_run > 0.f ? (m_run + __log2f(l_run)) * kLn2 : -INFINITY;
     }
+    if (row_ok) p.lse[((int64_t)b * p.H + h) * p.Tq + i] = l_run > 0.f ? (m_ref + __log2f(l_run)) * kLn2 : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -468,7 +539,8 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   uint64_t* ds_ready = sdp_full + 1;               // dS (bf16) is in TMEM (4 warp arrivals)
   uint64_t* dq_full = ds_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(dq_full + 1);
-  uint32_t* kmask_s = tmem_ptr + 2;
+  float* cs_s = reinterpret_cast<float*>(tmem_ptr + 2);  // [4][64] column-sum staging
+  uint32_t* kmask_s = reinterpret_cast<uint32_t*>(cs_s + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -583,46 +655,56 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kb * BN;
       const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
-      const int nch = (n + 31) >> 5;
+      const int nch = n >> 4;  // 16-column chunks, software-pipelined: chunk ch + 1 is in flight while chunk ch is processed
+      uint4 bu[2][HAS_BIAS ? 2 : 1];
+      if constexpr (HAS_BIAS) load_bias_raw<2>(brow, k0, p.bias_ld, row_ok, bu[0]);
       mbar_wait(sdp_full, kb & 1);
       tc_fence_after();
-      for (int ch = 0; ch < nch; ++ch) {
-        const int c0 = ch * 32;
-        uint32_t r[32], d[32], pk[16];
-        float bz[32];
-        tmem_ld32_nowait(tmem_S + lane_addr + c0, r);
-        tmem_ld32_nowait(tmem_dP + lane_addr + c0, d);
-        if (HAS_BIAS) load_bias32(brow, k0 + c0, p.bias_ld, row_ok, bz);
-        tmem_ld_wait();
-        const uint32_t km = kmask_s[(k0 + c0) >> 5];
+      uint32_t r[2][16], d[2][16];
+      tmem_ld16_nowait(tmem_S + lane_addr, r[0]);
+      tmem_ld16_nowait(tmem_dP + lane_addr, d[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = fmaf(__uint_as_float(r[j]), c2, -lse2);
-          if (HAS_BIAS) x += bz[j];
-          bool ok = (km >> j) & 1u;
-          if (p.causal) ok = ok && (k0 + c0 + j <= i);
-          const float pe = ok ? fast_ex2(x) : 0.f;
-          float dp = __uint_as_float(d[j]);
-          if (DROP) {  // dP = keep / (1 - p) * dP_drop
-            const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
-            dp = tc_keep(dkey, ij, p.drop.thresh32) ? dp * p.drop.inv_keep : 0.f;
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
+          const int c0 = ch * 16;
+          uint32_t pk[8];
+          tmem_ld_wait();
+          if (ch + 1 < nch) {
+            tmem_ld16_nowait(tmem_S + lane_addr + c0 + 16, r[(ch + 1) & 1]);
+            tmem_ld16_nowait(tmem_dP + lane_addr + c0 + 16, d[(ch + 1) & 1]);
+            if constexpr (HAS_BIAS) load_bias_raw<2>(brow, k0 + c0 + 16, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
           }
-          r[j] = __float_as_uint(ok ? pe * (dp - dl) : 0.f);  // dS (columns past the block's keys hold stale TMEM data: select, never multiply)
-        }
-        if (HAS_BIAS && dsrow != nullptr) {
+          const uint32_t km = kmask_s[(k0 + c0) >> 5] >> (c0 & 16);
+          float dsv[16];
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            if (k0 + c0 + 8 * v < p.bias_ld) {
-              f8 o8;
+          for (int j = 0; j < 16; ++j) {
+            float x = fmaf(__uint_as_float(r[ch & 1][j]), c2, -lse2);
+            if (HAS_BIAS) x += bias_at(bu[ch & 1], j);
+            bool ok = (km >> j) & 1u;
+            if (p.causal) ok = ok && (k0 + c0 + j <= i);
+            const float pe = ok ? fast_ex2(x) : 0.f;
+            float dp = __uint_as_float(d[ch & 1][j]);
+            if (DROP) {  // dP = keep / (1 - p) * dP_drop
+              const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
+              dp = tc_keep(dkey, ij, p.drop.thresh32) ? dp * p.drop.inv_keep : 0.f;
+            }
+            dsv[j] = ok ? pe * (dp - dl) : 0.f;  // dS (columns past the block's keys hold stale TMEM data: select, never multiply)
+          }
+          if (HAS_BIAS && dsrow != nullptr) {
 #pragma unroll
-              for (int e = 0; e < 8; ++e) o8.v[e] = __uint_as_float(r[8 * v + e]);
-              store8(dsrow + k0 + c0 + 8 * v, o8);
+            for (int v = 0; v < 2; ++v) {
+              if (k0 + c0 + 8 * v < p.bias_ld) {
+                f8 o8;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o8.v[e] = dsv[8 * v + e];
+                store8(dsrow + k0 + c0 + 8 * v, o8);
+              }
             }
           }
-        }
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) pk[j >> 1] = pack_bf16(__uint_as_float(r[j]) * p.scale, __uint_as_float(r[j + 1]) * p.scale);
-        tmem_st16(tmem_S + lane_addr + (c0 >> 1), pk);
+          for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16(dsv[j] * p.scale, dsv[j + 1] * p.scale);
+          tmem_st8(tmem_S + lane_addr + (c0 >> 1), pk);  // columns [8 ch, 8 ch + 8): below every chunk still to be read
+        }
       }
       tmem_st_wait();
       tc_fence_before();
@@ -631,21 +713,33 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
     }
     mbar_wait(dq_full, 0);
     tc_fence_after();
+    float lo[32], hi[32];
+    {
+      uint32_t r0[32], r1[32];
+      tmem_ld32_nowait(tmem_dQ + lane_addr, r0);
+      tmem_ld32(tmem_dQ + lane_addr + 32, r1);
 #pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      uint32_t r[32];
-      tmem_ld32(tmem_dQ + lane_addr + hf * 32, r);
-      if (row_ok) {
-        bf16* dqp = p.dq + (int64_t)b * p.dq_bs + (int64_t)i * p.dq_rs + h * 64 + hf * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          f8 v;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v.v[e] = __uint_as_float(r[j + e]);
-          store8(dqp + j, v);
-        }
+      for (int j = 0; j < 32; ++j) {
+        lo[j] = __uint_as_float(r0[j]);
+        hi[j] = __uint_as_float(r1[j]);
       }
     }
+    if (row_ok) {
+      bf16* dqp = p.dq + (int64_t)b * p.dq_bs + (int64_t)i * p.dq_rs + h * 64;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        f8 v, w;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          v.v[e] = lo[j + e];
+          w.v[e] = hi[j + e];
+        }
+        store8(dqp + j, v);
+        store8(dqp + 32 + j, w);
+      }
+    }
+    if (p.dq_colsum != nullptr)  // rows past Tq hold exact zeros (zero-filled Q / dO rows)
+      tile_colsum_out(lo, hi, cs_s, p.dq_colsum + ((int64_t)b * gridDim.x + qt) * (p.H * 64) + h * 64);
   }
   tc_fence_before();
   __syncthreads();
@@ -679,6 +773,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   uint64_t* ds_ready = sdp_full + 1;
   uint64_t* acc_full = ds_ready + 1;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(acc_full + 1);
+  float* cs_s = reinterpret_cast<float*>(tmem_ptr + 2);  // [4][64] column-sum staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
@@ -797,45 +892,62 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
       const int st = it % STAGES;
       const int q0 = qb * BQ;
       const int n = min(BQ, ((p.Tq - q0) + 15) & ~15);
-      const int nch = (n + 31) >> 5;
+      const int nch = n >> 4;
+      uint4 bu[2][HAS_BIAS ? 2 : 1];
+      if constexpr (HAS_BIAS) load_bias_raw<2>(brow, q0, p.bias_t_ld, row_ok, bu[0]);
       mbar_wait(sdp_full, it & 1);  // (the MMA issuer waited for full[st]: the lse / delta rows of this stage are visible)
       tc_fence_after();
       const float* lse2 = lse_s + st * BQ;
       const float* dls = dl_s + st * BQ;
-      for (int ch = 0; ch < nch; ++ch) {
-        const int c0 = ch * 32;
-        uint32_t r[32], d[32], pp[16], pd[16];
-        float bz[32];
-        tmem_ld32_nowait(tmem_S + lane_addr + c0, r);
-        tmem_ld32_nowait(tmem_dP + lane_addr + c0, d);
-        if (HAS_BIAS) load_bias32(brow, q0 + c0, p.bias_t_ld, row_ok, bz);
-        tmem_ld_wait();
+      uint32_t r[2][16], d[2][16];
+      tmem_ld16_nowait(tmem_S + lane_addr, r[0]);
+      tmem_ld16_nowait(tmem_dP + lane_addr, d[0]);
 #pragma unroll
-        for (int e = 0; e < 32; ++e) {
-          const int iq = q0 + c0 + e;
-          float x = fmaf(__uint_as_float(r[e]), c2, -lse2[c0 + e]);
-          if (HAS_BIAS) x += bz[e];
-          bool ok = key_ok && iq < p.Tq;
-          if (p.causal) ok = ok && (j <= iq);
-          const float pe = ok ? fast_ex2(x) : 0.f;
-          float dp = __uint_as_float(d[e]);
-          float pv = pe;
-          if (DROP) {
-            const uint32_t ij = (uint32_t)iq * (uint32_t)p.Tk + (uint32_t)j;
-            const bool keep = tc_keep(dkey, ij, p.drop.thresh32);
-            pv = keep ? pe * ik : 0.f;   // P_drop (dV = P_drop^T dO)
-            dp = keep ? dp * ik : 0.f;   // dP = keep / (1 - p) * dP_drop
+      for (int ch = 0; ch < 4; ++ch) {
+        if (ch < nch) {
+          const int c0 = ch * 16;
+          uint32_t pp[8], pd[8];
+          tmem_ld_wait();
+          if (ch + 1 < nch) {
+            tmem_ld16_nowait(tmem_S + lane_addr + c0 + 16, r[(ch + 1) & 1]);
+            tmem_ld16_nowait(tmem_dP + lane_addr + c0 + 16, d[(ch + 1) & 1]);
+            if constexpr (HAS_BIAS) load_bias_raw<2>(brow, q0 + c0 + 16, p.bias_t_ld, row_ok, bu[(ch + 1) & 1]);
           }
-          r[e] = __float_as_uint(ok ? pv : 0.f);
-          d[e] = __float_as_uint(ok ? pe * (dp - dls[c0 + e]) * p.scale : 0.f);  // scale * dS^T (stale columns: select, never multiply)
-        }
+          float pv[16], dsv[16];
 #pragma unroll
-        for (int e = 0; e < 32; e += 2) {
-          pp[e >> 1] = pack_bf16(__uint_as_float(r[e]), __uint_as_float(r[e + 1]));
-          pd[e >> 1] = pack_bf16(__uint_as_float(d[e]), __uint_as_float(d[e + 1]));
+          for (int e4 = 0; e4 < 16; e4 += 4) {
+            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + e4);  // broadcast reads (same address in every lane)
+            const float4 d4 = *reinterpret_cast<const float4*>(dls + c0 + e4);
+            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int e = e4 + u;
+              const int iq = q0 + c0 + e;
+              float x = fmaf(__uint_as_float(r[ch & 1][e]), c2, -lq[u]);
+              if (HAS_BIAS) x += bias_at(bu[ch & 1], e);
+              bool ok = key_ok && iq < p.Tq;
+              if (p.causal) ok = ok && (j <= iq);
+              const float pe = ok ? fast_ex2(x) : 0.f;
+              float dp = __uint_as_float(d[ch & 1][e]);
+              float pvv = pe;
+              if (DROP) {
+                const uint32_t ij = (uint32_t)iq * (uint32_t)p.Tk + (uint32_t)j;
+                const bool keep = tc_keep(dkey, ij, p.drop.thresh32);
+                pvv = keep ? pe * ik : 0.f;  // P_drop (dV = P_drop^T dO)
+                dp = keep ? dp * ik : 0.f;   // dP = keep / (1 - p) * dP_drop
+              }
+              pv[e] = ok ? pvv : 0.f;  // (stale TMEM columns: select, never multiply)
+              dsv[e] = ok ? pe * (dp - dq4[u]) * p.scale : 0.f;  // scale * dS^T
+            }
+          }
+#pragma unroll
+          for (int e = 0; e < 16; e += 2) {
+            pp[e >> 1] = pack_bf16(pv[e], pv[e + 1]);
+            pd[e >> 1] = pack_bf16(dsv[e], dsv[e + 1]);
+          }
+          tmem_st8(tmem_S + lane_addr + (c0 >> 1), pp);
+          tmem_st8(tmem_dP + lane_addr + (c0 >> 1), pd);
         }
-        tmem_st16(tmem_S + lane_addr + (c0 >> 1), pp);
-        tmem_st16(tmem_dP + lane_addr + (c0 >> 1), pd);
       }
       tmem_st_wait();
       tc_fence_before();
@@ -849,25 +961,37 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
 #pragma unroll
     for (int which = 0; which < 2; ++which) {
       bf16* base = which == 0 ? p.dk + (int64_t)b * p.dk_bs + (int64_t)j * p.dk_rs : p.dv + (int64_t)b * p.dv_bs + (int64_t)j * p.dv_rs;
+      float lo[32], hi[32];
+      if (qb0 < nqb) {
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait((which == 0 ? tmem_dK : tmem_dV) + lane_addr, r0);
+        tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + 32, r1);
 #pragma unroll
-      for (int hf = 0; hf < 2; ++hf) {
-        uint32_t r[32];
-        if (qb0 < nqb) tmem_ld32((which == 0 ? tmem_dK : tmem_dV) + lane_addr + hf * 32, r);
-        else {
-#pragma unroll
-          for (int e = 0; e < 32; ++e) r[e] = 0u;
+        for (int e = 0; e < 32; ++e) {
+          lo[e] = __uint_as_float(r0[e]);
+          hi[e] = __uint_as_float(r1[e]);
         }
-        if (row_ok) {
-          bf16* gp = base + h * 64 + hf * 32;
+      } else {
 #pragma unroll
-          for (int e0 = 0; e0 < 32; e0 += 8) {
-            f8 v;
+        for (int e = 0; e < 32; ++e) lo[e] = hi[e] = 0.f;
+      }
+      if (row_ok) {
+        bf16* gp = base + h * 64;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v.v[e] = __uint_as_float(r[e0 + e]);
-            store8(gp + e0, v);
+        for (int e0 = 0; e0 < 32; e0 += 8) {
+          f8 v, w;
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            v.v[e] = lo[e0 + e];
+            w.v[e] = hi[e0 + e];
           }
+          store8(gp + e0, v);
+          store8(gp + 32 + e0, w);
         }
       }
+      float* csout = which == 0 ? p.dk_colsum : p.dv_colsum;
+      if (csout != nullptr)  // rows past Tk hold exact zeros
+        tile_colsum_out(lo, hi, cs_s, csout + ((int64_t)b * gridDim.x + kt) * (p.H * 64) + h * 64);
     }
   }
   tc_fence_before();
@@ -1072,6 +1196,7 @@ int ofab_attn_tc_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) {
   p.dq = (bf16*)a->dq; p.dk = (bf16*)a->dk; p.dv = (bf16*)a->dv;
   p.dq_bs = a->dq_bs; p.dq_rs = a->dq_rs; p.dk_bs = a->dk_bs; p.dk_rs = a->dk_rs; p.dv_bs = a->dv_bs; p.dv_rs = a->dv_rs;
   p.ds = (bf16*)a->ds;
+  p.dq_colsum = a->dq_colsum; p.dk_colsum = a->dk_colsum; p.dv_colsum = a->dv_colsum;
   const ofab_attn_fwd_args& f = a->f;
   CUtensorMap q128, do128, k64, v64, k128, v128, q64, do64;
   const int C = f.H * 64;
@@ -1086,8 +1211,8 @@ int ofab_attn_tc_bwd(const ofab_attn_bwd_args* a, ofab_stream_t stream) {
   OFAB_REQUIRE(!hb || (f.bias_t_ld % 8 == 0 && f.bias_t_ld >= f.Tq && ((uintptr_t)f.bias_t & 15) == 0 && f.bias_t_hs % 8 == 0),
                "ofab_attn_bwd: bias_t needs 16-byte aligned rows with bias_t_ld >= Tq");
   const int nkb = (f.Tk + 63) / 64;
-  const int smem_q = 1024 + 2 * 128 * 128 + 2 * 2 * 64 * 128 + 16 * 8 + 16 + nkb * 2 * 4;
-  const int smem_kv = 1024 + 2 * 128 * 128 + 2 * 2 * 64 * 128 + 2 * 2 * 64 * 4 + 16 * 8 + 16;
+  const int smem_q = 1024 + 2 * 128 * 128 + 2 * 2 * 64 * 128 + 16 * 8 + 16 + 1024 + nkb * 2 * 4;
+  const int smem_kv = 1024 + 2 * 128 * 128 + 2 * 2 * 64 * 128 + 2 * 2 * 64 * 4 + 16 * 8 + 16 + 1024;
   dim3 gq((f.Tq + 127) / 128, f.H, f.B), gkv((f.Tk + 127) / 128, f.H, f.B);
   int rc;
 #define TC_BWD(HB, D)                                                                                      \

@@ -111,3 +111,72 @@ class GradBuckets:
             if scale is not None:
                 flat.mul_(scale)
             _lib.call("ofab_multi_copy", tu.data_ptr(), tu.shape[0], stream)
+
+
+class DataParallelModel(torch.nn.Module):
+    """The data-parallel wrapper surface the reference's trainer expects (`Trainer.model`, engine/trainer.py:352-364,
+    766-784; `FairseqOptimizer.all_reduce_grads`, engine/optim/fairseq_optimizer.py:99-103; the `legacy_ddp` wrapper of
+    distributed_model_dispatcher.py:76-84): anything with `.forward`, `.parameters()`, `.no_sync()` and
+    `.all_reduce_grads()`, forwarding every other attribute to the wrapped module like `ModuleProxyWrapper`.
+
+      with model.no_sync():            # delayed-update loop / all but the last task batch of a step: accumulate locally
+          loss.backward()
+      model.all_reduce_grads()         # ONE exchange per step: p.grad <- mean over ranks (missing grads count as zeros)
+      optimizer.multiply_grads(world_size / sum(sample_sizes))      # trainer.py:857-860
+
+    The exchange is GradBuckets (flat buckets, NCCL over NVLink) on CUDA gradients and the plain bucketed all-reduce
+    (gloo) on CPU ones.  Unused parameters -- a task that never touched an adaptor -- need no graph walk: they contribute
+    zeros (the reference relies on DDP's find_unused_parameters)."""
+
+    def __init__(self, module: torch.nn.Module, process_group=None, bucket_bytes: int = 64 << 20):
+        super().__init__()
+        self.module = module
+        self.process_group = process_group
+        self.bucket_bytes = bucket_bytes
+        self.accumulate_grads = False
+        self._buckets = None
+
+    def __getattr__(self, name):
+        try:
+            return super().__getattr__(name)
+        except AttributeError:
+            return getattr(super().__getattr__("module"), name)
+
+    def state_dict(self, *args, **kwargs):
+        return self.module.state_dict(*args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        return self.module.load_state_dict(*args, **kwargs)
+
+    def forward(self, *args, **kwargs):
+        return self.module(*args, **kwargs)
+
+    def no_sync(self):
+        """Context manager: all_reduce_grads() inside it is a no-op (gradients keep accumulating locally)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def ctx():
+            old = self.accumulate_grads
+            self.accumulate_grads = True
+            try:
+                yield
+            finally:
+                self.accumulate_grads = old
+
+        return ctx()
+
+    def all_reduce_grads(self, scale: Optional[float] = None):
+        if self.accumulate_grads or not (dist.is_available() and dist.is_initialized()):
+            return
+        if dist.get_world_size(self.process_group) == 1 and scale is None:
+            return
+        params = [p for p in self.module.parameters() if p.requires_grad]
+        if params and params[0].is_cuda:
+            if self._buckets is None:
+                self._buckets = GradBuckets(params, self.bucket_bytes)
+            self._buckets.allreduce(self.process_group, scale)
+        else:
+            if self._buckets is None:
+                self._buckets = build_buckets(params, self.bucket_bytes)
+            allreduce_grads(self._buckets, self.process_group, scale)

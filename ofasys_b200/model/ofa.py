@@ -124,7 +124,17 @@ class GeneralistModel(nn.Module):
         if cfg.arch:
             globals()["ofa_arch_" + cfg.arch](cfg)
 
+    def _check_kernel_limits(self):
+        """Reject geometries the kernels do not cover at construction time (not at the first forward)."""
+        d, f = self.cfg.encoder.embed_dim, self.cfg.encoder.ffn_embed_dim
+        if d % self.cfg.encoder.attention_heads != 0 or d // self.cfg.encoder.attention_heads != 64:
+            raise NotImplementedError(f"ofasys_b200: head_dim must be 64 (embed_dim {d}, heads {self.cfg.encoder.attention_heads})")
+        if d > 1024 or f > 4096:
+            raise NotImplementedError(f"ofasys_b200: embed_dim {d} / ffn_embed_dim {f} exceed the LayerNorm-family kernels' limits "
+                                      "(embed_dim <= 1024, ffn <= 4096: tiny .. large presets; `huge` (1280 / 5120) is not covered)")
+
     def initialize(self, global_dict):
+        self._check_kernel_limits()
         self.encoder = TransformerEncoder(self.cfg, global_dict)
         self.decoder = TransformerDecoder(self.cfg, global_dict, self.cfg.no_cross_attention)
         self.extra_models = nn.ModuleDict()

@@ -70,8 +70,10 @@ class MultiheadAttention(nn.Module):
         H = self.num_heads
         st = incremental_state.setdefault(self._state_key, {})
         bias = attn_bias if isinstance(attn_bias, ops.PositionBias) else None
-        fast = attn_bias is None and not static_kv
-        scale = float(self.head_dim) ** -0.5 if fast else self.scaling
+        # the reference takes the F.multi_head_attention_forward shortcut only when incremental_state is None
+        # (multihead_attention.py:155-160): with a cache it is always the manual path -- (head_dim * scale_factor)**-0.5, c_attn
+        fast = False
+        scale = self.scaling
         if static_kv:
             assert self.encoder_decoder_attention and not self.self_attention
             if "kv" not in st:  # first step: project the encoder output once (:188-196)

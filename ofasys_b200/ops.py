@@ -150,12 +150,15 @@ _BIAS_HINTS = {}
 def _hint_bias_grad(grad_tensor, colsum_vec):
     if len(_BIAS_HINTS) > 64:
         _BIAS_HINTS.clear()
-    _BIAS_HINTS[(grad_tensor.data_ptr(), grad_tensor.numel())] = (weakref.ref(grad_tensor), colsum_vec)
+    _BIAS_HINTS[(grad_tensor.data_ptr(), grad_tensor.numel())] = (weakref.ref(grad_tensor), colsum_vec, grad_tensor._version)
 
 
 def _take_bias_hint(grad_tensor, n):
+    """The hint is valid only for the same tensor object AND the same contents: autograd accumulates IN PLACE into the
+    first-arrived gradient of a tensor with several consumers (and tensor hooks may edit a gradient), which keeps the
+    object identity but bumps its version counter -- the column sums recorded before that are stale."""
     ent = _BIAS_HINTS.pop((grad_tensor.data_ptr(), grad_tensor.numel()), None)
-    if ent is None or ent[0]() is not grad_tensor:
+    if ent is None or ent[0]() is not grad_tensor or ent[2] != grad_tensor._version:
         return None
     return ent[1] if ent[1].numel() == n else None
 
@@ -615,28 +618,24 @@ class _AttentionFn(torch.autograd.Function):
             a.dtable = None
         delta = torch.empty((B, H, Tq), dtype=torch.float32, device=d_o.device)
         a.delta = delta.data_ptr()
-        # bias gradients of the q / k / v projections: the mma.sync kernels (structured position terms) leave one partial row
-        # of column sums per CTA (self-attention: Tq == Tk, one [3, B * tiles, d] buffer whose slabs reduce straight into the
-        # packed [3d] vector); the tcgen05 kernels do not (the Linear backward then sums its dY)
-        legacy = pq is not None or (rp_idx is not None and not dense)
-        if legacy:
-            nq, nk = (Tq + 63) // 64, (Tk + 63) // 64
-            if kv_src is None:
-                part = torch.empty((3, B * nq, d), dtype=torch.float32, device=d_o.device)
-                a.dq_colsum, a.dk_colsum, a.dv_colsum = part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr()
-            else:
-                part_q = torch.empty((1, B * nq, d), dtype=torch.float32, device=d_o.device)
-                part_kv = torch.empty((2, B * nk, d), dtype=torch.float32, device=d_o.device)
-                a.dq_colsum, a.dk_colsum, a.dv_colsum = part_q.data_ptr(), part_kv[0].data_ptr(), part_kv[1].data_ptr()
+        # bias gradients of the q / k / v projections: the kernels leave one partial row of column sums per CTA (fp32, straight
+        # from their accumulators) -- tiles of 128 rows on the tcgen05 path, 64 on the mma.sync one; the buffers are sized for
+        # the finer tiling and zeroed, rows a path does not write add nothing (self-attention: Tq == Tk, one [3, B * tiles, d]
+        # buffer whose slabs reduce straight into the packed [3d] vector)
+        nq, nk = (Tq + 63) // 64, (Tk + 63) // 64
+        if kv_src is None:
+            part = torch.zeros((3, B * nq, d), dtype=torch.float32, device=d_o.device)
+            a.dq_colsum, a.dk_colsum, a.dv_colsum = part[0].data_ptr(), part[1].data_ptr(), part[2].data_ptr()
         else:
-            a.dq_colsum = a.dk_colsum = a.dv_colsum = None
+            part_q = torch.zeros((1, B * nq, d), dtype=torch.float32, device=d_o.device)
+            part_kv = torch.zeros((2, B * nk, d), dtype=torch.float32, device=d_o.device)
+            a.dq_colsum, a.dk_colsum, a.dv_colsum = part_q.data_ptr(), part_kv[0].data_ptr(), part_kv[1].data_ptr()
         _lib.call("ofab_attn_bwd", ctypes.byref(a), _s())
-        if legacy:
-            for grad, partial in ((dq_src, part) if kv_src is None else (dq_src, part_q), (None, None) if kv_src is None else (dkv_src, part_kv)):
-                if grad is not None:
-                    vec = torch.empty(partial.shape[0] * d, dtype=torch.bfloat16, device=d_o.device)
-                    _lib.call("ofab_reduce_rows", _p(partial), partial.shape[0], partial.shape[1], d, _p(vec), BF16, _s())
-                    _hint_bias_grad(grad, vec)
+        for grad, partial in ((dq_src, part) if kv_src is None else (dq_src, part_q), (None, None) if kv_src is None else (dkv_src, part_kv)):
+            if grad is not None:
+                vec = torch.empty(partial.shape[0] * d, dtype=torch.bfloat16, device=d_o.device)
+                _lib.call("ofab_reduce_rows", _p(partial), partial.shape[0], partial.shape[1], d, _p(vec), BF16, _s())
+                _hint_bias_grad(grad, vec)
         dabs = None
         if dense:  # ONE reduction over the batch per layer: table histogram + abs-pos gradient
             dabs = torch.zeros(abs_shape, dtype=torch.float32, device=d_o.device)
@@ -839,6 +838,10 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
     def backward(ctx, g):
         x2, E, tgt, lse, logits = ctx.saved_tensors
         ignore_index, xshape, eps = ctx.meta
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("linear_cross_entropy: backward ran twice over the same graph (retain_graph): the logits scratch "
+                               "was overwritten by its gradient in the first pass; call forward again")
+        ctx.consumed = True
         M, K = x2.shape
         V = E.shape[0]
         Vp = logits.shape[1]

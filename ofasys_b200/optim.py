@@ -132,12 +132,49 @@ class FusedAdam:
         self._table_ready = False
 
     def state_dict(self):
-        return {"num_updates": self.num_updates, "lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay,
-                "master": self._master.clone(), "exp_avg": self._m.clone(), "exp_avg_sq": self._v.clone()}
+        """torch.optim-style layout, as the reference's fp32 optimizer emits through `fp32_optimizer.state_dict()`
+        (engine/optim/fp16_optimizer.py:104-124 -> torch.optim.Optimizer.state_dict): `state[i] = {step, exp_avg, exp_avg_sq}`
+        per parameter index (fp32, the parameter's shape) + one `param_groups` entry; the fp32 master copies ride along as
+        `master_params` (the reference keeps them as the fp32 optimizer's own parameters)."""
+        state = {i: {"step": self.num_updates, "exp_avg": self.exp_avg(i).clone(), "exp_avg_sq": self.exp_avg_sq(i).clone()}
+                 for i in range(len(self.params))}
+        group = {"lr": self.lr, "betas": self.betas, "eps": self.eps, "weight_decay": self.weight_decay, "amsgrad": False,
+                 "params": list(range(len(self.params)))}
+        return {"state": state, "param_groups": [group], "master_params": [self.master(i).clone() for i in range(len(self.params))]}
 
     def load_state_dict(self, sd):
-        self.num_updates, self.lr = int(sd["num_updates"]), float(sd["lr"])
-        self.betas, self.eps, self.weight_decay = tuple(sd["betas"]), float(sd["eps"]), float(sd["weight_decay"])
-        self._master.copy_(sd["master"])
-        self._m.copy_(sd["exp_avg"])
-        self._v.copy_(sd["exp_avg_sq"])
+        """Accepts the layout of state_dict() (and a reference / torch.optim Adam checkpoint of the same parameter order:
+        `master_params` optional -- the masters are then rebuilt from the bf16 parameters).  Shapes are validated; the bf16
+        parameters are re-synchronised from the masters."""
+        groups = sd["param_groups"]
+        if len(groups) != 1 or len(groups[0]["params"]) != len(self.params):
+            raise ValueError(f"FusedAdam.load_state_dict: expected one param group of {len(self.params)} parameters")
+        g = groups[0]
+        self.lr, self.betas, self.eps, self.weight_decay = float(g["lr"]), tuple(float(b) for b in g["betas"]), float(g["eps"]), float(g["weight_decay"])
+        state = sd["state"]
+        steps = set()
+        for i, p in enumerate(self.params):
+            st = state.get(i, state.get(str(i)))
+            if st is None:  # a parameter that never received a gradient has no state in torch's layout
+                self.exp_avg(i).zero_()
+                self.exp_avg_sq(i).zero_()
+                continue
+            for key, dst in (("exp_avg", self.exp_avg(i)), ("exp_avg_sq", self.exp_avg_sq(i))):
+                if tuple(st[key].shape) != tuple(p.shape):
+                    raise ValueError(f"FusedAdam.load_state_dict: state[{i}].{key} has shape {tuple(st[key].shape)}, parameter has {tuple(p.shape)}")
+                dst.copy_(st[key].to(self.device, torch.float32))
+            steps.add(int(st["step"]))
+        if len(steps) > 1:
+            raise ValueError(f"FusedAdam.load_state_dict: per-parameter step counts differ ({sorted(steps)}); one shared update count is kept")
+        self.num_updates = steps.pop() if steps else 0
+        masters = sd.get("master_params")
+        for i, p in enumerate(self.params):
+            if masters is not None:
+                if tuple(masters[i].shape) != tuple(p.shape):
+                    raise ValueError(f"FusedAdam.load_state_dict: master_params[{i}] has shape {tuple(masters[i].shape)}, parameter has {tuple(p.shape)}")
+                self.master(i).copy_(masters[i].to(self.device, torch.float32))
+                with torch.no_grad():
+                    p.copy_(self.master(i))  # the bf16 parameter is always bf16(master)
+            else:
+                self.master(i).copy_(p.detach().float())
+        self._table_ready = False

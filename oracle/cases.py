@@ -9,7 +9,7 @@ from typing import Dict, List, Tuple
 
 import torch
 
-from .oracle_model import AUDIO, IMAGE, PAD, TEXT, VIDEO, OracleConfig, OSlot
+from .oracle_model import AUDIO, BOX, IMAGE, PAD, TEXT, VIDEO, OracleConfig, OSlot
 
 # name -> dict(cfg=..., adaptors=..., inputs spec)
 CASES = {
@@ -61,6 +61,23 @@ CASES = {
     "large_A": dict(
         cfg=dict(embed_dim=1024, heads=16, ffn_dim=4096, enc_layers=3, dec_layers=2, vocab=512, mode="A"),
         adaptors=("text",), kind="text", B=3, S=40, T=24,
+    ),
+    # ---- BASELINE.json configs[3] / configs[4] at their full model size (oracle/make_golden_full.py; checksums, samples and
+    # projections only).  `tasks`: the task batches of ONE step, gradients accumulated over them.
+    "cfg4_cotrain_base": dict(
+        cfg=dict(embed_dim=768, heads=12, ffn_dim=3072, enc_layers=12, dec_layers=12, vocab=50265, mode="A", resnet_type="resnet101"),
+        adaptors=("text", "image_resnet"),
+        tasks=[dict(kind="resnet", B=2, S=8, T=64, image=224), dict(kind="resnet", B=2, S=16, T=8, image=224), dict(kind="text", B=2, S=128, T=128)],
+    ),
+    "cfg5_large_video": dict(
+        cfg=dict(embed_dim=1024, heads=16, ffn_dim=4096, enc_layers=24, dec_layers=12, vocab=51265, mode="A", resnet_type="resnet152"),
+        adaptors=("text", "image_resnet", "video_image_sequence"),
+        tasks=[dict(kind="video", B=1, S=8, T=64, image=224, frames=16)],
+    ),
+    "cfg5_large_grounding": dict(
+        cfg=dict(embed_dim=1024, heads=16, ffn_dim=4096, enc_layers=24, dec_layers=12, vocab=51265, mode="A", resnet_type="resnet152"),
+        adaptors=("text", "image_resnet", "video_image_sequence"),
+        tasks=[dict(kind="resnet", B=2, S=16, T=5, image=512, box=True)],
     ),
 }
 
@@ -165,6 +182,55 @@ def make_inputs(name: str, seed: int = 1234):
     target[torch.roll(prev == PAD, -1, dims=1)] = PAD
     target[:, -1] = torch.where(prev[:, -1] == PAD, torch.tensor(PAD), torch.tensor(2))
     return slots, target
+
+
+def make_task_inputs(name: str, seed: int = 1234):
+    """[(slots, target)] for the task batches of one step of a multi-task case (`tasks` in CASES)."""
+    c = CASES[name]
+    out = []
+    for ti, t in enumerate(c["tasks"]):
+        CASES["_task"] = dict(cfg=c["cfg"], adaptors=c["adaptors"], **t)
+        try:
+            slots, target = make_inputs("_task", seed + 101 * ti)
+        finally:
+            del CASES["_task"]
+        if t.get("box"):  # BOX target: bos + 4 `<bin>` tokens of the last 1000 vocabulary entries (preprocessor/default/box.py:101-110)
+            g = torch.Generator().manual_seed(seed + 101 * ti + 7)
+            V, B = c["cfg"]["vocab"], t["B"]
+            bins = V - 1000 + torch.randint(0, 1000, (B, 4), generator=g)
+            prev = torch.cat([torch.zeros(B, 1, dtype=torch.long), bins], dim=1)
+            target = torch.cat([bins, torch.full((B, 1), 2, dtype=torch.long)], dim=1)
+            slots = slots[:-1] + [OSlot(BOX, False, prev)]
+        out.append((slots, target))
+    return out
+
+
+# ---- full-tensor gradient probes (fixtures hold them instead of 10^8 gradient values) -------------------------------------
+GRAD_SAMPLES = 256   # elements at seeded positions per parameter
+GRAD_PROJ = 2        # seeded +-1 projections per parameter
+
+
+def grad_probe_indices(name, numel):
+    import zlib
+
+    g = torch.Generator().manual_seed(zlib.crc32(name.encode()) & 0x7FFFFFFF)
+    return torch.randint(0, numel, (1024,), generator=g)[:min(GRAD_SAMPLES, numel)]
+
+
+def grad_probe_vectors(name, numel):
+    import zlib
+
+    g = torch.Generator().manual_seed((zlib.crc32(name.encode()) ^ 0x5BD1E995) & 0x7FFFFFFF)
+    return torch.randint(0, 2, (GRAD_PROJ, numel), generator=g, dtype=torch.int8) * 2 - 1
+
+
+def grad_probes(name, grad):
+    """(samples fp32 [<=GRAD_SAMPLES], projections fp64 [GRAD_PROJ]) of one gradient tensor (any device / dtype)."""
+    gd = grad.detach().reshape(-1)
+    idx = grad_probe_indices(name, gd.numel()).to(gd.device)
+    r = grad_probe_vectors(name, gd.numel()).to(gd.device)
+    g64 = gd.double()
+    return g64[idx].float().cpu(), torch.stack([(g64 * r[i].double()).sum() for i in range(GRAD_PROJ)]).cpu()
 
 
 def param_spec_from_state_dict(sd) -> Dict[str, Tuple[int, ...]]:

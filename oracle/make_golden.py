@@ -83,6 +83,11 @@ def run_case(name):
             full[k] = gr.float().clone()
     g["grad_stats"] = grads
     g["grad_full"] = full
+    if lg.numel() > 1 << 18:  # full-size configs: probes of the FULL gradient tensors (seeded samples + random projections)
+        g["grad_samples"], g["grad_proj"] = {}, {}
+        for k, p in m.named_parameters():
+            if p.grad is not None:
+                g["grad_samples"][k], g["grad_proj"][k] = cases.grad_probes(k, p.grad)
     ints = {}
     for k, b in m.named_buffers():
         if k.endswith("rp_bucket"):

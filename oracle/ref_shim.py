@@ -247,6 +247,7 @@ def build_reference_model(
     seed=0,
     resnet_drop_path_rate=0.0,
     dims=None,
+    resnet_type=None,
 ):
     """Build the reference GeneralistModel with default_model.yaml settings, dropout 0.
 
@@ -296,6 +297,8 @@ def build_reference_model(
             a.drop_path_rate = resnet_drop_path_rate
     if "image_patch_embed" in adaptors:
         m.cfg.adaptor.image_patch_embed.embed_dim = m.cfg.encoder.embed_dim
+    if resnet_type is not None:  # the arch presets pick it (ofa.py:557-650: base resnet101, large resnet152)
+        m.cfg.adaptor.image_resnet.resnet_type = resnet_type
     torch.manual_seed(seed)
     m.initialize(ns.Dictionary(vocab))
     return m, ns

@@ -1,0 +1,104 @@
+"""GPU: BASELINE.json configs[3] and configs[4] at their FULL model sizes against dumps of the unmodified reference
+(tests/golden/cfg4_cotrain_base.pt, cfg5_large_grounding.pt, cfg5_large_video.pt; oracle/make_golden_full.py):
+
+  cfg4_cotrain_base     OFA-base 12L/12L, ResNet-101: caption + VQA + text_infilling batches of one step, gradients accumulated
+  cfg5_large_grounding  OFA-large 24L/12L d=1024 H=16, ResNet-152 @ 512^2 (S = 1040) -> BOX target
+  cfg5_large_video      the same model, 16 x 224^2 frames (S = 3144, one padded frame) -> 64-token caption
+
+Checked per task: loss, log-sum-exp per position, logits at 64 columns.  Checked on the FULL gradient tensors (positions and
+signs, not just norms): per parameter the L2 norm, 256 elements at seeded positions and 2 seeded +-1 projections
+(oracle/cases.py grad_probes) -- also for cfg2_base / cfg3_asr_base (tests/test_model_gpu.py checks their norms).
+Tolerances: bf16 operands (see tests/test_model_gpu.py); ResNet parameters are held to the norm gate only (ReLU-mask flips
+under bf16 storage, see test_model_fwd_bwd_parity).
+"""
+import pytest
+import torch
+
+from oracle import cases
+from util import build_product, load_golden, rel_l2, to_product_slots
+from test_model_gpu import _report
+
+pytestmark = pytest.mark.gpu
+
+
+def _check_grad_probes(name, m, g, tol=6e-2):
+    """full-tensor checks of every non-ResNet parameter gradient against the reference's probes"""
+    bad = {}
+    tot = sum(st[2].item() ** 2 for st in g["grad_stats"].values() if st is not None) ** 0.5
+    n_checked = 0
+    for k, p in m.named_parameters():
+        st = g["grad_stats"].get(k)
+        if st is None or k not in g["grad_samples"]:
+            assert p.grad is None or not p.grad.any(), k
+            continue
+        norm = st[2].item()
+        if norm <= 1e-3 * tot or "embed_images" in k:  # negligible tensors are noise; ResNet: norm gate below
+            continue
+        assert p.grad is not None, k
+        smp, prj = cases.grad_probes(k, p.grad)
+        ref_s = g["grad_samples"][k][: smp.numel()]
+        n = p.numel()
+        # sampled elements: error relative to the tensor's RMS (a permuted / sign-flipped tensor fails by ~1.4)
+        rms = norm / n ** 0.5
+        e_s = ((smp.double() - ref_s.double()).pow(2).mean().sqrt() / max(rms, 1e-30)).item()
+        # projections on +-1 vectors: <e, r> ~ N(0, |e|^2)  ->  |difference| <= 4 tol |g|
+        e_p = ((prj - g["grad_proj"][k]).abs().max() / max(norm, 1e-30)).item()
+        n_checked += 1
+        if e_s > 1.5 * tol or e_p > 4 * tol:
+            bad[k] = (e_s, e_p)
+    assert n_checked > 50
+    return bad
+
+
+@pytest.mark.parametrize("name", ["cfg4_cotrain_base", "cfg5_large_grounding", "cfg5_large_video"])
+def test_full_size_multitask_configs(name):
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    m = build_product(name)
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected
+    del sd
+    m = m.to(torch.bfloat16).to(dev).train()
+    rec = {}
+    for ti, ((slots, target), gt) in enumerate(zip(cases.make_task_inputs(name), g["tasks"])):
+        pslots = to_product_slots(slots, dev)
+        with torch.no_grad():
+            logits, _ = m(pslots)
+        e1 = rel_l2(logits[..., gt["logit_cols"].to(dev)].float(), gt["logits_sampled"])
+        e2 = rel_l2(torch.logsumexp(logits.float(), -1), gt["lse"])
+        del logits
+        loss = m.forward_loss(pslots, target.to(dev))
+        loss.backward()  # accumulates over the tasks of the step
+        e3 = abs(loss.item() - gt["loss"].item()) / gt["loss"].item()
+        rec[f"task{ti}"] = {"sampled_logits_rel_l2": e1, "lse_rel_l2": e2, "loss_rel": e3}
+        assert e1 <= 2e-2 and e2 <= 3e-3 and e3 <= 3e-3, (name, ti, e1, e2, e3)
+    torch.cuda.synchronize()
+    gn = {k: p.grad.double().norm().item() for k, p in m.named_parameters() if p.grad is not None}
+    res_tol = lambda k: 0.35 if "embed_images" in k else 6e-2
+    bad_norm = {k: (gn.get(k, 0.0), st[2].item()) for k, st in g["grad_stats"].items() if st is not None and st[2].item() > 1e-2
+                and abs(gn.get(k, 0.0) - st[2].item()) > res_tol(k) * st[2].item() + 5e-3}
+    bad_probe = _check_grad_probes(name, m, g)
+    rec["bad_grad_norms"], rec["bad_grad_probes"] = bad_norm, bad_probe
+    _report(name, rec)
+    assert not bad_norm, bad_norm
+    assert not bad_probe, bad_probe
+
+
+@pytest.mark.parametrize("name", ["cfg2_base", "cfg3_asr_base"])
+def test_full_gradient_tensors_of_the_single_task_configs(name):
+    """cfg2 (the bench workload) / cfg3 (ASR) at full size: every gradient TENSOR against the reference's probes."""
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    if "grad_samples" not in g:
+        pytest.skip("fixture predates the gradient probes")
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    m = build_product(name)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(torch.bfloat16).to(dev).train()
+    slots, target = cases.make_inputs(name)
+    m.forward_loss(to_product_slots(slots, dev), target.to(dev)).backward()
+    torch.cuda.synchronize()
+    bad = _check_grad_probes(name, m, g)
+    _report(name + "_grad_probes", {"bad": bad})
+    assert not bad, bad

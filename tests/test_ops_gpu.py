@@ -339,7 +339,7 @@ def attn_ref(q, k, v, pq, pk, table, idx, kpm, causal, scale, H):
 
 
 @pytest.mark.parametrize("mode", ["self", "cross"])
-@pytest.mark.parametrize("Tq,Tk", [(64, 64), (24, 24), (130, 130), (16, 265), (257, 257)])
+@pytest.mark.parametrize("Tq,Tk", [(64, 64), (24, 24), (130, 130), (16, 265), (257, 257), (700, 700), (1, 77)])
 @pytest.mark.parametrize("variant", ["plain", "pos", "pos_rel", "pos_rel_kpm_causal", "kpm", "causal"])
 def test_attention(mode, Tq, Tk, variant):
     from ofasys_b200 import ops
@@ -391,6 +391,77 @@ def test_attention(mode, Tq, Tk, variant):
     assert rel_l2(o, orf) <= 1e-2, (mode, Tq, Tk, variant)
     for t in leaves:
         assert rel_l2(t.grad, refs[id(t)].grad) <= 2e-2, (mode, Tq, Tk, variant, tuple(t.shape))
+
+
+@pytest.mark.parametrize("mode", ["self", "cross"])
+@pytest.mark.parametrize("Tq,Tk", [(64, 64), (24, 24), (130, 130), (16, 265), (257, 257), (520, 520), (200, 700)])
+@pytest.mark.parametrize("variant", ["pos", "pos_rel", "pos_rel_kpm_causal", "pos_kpm"])
+def test_attention_dense_bias(mode, Tq, Tk, variant):
+    """Mode A on the tcgen05 kernels: the position terms enter as ONE dense batch-invariant tile (abs_pos + table gather);
+    the gradients of pq / pk / table come back through the batch-reduced dS."""
+    from ofasys_b200 import ops
+
+    if mode == "self" and Tq != Tk:
+        pytest.skip("self-attention needs Tq == Tk")
+    if mode == "cross" and "causal" in variant:
+        pytest.skip("no causal cross-attention")
+    gen = g()
+    B, H = 3, 2
+    d = H * 64
+    scale = 128 ** -0.5
+    if mode == "self":
+        qkv = rnd(B, Tq, 3 * d, gen=gen).requires_grad_(True)
+        kv = None
+    else:
+        qkv = rnd(B, Tq, d, gen=gen).requires_grad_(True)
+        kv = rnd(B, Tk, 2 * d, gen=gen).requires_grad_(True)
+    table = idx = kpm = None
+    pq = rnd(1, Tq, d, gen=gen).requires_grad_(True)
+    pk = rnd(1, Tk, d, gen=gen).requires_grad_(True)
+    if "rel" in variant:
+        nb = 37
+        table = rnd(nb, H, gen=gen, scale=0.5).requires_grad_(True)
+        idx = torch.randint(-1, nb, (Tq, Tk), generator=gen).to(torch.int32).to(dev())
+    if "kpm" in variant:
+        kpm = torch.zeros(B, Tk, dtype=torch.bool)
+        kpm[1, Tk - max(1, Tk // 4):] = True
+        if Tk > 8:
+            kpm[0, 3] = True
+        kpm = kpm.to(dev())
+    causal = "causal" in variant
+    do = rnd(B, Tq, d, gen=gen)
+    o = ops.attention(qkv, kv, H, scale, ops.PositionBias(pq, pk, idx, table, abs=ops.abs_pos(pq, pk, H)), kpm, causal)
+    o.backward(do)
+    leaves = [t for t in (qkv, kv, pq, pk, table) if t is not None]
+    refs = {id(t): t.detach().float().requires_grad_(True) for t in leaves}
+    R = lambda t: None if t is None else refs[id(t)]
+    if mode == "self":
+        q_, k_, v_ = R(qkv)[..., :d], R(qkv)[..., d:2 * d], R(qkv)[..., 2 * d:]
+    else:
+        q_, k_, v_ = R(qkv), R(kv)[..., :d], R(kv)[..., d:]
+    orf = attn_ref(q_, k_, v_, R(pq).expand(B, -1, -1), R(pk).expand(B, -1, -1), R(table), idx, kpm, causal, scale, H)
+    orf.backward(do.float())
+    assert rel_l2(o, orf) <= 1e-2, (mode, Tq, Tk, variant)
+    for t in leaves:
+        assert rel_l2(t.grad, refs[id(t)].grad) <= 2e-2, (mode, Tq, Tk, variant, tuple(t.shape))
+
+
+def test_attention_legacy_kernels_agree():
+    """OFAB_ATTN_LEGACY keeps the mma.sync kernels reachable for A/B runs; structured position terms (no dense abs) still
+    take them (incremental decoding slices): both paths give the same numbers."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, H, T = 2, 2, 130
+    d = H * 64
+    qkv = rnd(B, T, 3 * d, gen=gen).requires_grad_(True)
+    pq = rnd(1, T, d, gen=gen)
+    pk = rnd(1, T, d, gen=gen)
+    table = rnd(37, H, gen=gen, scale=0.5)
+    idx = torch.randint(-1, 37, (T, T), generator=gen).to(torch.int32).to(dev())
+    o1 = ops.attention(qkv, None, H, 0.1, ops.PositionBias(pq, pk, idx, table), None, True)  # structured: mma.sync kernels
+    o2 = ops.attention(qkv, None, H, 0.1, ops.PositionBias(pq, pk, idx, table, abs=ops.abs_pos(pq, pk, H)), None, True)  # dense: tcgen05
+    assert rel_l2(o2, o1) <= 6e-3
 
 
 # ------------------------------------------------------------------------------- embed / CE
