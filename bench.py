@@ -598,6 +598,29 @@ def run_gpu(args, rank, world, local_rank):
         os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
         json.dump(out, open(os.path.join(ROOT, "gpurun_out", "breakdown.json"), "w"), indent=1)
 
+    # ---- the other BASELINE.json workloads (configs[2..4]: ASR, co-training, OFA-large video + grounding), same method, at
+    # this N -- every rank runs them (their steps end with the gradient exchange); see workloads.py
+    extra, dp_check = [], None
+    if not args.no_workloads:
+        import workloads as wl
+
+        state.clear()
+        del model, params
+        torch.cuda.empty_cache()
+        pk = peaks()
+        for nm in args.workloads.split(","):
+            try:
+                r = wl.run_workload(nm, dev, steps=max(3, min(args.steps, 5)), warmup=3, world=world)
+                r["model_frac_of_bf16_peak"] = r["model_tflops_per_gpu"] / pk["tf_sustained"]
+            except Exception as ex:
+                r = {"workload": nm, "error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+                torch.cuda.synchronize()
+            extra.append(r)
+        try:  # model-level data-parallel gate: N-rank gradients == one process on the concatenated batch
+            dp_check = wl.dp_equality_check(dev, world, rank)
+        except Exception as ex:
+            dp_check = {"ok": False, "error": f"{type(ex).__name__}: {str(ex)[:300]}"}
+
     if rank == 0:
         cpu = None
         if not args.no_cpu:
@@ -628,6 +651,8 @@ def run_gpu(args, rank, world, local_rank):
             "roofline": roof,
             "optimizer_step": optim_rec,
             "cpu_baseline": cpu,
+            "workloads": extra,
+            "dp_check": dp_check,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -646,6 +671,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     ap.add_argument("--no-overlap", action="store_true", help="N>1: average all gradients after the whole backward (no split)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--no-workloads", action="store_true", help="headline workload only (skip the configs[2..4] lines and the data-parallel gate)")
+    ap.add_argument("--workloads", default="asr,cotrain,large", help="comma-separated extra workloads (workloads.py)")
     ap.add_argument("--no-pdl", action="store_true", help="launch without programmatic dependent launch (A/B of the kernel-boundary overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -237,9 +237,9 @@ __device__ __forceinline__ void load_bias_raw(const __half* __restrict__ row, in
     if (row_ok && c + 8 * v < ld) u[v] = __ldg(reinterpret_cast<const uint4*>(row + c + 8 * v));
   }
 }
-__device__ __forceinline__ float bias_at(const uint4* u, int j) {  // element j of the raw chunk, times log2(e)
+__device__ __forceinline__ float bias_at(const uint4* u, int j) {  // element j of the raw chunk (the tile is stored in the log2 domain)
   const __half* h = reinterpret_cast<const __half*>(u);
-  return __half2float(h[j]) * kLog2e;
+  return __half2float(h[j]);
 }
 
 // Column sums over the warp's 32 rows of v[32] (one row per lane): a transpose-reduce of 31 shuffles; afterwards lane l
@@ -273,29 +273,93 @@ __device__ __forceinline__ void tile_colsum_out(float (&lo)[32], float (&hi)[32]
 }
 
 // ===================================================================================== forward
-// TMEM columns: S (fp32 scores; the bf16 probabilities are written over its first half) [0, 128) | O (fp32, accumulates P V over
-// the key blocks) [128, 192).
-// Online softmax over 128-key blocks with LAZY rescaling: probabilities are taken relative to a reference maximum m_ref that
-// is only raised -- and the O accumulator in TMEM rescaled -- when a block's maximum exceeds it by more than 2^8 (the row sum
-// and O then simply carry a common factor <= 256, exact after the final division).  With OFA's score ranges that happens in
-// the first block only, so the per-block work of a row is: one pass for the maximum, one pass of ex2, no output traffic.
+// TMEM columns: S0 | S1 (fp32 scores of the even / odd 64-key block) [0, 128) | P0 | P1 (their bf16 probabilities, the A operand
+// of P V) [128, 192) | O (fp32, accumulates P V over all key blocks) [192, 256).
+// The MMA warp runs one block ahead: S(kb+1) = Q K^T is issued before it waits for the probabilities of block kb, so the
+// tensor core works on the next scores while the softmax warps exponentiate the current ones; P V of block kb overlaps the
+// softmax of block kb+1.
+// Online softmax with LAZY, OPTIMISTIC rescaling: probabilities are taken relative to a reference maximum m_ref fixed by
+// the first block; later blocks are exponentiated in ONE pass against it while their maximum is tracked on the side, and
+// only if that exceeds m_ref by more than 2^8 is the reference raised, the O accumulator in TMEM rescaled and the block
+// redone (the scores are still in TMEM).  Otherwise the row sum and O simply carry a common factor <= 256, exact after
+// the final division.  With OFA's score ranges the redo path is taken (almost) never.
+template <bool MASKED, bool HAS_BIAS, bool DROP>
+__device__ __forceinline__ void fwd_chunk(const uint32_t (&r)[32], const uint4* bu, float c2, float m_use, uint32_t km, bool causal, int col0, int i,
+                                          float& mx, float& ls, uint32_t (&pk)[16], const uint2 dkey, const TcDrop& drop, int Tk) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    float pe[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      float x = fmaf(__uint_as_float(r[j + e]), c2, -m_use);  // relative to the reference maximum
+      if (HAS_BIAS) x += bias_at(bu, j + e);
+      if (MASKED) {
+        bool ok = (km >> (j + e)) & 1u;
+        if (causal) ok = ok && (col0 + j + e <= i);
+        x = ok ? x : -INFINITY;
+      }
+      mx = fmaxf(mx, x);
+      pe[e] = fast_ex2(x);
+    }
+    ls += pe[0] + pe[1];
+    if (DROP) {  // the row sum is that of the undropped probabilities; only P V sees the mask
+      const uint32_t ij = (uint32_t)i * (uint32_t)Tk + (uint32_t)(col0 + j);
+      pe[0] = tc_keep(dkey, ij, drop.thresh32) ? pe[0] * drop.inv_keep : 0.f;
+      pe[1] = tc_keep(dkey, ij + 1u, drop.thresh32) ? pe[1] * drop.inv_keep : 0.f;
+    }
+    pk[j >> 1] = pack_bf16(pe[0], pe[1]);
+  }
+}
+
+// Rare path of the forward kernel: the block's maximum exceeded the reference by more than 2^8 for some row of this warp.
+// Rescale the row sum and this warp's rows of the O accumulator to the new reference and exponentiate the block again
+// (its scores are still in TMEM).  Not inlined: keeps the common path's register budget small.
+template <bool HAS_BIAS, bool DROP>
+__device__ __noinline__ void fwd_redo_block(uint32_t tS, uint32_t tP, uint32_t tO, int nch, const __half* brow, const TcParams& p, float c2,
+                                            float m_ref, float m_new, uint32_t km0, uint32_t km1, int k0, int i, bool row_ok, float& l_run,
+                                            float& ls, const uint2 dkey) {
+  const float corr = (m_new != m_ref) ? fast_ex2(m_ref - m_new) : 1.0f;  // m_ref = -inf -> 0 (its O row and l are 0 anyway)
+#pragma unroll 1
+  for (int hf = 0; hf < 2; ++hf) {
+    uint32_t o[32];
+    tmem_ld32(tO + hf * 32, o);
+#pragma unroll
+    for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
+    tmem_st32(tO + hf * 32, o);
+  }
+  l_run *= corr;
+  const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
+  float mx = -INFINITY;
+  ls = 0.f;
+#pragma unroll 1
+  for (int ch = 0; ch < nch; ++ch) {
+    uint32_t r[32], pk[16];
+    uint4 bu[HAS_BIAS ? 4 : 1];
+    if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0 + ch * 32, p.bias_ld, row_ok, bu);
+    tmem_ld32(tS + ch * 32, r);
+    fwd_chunk<true, HAS_BIAS, DROP>(r, bu, c2, m_use, ch == 0 ? km0 : km1, p.causal, k0 + ch * 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
+    tmem_st16(tP + ch * 16, pk);
+  }
+}
+
 template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const TcParams p) {
-  constexpr int BM = 128, BN = 128, STAGES = 2;
+  constexpr int BM = 128, BN = 64, STAGES = 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sQ = smem;                              // 128 x 128 B
-  uint8_t* sK = sQ + BM * 128;                     // STAGES x (128 x 128 B)
-  uint8_t* sV = sK + STAGES * BN * 128;            // STAGES x (128 x 128 B)
+  uint8_t* sK = sQ + BM * 128;                     // STAGES x (64 x 128 B)
+  uint8_t* sV = sK + STAGES * BN * 128;            // STAGES x (64 x 128 B)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * BN * 128);
   uint64_t* q_full = bars;                         // 1
   uint64_t* full = bars + 1;                       // STAGES
   uint64_t* empty = full + STAGES;                 // STAGES
-  uint64_t* s_full = empty + STAGES;               // S = Q K^T of the block is in TMEM (and every earlier P V has retired)
-  uint64_t* p_ready = s_full + 1;                  // the block's P is in TMEM, O rescaled if needed (4 warp arrivals)
-  uint64_t* o_done = p_ready + 1;                  // the last P V has retired
+  uint64_t* s_full = empty + STAGES;               // [2] S(kb) is in TMEM buffer kb & 1
+  uint64_t* p_ready = s_full + 2;                  // [2] P(kb) is in TMEM buffer kb & 1 (4 warp arrivals)
+  uint64_t* pv_done = p_ready + 2;                 // one completion per P V product (waited for only before a rescale)
+  uint64_t* o_done = pv_done + 1;                  // the last P V has retired
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
   uint32_t* kmask_s = tmem_ptr + 2;
 
@@ -316,8 +380,11 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
       mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_ready, 4);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(s_full + i, 1);
+      mbar_init(p_ready + i, 4);
+    }
+    mbar_init(pv_done, 1);
     mbar_init(o_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -331,7 +398,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const uint32_t tmem_S = tmem_base, tmem_O = tmem_base + 128;
+  const uint32_t tmem_S = tmem_base, tmem_P = tmem_base + 128, tmem_O = tmem_base + 192;
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -357,25 +424,33 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     mbar_wait(q_full, 0);
     tc_fence_after();
     const uint32_t q_addr = smem_u32(sQ);
-    for (int kb = 0; kb < nkb; ++kb) {
+    auto issue_s = [&](int kb) {  // S(kb) = Q K(kb)^T into score buffer kb & 1
       const int st = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      const int n = min(BN, ((p.Tk - kb * BN) + 15) & ~15);  // keys of this block rounded up to the UMMA N granularity
-      mbar_wait(full + st, ph);
+      mbar_wait(full + st, (kb / STAGES) & 1);
       tc_fence_after();
-      const uint32_t k_addr = smem_u32(sK + st * BN * 128), v_addr = smem_u32(sV + st * BN * 128);
       if (issuer) {
+        const int n = min(BN, ((p.Tk - kb * BN) + 15) & ~15);  // keys of this block rounded up to the UMMA N granularity
         const uint32_t idesc = make_idesc(n, false);
+        const uint32_t k_addr = smem_u32(sK + st * BN * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_S, sdesc(q_addr + k * 32), sdesc(k_addr + k * 32), idesc, k != 0);
-        umma_commit(s_full);  // (tracks every MMA issued so far: when it fires, the previous block's P V has retired too)
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_S + (kb & 1) * BN, sdesc(q_addr + k * 32), sdesc(k_addr + k * 32), idesc, k != 0);
+        umma_commit(s_full + (kb & 1));  // (tracks every MMA issued so far)
       }
       __syncwarp();
-      mbar_wait(p_ready, kb & 1);
+    };
+    issue_s(0);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int st = kb % STAGES;
+      if (kb + 1 < nkb) issue_s(kb + 1);  // its buffer was freed by P(kb-1), which this warp has already waited for
+      mbar_wait(p_ready + (kb & 1), (kb >> 1) & 1);
       tc_fence_after();
       if (issuer) {
+        const int n = min(BN, ((p.Tk - kb * BN) + 15) & ~15);
         const uint32_t idesc = make_idesc(64, true);
-        for (int ks = 0; ks < n / 16; ++ks) umma_ts(tmem_O, tmem_S + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, (kb | ks) != 0);
+        const uint32_t v_addr = smem_u32(sV + st * BN * 128);
+        for (int ks = 0; ks < n / 16; ++ks)
+          umma_ts(tmem_O, tmem_P + (kb & 1) * (BN / 2) + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, (kb | ks) != 0);
+        umma_commit(pv_done);
         umma_commit(empty + st);
         if (kb == nkb - 1) umma_commit(o_done);
       }
@@ -396,98 +471,72 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kb * BN;
       const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
-      const int nch = (n + 31) >> 5;
+      const int nch = (n + 31) >> 5;  // 1 or 2 chunks of 32 columns
+      const uint32_t tS = tmem_S + lane_addr + (kb & 1) * BN, tP = tmem_P + lane_addr + (kb & 1) * (BN / 2);
+      const bool diag = p.causal && (k0 + BN - 1 > q0);  // some (i, j) of this tile may have j > i
       uint4 bu[2][HAS_BIAS ? 4 : 1];
-      if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);  // in flight while the MMAs run
-      mbar_wait(s_full, kb & 1);
+      if constexpr (HAS_BIAS) {  // in flight while the MMAs run
+        load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);
+        if (nch > 1) load_bias_raw<4>(brow, k0 + 32, p.bias_ld, row_ok, bu[1]);
+      }
+      const uint32_t km0 = kmask_s[k0 >> 5], km1 = kmask_s[(k0 >> 5) + 1];
+      const bool masked0 = diag || km0 != 0xffffffffu, masked1 = diag || km1 != 0xffffffffu;
+      mbar_wait(s_full + (kb & 1), (kb >> 1) & 1);
       tc_fence_after();
-      uint32_t r[2][32];
-      // ---- pass 1: block maximum of x = log2(e) * (scale * s + bias) over the visible keys
-      float mx = -INFINITY;
-      tmem_ld32_nowait(tmem_S + lane_addr, r[0]);
+      uint32_t r0[32], r1[32];
+      tmem_ld32_nowait(tS, r0);
+      if (nch > 1) tmem_ld32_nowait(tS + 32, r1);
+      tmem_ld_wait();
+      if (kb == 0) {  // the first block fixes the reference maximum
+        float mx = -INFINITY;
 #pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < nch) {
-          const int c0 = ch * 32;
-          tmem_ld_wait();
-          if (ch + 1 < nch) {
-            tmem_ld32_nowait(tmem_S + lane_addr + c0 + 32, r[(ch + 1) & 1]);
-            if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0 + c0 + 32, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
-          }
-          const uint32_t km = kmask_s[(k0 + c0) >> 5];
+        for (int j = 0; j < 32; ++j) {
+          float x = __uint_as_float(r0[j]) * c2;
+          if (HAS_BIAS) x += bias_at(bu[0], j);
+          bool ok = (km0 >> j) & 1u;
+          if (p.causal) ok = ok && (k0 + j <= i);
+          mx = fmaxf(mx, ok ? x : -INFINITY);
+        }
+        if (nch > 1) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[ch & 1][j]) * c2;
-            if (HAS_BIAS) x += bias_at(bu[ch & 1], j);
-            bool ok = (km >> j) & 1u;
-            if (p.causal) ok = ok && (k0 + c0 + j <= i);
+            float x = __uint_as_float(r1[j]) * c2;
+            if (HAS_BIAS) x += bias_at(bu[1], j);
+            bool ok = (km1 >> j) & 1u;
+            if (p.causal) ok = ok && (k0 + 32 + j <= i);
             mx = fmaxf(mx, ok ? x : -INFINITY);
           }
         }
+        m_ref = mx;
       }
-      // ---- reference maximum: raise it (and rescale l and the O accumulator) only when the block exceeds it by > 2^8
-      const float m_cand = fmaxf(m_ref, mx);
-      const bool raise = m_cand > m_ref + 8.0f || (m_ref == -INFINITY && m_cand != -INFINITY);
-      if (kb == 0) {
-        m_ref = m_cand;
-      } else if (__any_sync(0xffffffffu, raise)) {  // warp-uniform: the TMEM accesses below are collective
-        const float corr = raise ? fast_ex2(m_ref - m_cand) : 1.0f;  // m_ref = -inf -> 0 (its O row and l are 0 anyway)
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          uint32_t o[32];
-          tmem_ld32(tmem_O + lane_addr + hf * 32, o);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * corr);
-          tmem_st32(tmem_O + lane_addr + hf * 32, o);
+      {
+        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+        float mx = -INFINITY, ls = 0.f;  // mx: block maximum RELATIVE to m_use
+        uint32_t pk[16];
+        if (masked0) fwd_chunk<true, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
+        else fwd_chunk<false, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
+        tmem_st16(tP, pk);
+        if (nch > 1) {
+          if (masked1) fwd_chunk<true, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
+          else fwd_chunk<false, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
+          tmem_st16(tP + 16, pk);
         }
-        l_run *= corr;
-        if (raise) m_ref = m_cand;
-      }
-      const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-      // ---- pass 2: probabilities -> bf16 pairs over the first half of the score columns (the A operand of P V)
-      float ls = 0.f;
-      if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);  // (L1 / L2 hits: read in pass 1)
-      tmem_ld32_nowait(tmem_S + lane_addr, r[0]);
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) {
-        if (ch < nch) {
-          const int c0 = ch * 32;
-          uint32_t pk[16];
-          tmem_ld_wait();
-          if (ch + 1 < nch) {
-            tmem_ld32_nowait(tmem_S + lane_addr + c0 + 32, r[(ch + 1) & 1]);
-            if constexpr (HAS_BIAS) load_bias_raw<4>(brow, k0 + c0 + 32, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
-          }
-          const uint32_t km = kmask_s[(k0 + c0) >> 5];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float pe[2];
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              float x = fmaf(__uint_as_float(r[ch & 1][j + e]), c2, -m_use);
-              if (HAS_BIAS) x += bias_at(bu[ch & 1], j + e);
-              bool ok = (km >> (j + e)) & 1u;
-              if (p.causal) ok = ok && (k0 + c0 + j + e <= i);
-              pe[e] = ok ? fast_ex2(x) : 0.f;
-            }
-            ls += pe[0] + pe[1];
-            if (DROP) {  // the row sum is that of the undropped probabilities; only P V sees the mask
-              const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
-              pe[0] = tc_keep(dkey, ij, p.drop.thresh32) ? pe[0] * p.drop.inv_keep : 0.f;
-              pe[1] = tc_keep(dkey, ij + 1u, p.drop.thresh32) ? pe[1] * p.drop.inv_keep : 0.f;
-            }
-            pk[j >> 1] = pack_bf16(pe[0], pe[1]);
-          }
-          // P chunk ch lands on score columns [16 ch, 16 ch + 16): chunks 0 / 1 are in registers or consumed, the chunk being
-          // prefetched (ch + 1) starts at column 32 (ch + 1) >= 16 ch + 16
-          tmem_st16(tmem_S + lane_addr + (c0 >> 1), pk);
+        // optimistic pass done: was the reference maximum still good for every row of this warp?
+        const bool raise = kb > 0 && (mx > 8.0f || (m_ref == -INFINITY && mx != -INFINITY));
+        if (__any_sync(0xffffffffu, raise)) {  // rare (warp-uniform: the TMEM accesses of the redo are collective)
+          // every earlier P V must have retired: pv_done has completed kb - 1 or kb times here (s_full(kb) implies P V(kb-2))
+          mbar_wait(pv_done, (kb - 1) & 1);
+          tc_fence_after();
+          const float m_new = raise ? m_use + mx : m_ref;
+          fwd_redo_block<HAS_BIAS, DROP>(tS, tP, tmem_O + lane_addr, nch, brow, p, c2, m_ref, m_new, km0, km1, k0, i, row_ok, l_run, ls, dkey);
+          m_ref = m_new;
         }
+        l_run += ls;
       }
-      l_run += ls;
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready);
+      if (lane == 0) mbar_arrive(p_ready + (kb & 1));
     }
     mbar_wait(o_done, 0);
     tc_fence_after();
@@ -514,6 +563,31 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(256));
+  }
+}
+
+// One 16-column chunk of the dQ kernel: dS = P o (dP - delta) with P = ex2(x - lse), x in the log2 domain.
+// out_s: scale * dS (what dQ += dS K consumes); raw dS = out_s / scale is only needed for the bias gradient.
+template <bool MASKED, bool HAS_BIAS, bool DROP>
+__device__ __forceinline__ void dq_chunk(const uint32_t (&r)[16], const uint32_t (&d)[16], const uint4* bu, float c2, float lse2, float dls, float scale,
+                                         uint32_t km, bool causal, int col0, int i, float (&out_s)[16], const uint2 dkey, const TcDrop& drop, int Tk) {
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    float x = fmaf(__uint_as_float(r[j]), c2, -lse2);
+    if (HAS_BIAS) x += bias_at(bu, j);
+    float pe = fast_ex2(x);
+    float dp = __uint_as_float(d[j]);
+    if (DROP) {  // dP = keep / (1 - p) * dP_drop
+      const uint32_t ij = (uint32_t)i * (uint32_t)Tk + (uint32_t)(col0 + j);
+      dp = tc_keep(dkey, ij, drop.thresh32) ? dp * drop.inv_keep : 0.f;
+    }
+    float v = pe * fmaf(dp, scale, -dls);  // scale * P * (dP - delta)
+    if (MASKED) {  // (columns past the block's keys hold stale TMEM data: select, never multiply)
+      bool ok = (km >> j) & 1u;
+      if (causal) ok = ok && (col0 + j <= i);
+      v = ok ? v : 0.f;
+    }
+    out_s[j] = v;
   }
 }
 
@@ -652,6 +726,7 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
       p.delta[((int64_t)b * p.H + h) * p.Tq + i] = dl;
     }
     bf16* dsrow = (HAS_BIAS && p.ds != nullptr && row_ok) ? p.ds + (((int64_t)b * p.H + h) * p.Tq + i) * p.bias_ld : nullptr;
+    const float dls = dl * p.scale, inv_scale = 1.0f / p.scale;
     for (int kb = 0; kb < nkb; ++kb) {
       const int k0 = kb * BN;
       const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
@@ -674,35 +749,24 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
             tmem_ld16_nowait(tmem_dP + lane_addr + c0 + 16, d[(ch + 1) & 1]);
             if constexpr (HAS_BIAS) load_bias_raw<2>(brow, k0 + c0 + 16, p.bias_ld, row_ok, bu[(ch + 1) & 1]);
           }
-          const uint32_t km = kmask_s[(k0 + c0) >> 5] >> (c0 & 16);
-          float dsv[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float x = fmaf(__uint_as_float(r[ch & 1][j]), c2, -lse2);
-            if (HAS_BIAS) x += bias_at(bu[ch & 1], j);
-            bool ok = (km >> j) & 1u;
-            if (p.causal) ok = ok && (k0 + c0 + j <= i);
-            const float pe = ok ? fast_ex2(x) : 0.f;
-            float dp = __uint_as_float(d[ch & 1][j]);
-            if (DROP) {  // dP = keep / (1 - p) * dP_drop
-              const uint32_t ij = (uint32_t)i * (uint32_t)p.Tk + (uint32_t)(k0 + c0 + j);
-              dp = tc_keep(dkey, ij, p.drop.thresh32) ? dp * p.drop.inv_keep : 0.f;
-            }
-            dsv[j] = ok ? pe * (dp - dl) : 0.f;  // dS (columns past the block's keys hold stale TMEM data: select, never multiply)
-          }
+          const uint32_t km = (kmask_s[(k0 + c0) >> 5] >> (c0 & 16)) & 0xffffu;
+          const bool diag = p.causal && (k0 + c0 + 15 > q0);
+          float dsv[16];  // scale * dS
+          if (diag || km != 0xffffu) dq_chunk<true, HAS_BIAS, DROP>(r[ch & 1], d[ch & 1], bu[ch & 1], c2, lse2, dls, p.scale, km, p.causal, k0 + c0, i, dsv, dkey, p.drop, p.Tk);
+          else dq_chunk<false, HAS_BIAS, DROP>(r[ch & 1], d[ch & 1], bu[ch & 1], c2, lse2, dls, p.scale, km, p.causal, k0 + c0, i, dsv, dkey, p.drop, p.Tk);
           if (HAS_BIAS && dsrow != nullptr) {
 #pragma unroll
             for (int v = 0; v < 2; ++v) {
               if (k0 + c0 + 8 * v < p.bias_ld) {
                 f8 o8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o8.v[e] = dsv[8 * v + e];
+                for (int e = 0; e < 8; ++e) o8.v[e] = dsv[8 * v + e] * inv_scale;
                 store8(dsrow + k0 + c0 + 8 * v, o8);
               }
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16(dsv[j] * p.scale, dsv[j + 1] * p.scale);
+          for (int j = 0; j < 16; j += 2) pk[j >> 1] = pack_bf16(dsv[j], dsv[j + 1]);
           tmem_st8(tmem_S + lane_addr + (c0 >> 1), pk);  // columns [8 ch, 8 ch + 8): below every chunk still to be read
         }
       }
@@ -749,6 +813,44 @@ attn_tc_bwd_dq_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_co
   }
 }
 
+// One 16-column chunk of the dK/dV kernel on transposed scores: rows = keys, columns = queries (their lse * log2(e) and
+// scale * delta come from shared memory, broadcast reads).  out_p: P_drop^T (for dV), out_s: scale * dS^T (for dK).
+template <bool MASKED, bool HAS_BIAS, bool DROP>
+__device__ __forceinline__ void dkv_chunk(const uint32_t (&r)[16], const uint32_t (&d)[16], const uint4* bu, float c2, const float* __restrict__ lse2,
+                                          const float* __restrict__ dls, float scale, bool key_ok, bool causal, int qcol0, int jkey, int Tq,
+                                          float (&out_p)[16], float (&out_s)[16], const uint2 dkey, const TcDrop& drop, int Tk) {
+#pragma unroll
+  for (int e4 = 0; e4 < 16; e4 += 4) {
+    const float4 l4 = *reinterpret_cast<const float4*>(lse2 + e4);
+    const float4 d4 = *reinterpret_cast<const float4*>(dls + e4);
+    const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = e4 + u;
+      float x = fmaf(__uint_as_float(r[e]), c2, -lq[u]);
+      if (HAS_BIAS) x += bias_at(bu, e);
+      const float pe = fast_ex2(x);
+      float dp = __uint_as_float(d[e]);
+      float pv = pe;
+      if (DROP) {
+        const uint32_t ij = (uint32_t)(qcol0 + e) * (uint32_t)Tk + (uint32_t)jkey;
+        const bool keep = tc_keep(dkey, ij, drop.thresh32);
+        pv = keep ? pe * drop.inv_keep : 0.f;  // P_drop (dV = P_drop^T dO)
+        dp = keep ? dp * drop.inv_keep : 0.f;  // dP = keep / (1 - p) * dP_drop
+      }
+      float sv = pe * fmaf(dp, scale, -dq4[u]);  // scale * P * (dP - delta)
+      if (MASKED) {  // (stale TMEM columns: select, never multiply)
+        bool ok = key_ok && (qcol0 + e < Tq);
+        if (causal) ok = ok && (jkey <= qcol0 + e);
+        pv = ok ? pv : 0.f;
+        sv = ok ? sv : 0.f;
+      }
+      out_p[e] = pv;
+      out_s[e] = sv;
+    }
+  }
+}
+
 // ===================================================================================== backward: dK / dV
 // rows = 128 keys of the tile; loop over 64-query blocks on TRANSPOSED scores S^T[key, query].
 // TMEM columns: S^T / P^T [0, 64) | dP^T / dS^T [64, 128) | dK [128, 192) | dV [192, 256)
@@ -764,7 +866,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
   uint8_t* sQ = sV + BM * 128;                     // STAGES x (64 x 128 B)
   uint8_t* sDO = sQ + STAGES * BQ * 128;
   float* lse_s = reinterpret_cast<float*>(sDO + STAGES * BQ * 128);  // [STAGES][64] lse * log2(e) of the block's queries
-  float* dl_s = lse_s + STAGES * BQ;                                  // [STAGES][64] delta
+  float* dl_s = lse_s + STAGES * BQ;                                  // [STAGES][64] scale * delta
   uint64_t* bars = reinterpret_cast<uint64_t*>(dl_s + STAGES * BQ);
   uint64_t* kv_full = bars;
   uint64_t* full = bars + 1;
@@ -833,7 +935,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
         if (iq < p.Tq) {
           const float l = p.lse[((int64_t)b * p.H + h) * p.Tq + iq];
           if (l != -INFINITY) l2 = l * kLog2e;
-          dlv = p.delta[((int64_t)b * p.H + h) * p.Tq + iq];
+          dlv = p.delta[((int64_t)b * p.H + h) * p.Tq + iq] * p.scale;
         }
         lse_s[st * BQ + t * 32 + lane] = l2;
         dl_s[st * BQ + t * 32 + lane] = dlv;
@@ -886,7 +988,7 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
     const __half* brow = HAS_BIAS ? p.bias_t + (int64_t)h * p.bias_t_hs + (int64_t)(row_ok ? j : 0) * p.bias_t_ld : nullptr;
     uint2 dkey = make_uint2(0u, 1u);
     if (DROP) dkey = tc_drop_key(p.drop, b * p.H + h);
-    const float ik = DROP ? p.drop.inv_keep : 1.0f;
+    const bool warp_keys_ok = __all_sync(0xffffffffu, key_ok);
     for (int qb = qb0; qb < nqb; ++qb) {
       const int it = qb - qb0;
       const int st = it % STAGES;
@@ -914,32 +1016,10 @@ attn_tc_bwd_dkv_kernel(const __grid_constant__ CUtensorMap map_k, const __grid_c
             if constexpr (HAS_BIAS) load_bias_raw<2>(brow, q0 + c0 + 16, p.bias_t_ld, row_ok, bu[(ch + 1) & 1]);
           }
           float pv[16], dsv[16];
-#pragma unroll
-          for (int e4 = 0; e4 < 16; e4 += 4) {
-            const float4 l4 = *reinterpret_cast<const float4*>(lse2 + c0 + e4);  // broadcast reads (same address in every lane)
-            const float4 d4 = *reinterpret_cast<const float4*>(dls + c0 + e4);
-            const float lq[4] = {l4.x, l4.y, l4.z, l4.w}, dq4[4] = {d4.x, d4.y, d4.z, d4.w};
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const int e = e4 + u;
-              const int iq = q0 + c0 + e;
-              float x = fmaf(__uint_as_float(r[ch & 1][e]), c2, -lq[u]);
-              if (HAS_BIAS) x += bias_at(bu[ch & 1], e);
-              bool ok = key_ok && iq < p.Tq;
-              if (p.causal) ok = ok && (j <= iq);
-              const float pe = ok ? fast_ex2(x) : 0.f;
-              float dp = __uint_as_float(d[ch & 1][e]);
-              float pvv = pe;
-              if (DROP) {
-                const uint32_t ij = (uint32_t)iq * (uint32_t)p.Tk + (uint32_t)j;
-                const bool keep = tc_keep(dkey, ij, p.drop.thresh32);
-                pvv = keep ? pe * ik : 0.f;  // P_drop (dV = P_drop^T dO)
-                dp = keep ? dp * ik : 0.f;   // dP = keep / (1 - p) * dP_drop
-              }
-              pv[e] = ok ? pvv : 0.f;  // (stale TMEM columns: select, never multiply)
-              dsv[e] = ok ? pe * (dp - dq4[u]) * p.scale : 0.f;  // scale * dS^T
-            }
-          }
+          // fast path: every key row of this warp valid, every query column of the chunk < Tq, no causal diagonal
+          const bool masked = !warp_keys_ok || (q0 + c0 + 16 > p.Tq) || (p.causal && (k0 + BM - 1 > q0 + c0));
+          if (masked) dkv_chunk<true, HAS_BIAS, DROP>(r[ch & 1], d[ch & 1], bu[ch & 1], c2, lse2 + c0, dls + c0, p.scale, key_ok, p.causal, q0 + c0, j, p.Tq, pv, dsv, dkey, p.drop, p.Tk);
+          else dkv_chunk<false, HAS_BIAS, DROP>(r[ch & 1], d[ch & 1], bu[ch & 1], c2, lse2 + c0, dls + c0, p.scale, key_ok, p.causal, q0 + c0, j, p.Tq, pv, dsv, dkey, p.drop, p.Tk);
 #pragma unroll
           for (int e = 0; e < 16; e += 2) {
             pp[e >> 1] = pack_bf16(pv[e], pv[e + 1]);
@@ -1026,6 +1106,7 @@ __global__ void attn_bias_build_kernel(const float* __restrict__ abs, int abs_ld
         if (id >= 0) v += (float)table[(int64_t)id * H + h];
       }
     }
+    v *= kLog2e;  // the attention kernels work in the log2 domain: p = ex2(x)
     tile[r][tx] = v;
     if (i < Tq && j < ld) out[((int64_t)h * Tq + i) * ld + j] = __float2half_rn(v);
   }
@@ -1176,8 +1257,8 @@ int ofab_attn_tc_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) {
   if (!make_map3(&mq, a->q, a->H * 64, a->Tq, a->B, a->q_rs, a->q_bs, 128)) return 1;
   if (!make_map3(&mk, a->k, a->H * 64, a->Tk, a->B, a->k_rs, a->k_bs, 128)) return 1;
   if (!make_map3(&mv, a->v, a->H * 64, a->Tk, a->B, a->v_rs, a->v_bs, 128)) return 1;
-  const int nkb = (a->Tk + 127) / 128;
-  const int smem = 1024 + 128 * 128 + 2 * 2 * 128 * 128 + 16 * 8 + 16 + nkb * 4 * 4;
+  const int nkb = (a->Tk + 63) / 64;
+  const int smem = 1024 + 128 * 128 + 2 * 4 * 64 * 128 + 16 * 8 + 16 + (nkb + 1) * 2 * 4;
   dim3 grid((a->Tq + 127) / 128, a->H, a->B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool hb = a->bias != nullptr;

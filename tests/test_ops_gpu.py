@@ -792,6 +792,20 @@ def test_dp_nccl_two_gpus():
     assert "DP_NCCL_OK" in r.stdout
 
 
+def test_dp_model_equality():
+    """Model-level data-parallel gate: N-rank gradients after the exchange and the trainer's rescale == one
+    process on the concatenated batch, incl. an adaptor no batch touches.  Uses every visible GPU (a 1-GPU box runs world
+    size 1: the exchange is then the identity and the check covers the wrapper + rescale arithmetic)."""
+    import subprocess, sys, os
+
+    n = max(1, min(torch.cuda.device_count(), 8))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", "29537", os.path.join(root, "tests", "dp_model_worker.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "DP_MODEL_OK" in r.stdout, r.stdout[-2000:]
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 def test_video_frames_and_zero_mask(dtype):
     """clip -> frames transpose + the reference's all-zero-frame padding test (bit-exact)."""

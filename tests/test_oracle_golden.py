@@ -95,6 +95,55 @@ def test_full_size_configs(name):
             assert abs(grads[k].double().norm().item() - st[2].item()) <= 2e-4 * st[2].item() + 1e-6, k
 
 
+@pytest.mark.parametrize("name", ["cfg2_base", "cfg3_asr_base"])
+def test_full_gradient_probes_of_the_oracle(name):
+    """the FULL gradient tensors of the oracle against the reference's seeded samples / projections (positions and signs)"""
+    g = load(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    slots, target = cases.make_inputs(name)
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    _, _, grads = om.loss_and_grads(sd, cases.oracle_cfg(name), slots, target)
+    _check_probes(g, grads)
+
+
+def _check_probes(g, grads):
+    n = 0
+    tot = sum(st[2].item() ** 2 for st in g["grad_stats"].values() if st is not None) ** 0.5
+    for k, ref_s in g["grad_samples"].items():
+        norm = g["grad_stats"][k][2].item()
+        if norm <= 1e-6 * tot:  # k_proj.bias gradients are mathematically 0 (softmax shift invariance): rounding noise
+            continue
+        smp, prj = cases.grad_probes(k, grads[k])
+        rms = max(norm / grads[k].numel() ** 0.5, 1e-12)
+        assert ((smp.double() - ref_s.double()).pow(2).mean().sqrt() / rms).item() <= 1e-3, k
+        assert ((prj - g["grad_proj"][k]).abs().max() / max(norm, 1e-9)).item() <= 1e-3, k
+        n += 1
+    assert n > 50
+
+
+@pytest.mark.parametrize("name", ["cfg4_cotrain_base"] + (["cfg5_large_grounding", "cfg5_large_video"] if os.environ.get("OFAB_SLOW_TESTS") == "1" else []))
+def test_full_size_multitask_oracle(name):
+    """BASELINE.json configs[3] (co-training: caption + VQA + text_infilling batches of one step, gradients accumulated) at
+    full OFA-base size against the dump of the unmodified reference (oracle/make_golden_full.py).  The OFA-large configs[4]
+    cases (24L/12L, S = 1040 / 3144; minutes and tens of GB on CPU) run with OFAB_SLOW_TESTS=1."""
+    g = load(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    cfg = cases.oracle_cfg(name)
+    torch.set_num_threads(max(1, min(8, os.cpu_count() or 1)))
+    total = None
+    for (slots, target), gt in zip(cases.make_task_inputs(name), g["tasks"]):
+        loss, logits, grads = om.loss_and_grads(sd, cfg, slots, target)
+        assert int((target != 1).sum()) == gt["ntokens"]
+        assert abs(loss.item() - gt["loss"].item()) <= 1e-5 * abs(gt["loss"].item())
+        assert rel_l2(torch.logsumexp(logits, -1), gt["lse"]) <= 1e-5
+        assert rel_l2(logits[..., gt["logit_cols"]], gt["logits_sampled"]) <= 2e-5
+        total = grads if total is None else {k: total[k] + grads[k] for k in total}
+    for k, st in g["grad_stats"].items():
+        if st is not None:
+            assert abs(total[k].double().norm().item() - st[2].item()) <= 2e-4 * st[2].item() + 1e-6, k
+    _check_probes(g, total)
+
+
 def test_optimizer_oracle_matches_reference_adam():
     """oracle_optim.update (restatement of multiply_grads -> clip_grad_norm -> fp32 Adam -> bf16 copy) against the
     outputs of the reference's own Adam.step / clip_grad_norm_ (tests/golden/optim_adam.pt, oracle/make_golden_optim.py)."""

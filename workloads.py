@@ -252,3 +252,69 @@ if __name__ == "__main__":  # python workloads.py asr cotrain large   (1 GPU pro
             r = {"workload": nm, "error": f"{type(ex).__name__}: {ex}"}
             torch.cuda.synchronize()
         print(json.dumps(r), flush=True)
+
+
+def dp_equality_check(dev, world, rank):
+    """Data-parallel correctness gate (reference semantics engine/trainer.py:857-860): the gradients every rank
+    holds after `all_reduce_grads()` and the trainer's `world_size / sum(ntokens)` rescale equal the gradients ONE process
+    computes on the concatenated batch, divided by the total token count.  Text-only Mode A model with an audio adaptor that no
+    batch touches (unused parameters contribute zeros).  Runs on every rank; returns {"rel_l2", "worst", "ok"}."""
+    import torch.distributed as dist
+
+    import ofasys_b200 as ob
+    from ofasys_b200.distributed import DataParallelModel
+
+    cfg = ob.GeneralistModelConfig.default()
+    cfg.dropout = cfg.attention_dropout = 0.0
+    m = ob.GeneralistModel(cfg)  # tiny: 4L/4L d=256 H=4
+    for ad in ("text", "audio_fbank"):
+        getattr(m.cfg.adaptor, ad).is_active = True
+    torch.manual_seed(0)
+    V = 1000
+    m.initialize(ob.Dictionary(n_dummy=V - 4))
+    m = m.to(torch.bfloat16).to(dev).train()
+    model = DataParallelModel(m)
+    MT = ob.ModalityType
+
+    def shard(r):
+        g = torch.Generator().manual_seed(4242 + r)
+        B, S, T = 3, 20, 12
+        src = torch.randint(4, V, (B, S), generator=g)
+        src[-1, S - 5:] = 1
+        prev, tgt = _prev_target(g, B, T, V)
+        return src, prev, tgt
+
+    def run(src, prev, tgt):
+        for p in m.parameters():
+            p.grad = None
+        loss = model.module.forward_loss([ob.Slot(MT.TEXT, True, src.to(dev)), ob.Slot(MT.TEXT, False, prev.to(dev))], tgt.to(dev))
+        loss.backward()
+        return int((tgt != 1).sum())
+
+    ntok = run(*shard(rank))
+    model.all_reduce_grads()
+    tot = torch.tensor([float(ntok)], device=dev)
+    if world > 1:
+        dist.all_reduce(tot)
+    got = {k: (torch.zeros_like(p) if p.grad is None else p.grad.float() * (world / tot.item())) for k, p in m.named_parameters()}
+    parts = [shard(r) for r in range(world)]
+    n_all = run(*(torch.cat([p[i] for p in parts], 0) for i in range(3)))
+    assert n_all == int(tot.item())
+    num = den = 0.0
+    worst = ("", 0.0)
+    for k, p in m.named_parameters():
+        want = torch.zeros_like(p).float() if p.grad is None else p.grad.float() / n_all
+        num += (got[k] - want).pow(2).sum().item()
+        den += want.pow(2).sum().item()
+        nrm = want.norm().item()
+        if nrm > 1e-3 * (den ** 0.5 + 1e-30):
+            e = ((got[k] - want).norm() / nrm).item()
+            if e > worst[1]:
+                worst = (k, e)
+    unused_zero = all(not got[k].any() for k in got if "audio_fbank" in k)
+    e = (num / max(den, 1e-30)) ** 0.5
+    for p in m.parameters():
+        p.grad = None
+    return {"what": f"{world}-rank gradients after all_reduce_grads() x world/sum(ntokens) vs one process on the concatenated batch",
+            "rel_l2": e, "worst_param": worst[0], "worst_rel_l2": worst[1], "unused_adaptor_grads_zero": bool(unused_zero),
+            "ok": bool(e <= 2e-2 and worst[1] <= 6e-2 and unused_zero)}
