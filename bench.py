@@ -228,12 +228,24 @@ def run_gpu(args, rank, world, local_rank):
         loss.backward()
         return loss
 
-    from ofasys_b200.distributed import GradBuckets
+    from ofasys_b200.distributed import GradArena, GradBuckets
 
-    # N > 1: the backward is cut at the encoder/decoder boundary; the decoder-side gradients are averaged (NCCL, side
-    # stream) while the encoder backward runs, the rest after it.  N == 1: one graph, no exchange.
-    split = world > 1 and not args.no_overlap
+    # N > 1, default (--dp arena): the weight-gradient GEMMs write straight into one flat gradient arena (no pack / unpack
+    # copies); it is cut into 64 MB buckets in backward order and every bucket is all-reduced (NCCL over NVLink, side stream)
+    # as soon as its last gradient exists, while the rest of the backward runs -- the whole step incl. the collectives is ONE
+    # CUDA graph.  --dp split: the older scheme (backward cut at the encoder/decoder boundary, flat buckets packed by a
+    # multi-tensor copy).  N == 1: one graph, no exchange.
+    arena = GradArena(params) if (world > 1 and args.dp == "arena") else None
+    split = world > 1 and args.dp == "split"
     side = torch.cuda.Stream()
+    fwd_bwd_local = fwd_bwd  # no collectives: what the rank-0-only roofline / breakdown sections run
+    if arena is not None:
+        def fwd_bwd():  # noqa: F811  (the data-parallel step: exchange included)
+            arena.begin_step()
+            loss = model.forward_loss(to_slots(db), db["tgt"])
+            loss.backward()
+            arena.finish()
+            return loss
 
     def fwd_bwd_begin():
         for p in params:
@@ -301,7 +313,7 @@ def run_gpu(args, rank, world, local_rank):
                 loss = state["loss"]
             else:
                 loss = fwd_bwd()
-            if world > 1:  # unoverlapped exchange (--no-overlap)
+            if world > 1 and arena is None:  # unoverlapped exchange (--dp plain)
                 if buckets is None:
                     buckets = GradBuckets(params)
                 buckets.allreduce()
@@ -413,15 +425,17 @@ def run_gpu(args, rank, world, local_rank):
                 spec = (a[0], a[1], a[2], a[4], a[5], a[7], a[8], False, False, 0, a[10], a[11], True)
             recs.append((2.0 * a[0] * a[1] * a[2], s, e, spec))
 
+        if arena is not None:
+            arena.enabled = False  # the replays below are local (no collectives, no arena slots)
         _lib.call = call
         try:
             for _ in range(2):
-                fwd_bwd()
+                fwd_bwd_local()
             torch.cuda.synchronize()
             recs.clear()
             n_eager = max(2, min(args.steps, 5))
             for _ in range(n_eager):
-                fwd_bwd()
+                fwd_bwd_local()
             torch.cuda.synchronize()
         finally:
             _lib.call = orig
@@ -575,13 +589,13 @@ def run_gpu(args, rank, world, local_rank):
 
         _lib.call = call_all
         try:
-            fwd_bwd()
+            fwd_bwd_local()
             torch.cuda.synchronize()
             recs.clear()
             t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
             t0.record()
             for _ in range(3):
-                fwd_bwd()
+                fwd_bwd_local()
             t1.record()
             torch.cuda.synchronize()
         finally:
@@ -605,6 +619,8 @@ def run_gpu(args, rank, world, local_rank):
         import workloads as wl
 
         state.clear()
+        if arena is not None:
+            arena.close()
         del model, params
         torch.cuda.empty_cache()
         pk = peaks()
@@ -640,7 +656,7 @@ def run_gpu(args, rank, world, local_rank):
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "global_batch": gb, "per_gpu_batch": B, "src_len": 257 + PROMPT, "tgt_len": TGT,
                        "parallelism": f"dp{world}", "cuda_graph": bool(use_graph), "pdl": not args.no_pdl,
-                       "grad_exchange": (None if world == 1 else "NCCL all-reduce(avg) of flat 64 MB buckets" + ("; decoder-side buckets overlap the encoder backward" if split else "")), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
+                       "grad_exchange": (None if world == 1 else {"arena": "gradient arena (GEMMs write dW in place), NCCL all-reduce(avg) per 64 MB bucket as soon as its last gradient exists, overlapped with backward, captured in the step graph", "split": "NCCL all-reduce(avg) of packed 64 MB buckets; decoder-side buckets overlap the encoder backward", "plain": "NCCL all-reduce(avg) of packed 64 MB buckets after backward"}[args.dp]), "l2": "working set per step (0.4 GB weights + >5 GB activations) >> 126 MB L2; no flush needed",
                        "algorithmic_gflop_per_seq": 3 * FWD_GFLOP_PER_SEQ, "ntokens_per_rank": ntok},
             "clocks": clocks,
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
@@ -669,7 +685,7 @@ def main():
     ap.add_argument("--breakdown", action="store_true", help="also write gpurun_out/breakdown.json (per entry point device time)")
     ap.add_argument("--kprofile", action="store_true", help="also write gpurun_out/kprofile.json (per-kernel device time of the replayed step, CUPTI)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
-    ap.add_argument("--no-overlap", action="store_true", help="N>1: average all gradients after the whole backward (no split)")
+    ap.add_argument("--dp", default="arena", choices=["arena", "split", "plain"], help="N>1 gradient exchange: arena (gradients written into a flat arena, per-bucket all-reduce overlapped with backward), split (backward cut at the encoder/decoder boundary, packed buckets), plain (all after backward)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-workloads", action="store_true", help="headline workload only (skip the configs[2..4] lines and the data-parallel gate)")
     ap.add_argument("--workloads", default="asr,cotrain,large", help="comma-separated extra workloads (workloads.py)")

@@ -507,7 +507,9 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
             mx = fmaxf(mx, ok ? x : -INFINITY);
           }
         }
-        m_ref = mx;
+        // an INTEGER reference (log2 domain): every later rescaling is by an exact power of two, so the bf16 rounding of the
+        // probabilities does not depend on the key-block order (the oracle's storage model reproduces it without knowing it)
+        m_ref = ceilf(mx);
       }
       {
         const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
@@ -527,7 +529,7 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
           // every earlier P V must have retired: pv_done has completed kb - 1 or kb times here (s_full(kb) implies P V(kb-2))
           mbar_wait(pv_done, (kb - 1) & 1);
           tc_fence_after();
-          const float m_new = raise ? m_use + mx : m_ref;
+          const float m_new = raise ? ceilf(m_use + mx) : m_ref;
           fwd_redo_block<HAS_BIAS, DROP>(tS, tP, tmem_O + lane_addr, nch, brow, p, c2, m_ref, m_new, km0, km1, k0, i, row_ok, l_run, ls, dkey);
           m_ref = m_new;
         }
@@ -1255,8 +1257,8 @@ int ofab_attn_tc_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) {
   fill_tc(a, p, drop_on);
   CUtensorMap mq, mk, mv;
   if (!make_map3(&mq, a->q, a->H * 64, a->Tq, a->B, a->q_rs, a->q_bs, 128)) return 1;
-  if (!make_map3(&mk, a->k, a->H * 64, a->Tk, a->B, a->k_rs, a->k_bs, 128)) return 1;
-  if (!make_map3(&mv, a->v, a->H * 64, a->Tk, a->B, a->v_rs, a->v_bs, 128)) return 1;
+  if (!make_map3(&mk, a->k, a->H * 64, a->Tk, a->B, a->k_rs, a->k_bs, 64)) return 1;  // 64-key blocks
+  if (!make_map3(&mv, a->v, a->H * 64, a->Tk, a->B, a->v_rs, a->v_bs, 64)) return 1;
   const int nkb = (a->Tk + 63) / 64;
   const int smem = 1024 + 128 * 128 + 2 * 4 * 64 * 128 + 16 * 8 + 16 + (nkb + 1) * 2 * 4;
   dim3 grid((a->Tq + 127) / 128, a->H, a->B);

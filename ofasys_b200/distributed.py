@@ -180,3 +180,182 @@ class DataParallelModel(torch.nn.Module):
             if self._buckets is None:
                 self._buckets = build_buckets(params, self.bucket_bytes)
             allreduce_grads(self._buckets, self.process_group, scale)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Gradient arena: weight gradients are written by the backward GEMMs STRAIGHT into one flat buffer per model (no
+# pack / unpack copies around the collective), cut into ~64 MB buckets in the order gradients become ready; a bucket is
+# all-reduced (side stream) as soon as its last gradient has been produced, while the rest of the backward runs.
+# Reference: c10d DDP's Reducer with gradient_as_bucket_view + per-bucket ready hooks
+# (distributed_model_dispatcher.py:49-59, configs.py `gradient_as_bucket_view`, `bucket_cap_mb`).
+# ----------------------------------------------------------------------------------------------------------------------
+_ARENA_SLOTS = {}  # (data_ptr of the forward weight tensor, numel) -> (arena view, [params], arena)
+
+
+def grad_slot(weight: torch.Tensor, shape):
+    """Destination for the gradient of `weight` (a Parameter's tensor, or a packed view of several adjacent Parameters) inside
+    the active gradient arena, or None (no arena / slot already used in this step / a gradient is already accumulated there --
+    autograd then accumulates in place into the slot through p.grad)."""
+    if not _ARENA_SLOTS:
+        return None
+    ent = _ARENA_SLOTS.get((weight.data_ptr(), weight.numel()))
+    if ent is None:
+        return None
+    view, params, arena = ent
+    if not arena.enabled or any(p.grad is not None for p in params) or any(id(p) in arena._handed for p in params):
+        return None
+    for p in params:
+        arena._handed.add(id(p))
+    return view.view(shape)
+
+
+class GradArena:
+    """Flat gradient storage + bucketed, overlapped exchange for one model replica.
+
+        arena = GradArena(model.parameters())          # once (after the parameters are on the device / packed)
+        arena.begin_step()                             # p.grad = None for all, hooks armed
+        loss.backward()                                # GEMMs write dW into the arena; buckets all-reduce as they complete
+        arena.finish()                                 # leftovers copied in, remaining buckets reduced, streams joined
+        # now p.grad (views of the arena) hold the mean over ranks
+
+    Parameters whose storage is adjacent (ops.pack_params: q|k|v, k|v) get adjacent slots in the same order, so the packed
+    weight gradient of one GEMM is one contiguous slot.  Gradients that autograd had to sum from several consumers (the tied
+    embedding) or that small kernels produce (LayerNorm, biases, tables) arrive as ordinary tensors and are copied into their
+    slots by ONE multi-tensor copy per bucket.  A parameter without a gradient in a step (an adaptor no batch touched)
+    contributes zeros."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 64 << 20, group=None, overlap: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params and all(p.is_cuda for p in self.params), "GradArena needs CUDA parameters"
+        self.group = group
+        self.overlap = overlap
+        self.enabled = True
+        dt = self.params[0].dtype
+        assert all(p.dtype == dt for p in self.params), "one gradient dtype per arena"
+        es = self.params[0].element_size()
+        # adjacency groups (packed parameters): consecutive in memory inside one storage
+        by_addr = sorted(self.params, key=lambda p: p.data_ptr())
+        group_of, groups = {}, []
+        for p in by_addr:
+            if groups:
+                last = groups[-1][-1]
+                if (last.untyped_storage().data_ptr() == p.untyped_storage().data_ptr() and last.data_ptr() + last.numel() * es == p.data_ptr()
+                        and p.dim() == last.dim() and p.shape[1:] == last.shape[1:]):
+                    groups[-1].append(p)
+                    group_of[id(p)] = len(groups) - 1
+                    continue
+            groups.append([p])
+            group_of[id(p)] = len(groups) - 1
+        # slot order = reverse registration order (~ the order gradients become ready), whole groups at once
+        order, seen = [], set()
+        for p in reversed(self.params):
+            g = group_of[id(p)]
+            if g not in seen:
+                seen.add(g)
+                order.append(groups[g])
+        offs, off = {}, 0
+        self.buckets = []  # [start_elem, end_elem, [params]]
+        cur_start, cur = 0, []
+        for grp in order:
+            for p in grp:
+                offs[id(p)] = off
+                off += p.numel()
+                cur.append(p)
+            off = (off + 7) // 8 * 8  # 16-byte aligned group starts
+            if (off - cur_start) * es >= bucket_bytes:
+                self.buckets.append([cur_start, off, cur])
+                cur_start, cur = off, []
+        if cur:
+            self.buckets.append([cur_start, off, cur])
+        self.flat = torch.zeros(off, dtype=dt, device=self.params[0].device)
+        self._slot = {id(p): self.flat[offs[id(p)]:offs[id(p)] + p.numel()].view(p.shape) for p in self.params}
+        self._bucket_of = {}
+        for bi, (_, _, ps) in enumerate(self.buckets):
+            for p in ps:
+                self._bucket_of[id(p)] = bi
+        for grp in order:  # registry for the backward GEMMs: single parameters and whole packed groups
+            for p in grp:
+                _ARENA_SLOTS[(p.data_ptr(), p.numel())] = (self._slot[id(p)], [p], self)
+            if len(grp) > 1:
+                n = sum(p.numel() for p in grp)
+                o = offs[id(grp[0])]
+                _ARENA_SLOTS[(grp[0].data_ptr(), n)] = (self.flat[o:o + n], list(grp), self)
+            # (packed sub-groups, e.g. k|v of a q|k|v-adjacent triple, are registered too)
+            for a in range(len(grp)):
+                for b in range(a + 2, len(grp) + 1):
+                    if a == 0 and b == len(grp):
+                        continue
+                    n = sum(p.numel() for p in grp[a:b])
+                    o = offs[id(grp[a])]
+                    _ARENA_SLOTS[(grp[a].data_ptr(), n)] = (self.flat[o:o + n], list(grp[a:b]), self)
+        self._handed = set()
+        self._pending = [0] * len(self.buckets)
+        self._done = [False] * len(self.buckets)
+        self._tabs = [None] * len(self.buckets)
+        self.side = torch.cuda.Stream(device=self.flat.device)
+        self._hooks = [p.register_post_accumulate_grad_hook(self._on_grad) for p in self.params]
+        self._armed = False
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        for k in [k for k, v in _ARENA_SLOTS.items() if v[2] is self]:
+            del _ARENA_SLOTS[k]
+
+    # ---- one step
+    def begin_step(self):
+        for p in self.params:
+            p.grad = None
+        self._handed.clear()
+        self._pending = [len(ps) for _, _, ps in self.buckets]
+        self._done = [False] * len(self.buckets)
+        self._armed = True
+
+    def _on_grad(self, p):
+        if not self._armed:
+            return
+        bi = self._bucket_of[id(p)]
+        self._pending[bi] -= 1
+        if self._pending[bi] == 0 and self.overlap and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self._reduce_bucket(bi, async_side=True)
+
+    def _settle_bucket(self, bi):
+        """gradients of the bucket that did not land in their slots (small tensors; sums autograd formed from several
+        consumers, e.g. the tied embedding): one multi-tensor copy (capturable: no host table); missing ones: zeros"""
+        dst, src = [], []
+        for p in self.buckets[bi][2]:
+            slot = self._slot[id(p)]
+            g = p.grad
+            if g is None:
+                slot.zero_()
+            elif g.data_ptr() != slot.data_ptr():
+                dst.append(slot)
+                src.append(g if g.dtype == slot.dtype else g.to(slot.dtype))
+            p.grad = slot
+        if dst:
+            torch._foreach_copy_(dst, src)
+
+    def _reduce_bucket(self, bi, async_side):
+        if self._done[bi]:
+            return
+        self._done[bi] = True
+        self._settle_bucket(bi)
+        if not (dist.is_initialized() and dist.get_world_size(self.group) > 1):
+            return
+        a, b, _ = self.buckets[bi]
+        if async_side:
+            cur = torch.cuda.current_stream()
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):
+                dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG, group=self.group)
+        else:
+            dist.all_reduce(self.flat[a:b], op=dist.ReduceOp.AVG, group=self.group)
+
+    def finish(self, scale: Optional[float] = None):
+        """After backward: settle + reduce every bucket not yet reduced, join the side stream; p.grad = arena views."""
+        self._armed = False
+        for bi in range(len(self.buckets)):
+            self._reduce_bucket(bi, async_side=self.overlap)
+        torch.cuda.current_stream().wait_stream(self.side)
+        if scale is not None:
+            self.flat.mul_(scale)

@@ -130,8 +130,15 @@ class MultiheadAttention(nn.Module):
         return incremental_state
 
     def _cat(self, names, attr):
+        """The projections' weights (or biases) as ONE packed operand: the parameters share a storage (ops.pack_params), so
+        nothing is concatenated per forward and the packed gradient is handed back as slices (the reference computes three
+        separate F.linear calls, multihead_attention.py:199-218)."""
         ts = [getattr(getattr(self, n), attr) for n in names]
-        return None if ts[0] is None else torch.cat(ts, dim=0)
+        if ts[0] is None:
+            return None
+        if not ts[0].is_cuda:
+            return torch.cat(ts, dim=0)
+        return ops.pack_params(ts)
 
     def forward(self, query, key=None, value=None, key_padding_mask=None, incremental_state=None, need_weights=False,
                 static_kv=False, attn_mask=None, need_head_weights=False, attn_bias=None, batch_first=False, causal=None):

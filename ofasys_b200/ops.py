@@ -316,6 +316,12 @@ def gemm_splitk(M, N, K, A, lda, a_mn, B, ldb, b_mn, out, ldd):
     return out
 
 
+def _grad_slot(w, shape):
+    from .distributed import grad_slot
+
+    return grad_slot(w, shape)
+
+
 def _as2d(x):
     if x.dim() == 2 and x.stride(1) == 1 and x.stride(0) % 8 == 0:
         return x
@@ -364,7 +370,9 @@ class _LinearFn(torch.autograd.Function):
             gemm(M, K, N, dy2, ld, 0, w, K, 1, dx, K)  # dX = dY * W   (W read MN-major in place)
             dx = dx.view(ctx.xshape)
         if ctx.needs_input_grad[1]:
-            dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
+            dw = _grad_slot(w, (N, K))  # straight into the data-parallel gradient arena when one is active
+            if dw is None:
+                dw = torch.empty((N, K), dtype=torch.bfloat16, device=dy.device)
             gemm_splitk(N, K, M, dy2, ld, 1, x2, x2.stride(0), 1, dw, K)  # dW = dY^T * X  (both read transposed in place)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = _take_bias_hint(dy, N)  # produced for free by the LayerNorm backward that emitted dy
@@ -378,6 +386,53 @@ class _LinearFn(torch.autograd.Function):
 def linear(x, weight, bias=None, residual=None):
     """y = x W^T + b (bf16) ; with `residual` (fp32): y = residual + x W^T + b in fp32."""
     return _LinearFn.apply(x, weight, bias, residual)
+
+
+class _PackedParamsFn(torch.autograd.Function):
+    """Several parameters that sit back to back in ONE storage (pack_params) seen as a single [sum(rows), ...] operand, and
+    their gradients as slices of ONE gradient tensor: the packed q|k|v (or k|v) projection runs as one GEMM without a
+    per-forward torch.cat of the weights and without splitting copies of the packed gradient in backward."""
+
+    @staticmethod
+    def forward(ctx, *ps):
+        first = ps[0]
+        rows = sum(p.shape[0] for p in ps)
+        out = first.detach().new_empty(0).set_(first.untyped_storage(), first.storage_offset(), (rows,) + tuple(first.shape[1:]))
+        ctx.rows = [p.shape[0] for p in ps]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        outs, o = [], 0
+        for r in ctx.rows:
+            outs.append(g[o:o + r])
+            o += r
+        return tuple(outs)
+
+
+def pack_params(params):
+    """Returns the parameters viewed as one tensor (rows concatenated).  The first call after the parameters were
+    (re)allocated -- construction, .to(device / dtype) -- moves them into one shared storage (their .data become views of it);
+    later calls are pointer arithmetic only.  Names, shapes and values of the parameters are unchanged."""
+    first = params[0]
+    es = first.element_size()
+    adj = all(p.is_contiguous() and p.dtype == first.dtype and p.device == first.device for p in params)
+    if adj:
+        ptr = first.data_ptr()
+        for p in params:
+            if p.data_ptr() != ptr or p.untyped_storage().data_ptr() != first.untyped_storage().data_ptr():
+                adj = False
+                break
+            ptr += p.numel() * es
+    if not adj:
+        with torch.no_grad():
+            buf = torch.cat([p.detach().reshape(-1) for p in params])
+            o = 0
+            for p in params:
+                p.data = buf[o:o + p.numel()].view(p.shape)
+                o += p.numel()
+    return _PackedParamsFn.apply(*params)
 
 
 class _ScaleColsFn(torch.autograd.Function):
@@ -394,7 +449,9 @@ class _ScaleColsFn(torch.autograd.Function):
     def backward(ctx, dWe):
         W, c = ctx.saved_tensors
         dWe = _c(dWe)
-        dW = torch.empty_like(W)
+        dW = _grad_slot(W, W.shape)
+        if dW is None:
+            dW = torch.empty_like(W)
         dc = torch.zeros(c.shape, dtype=torch.float32, device=W.device)
         _lib.call("ofab_scale_cols_bwd", _p(dWe), _p(W), _p(c), _p(dW), _p(dc), W.shape[0], W.shape[1], ctx.group, _s())
         return dW, cast_bf16(dc), None

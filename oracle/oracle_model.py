@@ -123,14 +123,64 @@ def _drop(kind, x):
     return x if DROP_HOOK is None else x * DROP_HOOK(kind, x)
 
 
+# bf16 activation STORAGE model ("parity mode" of the oracle).  The CUDA path computes every contraction with fp32
+# accumulation and keeps the residual stream, LayerNorm statistics, softmax and reductions in fp32, but STORES GEMM operands
+# and outputs in bf16 (the reference's own common.bf16 mode stores everything in bf16, trainer.py:215-219).  With
+# STORE_BF16 the oracle -- arithmetic still fp32, same algorithm, same order of reference lines -- rounds exactly at those
+# storage points: Linear / conv outputs, the LayerNorm outputs that feed a GEMM, q / k / v, the attention probabilities
+# before P V, the attention output, the per-head-scaled out_proj weight, the fp16 position-bias tile, the logits.  What is
+# left between the CUDA path and this oracle is accumulation order (and one-ulp bf16 flips it causes): rounding and
+# defects become separable -- tests/test_model_gpu.py gates the logits at 1e-3 rel-L2 against it (BASELINE north_star).
+# It also serves the ResNet: a ReLU network's gradient is discontinuous in forward perturbations (a pre-activation that
+# crosses 0 flips a whole gradient element; ~0.3 % of masks per ReLU, 20-48 % per parameter over 49 ReLUs), so the
+# ResNet gradients are compared under the same storage model.
+STORE_BF16 = False
+
+
+class _RoundBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.bfloat16().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _st(x):
+    return _RoundBf16.apply(x) if STORE_BF16 else x
+
+
+class _RoundFp16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return x.half().to(x.dtype)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _st_bias(b):
+    """the additive position tile is stored in fp16 in the log2 domain (csrc/attn_tc.cu attn_bias_build_kernel)"""
+    if not STORE_BF16 or b is None:
+        return b
+    log2e = 1.4426950408889634
+    return _RoundFp16.apply(b * log2e) / log2e
+
+
+
 # ------------------------------------------------------------------ small modules
-def layer_norm(x, sd, prefix, eps=1e-5):
-    """module/layer_norm.py:27-32 -> torch.nn.LayerNorm."""
-    return F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+def layer_norm(x, sd, prefix, eps=1e-5, st=False):
+    """module/layer_norm.py:27-32 -> torch.nn.LayerNorm.  st: the output feeds a GEMM (stored bf16 under STORE_BF16)."""
+    y = F.layer_norm(x, (x.shape[-1],), sd[prefix + ".weight"], sd[prefix + ".bias"], eps)
+    return _st(y) if st else y
 
 
-def linear(x, sd, prefix):
-    return F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+def linear(x, sd, prefix, st=True):
+    """st: the CUDA path stores this GEMM's output in bf16 (fp32 when it lands on the residual stream)."""
+    y = F.linear(x, sd[prefix + ".weight"], sd.get(prefix + ".bias"))
+    return _st(y) if st else y
 
 
 def gelu(x):
@@ -160,18 +210,32 @@ def mha(sd, prefix, cfg: OracleConfig, query, key, kpm, attn_mask, attn_bias, fa
     v = v.contiguous().view(S, B * H, dh).transpose(0, 1)
     w = torch.bmm(q, k.transpose(1, 2))  # :308
     if attn_bias is not None:
-        w = w + attn_bias  # :311-312
+        w = w + _st_bias(attn_bias)  # :311-312
     if attn_mask is not None:
         w = torch.nan_to_num(w)  # :314-317
         w = w + attn_mask.to(w.dtype).unsqueeze(0)  # buffered_future_mask is cast to the activations (transformer.py:537)
     if kpm is not None:
         w = w.view(B, H, T, S).masked_fill(kpm.unsqueeze(1).unsqueeze(2).to(torch.bool), float("-inf"))
         w = w.view(B * H, T, S)  # :319-326
-    p = F.softmax(w.float(), dim=-1).type_as(w)  # :333-334 (module/utils.py:451)
-    p = _drop("attn_probs", p)  # :335
-    a = torch.bmm(p, v)  # :338
-    a = a.transpose(0, 1).contiguous().view(T, B, C)
+    if STORE_BF16:
+        # storage model of the fused kernel: P V consumes UNNORMALISED probabilities 2^(x - m), m = the row maximum rounded up
+        # to an integer in the log2 domain (any integer shift gives the same bf16 rounding), stored in bf16; the row sum is
+        # that of the unrounded values and divides the product afterwards
+        x2 = w.float() * 1.4426950408889634
+        m = torch.ceil(x2.amax(dim=-1, keepdim=True))
+        m = torch.where(torch.isinf(m), torch.zeros_like(m), m)
+        pu = torch.exp2(x2 - m)
+        l = pu.sum(dim=-1, keepdim=True)
+        a = torch.bmm(_st(_drop("attn_probs", pu)), v) / l.clamp_min(1e-38)
+    else:
+        p = F.softmax(w.float(), dim=-1).type_as(w)  # :333-334 (module/utils.py:451)
+        p = _drop("attn_probs", p)  # :335
+        a = torch.bmm(p, v)  # :338
+    a = _st(a.transpose(0, 1).contiguous().view(T, B, C))
     if not fast_path and (prefix + ".c_attn") in sd:
+        if STORE_BF16:  # the CUDA path folds the per-head scale into out_proj's weight columns (exact in real arithmetic)
+            w_eff = _st(sd[prefix + ".out_proj.weight"] * sd[prefix + ".c_attn"].repeat_interleave(dh).unsqueeze(0))
+            return _st(F.linear(a, w_eff, sd.get(prefix + ".out_proj.bias")))
         a = a.view(T, B, H, dh)
         a = torch.einsum("tbhd,h->tbhd", a, sd[prefix + ".c_attn"])  # :342-345
         a = a.reshape(T, B, C)
@@ -183,20 +247,20 @@ def ffn(sd, prefix, x):
     x = gelu(linear(x, sd, prefix + ".fc1"))
     x = _drop("act", x)  # :195 / :481
     if (prefix + ".ffn_layernorm.weight") in sd:
-        x = layer_norm(x, sd, prefix + ".ffn_layernorm")
+        x = layer_norm(x, sd, prefix + ".ffn_layernorm", st=True)
     return linear(x, sd, prefix + ".fc2")
 
 
 def encoder_layer(sd, prefix, cfg, x, kpm, self_attn_bias):
     """module/transformer_layer.py:132-209 (pre-LN, normformer extras on; dropout 0)."""
     residual = x
-    x = layer_norm(x, sd, prefix + ".self_attn_layer_norm")
+    x = layer_norm(x, sd, prefix + ".self_attn_layer_norm", st=True)
     x = mha(sd, prefix + ".self_attn", cfg, x, x, kpm, None, self_attn_bias, fast_path=self_attn_bias is None)
     if (prefix + ".attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".attn_ln")
     x = residual + _drop("branch", x)  # :181, :87
     residual = x
-    x = layer_norm(x, sd, prefix + ".final_layer_norm")
+    x = layer_norm(x, sd, prefix + ".final_layer_norm", st=True)
     x = ffn(sd, prefix, x)
     return residual + _drop("branch", x)  # :203, :87
 
@@ -205,19 +269,19 @@ def decoder_layer(sd, prefix, cfg, x, enc, enc_kpm, self_mask, self_kpm, self_bi
     """module/transformer_layer.py:351-495.  Decoder self-attention always takes the manual path
     (transformer.py:476-477 passes False, not None, when biases are off)."""
     residual = x
-    x = layer_norm(x, sd, prefix + ".self_attn_layer_norm")
+    x = layer_norm(x, sd, prefix + ".self_attn_layer_norm", st=True)
     x = mha(sd, prefix + ".self_attn", cfg, x, x, self_kpm, self_mask, self_bias, fast_path=False)
     if (prefix + ".self_attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".self_attn_ln")
     x = residual + _drop("branch", x)  # :433, :333
     residual = x
-    x = layer_norm(x, sd, prefix + ".encoder_attn_layer_norm")
+    x = layer_norm(x, sd, prefix + ".encoder_attn_layer_norm", st=True)
     x = mha(sd, prefix + ".encoder_attn", cfg, x, enc, enc_kpm, None, cross_bias, fast_path=False)
     if (prefix + ".cross_attn_ln.weight") in sd:
         x = layer_norm(x, sd, prefix + ".cross_attn_ln")
     x = residual + _drop("branch", x)  # :466, :333
     residual = x
-    x = layer_norm(x, sd, prefix + ".final_layer_norm")
+    x = layer_norm(x, sd, prefix + ".final_layer_norm", st=True)
     x = ffn(sd, prefix, x)
     return residual + _drop("branch", x)  # :489, :333
 
@@ -242,7 +306,7 @@ def _hook(sd, ap, cfg: OracleConfig, slot: OSlot, out: AOut, num_layers: int, re
         embed = embed + sd[ap + ".type_embedding.weight"].squeeze()  # :172-173
     embed = layer_norm(embed, sd, ap + ".layernorm_embedding")
     if out.pos_embed is not None:
-        out.pos_embed = layer_norm(out.pos_embed, sd, ap + ".layernorm_position")
+        out.pos_embed = layer_norm(out.pos_embed, sd, ap + ".layernorm_position", st=True)
     out.embed = _drop("embed", embed)  # :181
     if not out.self_attn_bias and cfg.mode == "A":
         B, T = embed.shape[:2]
@@ -274,7 +338,7 @@ def patch_embed_adaptor(sd, gp, cfg, slot, num_layers):
     ap = gp + ".image_patch_embed"
     img = slot.value
     B = img.shape[0]
-    x = F.conv2d(img, sd[ap + ".proj.weight"], sd[ap + ".proj.bias"], stride=cfg.patch)
+    x = _st(F.conv2d(_st(img), sd[ap + ".proj.weight"], sd[ap + ".proj.bias"], stride=cfg.patch))
     x = x.flatten(2).transpose(1, 2)
     x = torch.cat((sd[ap + ".cls_token"].expand(B, -1, -1), x), dim=1)
     T = x.shape[1]
@@ -290,8 +354,8 @@ def audio_adaptor(sd, gp, cfg, slot, num_layers):
     ap = gp + ".audio_fbank"
     fbank, lens = slot.value["fbank"], slot.value["fbank_lengths"]
     x = fbank.unsqueeze(1)
-    x = F.relu(F.conv2d(x, sd[ap + ".subsample.conv.0.weight"], sd[ap + ".subsample.conv.0.bias"], stride=2))
-    x = F.relu(F.conv2d(x, sd[ap + ".subsample.conv.2.weight"], sd[ap + ".subsample.conv.2.bias"], stride=2))
+    x = _st(F.relu(F.conv2d(x, sd[ap + ".subsample.conv.0.weight"], sd[ap + ".subsample.conv.0.bias"], stride=2)))
+    x = _st(F.relu(F.conv2d(x, sd[ap + ".subsample.conv.2.weight"], sd[ap + ".subsample.conv.2.bias"], stride=2)))
     b, c, t, f = x.shape
     x = linear(x.transpose(1, 2).contiguous().view(b, t, c * f), sd, ap + ".subsample.out.0")
     out_lens = audio_out_lengths(lens)
@@ -319,29 +383,6 @@ def _bn(x, sd, p, training):
         x, sd[p + ".running_mean"].clone(), sd[p + ".running_var"].clone(), sd[p + ".weight"], sd[p + ".bias"],
         training=training, momentum=0.1, eps=1e-5,
     )
-
-
-# bf16 activation storage model.  A ReLU network's gradient is discontinuous in forward perturbations (a pre-activation
-# that crosses 0 flips a whole gradient element), so an implementation that stores activations in bf16 -- the
-# reference's own common.bf16 mode does, trainer.py:215-219 -- cannot be compared gradient-by-gradient with an fp32
-# forward: ~0.3 % of masks flip per ReLU and the error adds up in quadrature over 49 ReLUs (measured: 20-48 % per
-# parameter).  With STORE_BF16 the oracle rounds at the storage points of a bf16 run (conv outputs, BN(+add)+ReLU
-# outputs, the input image); arithmetic stays fp32.
-STORE_BF16 = False
-
-
-class _RoundBf16(torch.autograd.Function):
-    @staticmethod
-    def forward(ctx, x):
-        return x.bfloat16().to(x.dtype)
-
-    @staticmethod
-    def backward(ctx, g):
-        return g
-
-
-def _st(x):
-    return _RoundBf16.apply(x) if STORE_BF16 else x
 
 
 def _bottleneck(x, sd, p, stride, has_down, training):
@@ -451,7 +492,7 @@ def general_adaptor(sd, gp, cfg: OracleConfig, slots: List[OSlot], is_src: bool)
     B, S = pos.shape[:2]
     H = cfg.heads
     s = float(cfg.embed_dim / cfg.heads * cfg.attn_scale_factor) ** -0.5  # general.py:98
-    pq = linear(pos, sd, gp + ".pos_q_linear").view(B, S, H, -1).transpose(1, 2) * s
+    pq = linear(pos, sd, gp + ".pos_q_linear").view(B, S, H, -1).transpose(1, 2) * s  # (s on the fp32 product in the CUDA path)
     pk = linear(pos, sd, gp + ".pos_k_linear").view(B, S, H, -1).transpose(1, 2)
     abs_bias = torch.matmul(pq, pk.transpose(2, 3))  # :223-243
     biases = []
@@ -478,7 +519,7 @@ def encoder_forward(sd, cfg: OracleConfig, slots: List[OSlot]):
     for i in range(cfg.enc_layers):
         bias = biases[i].reshape(-1, x.size(0), x.size(0)) if biases is not None else None
         x = encoder_layer(sd, f"encoder.layers.{i}", cfg, x, masks if has_pad else None, bias)
-    x = layer_norm(x, sd, "encoder.layer_norm")
+    x = layer_norm(x, sd, "encoder.layer_norm", st=True)
     return {"encoder_out": x, "encoder_padding_mask": masks, "position_embeddings": pos}
 
 
@@ -503,8 +544,8 @@ def decoder_forward(sd, cfg: OracleConfig, slots: List[OSlot], enc):
         x = decoder_layer(
             sd, f"decoder.layers.{i}", cfg, x, enc["encoder_out"], enc["encoder_padding_mask"], future, masks, bias, cross
         )
-    x = layer_norm(x, sd, "decoder.layer_norm").transpose(0, 1)
-    logits = F.linear(x, sd["decoder.adaptor.embed_tokens.weight"])
+    x = layer_norm(x, sd, "decoder.layer_norm", st=True).transpose(0, 1)
+    logits = _st(F.linear(x, sd["decoder.adaptor.embed_tokens.weight"]))
     return logits, x
 
 

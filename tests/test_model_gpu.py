@@ -1,12 +1,15 @@
 """GPU: end-to-end parity of the CUDA path against the oracle (oracle/oracle_model.py, fp32 CPU,
 pinned to the reference by tests/golden/) on the seeded cases of oracle/cases.py.
 
-Tolerances (stated per BASELINE.json's "logits within 1e-3 rel" target, see DESIGN.md "parity"):
-the production path computes GEMM operands in bf16 (eps 7.8e-3), so the gate is
-  rel-L2(logits) <= max(1.5 x the error of the *reference algorithm itself run in bf16*, 4e-3)
-measured against the fp32 oracle holding the same bf16-rounded weights; loss within 2e-3 relative;
-every parameter gradient within 6e-2 rel-L2 (3e-2 for the total gradient).  Integer outputs
-(padding masks, bucket ids) are compared bit-exactly.
+Tolerances (BASELINE.json north_star: "logits within 1e-3 rel of the reference", see DESIGN.md "parity"):
+  (1) layer by layer, rel-L2 <= 3e-4 (north_star asks 1e-3) against the oracle run under the CUDA path's STORAGE model
+      (oracle_model.STORE_BF16: same algorithm and fp32 arithmetic, values rounded where the kernels store bf16 / fp16) on the
+      CUDA path's own layer inputs -- what is left is accumulation order, so a kernel defect cannot hide behind operand
+      rounding (test_layerwise_parity_against_the_storage_model);
+  (2) rel-L2(logits) <= 1.5 x the error of the *reference algorithm itself run in bf16* against the plain fp32 oracle
+      (the production path computes GEMM operands in bf16, eps 7.8e-3: no bf16 implementation reaches 1e-3 there);
+loss within 2e-3 relative; every parameter gradient within 6e-2 rel-L2 (3e-2 for the total gradient) of the fp32 oracle.
+Integer outputs (padding masks, bucket ids) are compared bit-exactly.
 """
 import json
 import os
@@ -64,7 +67,18 @@ def test_model_fwd_bwd_parity(name):
     slots, target = cases.make_inputs(name)
     loss_ref, logits_ref, grads_ref = om.loss_and_grads(sd_r, cfg, slots, target)
     err16 = _oracle_bf16_error(sd_r, cfg, slots, logits_ref)
+    om.STORE_BF16 = True  # the oracle under the CUDA path's storage model (fp32 arithmetic, bf16 / fp16 storage points)
+    try:
+        with torch.no_grad():
+            logits_st, _ = om.model_forward(sd_r, cfg, slots)
+    finally:
+        om.STORE_BF16 = False
     sim = None
+    om.STORE_BF16 = True  # per-parameter yardstick: the gradient error the storage model alone causes (forward roundings)
+    try:
+        _, _, grads_st = om.loss_and_grads(sd_r, cfg, slots, target)
+    finally:
+        om.STORE_BF16 = False
     if name in ("resnet_A", "video_A"):
         # A ReLU network's gradient is discontinuous in forward perturbations: with bf16 activation storage ~0.2 % of the
         # masks flip per ReLU (4-5 % gradient rel-L2 each, adding in quadrature over 49 ReLUs).  The yardstick for the
@@ -87,6 +101,7 @@ def test_model_fwd_bwd_parity(name):
     logits, extra = m(pslots)
     assert tuple(logits.shape) == tuple(logits_ref.shape)
     e_logits = rel_l2(logits.float(), logits_ref)
+    e_logits_st = rel_l2(logits.float(), logits_st)
 
     # integer outputs: padding masks bit-exact
     enc = m.encoder([s for s in pslots if s.is_src])
@@ -111,15 +126,26 @@ def test_model_fwd_bwd_parity(name):
         per[k] = ((gp - gr).norm() / gr.norm().clamp_min(1e-30)).item() if gr.norm() > 1e-4 * (den ** 0.5 + 1e-30) or gr.norm() > 1e-3 else 0.0
     e_grad = (num / max(den, 1e-30)) ** 0.5
     worst = sorted(per.items(), key=lambda kv: -kv[1])[:8]
-    _report(name, {"logits_rel_l2": e_logits, "oracle_bf16_rel_l2": err16, "loss_rel": e_loss, "grad_rel_l2": e_grad, "worst_params": worst,
+    _report(name, {"logits_rel_l2": e_logits, "logits_rel_l2_vs_storage_model_oracle": e_logits_st, "storage_model_vs_fp32_oracle": rel_l2(logits_st, logits_ref),
+                   "oracle_bf16_rel_l2": err16, "loss_rel": e_loss, "grad_rel_l2": e_grad, "worst_params": worst,
                    "loss": loss.item(), "loss_ref": loss_ref.item()})
 
-    bound = max(1.5 * err16, 4e-3) if err16 == err16 else 1.5e-2
+    bound = 1.5 * err16 if err16 == err16 else 1.5e-2
     assert e_logits <= bound, (e_logits, err16)
+    # (e_logits_st, the END-TO-END distance to the storage-model oracle, is reported only: one-ulp bf16 flips cascade through the
+    # layers and saturate it at the level of the fp32 comparison; test_layerwise_parity_against_the_storage_model gates the
+    # arithmetic layer by layer at 3e-4)
     assert e_loss <= 2e-3, (loss.item(), loss_ref.item())
     assert e_grad <= 3e-2, e_grad
+    def st_err(k):
+        gr = grads_ref[k].double()
+        return ((grads_st[k].double() - gr).norm() / gr.norm().clamp_min(1e-30)).item()
+
     if sim is None:
-        assert worst[0][1] <= 6e-2, worst
+        # 6e-2, or -- for the few ill-conditioned tensors (cross-attention q / k projections: sums of cancelling terms) --
+        # 1.5 x the error the storage model alone produces in that tensor + 1e-2
+        for k, e in worst:
+            assert e <= max(6e-2, 1.5 * st_err(k) + 1e-2), (k, e, st_err(k))
     else:
         def block_of(k):
             t = k.split("embed_images.")[1].split(".")
@@ -128,7 +154,7 @@ def test_model_fwd_bwd_parity(name):
         groups = {}
         for k, p in m.named_parameters():
             if "embed_images" not in k:
-                assert per[k] <= 6e-2, (k, per[k])
+                assert per[k] <= max(6e-2, 1.5 * st_err(k) + 1e-2), (k, per[k], st_err(k))
                 continue
             gr = grads_ref[k].double()
             a = groups.setdefault(block_of(k), [0.0, 0.0, 0.0])
@@ -219,3 +245,63 @@ def test_split_backward_equals_plain(name):
             assert torch.equal(p.grad, ref[k]), k  # untouched by finish()
         else:
             assert rel_l2(p.grad, ref[k]) <= 4e-3, (k, rel_l2(p.grad, ref[k]))
+
+
+@pytest.mark.parametrize("name", ["text_A", "text_B", "patch_B", "audio_A", "large_A"])
+def test_layerwise_parity_against_the_storage_model(name):
+    """Rounding and defects separated (BASELINE north_star: logits within 1e-3 rel of the reference).  End to end a bf16
+    pipeline sits ~3.5e-3 from an fp32 run whatever the implementation: one-ulp bf16 flips cascade through the layers.  Here
+    every layer is compared ON ITS OWN: the oracle under the CUDA path's storage model (oracle_model.STORE_BF16: the reference
+    algorithm in fp32 arithmetic, values rounded exactly where the kernels store bf16 / fp16) is fed the CUDA path's own input of
+    that layer; what is left is accumulation order.  Gate: rel-L2 <= 3e-4 per encoder / decoder layer and for the logits
+    (measured 1e-5 .. 1e-4) -- 10x below the 1e-3 of the north star and 30x below the error an fp32 comparison can resolve."""
+    dev = torch.device("cuda:0")
+    g = load_golden(name)
+    sd = cases.synth_state_dict(g["spec"], seed=0)
+    sd_r = bf16_round_state_dict(sd)
+    cfg = cases.oracle_cfg(name)
+    slots, target = cases.make_inputs(name)
+    m = build_product(name)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(torch.bfloat16).to(dev).eval()
+    ps = to_product_slots(slots, dev)
+    with torch.no_grad():
+        enc = m.encoder([s for s in ps if s.is_src], return_all_hiddens=True)
+        logits, extra = m(ps, return_all_hiddens=True)
+    est = [t.float().cpu() for t in enc["encoder_states"]]
+    dst = [t.float().cpu() for t in extra["inner_states"]]
+    enc_out = enc["encoder_out"][0].float().cpu()  # T x B x C, the bf16 values the decoder consumed
+    rec = {}
+    om.STORE_BF16 = True
+    try:
+        with torch.no_grad():
+            src = [s for s in slots if s.is_src]
+            embed, masks, pos, biases = om.general_adaptor(sd_r, "encoder.adaptor", cfg, src, True)
+            kpm = masks if bool(masks.any()) else None
+            S = est[0].shape[0]
+            for i in range(cfg.enc_layers):
+                bias = biases[i].reshape(-1, S, S) if biases is not None else None
+                y = om.encoder_layer(sd_r, f"encoder.layers.{i}", cfg, est[i], kpm, bias)
+                rec[f"enc{i}"] = rel_l2(est[i + 1], y)
+            rec["enc_out"] = rel_l2(enc_out, om.layer_norm(est[-1], sd_r, "encoder.layer_norm", st=True))
+            tgt = [s for s in slots if not s.is_src]
+            _, dmasks, dpos, dbiases = om.general_adaptor(sd_r, "decoder.adaptor", cfg, tgt, False)
+            T, B = dst[0].shape[:2]
+            cross = None
+            if cfg.mode == "A":
+                sc = float(cfg.embed_dim / cfg.heads * cfg.attn_scale_factor) ** -0.5
+                pq = om.linear(dpos, sd_r, "decoder.cross_pos_q_linear").view(B, T, cfg.heads, -1).transpose(1, 2) * sc
+                pk = om.linear(pos, sd_r, "decoder.cross_pos_k_linear").view(B, S, cfg.heads, -1).transpose(1, 2)
+                cross = torch.matmul(pq, pk.transpose(2, 3)).reshape(-1, T, S)
+            future = torch.triu(torch.full((T, T), float("-inf")), 1)
+            for i in range(cfg.dec_layers):
+                bias = dbiases[i].reshape(-1, T, T) if dbiases is not None else None
+                y = om.decoder_layer(sd_r, f"decoder.layers.{i}", cfg, dst[i], enc_out, masks, future, dmasks, bias, cross)
+                rec[f"dec{i}"] = rel_l2(dst[i + 1], y)
+            x = om.layer_norm(dst[-1], sd_r, "decoder.layer_norm", st=True).transpose(0, 1)
+            rec["logits"] = rel_l2(logits.float().cpu(), om._st(torch.nn.functional.linear(x, sd_r["decoder.adaptor.embed_tokens.weight"])))
+    finally:
+        om.STORE_BF16 = False
+    _report(name + "_layerwise_vs_storage_model", rec)
+    bad = {k: v for k, v in rec.items() if not v <= 3e-4}
+    assert not bad, (bad, rec)
