@@ -235,13 +235,16 @@ def run_gpu(args, rank, world, local_rank):
     # as soon as its last gradient exists, while the rest of the backward runs -- the whole step incl. the collectives is ONE
     # CUDA graph.  --dp split: the older scheme (backward cut at the encoder/decoder boundary, flat buckets packed by a
     # multi-tensor copy).  N == 1: one graph, no exchange.
+    if world > 1 and args.dp == "arena":
+        fwd_bwd()  # the first forward packs the q|k|v parameter storages: the arena keys its slots by parameter address
+        torch.cuda.synchronize()
     arena = GradArena(params) if (world > 1 and args.dp == "arena") else None
     split = world > 1 and args.dp == "split"
     side = torch.cuda.Stream()
     fwd_bwd_local = fwd_bwd  # no collectives: what the rank-0-only roofline / breakdown sections run
     if arena is not None:
         def fwd_bwd():  # noqa: F811  (the data-parallel step: exchange included)
-            arena.begin_step()
+            arena.begin_step(arm=True)
             loss = model.forward_loss(to_slots(db), db["tgt"])
             loss.backward()
             arena.finish()

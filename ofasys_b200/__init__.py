@@ -5,5 +5,7 @@ from .configure import BaseDataclass, ConfigStore, register_config
 from .preprocessor import Dictionary, ModalityType, Slot
 from .model import GeneralistModel, GeneralistModelConfig
 from .optim import FusedAdam
+from .criterion import LabelSmoothedCrossEntropyCriterion, SpeechToTextLossCriterion
 
-__all__ = ["ModalityType", "Slot", "Dictionary", "GeneralistModel", "GeneralistModelConfig", "BaseDataclass", "ConfigStore", "register_config", "FusedAdam"]
+__all__ = ["ModalityType", "Slot", "Dictionary", "GeneralistModel", "GeneralistModelConfig", "BaseDataclass", "ConfigStore", "register_config", "FusedAdam",
+           "LabelSmoothedCrossEntropyCriterion", "SpeechToTextLossCriterion"]

@@ -37,6 +37,12 @@ class CtcArgs(Structure):
                 ("lse", c_void_p), ("alpha", c_void_p), ("nll", c_void_p), ("gscale", c_void_p), ("dlogits", c_void_p)]
 
 
+class CeRowsArgs(Structure):
+    _fields_ = [("logits", c_void_p), ("rows", c_int64), ("V", c_int64), ("ld", c_int64), ("target", c_void_p), ("ignore_index", c_int64),
+                ("cmask", c_void_p), ("c_lo", c_int64), ("c_hi", c_int64), ("label_smoothing", c_float),
+                ("lse", c_void_p), ("n_allowed", c_void_p), ("row_loss", c_void_p), ("row_nll", c_void_p), ("row_scale", c_void_p), ("dlogits", c_void_p)]
+
+
 class AttnFwdArgs(Structure):
     _fields_ = [
         ("B", c_int), ("H", c_int), ("Tq", c_int), ("Tk", c_int),
@@ -111,6 +117,8 @@ _SIGS = {
     "ofab_embed_ln_bwd": (c_int, [POINTER(EmbedLnBwdArgs), c_void_p]),
     "ofab_ce_fwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_float, c_void_p, c_void_p]),
     "ofab_ce_bwd": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+    "ofab_ce_rows_fwd": (c_int, [POINTER(CeRowsArgs), c_void_p]),
+    "ofab_ce_rows_bwd": (c_int, [POINTER(CeRowsArgs), c_void_p]),
     "ofab_cast_f32_bf16": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_cast_bf16_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "ofab_video_frames": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p]),
@@ -139,6 +147,9 @@ _SIGS = {
     "ofab_bn_bwd_eval": (c_int, [c_void_p] * 9 + [c_int64, c_int, c_float, c_int, c_void_p, c_void_p]),
     "ofab_fbank": (c_int, [c_void_p, c_int64, c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p, c_int, c_void_p]),
     "ofab_utterance_cmvn": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p]),
+    "ofab_spec_augment": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_float, c_int, c_void_p, c_void_p]),
+    "ofab_image_normalize": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_float), POINTER(c_float), c_void_p, c_int, c_void_p]),
+    "ofab_box_bins": (c_int, [c_void_p, c_int64, c_float, c_int, c_int64, c_void_p, c_void_p]),
     "ofab_ctc_fwd": (c_int, [POINTER(CtcArgs), c_void_p]),
     "ofab_ctc_bwd": (c_int, [POINTER(CtcArgs), c_void_p]),
     "ofab_adam_chunk_elems": (c_int, []),

@@ -311,6 +311,98 @@ __global__ void __launch_bounds__(256) ce_bwd_kernel(const bf16* __restrict__ lo
   }
 }
 
+// ---- per-row criterion with constraint masks (label_smoothed_cross_entropy.py:62-92,147-191) ----------------------------------
+// Allowed entries of row r: cmask[r, c] != 0 (when given) AND (c < 4 or c_lo <= c < c_hi) (when c_lo >= 0: `constraint_range`,
+// get_constraint_masks :147-157); disallowed logits count as -inf.  Per counted row (target != ignore):
+//   nll = lse_allowed - x_t;   smooth = sum_{allowed} (lse - x_c);   eps_i = eps / (n_allowed - 1 + 1e-6)  [constraints] or eps / (V - 1)
+//   loss = (1 - eps - eps_i) * nll + eps_i * smooth
+// The per-row losses go to row_loss / row_nll (the caller applies drop_worst = a top-k over them and sums); the backward takes
+// the per-row weight d total / d row_loss.
+struct CeRows {
+  const bf16* logits;
+  int64_t V, ld;
+  const int64_t* target;
+  int64_t ignore_index;
+  const uint8_t* cmask;
+  int64_t c_lo, c_hi;
+  float eps;
+  float *lse, *row_loss, *row_nll, *n_allowed;
+  const float* row_scale;
+  bf16* dlogits;
+};
+__device__ __forceinline__ bool ce_allowed(const CeRows& a, int64_t r, int64_t c) {
+  bool ok = a.cmask == nullptr || a.cmask[r * a.V + c] != 0;
+  if (a.c_lo >= 0) ok = ok && (c < 4 || (c >= a.c_lo && c < a.c_hi));
+  return ok;
+}
+__global__ void __launch_bounds__(256) ce_rows_fwd_kernel(const CeRows a) {
+  __shared__ float sm_m[8], sm_s[8], sm_x[8], sm_n[8];
+  const int64_t r = blockIdx.x;
+  const bf16* row = a.logits + r * a.ld;
+  float m = -INFINITY, s = 0.f, xs = 0.f, na = 0.f;
+  for (int64_t i = threadIdx.x; i < a.V; i += 256) {
+    if (!ce_allowed(a, r, i)) continue;
+    const float x = __bfloat162float(row[i]);
+    online_merge(m, s, x, 1.f);
+    xs += x;
+    na += 1.f;
+  }
+  xs = warp_sum(xs);
+  na = warp_sum(na);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float m2 = __shfl_xor_sync(0xffffffffu, m, o), s2 = __shfl_xor_sync(0xffffffffu, s, o);
+    online_merge(m, s, m2, s2);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sm_m[threadIdx.x >> 5] = m; sm_s[threadIdx.x >> 5] = s; sm_x[threadIdx.x >> 5] = xs; sm_n[threadIdx.x >> 5] = na;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float M = sm_m[0], S = sm_s[0], X = sm_x[0], N = sm_n[0];
+    for (int w = 1; w < 8; ++w) {
+      online_merge(M, S, sm_m[w], sm_s[w]);
+      X += sm_x[w];
+      N += sm_n[w];
+    }
+    const float l = M + logf(S);
+    a.lse[r] = l;
+    a.n_allowed[r] = N;
+    const int64_t tg = a.target[r];
+    float loss = 0.f, nll = 0.f;
+    if (tg != a.ignore_index) {
+      nll = l - __bfloat162float(row[tg]);  // (a target outside the allowed set gives +inf, as the reference's gather on -inf lprobs)
+      if (!ce_allowed(a, r, tg)) nll = INFINITY;
+      loss = nll;
+      if (a.eps > 0.f) {
+        const bool constrained = a.cmask != nullptr || a.c_lo >= 0;
+        const float eps_i = constrained ? a.eps / (N - 1.0f + 1e-6f) : a.eps / (float)(a.V - 1);
+        loss = (1.0f - a.eps - eps_i) * nll + eps_i * (N * l - X);
+      }
+    }
+    a.row_loss[r] = loss;
+    a.row_nll[r] = nll;
+  }
+}
+__global__ void __launch_bounds__(256) ce_rows_bwd_kernel(const CeRows a) {
+  // d row_loss / d x_c = softmax_c - (1 - eps - eps_i) [c == target] - eps_i   on the allowed entries, 0 elsewhere
+  const int64_t r = blockIdx.x;
+  const bf16* row = a.logits + r * a.ld;
+  bf16* drow = a.dlogits + r * a.ld;
+  const int64_t tg = a.target[r];
+  const bool counted = tg != a.ignore_index;
+  const float g = counted ? a.row_scale[r] : 0.f;
+  const float l = a.lse[r];
+  const bool constrained = a.cmask != nullptr || a.c_lo >= 0;
+  const float eps_i = a.eps > 0.f ? (constrained ? a.eps / (a.n_allowed[r] - 1.0f + 1e-6f) : a.eps / (float)(a.V - 1)) : 0.f;
+  const float w_t = 1.0f - a.eps - eps_i;
+  for (int64_t i = threadIdx.x; i < a.ld; i += 256) {
+    float v = 0.f;
+    if (i < a.V && g != 0.f && ce_allowed(a, r, i)) v = g * (__expf(__bfloat162float(row[i]) - l) - (i == tg ? w_t : 0.f) - eps_i);
+    drow[i] = __float2bfloat16(v);
+  }
+}
+
 int to_args(const ofab_embed_ln_args* a, EmbedArgs& e, const char* who) {
   OFAB_REQUIRE(a->B > 0 && a->T > 0 && a->d >= 8 && a->d <= 1024 && a->d % 8 == 0, "%s: bad shape B=%d T=%d d=%d (d multiple of 8, <= 1024)", who, a->B, a->T, a->d);
   OFAB_REQUIRE((a->tokens != nullptr) != (a->dense != nullptr || (a->has_cls && a->T == 1)), "%s: exactly one of tokens / dense must be given", who);
@@ -361,6 +453,36 @@ extern "C" int ofab_ce_fwd(const void* logits, int64_t rows, int64_t V, int64_t 
   OFAB_REQUIRE(label_smoothing >= 0.f && label_smoothing < 1.f, "ofab_ce_fwd: label_smoothing=%g out of [0, 1)", (double)label_smoothing);
   ce_fwd_kernel<<<(unsigned)rows, 256, 0, (cudaStream_t)stream>>>((const bf16*)logits, V, ld, target, ignore_index, lse, loss_sum, label_smoothing, nll_sum);
   OFAB_LAUNCH_CHECK("ofab_ce_fwd");
+  return OFAB_OK;
+}
+
+static int ce_rows_args(const ofab_ce_rows_args* a, CeRows& c, const char* who) {
+  OFAB_REQUIRE(a->rows > 0 && a->V > 1 && a->ld >= a->V && a->ld % 8 == 0, "%s: bad shape rows=%lld V=%lld ld=%lld", who, (long long)a->rows, (long long)a->V, (long long)a->ld);
+  OFAB_REQUIRE(a->label_smoothing >= 0.f && a->label_smoothing < 1.f, "%s: label_smoothing=%g out of [0, 1)", who, (double)a->label_smoothing);
+  OFAB_REQUIRE(a->logits && a->target && a->lse && a->n_allowed, "%s: NULL tensor", who);
+  OFAB_REQUIRE(a->c_lo < 0 || (a->c_lo >= 4 && a->c_hi > a->c_lo && a->c_hi <= a->V), "%s: constraint range [%lld, %lld) outside [4, V]", who, (long long)a->c_lo, (long long)a->c_hi);
+  c.logits = (const bf16*)a->logits; c.V = a->V; c.ld = a->ld; c.target = a->target; c.ignore_index = a->ignore_index;
+  c.cmask = a->cmask; c.c_lo = a->c_lo; c.c_hi = a->c_hi; c.eps = a->label_smoothing;
+  c.lse = a->lse; c.row_loss = a->row_loss; c.row_nll = a->row_nll; c.n_allowed = a->n_allowed;
+  c.row_scale = a->row_scale; c.dlogits = (bf16*)a->dlogits;
+  return OFAB_OK;
+}
+extern "C" int ofab_ce_rows_fwd(const ofab_ce_rows_args* a, ofab_stream_t stream) {
+  CeRows c;
+  int rc = ce_rows_args(a, c, "ofab_ce_rows_fwd");
+  if (rc) return rc;
+  OFAB_REQUIRE(a->row_loss && a->row_nll, "ofab_ce_rows_fwd: row_loss / row_nll NULL");
+  ce_rows_fwd_kernel<<<(unsigned)a->rows, 256, 0, (cudaStream_t)stream>>>(c);
+  OFAB_LAUNCH_CHECK("ofab_ce_rows_fwd");
+  return OFAB_OK;
+}
+extern "C" int ofab_ce_rows_bwd(const ofab_ce_rows_args* a, ofab_stream_t stream) {
+  CeRows c;
+  int rc = ce_rows_args(a, c, "ofab_ce_rows_bwd");
+  if (rc) return rc;
+  OFAB_REQUIRE(a->row_scale && a->dlogits, "ofab_ce_rows_bwd: row_scale / dlogits NULL");
+  ce_rows_bwd_kernel<<<(unsigned)a->rows, 256, 0, (cudaStream_t)stream>>>(c);
+  OFAB_LAUNCH_CHECK("ofab_ce_rows_bwd");
   return OFAB_OK;
 }
 

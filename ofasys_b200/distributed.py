@@ -213,10 +213,16 @@ class GradArena:
     """Flat gradient storage + bucketed, overlapped exchange for one model replica.
 
         arena = GradArena(model.parameters())          # once (after the parameters are on the device / packed)
-        arena.begin_step()                             # p.grad = None for all, hooks armed
+        arena.begin_step()                             # p.grad = None for all
+        ... loss_k.backward() for all but the last task batch of the step (gradients accumulate locally) ...
+        arena.arm()                                    # the next backward completes the step's gradients
         loss.backward()                                # GEMMs write dW into the arena; buckets all-reduce as they complete
         arena.finish()                                 # leftovers copied in, remaining buckets reduced, streams joined
         # now p.grad (views of the arena) hold the mean over ranks
+
+    A bucket counts as complete when as many of its gradients have been produced in the armed pass as in the previous step's
+    armed pass (learned: a pass need not touch every parameter -- an adaptor no batch uses, a text-only task); the first step
+    reduces everything in finish().
 
     Parameters whose storage is adjacent (ops.pack_params: q|k|v, k|v) get adjacent slots in the same order, so the packed
     weight gradient of one GEMM is one contiguous slot.  Gradients that autograd had to sum from several consumers (the tied
@@ -289,7 +295,8 @@ class GradArena:
                     o = offs[id(grp[a])]
                     _ARENA_SLOTS[(grp[a].data_ptr(), n)] = (self.flat[o:o + n], list(grp[a:b]), self)
         self._handed = set()
-        self._pending = [0] * len(self.buckets)
+        self._fired = [0] * len(self.buckets)
+        self._expected = [None] * len(self.buckets)
         self._done = [False] * len(self.buckets)
         self._tabs = [None] * len(self.buckets)
         self.side = torch.cuda.Stream(device=self.flat.device)
@@ -303,20 +310,26 @@ class GradArena:
             del _ARENA_SLOTS[k]
 
     # ---- one step
-    def begin_step(self):
+    def begin_step(self, arm: bool = False):
         for p in self.params:
             p.grad = None
         self._handed.clear()
-        self._pending = [len(ps) for _, _, ps in self.buckets]
         self._done = [False] * len(self.buckets)
+        self._armed = False
+        if arm:
+            self.arm()
+
+    def arm(self):
+        """The next backward pass completes this step's gradients: buckets may be reduced as they fill."""
+        self._fired = [0] * len(self.buckets)
         self._armed = True
 
     def _on_grad(self, p):
         if not self._armed:
             return
         bi = self._bucket_of[id(p)]
-        self._pending[bi] -= 1
-        if self._pending[bi] == 0 and self.overlap and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        self._fired[bi] += 1
+        if self._fired[bi] == self._expected[bi] and self.overlap and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self._reduce_bucket(bi, async_side=True)
 
     def _settle_bucket(self, bi):
@@ -353,6 +366,8 @@ class GradArena:
 
     def finish(self, scale: Optional[float] = None):
         """After backward: settle + reduce every bucket not yet reduced, join the side stream; p.grad = arena views."""
+        if self._armed:
+            self._expected = list(self._fired)  # (static graphs: the same parameters fire in the same pass every step)
         self._armed = False
         for bi in range(len(self.buckets)):
             self._reduce_bucket(bi, async_side=self.overlap)

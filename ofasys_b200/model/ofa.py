@@ -144,6 +144,19 @@ class GeneralistModel(nn.Module):
             self.encoder.requires_grad_(False)
         self.global_dict = global_dict
 
+    def pack_parameters(self):
+        """Move the q|k|v (self-attention) and k|v (cross-attention) projection parameters of every attention module into
+        shared storages now (otherwise the first forward on the device does it): call after .to(device / dtype) and before
+        anything that records parameter addresses (GradArena, FusedAdam tables)."""
+        from ..module.multihead_attention import MultiheadAttention
+
+        for mod in self.modules():
+            if isinstance(mod, MultiheadAttention) and mod.q_proj.weight.is_cuda:
+                names = ("q_proj", "k_proj", "v_proj") if mod.self_attention else ("k_proj", "v_proj")
+                mod._cat(names, "weight")
+                mod._cat(names, "bias")
+        return self
+
     def get_active_executor(self):
         return self.active_executor
 

@@ -869,6 +869,61 @@ def cross_entropy_sum(logits, target, ignore_index=1, label_smoothing=0.0):
     return _CrossEntropyFn.apply(logits, target, ignore_index, label_smoothing)
 
 
+class _CrossEntropyRowsFn(torch.autograd.Function):
+    """Per-row (label-smoothed) cross entropy with constraint masks: returns (row_loss, row_nll) fp32 [rows]."""
+
+    @staticmethod
+    def forward(ctx, logits, target, ignore_index, label_smoothing, cmask, c_lo, c_hi):
+        _need_cuda(logits, target)
+        V = logits.shape[-1]
+        l2 = logits.reshape(-1, V)
+        if l2.dtype != torch.bfloat16 or l2.stride(1) != 1 or l2.stride(0) % 8 != 0:
+            Vp = (V + 7) // 8 * 8
+            buf = torch.zeros((l2.shape[0], Vp), dtype=torch.bfloat16, device=logits.device)
+            buf[:, :V].copy_(l2)
+            l2 = buf[:, :V]
+        rows, ld = l2.shape[0], l2.stride(0)
+        tgt = _c(target.reshape(-1))
+        if cmask is not None:
+            cmask = _c(cmask.reshape(rows, V).to(torch.uint8))
+        dev = logits.device
+        lse, nal, rl, rn = (torch.empty(rows, dtype=torch.float32, device=dev) for _ in range(4))
+        a = _lib.CeRowsArgs()
+        a.logits, a.rows, a.V, a.ld, a.target, a.ignore_index = l2.data_ptr(), rows, V, ld, tgt.data_ptr(), ignore_index
+        a.cmask = None if cmask is None else cmask.data_ptr()
+        a.c_lo, a.c_hi, a.label_smoothing = c_lo, c_hi, float(label_smoothing)
+        a.lse, a.n_allowed, a.row_loss, a.row_nll = lse.data_ptr(), nal.data_ptr(), rl.data_ptr(), rn.data_ptr()
+        _lib.call("ofab_ce_rows_fwd", ctypes.byref(a), _s())
+        ctx.save_for_backward(l2, tgt, cmask, lse, nal)
+        ctx.meta = (ignore_index, logits.shape, float(label_smoothing), c_lo, c_hi)
+        ctx.mark_non_differentiable(rn)
+        return rl, rn
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_nll):
+        l2, tgt, cmask, lse, nal = ctx.saved_tensors
+        ignore_index, shape, eps, c_lo, c_hi = ctx.meta
+        rows, V = l2.shape
+        ld = l2.stride(0)
+        dl = torch.empty((rows, ld), dtype=torch.bfloat16, device=l2.device)
+        gs = _c(g_loss.to(torch.float32))
+        a = _lib.CeRowsArgs()
+        a.logits, a.rows, a.V, a.ld, a.target, a.ignore_index = l2.data_ptr(), rows, V, ld, tgt.data_ptr(), ignore_index
+        a.cmask = None if cmask is None else cmask.data_ptr()
+        a.c_lo, a.c_hi, a.label_smoothing = c_lo, c_hi, eps
+        a.lse, a.n_allowed, a.row_scale, a.dlogits = lse.data_ptr(), nal.data_ptr(), gs.data_ptr(), dl.data_ptr()
+        _lib.call("ofab_ce_rows_bwd", ctypes.byref(a), _s())
+        d = dl[:, :V]
+        return (d.view(shape) if ld == V else d.unflatten(0, shape[:-1])), None, None, None, None, None, None
+
+
+def cross_entropy_rows(logits, target, ignore_index=1, label_smoothing=0.0, constraint_masks=None, constraint_range=None):
+    """Per-row criterion of label_smoothed_cross_entropy.py:62-92 with constraint masks (bool [.., V], True = allowed) and / or
+    `constraint_range` = (start, end): returns (row_loss, row_nll) fp32 [rows]; ignored rows give 0."""
+    c_lo, c_hi = (-1, -1) if constraint_range is None else (int(constraint_range[0]), int(constraint_range[1]))
+    return _CrossEntropyRowsFn.apply(logits, target, ignore_index, label_smoothing, constraint_masks, c_lo, c_hi)
+
+
 class _LinearCrossEntropyFn(torch.autograd.Function):
     """loss = sum-CE(x E^T, target): the tied output projection (adaptor/base.py:131) fused with the
     criterion (cross_entropy.py:62-67) so the [rows, V] logits live only as one bf16 scratch."""

@@ -92,3 +92,53 @@ def utterance_cmvn_(feats: torch.Tensor, n_frames: torch.Tensor = None, norm_mea
     _lib.call("ofab_utterance_cmvn", ctypes.c_void_p(feats.data_ptr()), None if nf is None else ctypes.c_void_p(nf.data_ptr()), B, T, F,
               int(norm_means), int(norm_vars), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     return feats
+
+
+class SpecAugment:
+    """The training-time masking of `SpecAugmentTransform` (utils/audio_feature_transforms/specaugment.py:79-126) on device
+    features [B, max_frames, n_feat]: `freq_mask_n` bands of width < `freq_mask_f`, `time_mask_n` bands of width <
+    min(time_mask_t, floor(n_frames * time_mask_p)), filled with `mask_value` (None: the utterance mean).  The random draws are
+    made on the host with numpy's global generator in the reference's own order, one utterance after the other, so a run seeded
+    like the reference masks the same bands.  `time_warp_w` (cv2 resize) is not implemented."""
+
+    def __init__(self, time_warp_w=0, freq_mask_n=0, freq_mask_f=0, time_mask_n=0, time_mask_t=0, time_mask_p=0.0, mask_value=0.0):
+        if time_warp_w:
+            raise NotImplementedError("SpecAugment time warping (cv2 resize) is not implemented on the device path")
+        self.freq_mask_n, self.freq_mask_f = int(freq_mask_n), int(freq_mask_f)
+        self.time_mask_n, self.time_mask_t, self.time_mask_p = int(time_mask_n), int(time_mask_t), float(time_mask_p)
+        self.mask_value = mask_value
+
+    def draw(self, n_frames, n_freqs):
+        """host: the (start, width) pairs one call of the reference transform would draw for one utterance"""
+        import numpy as np
+
+        bands = []
+        if n_frames == 0 or n_freqs < self.freq_mask_f:
+            return [(0, 0)] * (self.freq_mask_n + self.time_mask_n)
+        for _ in range(self.freq_mask_n):
+            f = np.random.randint(0, self.freq_mask_f)
+            f0 = np.random.randint(0, n_freqs - f)
+            bands.append((f0, f))
+        max_t = min(self.time_mask_t, math.floor(n_frames * self.time_mask_p))
+        for _ in range(self.time_mask_n):
+            if max_t < 1:
+                bands.append((0, 0))
+                continue
+            t = np.random.randint(0, max_t)
+            t0 = np.random.randint(0, n_frames - t)
+            bands.append((t0, t))
+        return bands
+
+    def __call__(self, feats, n_frames=None):
+        if not feats.is_cuda or feats.dtype != torch.float32 or not feats.is_contiguous():
+            raise _lib.OfabError("SpecAugment needs a contiguous fp32 CUDA tensor [B, max_frames, n_feat] (no CPU fallback)")
+        B, L, F = feats.shape
+        lens = [L] * B if n_frames is None else [int(v) for v in n_frames.tolist()]
+        table = torch.tensor([self.draw(min(n, L), F) for n in lens], dtype=torch.int32).reshape(B, -1, 2).to(feats.device)
+        nf = None if n_frames is None else n_frames.to(device=feats.device, dtype=torch.int64).contiguous()
+        use_mean = self.mask_value is None
+        scratch = torch.empty(B, dtype=torch.float32, device=feats.device) if use_mean else None
+        _lib.call("ofab_spec_augment", ctypes.c_void_p(feats.data_ptr()), None if nf is None else ctypes.c_void_p(nf.data_ptr()), B, L, F,
+                  ctypes.c_void_p(table.data_ptr()), self.freq_mask_n, self.time_mask_n, 0.0 if use_mean else float(self.mask_value), int(use_mean),
+                  None if scratch is None else ctypes.c_void_p(scratch.data_ptr()), ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
+        return feats

@@ -42,6 +42,35 @@ def main():
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ls_ce.pt")
     torch.save(out, path)
     print("wrote", path, os.path.getsize(path), "bytes; loss", float(loss), "nll", float(nll), "ntokens", ntokens)
+    # ---- constraint masks / constraint_range / drop-worst: the reference function on the reference's own masking recipe
+    # (get_constraint_masks :147-157, get_lprobs_and_target :159-173, compute_loss :175-191 written out)
+    import math
+
+    logits, target, masks, (lo, hi) = om.make_constraint_case()
+    res = {}
+    for tag, use_masks, use_range, dw in (("range", False, True, 0.0), ("masks", True, False, 0.0), ("both", True, True, 0.0), ("dropworst", False, True, 0.25)):
+        x = logits.float().requires_grad_(True)
+        cm = None
+        if use_range:
+            cm = torch.ones(x.shape, dtype=torch.bool)
+            cm[..., 4:lo] = 0
+            cm[..., hi:] = 0
+            if use_masks:
+                cm = torch.logical_and(masks, cm)
+        elif use_masks:
+            cm = masks
+        xm = x.masked_fill(~cm, -math.inf)
+        lprobs = torch.log_softmax(xm, dim=-1).view(-1, x.size(-1))
+        tgt = target.view(-1)
+        cmf = cm.reshape(-1, cm.size(-1))
+        keep = tgt != om.PAD
+        l, n, nt = fn(lprobs[keep], tgt[keep], 0.1, update_num=5, drop_worst_ratio=dw, drop_worst_after=2, constraint_masks=cmf[keep])
+        l.backward()
+        res[tag] = {"loss": l.detach(), "nll_loss": n.detach(), "ntokens": nt, "dlogits": x.grad.clone()}
+        print(tag, float(l), float(n), nt)
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "ls_ce_constraints.pt")
+    torch.save(res, path)
+    print("wrote", path, os.path.getsize(path), "bytes")
 
 
 if __name__ == "__main__":

@@ -78,3 +78,33 @@ def make_case(seed=11, B=3, n=16000 * 2 + 123):
     wav[1, 20000:] *= 0.01  # a quiet tail
     lengths = torch.tensor([n, n - 7000, 5000][:B], dtype=torch.long)
     return wav, lengths
+
+
+def spec_augment(spectrogram, time_warp_w=0, freq_mask_n=0, freq_mask_f=0, time_mask_n=0, time_mask_t=0, time_mask_p=0.0, mask_value=0.0):
+    """utils/audio_feature_transforms/specaugment.py:79-126 (SpecAugmentTransform.__call__, no time warping): numpy in, numpy
+    out; draws from numpy's global generator in the reference's order."""
+    import math
+
+    import numpy as np
+
+    assert time_warp_w == 0
+    distorted = spectrogram.copy()
+    num_frames, num_freqs = spectrogram.shape
+    if mask_value is None:
+        mask_value = spectrogram.mean()
+    if num_frames == 0 or num_freqs < freq_mask_f:
+        return spectrogram
+    for _ in range(freq_mask_n):
+        f = np.random.randint(0, freq_mask_f)
+        f0 = np.random.randint(0, num_freqs - f)
+        if f != 0:
+            distorted[:, f0:f0 + f] = mask_value
+    max_t = min(time_mask_t, math.floor(num_frames * time_mask_p))
+    if max_t < 1:
+        return distorted
+    for _ in range(time_mask_n):
+        t = np.random.randint(0, max_t)
+        t0 = np.random.randint(0, num_frames - t)
+        if t != 0:
+            distorted[t0:t0 + t, :] = mask_value
+    return distorted

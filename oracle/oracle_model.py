@@ -578,6 +578,58 @@ def label_smoothed_cross_entropy_sum(logits, target, epsilon, pad=PAD):
     return loss.sum(), nll.sum(), loss.numel()
 
 
+def label_smoothed_nll_loss(lprobs, target, epsilon, update_num, drop_worst_ratio=0.0, drop_worst_after=0, constraint_masks=None):
+    """engine/criterion/label_smoothed_cross_entropy.py:62-92 in full (constraint masks :72-77, drop-worst :79-82).
+    lprobs: fp32 [n, V] of the counted rows (disallowed entries -inf under constraints).  Returns (loss, nll, ntokens)."""
+    nll = -lprobs.gather(dim=-1, index=target.unsqueeze(-1)).squeeze(-1)
+    if constraint_masks is not None:
+        smooth = -lprobs.masked_fill(~constraint_masks, 0).sum(dim=-1)
+        eps_i = epsilon / (constraint_masks.sum(1) - 1 + 1e-6)
+    else:
+        smooth = -lprobs.sum(dim=-1)
+        eps_i = epsilon / (lprobs.size(-1) - 1)
+    loss = (1.0 - epsilon - eps_i) * nll + eps_i * smooth
+    if drop_worst_ratio > 0 and update_num > drop_worst_after:
+        loss, idx = torch.topk(loss, k=int(loss.shape[0] * (1 - drop_worst_ratio)), largest=False)
+        nll = nll[idx]
+    return loss.sum(), nll.sum(), loss.numel()
+
+
+def constrained_criterion(logits, target, epsilon, constraint_range=None, constraint_masks=None, update_num=0, drop_worst_ratio=0.0,
+                          drop_worst_after=0, pad=PAD):
+    """LabelSmoothedCrossEntropyCriterion.compute_loss with constraints (label_smoothed_cross_entropy.py:147-191):
+    get_constraint_masks (range: entries [4, start) and [end, V) off, AND the sample's masks), logits masked to -inf, fp32
+    log-softmax, padding rows dropped, label_smoothed_nll_loss."""
+    V = logits.size(-1)
+    cm = constraint_masks
+    if constraint_range is not None:
+        rm = torch.ones(logits.shape, dtype=torch.bool)
+        rm[..., 4:constraint_range[0]] = False
+        rm[..., constraint_range[1]:] = False
+        cm = rm if cm is None else torch.logical_and(cm, rm)
+    x = logits.float()
+    if cm is not None:
+        x = x.masked_fill(~cm, float("-inf"))
+    lprobs = F.log_softmax(x, dim=-1).view(-1, V)
+    tgt = target.view(-1)
+    keep = tgt != pad
+    cmk = None if cm is None else cm.reshape(-1, V)[keep]
+    return label_smoothed_nll_loss(lprobs[keep], tgt[keep], epsilon, update_num, drop_worst_ratio, drop_worst_after, cmk)
+
+
+def make_constraint_case(seed=11, B=3, T=7, V=203, lo=50, hi=120):
+    """Seeded logits (bf16 values) / targets inside the constraint range / extra trie-style masks, for the constrained criterion."""
+    g = torch.Generator().manual_seed(seed)
+    logits = (torch.randn(B, T, V, generator=g) * 2.0).to(torch.bfloat16)
+    target = torch.randint(lo, hi, (B, T), generator=g)
+    target[0, -2:] = PAD
+    target[2, -1] = PAD
+    masks = torch.rand(B, T, V, generator=g) > 0.3
+    masks.scatter_(-1, target.unsqueeze(-1), True)  # the target is always allowed
+    masks[..., :4] = True
+    return logits, target, masks, (lo, hi)
+
+
 def make_ls_case(seed=7, rows=37, V=1003, eps=0.1):
     """Seeded logits (bf16 values) / targets with padding for the label-smoothed criterion fixtures."""
     g = torch.Generator().manual_seed(seed)

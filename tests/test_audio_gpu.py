@@ -86,3 +86,51 @@ def test_fbank_feeds_the_audio_adaptor_contract():
     assert feats.dtype == torch.float32 and n_frames.dtype == torch.int64 and feats.is_contiguous()
     with pytest.raises(Exception):
         Fbank()(wav)  # CPU tensor: no fallback
+
+
+def test_spec_augment_masks_the_reference_bands():
+    """SpecAugment masking on device == the reference transform's own arithmetic (restated in
+    oracle_audio.spec_augment, utils/audio_feature_transforms/specaugment.py:79-126) under the same numpy seed, bit-exact for a
+    numeric mask value; the utterance-mean fill within fp32 summation order."""
+    import numpy as np
+    from oracle import oracle_audio as oa
+    from ofasys_b200.preprocessor.audio import SpecAugment
+
+    g = torch.Generator().manual_seed(5)
+    B, L, F = 3, 120, 80
+    feats = torch.randn(B, L, F, generator=g)
+    lens = torch.tensor([120, 97, 64])
+    for mv in (0.0, None):
+        kw = dict(freq_mask_n=2, freq_mask_f=27, time_mask_n=2, time_mask_t=40, time_mask_p=0.2, mask_value=mv)
+        np.random.seed(7)
+        want = [oa.spec_augment(feats[b, : int(lens[b])].numpy(), **kw) for b in range(B)]
+        np.random.seed(7)
+        x = feats.clone().cuda()
+        SpecAugment(**kw)(x, lens.cuda())
+        for b in range(B):
+            n = int(lens[b])
+            got = x[b, :n].cpu()
+            if mv is None:
+                assert (got - torch.from_numpy(want[b])).abs().max().item() <= 1e-6
+            else:
+                assert torch.equal(got, torch.from_numpy(want[b]))
+            assert torch.equal(x[b, n:].cpu(), feats[b, n:])  # rows past the utterance untouched
+        assert (x.cpu() != feats).any()
+
+
+def test_image_normalize_and_box_bins_bit_exact():
+    """ToTensor + Normalize (preprocessor/default/image.py:110-116) and the `<bin>` quantisation (box.py:101-110) on device,
+    bit-exact against the same torch arithmetic the reference runs."""
+    from ofasys_b200.preprocessor.image import IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD, box_to_tokens, normalize_images
+    from oracle import oracle_model as om
+
+    g = torch.Generator().manual_seed(3)
+    px = torch.randint(0, 256, (2, 37, 53, 3), generator=g, dtype=torch.uint8)
+    for mean, std in (((0.5, 0.5, 0.5), (0.5, 0.5, 0.5)), (IMAGENET_DEFAULT_MEAN, IMAGENET_DEFAULT_STD)):
+        want = px.permute(0, 3, 1, 2).float().div(255)  # ToTensor
+        want = want.sub(torch.tensor(mean).view(1, 3, 1, 1)).div(torch.tensor(std).view(1, 3, 1, 1))  # Normalize
+        got = normalize_images(px.cuda(), mean, std)
+        assert torch.equal(got.cpu(), want)
+    coords = torch.cat([torch.rand(4000, generator=g) * 512, torch.tensor([0.0, 511.0, 512.0, 255.6, 0.2563, 256.2563])])
+    want = 50265 + om.quantize_box(coords, 512, 1000)
+    assert torch.equal(box_to_tokens(coords.cuda(), 50265).cpu(), want)

@@ -203,7 +203,7 @@ def test_ctypes_binding_matches_the_header():
         pytest.skip("no C compiler")
     structs = {"ofab_dropout": _lib.Dropout, "ofab_attn_fwd_args": _lib.AttnFwdArgs, "ofab_attn_bwd_args": _lib.AttnBwdArgs,
                "ofab_embed_ln_args": _lib.EmbedLnArgs, "ofab_embed_ln_bwd_args": _lib.EmbedLnBwdArgs, "ofab_ctc_args": _lib.CtcArgs,
-               "ofab_adam_tensor": _lib.AdamTensor, "ofab_adam_hyper": _lib.AdamHyper}
+               "ofab_adam_tensor": _lib.AdamTensor, "ofab_adam_hyper": _lib.AdamHyper, "ofab_ce_rows_args": _lib.CeRowsArgs}
     assert set(structs) == set(re.findall(r"}\s*(ofab_[a-z_]+)\s*;", code))  # every typedef'd struct of the header is bound
     with tempfile.TemporaryDirectory() as td:
         src = os.path.join(td, "s.c")

@@ -977,6 +977,7 @@ def test_grad_arena_matches_plain_backward():
         assert len(arena.buckets) > 3
         arena.begin_step()
         run()
+        arena.arm()
         run()
         arena.finish()
         torch.cuda.synchronize()
@@ -994,3 +995,95 @@ def test_grad_arena_matches_plain_backward():
         assert a.q_proj.weight.grad.data_ptr() + a.q_proj.weight.numel() * 2 == a.k_proj.weight.grad.data_ptr()  # packed slots
     finally:
         arena.close()
+
+
+@pytest.mark.parametrize("tag,use_masks,use_range,dw", [("range", False, True, 0.0), ("masks", True, False, 0.0), ("both", True, True, 0.0), ("dropworst", False, True, 0.25)])
+def test_constrained_label_smoothed_criterion(tag, use_masks, use_range, dw):
+    """constraint_range / constraint masks / drop-worst of the label-smoothed criterion on the per-row CE
+    kernels (ops.cross_entropy_rows + criterion.LabelSmoothedCrossEntropyCriterion) against the reference's own numbers
+    (tests/golden/ls_ce_constraints.pt) and the oracle."""
+    import os
+    from ofasys_b200.criterion import LabelSmoothedCrossEntropyCriterion
+    from oracle import oracle_model as om
+
+    fx = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ls_ce_constraints.pt"), weights_only=False)[tag]
+    logits, target, masks, rng = om.make_constraint_case()
+    x = logits.to(dev()).requires_grad_(True)
+
+    class _M:  # the criterion only needs model(**net_input) -> (logits, extra) and get_targets
+        def __call__(self, **kw):
+            return x, {}
+
+        def get_targets(self, sample, net_output):
+            return sample["target"]
+
+    sample = {"net_input": {}, "target": target.to(dev()), "ntokens": int((target != 1).sum()), "nsentences": target.shape[0]}
+    if use_masks:
+        sample["constraint_masks"] = masks.to(dev())
+    crit = LabelSmoothedCrossEntropyCriterion(label_smoothing=0.1, drop_worst_ratio=dw, drop_worst_after=2,
+                                              constraint_range=f"{rng[0]},{rng[1]}" if use_range else None)
+    loss, sample_size, log = crit(_M(), sample, update_num=5)
+    loss.backward()
+    assert sample_size == fx["ntokens"]
+    assert abs(float(loss) - float(fx["loss"])) <= 2e-5 * abs(float(fx["loss"]))
+    assert abs(float(log["nll_loss"]) - float(fx["nll_loss"])) <= 2e-5 * abs(float(fx["nll_loss"]))
+    assert rel_l2(x.grad.float(), fx["dlogits"]) <= 6e-3  # bf16 gradient storage
+    disallowed = ~masks if use_masks else torch.zeros_like(masks)
+    if use_range:
+        disallowed = disallowed.clone()
+        disallowed[..., 4:rng[0]] = True
+        disallowed[..., rng[1]:] = True
+    assert not x.grad.cpu()[disallowed].any()  # exact zeros outside the constraint set
+
+
+def test_speech_to_text_criterion_ce_plus_ctc():
+    """the composed ASR criterion (speech_to_text_loss.py:206-237): ce_weight * label-smoothed CE + ctc_weight *
+    CTC on F.linear(encoder_out, E[dict_start:dict_end]) -- against the oracle model + the oracle's criterion pieces."""
+    from ofasys_b200.criterion import SpeechToTextLossCriterion
+    from oracle import cases
+    from oracle import oracle_model as om
+    from util import bf16_round_state_dict, build_product, load_golden as _lg, to_product_slots
+
+    name = "audio_A"
+    gold = _lg(name)
+    sd = cases.synth_state_dict(gold["spec"], seed=0)
+    sd_r = bf16_round_state_dict(sd)
+    cfg = cases.oracle_cfg(name)
+    slots, target = cases.make_inputs(name)
+    m = build_product(name)
+    m.load_state_dict(sd, strict=False)
+    m = m.to(torch.bfloat16).to(dev()).train()
+    gen = g()
+    B = target.shape[0]
+    d0, d1 = 100, 160  # phone range of the vocabulary; blank = first entry
+    L = 9
+    et = torch.randint(d0 + 1, d1, (B, L), generator=gen)
+    et[:, -1] = 2  # eos
+    et[1, 5:-1] = 1  # padding
+    sample = {"net_input": {"slots": to_product_slots(slots, dev())}, "target": target.to(dev()), "ntokens": int((target != 1).sum()),
+              "nsentences": B, "encoder_target": et.to(dev())}
+    crit = SpeechToTextLossCriterion(d0, d1, blank_idx=0, ce_weight=0.7, ctc_weight=0.3, zero_infinity=True, label_smoothing=0.1)
+    loss, sample_size, log = crit(m, sample)
+    loss.backward()
+    # oracle: the same composition from the oracle model
+    leaf = {k: v.clone().requires_grad_(True) for k, v in sd_r.items() if v.is_floating_point() and "running_" not in k}
+    leaf["decoder.adaptor.embed_tokens.weight"] = leaf["encoder.adaptor.embed_tokens.weight"]
+    full = dict(sd_r)
+    full.update(leaf)
+    logits, extra = om.model_forward(full, cfg, slots)
+    ce, _, _ = om.constrained_criterion(logits, target, 0.1)
+    enc = extra["encoder_out"]
+    xc = torch.nn.functional.linear(enc["encoder_out"], full["decoder.adaptor.embed_tokens.weight"][d0:d1])  # T x B x C
+    lens = (~enc["encoder_padding_mask"]).long().sum(-1)
+    pm = (et != 1) & (et != 2)
+    tl = pm.sum(-1)
+    lp = torch.log_softmax(xc.float(), -1)
+    ctc = torch.nn.functional.ctc_loss(lp, (et - d0).masked_select(pm), lens, tl, blank=0, reduction="sum", zero_infinity=True)
+    ref = 0.7 * ce + 0.3 * ctc
+    ref.backward()
+    assert abs(float(log["ctc_loss"]) - float(ctc)) <= 5e-3 * abs(float(ctc)), (float(log["ctc_loss"]), float(ctc))
+    assert abs(float(loss) - float(ref)) <= 3e-3 * abs(float(ref)), (float(loss), float(ref))
+    gE = dict(m.named_parameters())["encoder.adaptor.embed_tokens.weight"].grad.float().cpu()
+    assert rel_l2(gE, leaf["encoder.adaptor.embed_tokens.weight"].grad) <= 3e-2
+    k = "encoder.layers.1.fc1.weight"
+    assert rel_l2(dict(m.named_parameters())[k].grad.float().cpu(), leaf[k].grad) <= 3e-2

@@ -183,6 +183,23 @@ def test_label_smoothed_criterion_oracle_matches_reference():
     assert abs(float(l0) - float(om.cross_entropy_sum(logits.float(), target))) <= 1e-6 * abs(float(l0)) and float(l0) == float(n0)
 
 
+def test_constrained_criterion_oracle_matches_reference():
+    """oracle_model.constrained_criterion (constraint_range / constraint masks / drop-worst, label_smoothed_cross_entropy.py:62-92,
+    147-191) against the reference's own label_smoothed_nll_loss on its own masking recipe (tests/golden/ls_ce_constraints.pt)."""
+    fx = torch.load(os.path.join(GOLD, "ls_ce_constraints.pt"), weights_only=False)
+    logits, target, masks, rng = om.make_constraint_case()
+    for tag, use_masks, use_range, dw in (("range", False, True, 0.0), ("masks", True, False, 0.0), ("both", True, True, 0.0), ("dropworst", False, True, 0.25)):
+        x = logits.float().requires_grad_(True)
+        loss, nll, ntok = om.constrained_criterion(x, target, 0.1, rng if use_range else None, masks if use_masks else None, update_num=5,
+                                                   drop_worst_ratio=dw, drop_worst_after=2)
+        loss.backward()
+        f = fx[tag]
+        assert ntok == f["ntokens"], tag
+        assert abs(float(loss) - float(f["loss"])) <= 1e-6 * abs(float(f["loss"])), tag
+        assert abs(float(nll) - float(f["nll_loss"])) <= 1e-6 * abs(float(f["nll_loss"])), tag
+        assert ((x.grad - f["dlogits"]).norm() / f["dlogits"].norm()).item() <= 1e-6, tag
+
+
 def test_audio_front_end_oracle_matches_torchaudio_and_reference_cmvn():
     """oracle_audio.fbank against tests/golden/fbank.pt (torchaudio.compliance.kaldi.fbank, the function the reference
     calls, + the reference's own UtteranceCMVN) and, when torchaudio is importable, against torchaudio directly.
@@ -317,3 +334,17 @@ def test_box_target_golden_from_reference():
     assert tuple(logits.shape) == tuple(fx["logits"].shape) == (4, 5, 512)
     assert ((logits - fx["logits"]).norm() / fx["logits"].norm()).item() <= 1e-5
     assert abs(float(om.cross_entropy_sum(logits, target)) - float(fx["loss"])) <= 1e-5 * abs(float(fx["loss"]))
+
+
+def test_spec_augment_oracle_matches_reference_transform():
+    """oracle_audio.spec_augment against the output of the reference's own SpecAugmentTransform under the same numpy seed
+    (tests/golden/specaugment.pt, oracle/make_golden_specaugment.py): bit-exact (integer draws + assignments)."""
+    import numpy as np
+    from oracle import oracle_audio as oa
+    from oracle.make_golden_specaugment import CASE, case_input
+
+    fx = torch.load(os.path.join(GOLD, "specaugment.pt"), weights_only=False)
+    x = case_input()
+    for tag, mv in (("zero", 0.0), ("mean", None)):
+        np.random.seed(7)
+        assert torch.equal(torch.from_numpy(oa.spec_augment(x, mask_value=mv, **CASE)), fx[tag]), tag

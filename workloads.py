@@ -152,7 +152,7 @@ def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=123
     import torch.distributed as dist
 
     from ofasys_b200 import _lib
-    from ofasys_b200.distributed import GradBuckets
+    from ofasys_b200.distributed import GradArena
 
     w = WORKLOADS[name]
     tasks = w["tasks"]
@@ -162,19 +162,33 @@ def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=123
     batches = [{k: v.to(dev) for k, v in host_batch(t, w["vocab"], seed + 17 * i + 1000 * rank).items()} for i, t in enumerate(tasks)]
     state = {}
 
+    # world > 1: gradients land in the flat arena, buckets are all-reduced as the LAST task's backward fills them (the
+    # exchange is part of the step and of its CUDA graph)
+    arena = None
+
     def compute():
-        for p in params:
-            p.grad = None
+        if arena is not None:
+            arena.begin_step()
+        else:
+            for p in params:
+                p.grad = None
         losses = []
-        for t, b in zip(tasks, batches):
+        for k, (t, b) in enumerate(zip(tasks, batches)):
             loss = model.forward_loss(to_slots(t, b), b["tgt"])
+            if arena is not None and k == len(tasks) - 1:
+                arena.arm()
             loss.backward()  # accumulates over the tasks of the step (trainer.py:752-830)
             losses.append(loss)
+        if arena is not None:
+            arena.finish()
         return losses
 
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
+        state["losses"] = compute()  # (packs the q|k|v parameter storages before the arena looks at their addresses)
+        if world > 1:
+            arena = GradArena(params)
         for _ in range(2):
             state["losses"] = compute()
     torch.cuda.current_stream().wait_stream(side)
@@ -196,15 +210,11 @@ def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=123
             print(f"[workloads] {name}: CUDA graph capture failed ({type(ex).__name__}: {ex}); eager", file=sys.stderr)
             torch.cuda.synchronize()
             graph = None
-    buckets = GradBuckets(params) if world > 1 else None
-
     def step():
         if graph is not None:
             graph.replay()
         else:
             state["losses"] = compute()
-        if buckets is not None:
-            buckets.allreduce()
 
     for _ in range(warmup):
         step()
@@ -232,7 +242,9 @@ def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=123
            "seqs_per_step": seqs, "cuda_graph": graph is not None, "gpu_launches": (launches or 0) + eager_l,
            "algorithmic_gflop_per_step_per_gpu": gflop_per_step(name), "model_tflops_per_gpu": tf,
            "losses": [float(x) for x in state["losses"]], "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 1e9}
-    del graph, model, batches, buckets
+    if arena is not None:
+        arena.close()
+    del graph, model, batches
     state.clear()
     torch.cuda.empty_cache()
     return out
