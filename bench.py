@@ -212,6 +212,8 @@ def run_gpu(args, rank, world, local_rank):
     if args.no_pdl:
         _lib.lib().ofab_set_pdl(0)
     if world > 1:
+        # 64 MB gradient buckets: the Simple protocol (LL / LL128 trade bandwidth for latency); measured at N=2: 28.17 vs 28.67 ms
+        os.environ.setdefault("NCCL_PROTO", "Simple")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     model = build_model(dev)
@@ -495,13 +497,19 @@ def run_gpu(args, rank, world, local_rank):
         pool.clear()
         # DRAM traffic of the dominant kernel: measured once under ncu (dram__bytes_read.sum + dram__bytes_write.sum over the
         # GEMM launches of one step, tools/launch_list_summary.py -> profiles/r01_gemm_traffic.json), per launch like `achieved`
+        # (profiles/r02_gemm_traffic.json, written by tools/launch_list_summary.py; only valid for the build it was captured on:
+        # the file carries the hash of the kernel sources -- a stale capture is reported as null, not as evidence)
         traffic = traffic_note = None
-        tp = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        tp = os.path.join(ROOT, "profiles", "r02_gemm_traffic.json")
         if os.path.exists(tp):
             try:
                 tj = json.load(open(tp))
-                if int(tj.get("per_gpu_batch", -1)) == B:
+                from ofasys_b200.build import _stamp
+
+                if int(tj.get("per_gpu_batch", -1)) == B and tj.get("build_stamp") == _stamp():
                     traffic, traffic_note = tj["dram_bytes_per_launch"], tj.get("note")
+                else:
+                    traffic_note = "profiles/r02_gemm_traffic.json was captured on a different build or batch: not reported"
             except Exception:
                 pass
         roof = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05)", "achieved": ach, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
@@ -675,7 +683,16 @@ def run_gpu(args, rank, world, local_rank):
         }
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Leave without tearing the communicator down: destroy_process_group() after NCCL kernels were captured into CUDA
+        # graphs was observed to hang (both ranks idle after the line was printed).  Everything measured is on stdout.
+        torch.cuda.synchronize()
+        try:
+            dist.barrier()
+        except Exception:
+            pass
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

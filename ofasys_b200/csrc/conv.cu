@@ -10,6 +10,8 @@ namespace {
 template <typename TIN>
 __global__ void __launch_bounds__(128) conv1_relu_fwd_kernel(const TIN* __restrict__ x, int B, int L, int F, const bf16* __restrict__ w,
                                                              const bf16* __restrict__ bias, int C, bf16* __restrict__ out, int H1, int W1) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   extern __shared__ float xs[];  // 3 x F
   const int b = blockIdx.x / H1, h = blockIdx.x % H1;
   for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) xs[i] = (float)x[((int64_t)b * L + 2 * h + i / F) * F + i % F];
@@ -44,6 +46,8 @@ template <typename TIN>
 __global__ void __launch_bounds__(128) conv1_relu_bwd_kernel(const TIN* __restrict__ x, int B, int L, int F, const bf16* __restrict__ y,
                                                              const bf16* __restrict__ dy, int C, float* __restrict__ dw, float* __restrict__ db,
                                                              int H1, int W1) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   extern __shared__ float xs[];
   const int cg = threadIdx.x;  // one 8-channel group per thread; host guarantees C/8 <= blockDim.x
   const bool live = cg * 8 < C;
@@ -88,6 +92,8 @@ __global__ void __launch_bounds__(128) conv1_relu_bwd_kernel(const TIN* __restri
 
 // cols[(b, ho, wo), (kh*3+kw)*C + c] = x[b, 2ho+kh, 2wo+kw, c]
 __global__ void im2col_3x3s2_kernel(const bf16* __restrict__ x, int B, int Hin, int Win, int C, bf16* __restrict__ cols, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = (int64_t)B * Ho * Wo * 9 * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -101,6 +107,8 @@ __global__ void im2col_3x3s2_kernel(const bf16* __restrict__ x, int B, int Hin, 
 }
 // dx[b, h, w, c] = sum over (kh, kw) with h = 2ho+kh, w = 2wo+kw of dcols[(b,ho,wo), (kh*3+kw)*C + c]
 __global__ void col2im_3x3s2_kernel(const bf16* __restrict__ dcols, int B, int Hin, int Win, int C, bf16* __restrict__ dx, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = (int64_t)B * Hin * Win * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -128,6 +136,8 @@ __global__ void col2im_3x3s2_kernel(const bf16* __restrict__ dcols, int B, int H
 }
 // out[o, b, a] = in[o, a, b]   (32x32 smem tiles)
 __global__ void transpose_last2_kernel(const bf16* __restrict__ in, bf16* __restrict__ out, int A, int Bd) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   __shared__ bf16 tile[32][33];
   const int64_t o = blockIdx.z;
   const int a0 = blockIdx.y * 32, b0 = blockIdx.x * 32;
@@ -154,9 +164,9 @@ extern "C" int ofab_conv1_relu_fwd(const void* fbank, int in_dt, int B, int L, i
   const int H1 = (L - 3) / 2 + 1, W1 = (F - 3) / 2 + 1;
   const int smem = 3 * F * 4;
   if (in_dt == OFAB_F32)
-    conv1_relu_fwd_kernel<float><<<B * H1, 128, smem, (cudaStream_t)stream>>>((const float*)fbank, B, L, F, (const bf16*)w, (const bf16*)bias, C, (bf16*)out, H1, W1);
+    ofab_launch(conv1_relu_fwd_kernel<float>, dim3(B * H1), dim3(128), (size_t)(smem), (cudaStream_t)stream, (const float*)fbank, B, L, F, (const bf16*)w, (const bf16*)bias, C, (bf16*)out, H1, W1);
   else
-    conv1_relu_fwd_kernel<bf16><<<B * H1, 128, smem, (cudaStream_t)stream>>>((const bf16*)fbank, B, L, F, (const bf16*)w, (const bf16*)bias, C, (bf16*)out, H1, W1);
+    ofab_launch(conv1_relu_fwd_kernel<bf16>, dim3(B * H1), dim3(128), (size_t)(smem), (cudaStream_t)stream, (const bf16*)fbank, B, L, F, (const bf16*)w, (const bf16*)bias, C, (bf16*)out, H1, W1);
   OFAB_LAUNCH_CHECK("ofab_conv1_relu_fwd");
   return OFAB_OK;
 }
@@ -167,9 +177,9 @@ extern "C" int ofab_conv1_relu_bwd(const void* fbank, int in_dt, int B, int L, i
   const int smem = 3 * F * 4;
   const int grid = B * H1 < 592 ? B * H1 : 592;
   if (in_dt == OFAB_F32)
-    conv1_relu_bwd_kernel<float><<<grid, 128, smem, (cudaStream_t)stream>>>((const float*)fbank, B, L, F, (const bf16*)y, (const bf16*)dy, C, dw, db, H1, W1);
+    ofab_launch(conv1_relu_bwd_kernel<float>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)stream, (const float*)fbank, B, L, F, (const bf16*)y, (const bf16*)dy, C, dw, db, H1, W1);
   else
-    conv1_relu_bwd_kernel<bf16><<<grid, 128, smem, (cudaStream_t)stream>>>((const bf16*)fbank, B, L, F, (const bf16*)y, (const bf16*)dy, C, dw, db, H1, W1);
+    ofab_launch(conv1_relu_bwd_kernel<bf16>, dim3(grid), dim3(128), (size_t)(smem), (cudaStream_t)stream, (const bf16*)fbank, B, L, F, (const bf16*)y, (const bf16*)dy, C, dw, db, H1, W1);
   OFAB_LAUNCH_CHECK("ofab_conv1_relu_bwd");
   return OFAB_OK;
 }
@@ -177,7 +187,7 @@ extern "C" int ofab_im2col_3x3s2(const void* x, int B, int Hin, int Win, int C, 
   OFAB_REQUIRE(Hin >= 3 && Win >= 3 && C % 8 == 0, "ofab_im2col_3x3s2: bad shape");
   const int Ho = (Hin - 3) / 2 + 1, Wo = (Win - 3) / 2 + 1;
   const int64_t total = (int64_t)B * Ho * Wo * 9 * (C / 8);
-  im2col_3x3s2_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, Hin, Win, C, (bf16*)cols, Ho, Wo);
+  ofab_launch(im2col_3x3s2_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, B, Hin, Win, C, (bf16*)cols, Ho, Wo);
   OFAB_LAUNCH_CHECK("ofab_im2col_3x3s2");
   return OFAB_OK;
 }
@@ -185,14 +195,14 @@ extern "C" int ofab_col2im_3x3s2(const void* dcols, int B, int Hin, int Win, int
   OFAB_REQUIRE(Hin >= 3 && Win >= 3 && C % 8 == 0, "ofab_col2im_3x3s2: bad shape");
   const int Ho = (Hin - 3) / 2 + 1, Wo = (Win - 3) / 2 + 1;
   const int64_t total = (int64_t)B * Hin * Win * (C / 8);
-  col2im_3x3s2_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dcols, B, Hin, Win, C, (bf16*)dx, Ho, Wo);
+  ofab_launch(col2im_3x3s2_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)dcols, B, Hin, Win, C, (bf16*)dx, Ho, Wo);
   OFAB_LAUNCH_CHECK("ofab_col2im_3x3s2");
   return OFAB_OK;
 }
 extern "C" int ofab_transpose_last2(const void* in, void* out, int64_t O, int A, int Bd, ofab_stream_t stream) {
   OFAB_REQUIRE(O > 0 && O < 65536 && A > 0 && Bd > 0, "ofab_transpose_last2: bad shape O=%lld A=%d B=%d (O < 65536)", (long long)O, A, Bd);
   dim3 grid((Bd + 31) / 32, (A + 31) / 32, (unsigned)O), block(32, 8);
-  transpose_last2_kernel<<<grid, block, 0, (cudaStream_t)stream>>>((const bf16*)in, (bf16*)out, A, Bd);
+  ofab_launch(transpose_last2_kernel, dim3(grid), dim3(block), (size_t)(0), (cudaStream_t)stream, (const bf16*)in, (bf16*)out, A, Bd);
   OFAB_LAUNCH_CHECK("ofab_transpose_last2");
   return OFAB_OK;
 }

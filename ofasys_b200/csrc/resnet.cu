@@ -17,6 +17,8 @@ inline int ew_grid(int64_t work, int threads) {
 template <typename T>
 __global__ void im2col_nchw_kernel(const T* __restrict__ img, int B, int C, int H, int W, int k, int stride, int pad, int Ho, int Wo,
                                    bf16* __restrict__ cols, int64_t ldk) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int kk = C * k * k;
   const int64_t total = (int64_t)B * Ho * Wo * ldk;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -37,6 +39,8 @@ __global__ void im2col_nchw_kernel(const T* __restrict__ img, int B, int C, int 
 // cols[(b,ho,wo), (i*k + j)*C + c] = x[b, ho*stride - pad + i, wo*stride - pad + j, c]
 __global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
                                    bf16* __restrict__ cols) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8, kk = k * k;
   const int64_t total = (int64_t)B * Ho * Wo * kk * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -53,6 +57,8 @@ __global__ void im2col_nhwc_kernel(const bf16* __restrict__ x, int B, int H, int
 // adjoint (gather form, no atomics): dx[b,y,x,c] = sum over taps (i,j) and outputs (ho,wo) with ho*stride - pad + i == y ...
 __global__ void col2im_nhwc_kernel(const bf16* __restrict__ dcols, int B, int H, int W, int C, int k, int stride, int pad, int Ho, int Wo,
                                    bf16* __restrict__ dx) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8, kk = k * k;
   const int64_t total = (int64_t)B * H * W * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -79,6 +85,8 @@ __global__ void col2im_nhwc_kernel(const bf16* __restrict__ dcols, int B, int H,
 
 // ---- spatial stride-2 subsampling (1x1 stride-2 downsample convs) and its adjoint
 __global__ void subsample2_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ y, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = (int64_t)B * Ho * Wo * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -89,6 +97,8 @@ __global__ void subsample2_kernel(const bf16* __restrict__ x, int B, int H, int 
   }
 }
 __global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, int B, int H, int W, int C, bf16* __restrict__ dx, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = (int64_t)B * H * W * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -103,6 +113,8 @@ __global__ void subsample2_bwd_kernel(const bf16* __restrict__ dy, int B, int H,
 
 // ---- max pooling 3x3 stride 2 pad 1 (channel-last); argmax tap (0..8, first maximum as torch) saved for backward
 __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int B, int H, int W, int C, bf16* __restrict__ y, uint8_t* __restrict__ arg, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int64_t total = (int64_t)B * Ho * Wo * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -123,6 +135,8 @@ __global__ void maxpool_fwd_kernel(const bf16* __restrict__ x, int B, int H, int
   }
 }
 __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* __restrict__ arg, int B, int H, int W, int C, bf16* __restrict__ dx, int Ho, int Wo) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int64_t total = (int64_t)B * H * W * C;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
@@ -144,6 +158,8 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
 // stage 1: partial (sum, sum of squares) of (x - shift[c]) per row chunk; shift = first row (conditioning)
 #define BN_CHUNKS 64
 __global__ void bn_stats_stage1(const bf16* __restrict__ x, int64_t R, int C, float* __restrict__ part /* [2][CHUNKS][C] */) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   __shared__ float s1[4][64], s2[4][64];
   const int c = blockIdx.x * 64 + threadIdx.x;
   const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
@@ -169,6 +185,8 @@ __global__ void bn_stats_stage1(const bf16* __restrict__ x, int64_t R, int C, fl
 template <typename TR>
 __global__ void bn_stats_stage2(const bf16* __restrict__ x, const float* __restrict__ part, int64_t R, int C, float* __restrict__ mean,
                                 float* __restrict__ var, TR* __restrict__ run_mean, TR* __restrict__ run_var, float momentum) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, q = 0.f;
@@ -190,6 +208,8 @@ __global__ void bn_stats_stage2(const bf16* __restrict__ x, const float* __restr
 // y = relu?( (x - mean) * rstd * gamma + beta (+ residual) )
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var, const bf16* __restrict__ gamma,
                                 const bf16* __restrict__ beta, const bf16* __restrict__ res, bf16* __restrict__ y, int64_t R, int C, float eps, int relu) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = R * C8;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -210,6 +230,8 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restr
 // backward stage 1: per-channel partial sums of g and g*xhat, g = dy * (y > 0 if relu)
 __global__ void bn_bwd_stage1(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
                               const float* __restrict__ var, int64_t R, int C, float eps, int relu, float* __restrict__ part) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   __shared__ float s1[4][64], s2[4][64];
   const int c = blockIdx.x * 64 + threadIdx.x;
   const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
@@ -233,6 +255,8 @@ __global__ void bn_bwd_stage1(const bf16* __restrict__ dy, const bf16* __restric
   }
 }
 __global__ void bn_bwd_stage2(const float* __restrict__ part, int C, float* __restrict__ sums /* [2][C]: sum g, sum g*xhat */) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   float a = 0.f, q = 0.f;
@@ -247,6 +271,8 @@ __global__ void bn_bwd_stage2(const float* __restrict__ part, int C, float* __re
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
                                     const float* __restrict__ var, const bf16* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ dx,
                                     bf16* __restrict__ dres, int64_t R, int C, float eps, int relu, int frozen_stats) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = R * C8;
   const float invR = 1.0f / (float)R;
@@ -279,6 +305,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
 namespace {
 template <typename T>
 __global__ void video_frames_kernel(const T* __restrict__ vid, int C, int F, int64_t HW, bf16* __restrict__ frames, uint8_t* __restrict__ zero) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
   const int b = blockIdx.x / F, f = blockIdx.x % F;
   int any = 0;
   for (int c = 0; c < C; ++c) {
@@ -298,9 +326,9 @@ extern "C" int ofab_video_frames(const void* video, int dt, int B, int C, int F,
   OFAB_REQUIRE(B > 0 && C > 0 && F > 0 && HW > 0, "ofab_video_frames: empty clip");
   OFAB_REQUIRE(dt == OFAB_F32 || dt == OFAB_BF16, "ofab_video_frames: dtype must be f32 or bf16");
   if (dt == OFAB_F32)
-    video_frames_kernel<float><<<B * F, 256, 0, (cudaStream_t)stream>>>((const float*)video, C, F, HW, (bf16*)frames, zero);
+    ofab_launch(video_frames_kernel<float>, dim3(B * F), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)video, C, F, HW, (bf16*)frames, zero);
   else
-    video_frames_kernel<bf16><<<B * F, 256, 0, (cudaStream_t)stream>>>((const bf16*)video, C, F, HW, (bf16*)frames, zero);
+    ofab_launch(video_frames_kernel<bf16>, dim3(B * F), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)video, C, F, HW, (bf16*)frames, zero);
   OFAB_LAUNCH_CHECK("ofab_video_frames");
   return OFAB_OK;
 }
@@ -310,9 +338,9 @@ extern "C" int ofab_im2col_nchw(const void* img, int img_dt, int B, int C, int H
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t total = (int64_t)B * Ho * Wo * ldk;
   if (img_dt == OFAB_F32)
-    im2col_nchw_kernel<float><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const float*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
+    ofab_launch(im2col_nchw_kernel<float>, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
   else
-    im2col_nchw_kernel<bf16><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
+    ofab_launch(im2col_nchw_kernel<bf16>, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)img, B, C, H, W, k, stride, pad, Ho, Wo, (bf16*)cols, ldk);
   OFAB_LAUNCH_CHECK("ofab_im2col_nchw");
   return OFAB_OK;
 }
@@ -320,7 +348,7 @@ extern "C" int ofab_im2col_nhwc(const void* x, int B, int H, int W, int C, int k
   OFAB_REQUIRE(C % 8 == 0 && k > 0 && stride > 0 && pad >= 0, "ofab_im2col_nhwc: bad geometry (C %% 8 == 0)");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t total = (int64_t)B * Ho * Wo * k * k * (C / 8);
-  im2col_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)cols);
+  ofab_launch(im2col_nhwc_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)cols);
   OFAB_LAUNCH_CHECK("ofab_im2col_nhwc");
   return OFAB_OK;
 }
@@ -328,7 +356,7 @@ extern "C" int ofab_col2im_nhwc(const void* dcols, int B, int H, int W, int C, i
   OFAB_REQUIRE(C % 8 == 0 && k > 0 && stride > 0 && pad >= 0, "ofab_col2im_nhwc: bad geometry (C %% 8 == 0)");
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   const int64_t total = (int64_t)B * H * W * (C / 8);
-  col2im_nhwc_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dcols, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)dx);
+  ofab_launch(col2im_nhwc_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)dcols, B, H, W, C, k, stride, pad, Ho, Wo, (bf16*)dx);
   OFAB_LAUNCH_CHECK("ofab_col2im_nhwc");
   return OFAB_OK;
 }
@@ -337,10 +365,10 @@ extern "C" int ofab_subsample2(const void* x, int B, int H, int W, int C, void* 
   const int Ho = (H - 1) / 2 + 1, Wo = (W - 1) / 2 + 1;
   if (!backward) {
     const int64_t total = (int64_t)B * Ho * Wo * (C / 8);
-    subsample2_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
+    ofab_launch(subsample2_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
   } else {  // x = dy [B,Ho,Wo,C], y = dx [B,H,W,C]
     const int64_t total = (int64_t)B * H * W * (C / 8);
-    subsample2_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
+    ofab_launch(subsample2_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, B, H, W, C, (bf16*)y, Ho, Wo);
   }
   OFAB_LAUNCH_CHECK("ofab_subsample2");
   return OFAB_OK;
@@ -348,14 +376,14 @@ extern "C" int ofab_subsample2(const void* x, int B, int H, int W, int C, void* 
 extern "C" int ofab_maxpool3x3s2_fwd(const void* x, int B, int H, int W, int C, void* y, uint8_t* argmax, ofab_stream_t stream) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)B * Ho * Wo * C;
-  maxpool_fwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, B, H, W, C, (bf16*)y, argmax, Ho, Wo);
+  ofab_launch(maxpool_fwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, B, H, W, C, (bf16*)y, argmax, Ho, Wo);
   OFAB_LAUNCH_CHECK("ofab_maxpool3x3s2_fwd");
   return OFAB_OK;
 }
 extern "C" int ofab_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int B, int H, int W, int C, void* dx, ofab_stream_t stream) {
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const int64_t total = (int64_t)B * H * W * C;
-  maxpool_bwd_kernel<<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)dy, argmax, B, H, W, C, (bf16*)dx, Ho, Wo);
+  ofab_launch(maxpool_bwd_kernel, dim3(ew_grid(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)dy, argmax, B, H, W, C, (bf16*)dx, Ho, Wo);
   OFAB_LAUNCH_CHECK("ofab_maxpool3x3s2_bwd");
   return OFAB_OK;
 }
@@ -366,19 +394,19 @@ extern "C" int ofab_bn_stats(const void* x, int64_t R, int C, float* mean, float
   OFAB_REQUIRE(R > 0 && C > 0 && scratch != nullptr, "ofab_bn_stats: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
-  bn_stats_stage1<<<grid, block, 0, st>>>((const bf16*)x, R, C, scratch);
+  ofab_launch(bn_stats_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)x, R, C, scratch);
   OFAB_LAUNCH_CHECK("ofab_bn_stats stage1");
   if (run_dt == OFAB_F32)
-    bn_stats_stage2<float><<<(C + 127) / 128, 128, 0, st>>>((const bf16*)x, scratch, R, C, mean, var, (float*)run_mean, (float*)run_var, momentum);
+    ofab_launch(bn_stats_stage2<float>, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, (const bf16*)x, scratch, R, C, mean, var, (float*)run_mean, (float*)run_var, momentum);
   else
-    bn_stats_stage2<bf16><<<(C + 127) / 128, 128, 0, st>>>((const bf16*)x, scratch, R, C, mean, var, (bf16*)run_mean, (bf16*)run_var, momentum);
+    ofab_launch(bn_stats_stage2<bf16>, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, (const bf16*)x, scratch, R, C, mean, var, (bf16*)run_mean, (bf16*)run_var, momentum);
   OFAB_LAUNCH_CHECK("ofab_bn_stats stage2");
   return OFAB_OK;
 }
 extern "C" int ofab_bn_apply(const void* x, const float* mean, const float* var, const void* gamma, const void* beta, const void* residual,
                              void* y, int64_t R, int C, float eps, int relu, ofab_stream_t stream) {
   OFAB_REQUIRE(C % 8 == 0, "ofab_bn_apply: C %% 8 != 0");
-  bn_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>((const bf16*)x, mean, var, (const bf16*)gamma, (const bf16*)beta,
+  ofab_launch(bn_apply_kernel, dim3(ew_grid(R * (C / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const bf16*)x, mean, var, (const bf16*)gamma, (const bf16*)beta,
                                                                               (const bf16*)residual, (bf16*)y, R, C, eps, relu);
   OFAB_LAUNCH_CHECK("ofab_bn_apply");
   return OFAB_OK;
@@ -389,11 +417,11 @@ extern "C" int ofab_bn_bwd(const void* dy, const void* x, const void* y, const f
   OFAB_REQUIRE(!relu || y != nullptr, "ofab_bn_bwd: relu needs the forward output");
   cudaStream_t st = (cudaStream_t)stream;
   dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
-  bn_bwd_stage1<<<grid, block, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
+  ofab_launch(bn_bwd_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd stage1");
-  bn_bwd_stage2<<<(C + 127) / 128, 128, 0, st>>>(scratch, C, sums);
+  ofab_launch(bn_bwd_stage2, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, scratch, C, sums);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd stage2");
-  bn_bwd_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
+  ofab_launch(bn_bwd_apply_kernel, dim3(ew_grid(R * (C / 8), 256)), dim3(256), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
                                                                 (bf16*)dx, (bf16*)dres, R, C, eps, relu, 0);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd apply");
   return OFAB_OK;
@@ -408,12 +436,12 @@ extern "C" int ofab_bn_bwd_eval(const void* dy, const void* x, const void* y, co
   cudaStream_t st = (cudaStream_t)stream;
   if (sums != nullptr) {  // dbeta / dgamma wanted (BatchNorm affine parameters not frozen)
     dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
-    bn_bwd_stage1<<<grid, block, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
+    ofab_launch(bn_bwd_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
     OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage1");
-    bn_bwd_stage2<<<(C + 127) / 128, 128, 0, st>>>(scratch, C, sums);
+    ofab_launch(bn_bwd_stage2, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, scratch, C, sums);
     OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage2");
   }
-  bn_bwd_apply_kernel<<<ew_grid(R * (C / 8), 256), 256, 0, st>>>((const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
+  ofab_launch(bn_bwd_apply_kernel, dim3(ew_grid(R * (C / 8), 256)), dim3(256), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
                                                                 (bf16*)dx, (bf16*)dres, R, C, eps, relu, 1);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval apply");
   return OFAB_OK;

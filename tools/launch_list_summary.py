@@ -1,8 +1,9 @@
 """Summarise an ncu launch list of one bench step (gpu__time_duration.sum + dram bytes per launch, CSV from
 `ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --csv`) by kernel family and write
-the GEMM's average DRAM traffic per launch to profiles/r01_gemm_traffic.json (bench.py reports it as roofline.traffic).
+the GEMM's average DRAM traffic per launch to profiles/<tag>_gemm_traffic.json, stamped with the hash of the kernel sources the
+capture ran on (bench.py reports it as roofline.traffic only when the stamp equals the current build's).
 
-    python tools/launch_list_summary.py gpurun_out/launches_v9.csv 64 > profiles/r01_launches_v9_summary.txt
+    python tools/launch_list_summary.py gpurun_out/launches.csv 64 r02 > profiles/r02_launches_summary.txt
 """
 import csv
 import json
@@ -10,6 +11,7 @@ import os
 import sys
 
 path, batch = sys.argv[1], int(sys.argv[2])
+tag = sys.argv[3] if len(sys.argv) > 3 else "r02"
 rows = [r for r in csv.reader(open(path, errors="replace")) if len(r) > 10]
 hdr = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
 h = rows[hdr]
@@ -58,5 +60,6 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 g = agg.get("gemm (tcgen05)")
 if g and g[0]:
     out = {"per_gpu_batch": batch, "dram_bytes_per_launch": g[2] / g[0], "gemm_launches": g[0], "gemm_time_share": g[1] / tot,
+           "build_stamp": open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "ofasys_b200", "build", "stamp")).read().strip(),
            "note": f"ncu dram__bytes_read.sum + dram__bytes_write.sum over the {g[0]} GEMM launches captured from one eager step at B={batch} ({os.path.basename(path)})"}
-    json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_gemm_traffic.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", f"{tag}_gemm_traffic.json"), "w"), indent=1)

@@ -146,7 +146,7 @@ def seqs_per_step(name):
     return sum(t["B"] for t in WORKLOADS[name]["tasks"])
 
 
-def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=1234, layers=None):
+def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=1234, layers=None, kprofile=None):
     """Time `steps` steps of workload `name` on `dev` (inputs resident, CUDA events on the launch stream; with world > 1
     every step ends with the gradient average over ranks and the time is the max over ranks).  Returns a dict."""
     import torch.distributed as dist
@@ -231,6 +231,24 @@ def run_workload(name, dev, steps=5, warmup=3, world=1, use_graph=True, seed=123
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    if kprofile:  # per-kernel device time of the replayed step (CUPTI via torch.profiler) -> json file
+        import json as _json
+
+        from torch.profiler import ProfilerActivity, profile
+
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(3):
+                step()
+            torch.cuda.synchronize()
+        agg = {}
+        for evt in prof.events():
+            if evt.device_type is not None and "cuda" in str(evt.device_type).lower():
+                a = agg.setdefault(evt.name, [0, 0.0])
+                a[0] += 1
+                a[1] += evt.device_time if hasattr(evt, "device_time") else evt.cuda_time
+        rows = sorted(((k, v[0] / 3, v[1] / 3 / 1e3) for k, v in agg.items()), key=lambda r: -r[2])
+        _json.dump({"workload": name, "step_kernel_ms": sum(r[2] for r in rows),
+                    "kernels": [{"name": k[:160], "launches_per_step": n, "ms_per_step": m_} for k, n, m_ in rows]}, open(kprofile, "w"), indent=1)
     ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -256,9 +274,10 @@ if __name__ == "__main__":  # python workloads.py asr cotrain large   (1 GPU pro
     import traceback
 
     dev = torch.device("cuda:0")
-    for nm in sys.argv[1:] or ["asr", "cotrain", "large"]:
+    kp = "--kprofile" in sys.argv
+    for nm in [a for a in sys.argv[1:] if not a.startswith("--")] or ["asr", "cotrain", "large"]:
         try:
-            r = run_workload(nm, dev)
+            r = run_workload(nm, dev, kprofile=f"gpurun_out/r02_kprofile_{nm}.json" if kp else None)
         except Exception as ex:
             traceback.print_exc()
             r = {"workload": nm, "error": f"{type(ex).__name__}: {ex}"}
