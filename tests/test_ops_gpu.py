@@ -699,6 +699,84 @@ def test_batch_norm_train(relu, with_res):
         assert rel_l2(res.grad.permute(0, 3, 1, 2), rr.grad) <= TOL16
 
 
+@pytest.mark.parametrize("relu,with_res,frozen", [(True, False, False), (True, True, False), (False, False, True), (True, True, True)])
+def test_batch_norm_eval_and_frozen(relu, with_res, frozen):
+    """nn.BatchNorm2d in eval mode (model.eval(), or `freeze_resnet`: adaptor/image_resnet.py:107-114 -- BatchNorm in eval mode
+    with frozen affine parameters while the convolutions keep training) against F.batch_norm(training=False): the running
+    statistics are used and NOT updated, dx = gamma * rstd * g, the affine gradients only when they are trainable."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    B, H, W, C = 4, 7, 9, 64
+    x = (rnd(B, H, W, C, gen=gen).float() * 2 + 0.7).bfloat16().requires_grad_(True)
+    res = rnd(B, H, W, C, gen=gen).requires_grad_(True) if with_res else None
+    gam = (torch.rand(C, generator=gen) + 0.5).bfloat16().to(dev()).requires_grad_(not frozen)
+    bet = rnd(C, gen=gen, scale=0.1).requires_grad_(not frozen)
+    rm = (torch.randn(C, generator=gen) * 0.3 + 0.5).to(dev())
+    rv = (torch.rand(C, generator=gen) * 2 + 0.5).to(dev())
+    rm0, rv0 = rm.clone(), rv.clone()
+    y = ops.batch_norm_eval(x, gam, bet, rm, rv, res, relu, 1e-5)
+    dy = rnd(B, H, W, C, gen=gen)
+    y.backward(dy)
+    assert torch.equal(rm, rm0) and torch.equal(rv, rv0)
+    xr = x.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+    gr, br = gam.detach().float().requires_grad_(True), bet.detach().float().requires_grad_(True)
+    yr = F.batch_norm(xr, rm0.clone(), rv0.clone(), gr, br, False, 0.1, 1e-5)
+    if with_res:
+        rr = res.detach().float().permute(0, 3, 1, 2).requires_grad_(True)
+        yr = yr + rr
+    if relu:
+        yr = F.relu(yr)
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    assert rel_l2(y.permute(0, 3, 1, 2), yr) <= TOL16
+    assert rel_l2(x.grad.permute(0, 3, 1, 2), xr.grad) <= 2e-2
+    if frozen:
+        assert gam.grad is None and bet.grad is None
+    else:
+        assert rel_l2(gam.grad, gr.grad) <= 2e-2 and rel_l2(bet.grad, br.grad) <= 2e-2
+    if with_res:
+        assert rel_l2(res.grad.permute(0, 3, 1, 2), rr.grad) <= TOL16
+
+
+def test_freeze_resnet_adaptor_matches_the_oracle_in_eval_statistics():
+    """`freeze_resnet=True` (docs/source/howto/train.rst:66-69 fine-tuning recipe): after model.train() the backbone's BatchNorms
+    are in eval mode with frozen affine parameters; the forward equals the oracle's backbone run with training=False and the
+    convolution weights still receive gradients."""
+    from ofasys_b200.module.resnet import resnet50_backbone
+    from oracle import oracle_model as om
+    import torch.nn as nn
+
+    gen = g()
+    net = resnet50_backbone().to(dev())
+    with torch.no_grad():
+        for n, p in net.named_parameters():
+            if p.dim() == 4:
+                p.copy_(torch.randn(p.shape, generator=gen) * (2.0 / (p.shape[1] * p.shape[2] * p.shape[3])) ** 0.5)
+        for m_ in net.modules():
+            if isinstance(m_, nn.BatchNorm2d):
+                m_.running_mean.copy_(torch.randn(m_.running_mean.shape, generator=gen) * 0.1)
+                m_.running_var.copy_(torch.rand(m_.running_var.shape, generator=gen) + 0.5)
+                m_.weight.copy_(torch.rand(m_.weight.shape, generator=gen) * 0.5 + 0.5)
+    sd = {"r." + k: v.detach().float().cpu() for k, v in net.state_dict().items() if v.is_floating_point()}
+    net = net.bfloat16()
+    net.train()
+    for m_ in net.modules():  # what ImageResnetAdaptor.train() does with freeze_resnet
+        if isinstance(m_, nn.BatchNorm2d):
+            m_.eval()
+            m_.weight.requires_grad = False
+            m_.bias.requires_grad = False
+    x = torch.randn(2, 3, 64, 64, generator=gen).to(dev())
+    y = net(x)  # [B, h, w, 1024]
+    y.float().sum().backward()
+    sd16 = {k: v.bfloat16().float() for k, v in sd.items()}
+    yr = om.resnet_backbone(x.cpu().bfloat16().float(), sd16, "r", "resnet50", training=False)
+    assert rel_l2(y.permute(0, 3, 1, 2), yr) <= 3e-2
+    assert net.conv1.weight.grad is not None and net.layer3[0].conv2.weight.grad.abs().sum() > 0
+    assert all(m_.weight.grad is None for m_ in net.modules() if isinstance(m_, nn.BatchNorm2d))
+    nbt = [int(m_.num_batches_tracked) for m_ in net.modules() if isinstance(m_, nn.BatchNorm2d)]
+    assert all(n == 0 for n in nbt)  # eval-mode BatchNorms do not count batches
+
+
 def test_resnet50_backbone_vs_oracle():
     """whole C1..C4 backbone (train-mode BN) against the oracle's restatement run on the GPU in fp32."""
     from ofasys_b200.module.resnet import resnet50_backbone
