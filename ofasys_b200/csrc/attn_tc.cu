@@ -213,6 +213,7 @@ struct TcParams {
   float *dq_colsum, *dk_colsum, *dv_colsum;  // [B * tiles, H * 64] per-CTA column sums or NULL
   bf16* ds;               // [B, H, Tq, bias_ld] raw dS = P o (dP - delta) (the gradient of the additive bias, per batch) or NULL
   TcDrop drop;
+  int hpc;                // forward: heads per CTA (the CTA works on heads [blockIdx.y * hpc, +hpc) one after the other)
 };
 
 // Key-validity bitmap: bit j of word j / 32 set <=> key j < Tk and not padding; `words` 32-bit words are written.
@@ -342,6 +343,11 @@ __device__ __noinline__ void fwd_redo_block(uint32_t tS, uint32_t tP, uint32_t t
   }
 }
 
+// One CTA works on `hpc` heads of one (batch, 128-query tile) one after the other: TMEM allocation, barrier set-up and the key
+// bitmap are paid once, and the producer / MMA warps run ahead ACROSS heads (Q double-buffered; the next head's first scores are
+// issued while the current head's last block is exponentiated), so the per-work-item prologue that dominated the one-head-per-CTA
+// form (ncu: ~10 us CTA lifetime for ~3 us of math) is hidden.  `g` counts key blocks over all heads of the CTA: ring stages and
+// score / probability buffers are indexed by it.
 template <bool HAS_BIAS, bool DROP>
 __global__ void __launch_bounds__(kThreads, 2)
 attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
@@ -349,43 +355,50 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   constexpr int BM = 128, BN = 64, STAGES = 4;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint8_t* sQ = smem;                              // 128 x 128 B
-  uint8_t* sK = sQ + BM * 128;                     // STAGES x (64 x 128 B)
+  uint8_t* sQ = smem;                              // 2 x (128 x 128 B)
+  uint8_t* sK = sQ + 2 * BM * 128;                 // STAGES x (64 x 128 B)
   uint8_t* sV = sK + STAGES * BN * 128;            // STAGES x (64 x 128 B)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + STAGES * BN * 128);
-  uint64_t* q_full = bars;                         // 1
-  uint64_t* full = bars + 1;                       // STAGES
+  uint64_t* q_full = bars;                         // [2]
+  uint64_t* q_empty = q_full + 2;                  // [2] every S product of the head that used this Q buffer has retired
+  uint64_t* full = q_empty + 2;                    // STAGES
   uint64_t* empty = full + STAGES;                 // STAGES
-  uint64_t* s_full = empty + STAGES;               // [2] S(kb) is in TMEM buffer kb & 1
-  uint64_t* p_ready = s_full + 2;                  // [2] P(kb) is in TMEM buffer kb & 1 (4 warp arrivals)
+  uint64_t* s_full = empty + STAGES;               // [2] S(g) is in TMEM buffer g & 1
+  uint64_t* p_ready = s_full + 2;                  // [2] P(g) is in TMEM buffer g & 1 (4 warp arrivals)
   uint64_t* pv_done = p_ready + 2;                 // one completion per P V product (waited for only before a rescale)
-  uint64_t* o_done = pv_done + 1;                  // the last P V has retired
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_done + 1);
+  uint64_t* o_done = pv_done + 1;                  // the head's last P V has retired
+  uint64_t* o_free = o_done + 1;                   // the head's output has been read out of TMEM (4 warp arrivals)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(o_free + 1);
   uint32_t* kmask_s = tmem_ptr + 2;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int qt = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+  const int qt = blockIdx.x, b = blockIdx.z;
+  const int h0 = blockIdx.y * p.hpc;
+  const int nh = min(p.hpc, p.H - h0);             // heads of this CTA
   const int q0 = qt * BM;
   int nkb = (p.Tk + BN - 1) / BN;
   if (p.causal) nkb = min(nkb, (q0 + BM - 1) / BN + 1);  // key blocks past the last query of the tile see nothing
   const int kwords = nkb * (BN / 32);
+  const int total = nh * nkb;
 
   pdl_launch();
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_q) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_k) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_v) : "memory");
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(q_full + i, 1);
+      mbar_init(q_empty + i, 1);
+      mbar_init(s_full + i, 1);
+      mbar_init(p_ready + i, 4);
+    }
     for (int i = 0; i < STAGES; ++i) {
       mbar_init(full + i, 1);
       mbar_init(empty + i, 1);
     }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(s_full + i, 1);
-      mbar_init(p_ready + i, 4);
-    }
     mbar_init(pv_done, 1);
     mbar_init(o_done, 1);
+    mbar_init(o_free, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -403,53 +416,64 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     const bool issuer = elect_one();
-    if (issuer) {
-      mbar_expect_tx(q_full, BM * 128);
-      tma_load_3d(sQ, &map_q, q_full, h * 64, q0, b);
-    }
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % STAGES;
-      const uint32_t ph = (kb / STAGES) & 1;
-      mbar_wait(empty + st, ph ^ 1);
+    auto load_q = [&](int hi) {  // Q tile of the CTA's head hi into buffer hi & 1 (free once head hi - 2 has issued all its S)
+      mbar_wait(q_empty + (hi & 1), ((hi >> 1) & 1) ^ 1);
       if (issuer) {
-        mbar_expect_tx(full + st, 2 * BN * 128);
-        tma_load_3d(sK + st * BN * 128, &map_k, full + st, h * 64, kb * BN, b);
-        tma_load_3d(sV + st * BN * 128, &map_v, full + st, h * 64, kb * BN, b);
+        mbar_expect_tx(q_full + (hi & 1), BM * 128);
+        tma_load_3d(sQ + (hi & 1) * BM * 128, &map_q, q_full + (hi & 1), (h0 + hi) * 64, q0, b);
       }
       __syncwarp();
+    };
+    load_q(0);
+    for (int g = 0; g < total; ++g) {
+      const int hi = g / nkb, kb = g - hi * nkb;
+      const int st = g % STAGES;
+      mbar_wait(empty + st, ((g / STAGES) & 1) ^ 1);
+      if (issuer) {
+        mbar_expect_tx(full + st, 2 * BN * 128);
+        tma_load_3d(sK + st * BN * 128, &map_k, full + st, (h0 + hi) * 64, kb * BN, b);
+        tma_load_3d(sV + st * BN * 128, &map_v, full + st, (h0 + hi) * 64, kb * BN, b);
+      }
+      __syncwarp();
+      if (kb == 0 && hi + 1 < nh) load_q(hi + 1);  // the next head's queries arrive under this head's math
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const bool issuer = elect_one();
-    mbar_wait(q_full, 0);
-    tc_fence_after();
-    const uint32_t q_addr = smem_u32(sQ);
-    auto issue_s = [&](int kb) {  // S(kb) = Q K(kb)^T into score buffer kb & 1
-      const int st = kb % STAGES;
-      mbar_wait(full + st, (kb / STAGES) & 1);
+    auto issue_s = [&](int g) {  // S(g) = Q K^T into score buffer g & 1
+      const int hi = g / nkb, kb = g - hi * nkb;
+      const int st = g % STAGES;
+      if (kb == 0) {
+        mbar_wait(q_full + (hi & 1), (hi >> 1) & 1);
+        tc_fence_after();
+      }
+      mbar_wait(full + st, (g / STAGES) & 1);
       tc_fence_after();
       if (issuer) {
         const int n = min(BN, ((p.Tk - kb * BN) + 15) & ~15);  // keys of this block rounded up to the UMMA N granularity
         const uint32_t idesc = make_idesc(n, false);
-        const uint32_t k_addr = smem_u32(sK + st * BN * 128);
+        const uint32_t q_addr = smem_u32(sQ + (hi & 1) * BM * 128), k_addr = smem_u32(sK + st * BN * 128);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) umma_ss(tmem_S + (kb & 1) * BN, sdesc(q_addr + k * 32), sdesc(k_addr + k * 32), idesc, k != 0);
-        umma_commit(s_full + (kb & 1));  // (tracks every MMA issued so far)
+        for (int k = 0; k < 4; ++k) umma_ss(tmem_S + (g & 1) * BN, sdesc(q_addr + k * 32), sdesc(k_addr + k * 32), idesc, k != 0);
+        umma_commit(s_full + (g & 1));  // (tracks every MMA issued so far)
+        if (kb == nkb - 1) umma_commit(q_empty + (hi & 1));  // the head's last use of its Q buffer
       }
       __syncwarp();
     };
     issue_s(0);
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int st = kb % STAGES;
-      if (kb + 1 < nkb) issue_s(kb + 1);  // its buffer was freed by P(kb-1), which this warp has already waited for
-      mbar_wait(p_ready + (kb & 1), (kb >> 1) & 1);
+    for (int g = 0; g < total; ++g) {
+      const int hi = g / nkb, kb = g - hi * nkb;
+      const int st = g % STAGES;
+      if (g + 1 < total) issue_s(g + 1);  // one block ahead (its buffer was freed by P(g-1), which this warp has already waited for)
+      mbar_wait(p_ready + (g & 1), (g >> 1) & 1);
+      if (kb == 0 && hi > 0) mbar_wait(o_free, (hi - 1) & 1);  // the previous head's output has left TMEM
       tc_fence_after();
       if (issuer) {
         const int n = min(BN, ((p.Tk - kb * BN) + 15) & ~15);
         const uint32_t idesc = make_idesc(64, true);
         const uint32_t v_addr = smem_u32(sV + st * BN * 128);
         for (int ks = 0; ks < n / 16; ++ks)
-          umma_ts(tmem_O, tmem_P + (kb & 1) * (BN / 2) + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, (kb | ks) != 0);
+          umma_ts(tmem_O, tmem_P + (g & 1) * (BN / 2) + ks * 8, sdesc(v_addr + ks * 2048, BN * 128), idesc, (kb | ks) != 0);
         umma_commit(pv_done);
         umma_commit(empty + st);
         if (kb == nkb - 1) umma_commit(o_done);
@@ -464,101 +488,108 @@ attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_const
     const bool row_ok = i < p.Tq;
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const float c2 = p.scale * kLog2e;
-    const __half* brow = HAS_BIAS ? p.bias + (int64_t)h * p.bias_hs + (int64_t)(row_ok ? i : 0) * p.bias_ld : nullptr;
-    uint2 dkey = make_uint2(0u, 1u);
-    if (DROP) dkey = tc_drop_key(p.drop, b * p.H + h);
-    float m_ref = -INFINITY, l_run = 0.f;
-    for (int kb = 0; kb < nkb; ++kb) {
-      const int k0 = kb * BN;
-      const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
-      const int nch = (n + 31) >> 5;  // 1 or 2 chunks of 32 columns
-      const uint32_t tS = tmem_S + lane_addr + (kb & 1) * BN, tP = tmem_P + lane_addr + (kb & 1) * (BN / 2);
-      const bool diag = p.causal && (k0 + BN - 1 > q0);  // some (i, j) of this tile may have j > i
-      uint4 bu[2][HAS_BIAS ? 4 : 1];
-      if constexpr (HAS_BIAS) {  // in flight while the MMAs run
-        load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);
-        if (nch > 1) load_bias_raw<4>(brow, k0 + 32, p.bias_ld, row_ok, bu[1]);
-      }
-      const uint32_t km0 = kmask_s[k0 >> 5], km1 = kmask_s[(k0 >> 5) + 1];
-      const bool masked0 = diag || km0 != 0xffffffffu, masked1 = diag || km1 != 0xffffffffu;
-      mbar_wait(s_full + (kb & 1), (kb >> 1) & 1);
-      tc_fence_after();
-      uint32_t r0[32], r1[32];
-      tmem_ld32_nowait(tS, r0);
-      if (nch > 1) tmem_ld32_nowait(tS + 32, r1);
-      tmem_ld_wait();
-      if (kb == 0) {  // the first block fixes the reference maximum
-        float mx = -INFINITY;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float x = __uint_as_float(r0[j]) * c2;
-          if (HAS_BIAS) x += bias_at(bu[0], j);
-          bool ok = (km0 >> j) & 1u;
-          if (p.causal) ok = ok && (k0 + j <= i);
-          mx = fmaxf(mx, ok ? x : -INFINITY);
+    for (int hi = 0; hi < nh; ++hi) {
+      const int h = h0 + hi;
+      const __half* brow = HAS_BIAS ? p.bias + (int64_t)h * p.bias_hs + (int64_t)(row_ok ? i : 0) * p.bias_ld : nullptr;
+      uint2 dkey = make_uint2(0u, 1u);
+      if (DROP) dkey = tc_drop_key(p.drop, b * p.H + h);
+      float m_ref = -INFINITY, l_run = 0.f;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int g = hi * nkb + kb;
+        const int k0 = kb * BN;
+        const int n = min(BN, ((p.Tk - k0) + 15) & ~15);
+        const int nch = (n + 31) >> 5;  // 1 or 2 chunks of 32 columns
+        const uint32_t tS = tmem_S + lane_addr + (g & 1) * BN, tP = tmem_P + lane_addr + (g & 1) * (BN / 2);
+        const bool diag = p.causal && (k0 + BN - 1 > q0);  // some (i, j) of this tile may have j > i
+        uint4 bu[2][HAS_BIAS ? 4 : 1];
+        if constexpr (HAS_BIAS) {  // in flight while the MMAs run
+          load_bias_raw<4>(brow, k0, p.bias_ld, row_ok, bu[0]);
+          if (nch > 1) load_bias_raw<4>(brow, k0 + 32, p.bias_ld, row_ok, bu[1]);
         }
-        if (nch > 1) {
+        const uint32_t km0 = kmask_s[k0 >> 5], km1 = kmask_s[(k0 >> 5) + 1];
+        const bool masked0 = diag || km0 != 0xffffffffu, masked1 = diag || km1 != 0xffffffffu;
+        mbar_wait(s_full + (g & 1), (g >> 1) & 1);
+        tc_fence_after();
+        uint32_t r0[32], r1[32];
+        tmem_ld32_nowait(tS, r0);
+        if (nch > 1) tmem_ld32_nowait(tS + 32, r1);
+        tmem_ld_wait();
+        if (kb == 0) {  // the first block fixes the reference maximum
+          float mx = -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r1[j]) * c2;
-            if (HAS_BIAS) x += bias_at(bu[1], j);
-            bool ok = (km1 >> j) & 1u;
-            if (p.causal) ok = ok && (k0 + 32 + j <= i);
+            float x = __uint_as_float(r0[j]) * c2;
+            if (HAS_BIAS) x += bias_at(bu[0], j);
+            bool ok = (km0 >> j) & 1u;
+            if (p.causal) ok = ok && (k0 + j <= i);
             mx = fmaxf(mx, ok ? x : -INFINITY);
           }
+          if (nch > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float x = __uint_as_float(r1[j]) * c2;
+              if (HAS_BIAS) x += bias_at(bu[1], j);
+              bool ok = (km1 >> j) & 1u;
+              if (p.causal) ok = ok && (k0 + 32 + j <= i);
+              mx = fmaxf(mx, ok ? x : -INFINITY);
+            }
+          }
+          // an INTEGER reference (log2 domain): every later rescaling is by an exact power of two, so the bf16 rounding of the
+          // probabilities does not depend on the key-block order (the oracle's storage model reproduces it without knowing it)
+          m_ref = ceilf(mx);
         }
-        // an INTEGER reference (log2 domain): every later rescaling is by an exact power of two, so the bf16 rounding of the
-        // probabilities does not depend on the key-block order (the oracle's storage model reproduces it without knowing it)
-        m_ref = ceilf(mx);
+        {
+          const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+          float mx = -INFINITY, ls = 0.f;  // mx: block maximum RELATIVE to m_use
+          uint32_t pk[16];
+          if (masked0) fwd_chunk<true, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
+          else fwd_chunk<false, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
+          tmem_st16(tP, pk);
+          if (nch > 1) {
+            if (masked1) fwd_chunk<true, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
+            else fwd_chunk<false, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
+            tmem_st16(tP + 16, pk);
+          }
+          // optimistic pass done: was the reference maximum still good for every row of this warp?
+          const bool raise = kb > 0 && (mx > 8.0f || (m_ref == -INFINITY && mx != -INFINITY));
+          if (__any_sync(0xffffffffu, raise)) {  // rare (warp-uniform: the TMEM accesses of the redo are collective)
+            // every earlier P V must have retired: pv_done has completed g - 1 or g times here (s_full(g) implies P V(g-2))
+            mbar_wait(pv_done, (g - 1) & 1);
+            tc_fence_after();
+            const float m_new = raise ? ceilf(m_use + mx) : m_ref;
+            fwd_redo_block<HAS_BIAS, DROP>(tS, tP, tmem_O + lane_addr, nch, brow, p, c2, m_ref, m_new, km0, km1, k0, i, row_ok, l_run, ls, dkey);
+            m_ref = m_new;
+          }
+          l_run += ls;
+        }
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_ready + (g & 1));
       }
-      {
-        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-        float mx = -INFINITY, ls = 0.f;  // mx: block maximum RELATIVE to m_use
-        uint32_t pk[16];
-        if (masked0) fwd_chunk<true, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
-        else fwd_chunk<false, HAS_BIAS, DROP>(r0, bu[0], c2, m_use, km0, p.causal, k0, i, mx, ls, pk, dkey, p.drop, p.Tk);
-        tmem_st16(tP, pk);
-        if (nch > 1) {
-          if (masked1) fwd_chunk<true, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
-          else fwd_chunk<false, HAS_BIAS, DROP>(r1, bu[1], c2, m_use, km1, p.causal, k0 + 32, i, mx, ls, pk, dkey, p.drop, p.Tk);
-          tmem_st16(tP + 16, pk);
+      mbar_wait(o_done, hi & 1);
+      tc_fence_after();
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        uint32_t r[32];
+        tmem_ld32(tmem_O + lane_addr + hf * 32, r);
+        if (row_ok) {
+          bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)i * p.o_rs + h * 64 + hf * 32;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            f8 v;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v.v[e] = __uint_as_float(r[j + e]) * inv;
+            store8(op + j, v);
+          }
         }
-        // optimistic pass done: was the reference maximum still good for every row of this warp?
-        const bool raise = kb > 0 && (mx > 8.0f || (m_ref == -INFINITY && mx != -INFINITY));
-        if (__any_sync(0xffffffffu, raise)) {  // rare (warp-uniform: the TMEM accesses of the redo are collective)
-          // every earlier P V must have retired: pv_done has completed kb - 1 or kb times here (s_full(kb) implies P V(kb-2))
-          mbar_wait(pv_done, (kb - 1) & 1);
-          tc_fence_after();
-          const float m_new = raise ? ceilf(m_use + mx) : m_ref;
-          fwd_redo_block<HAS_BIAS, DROP>(tS, tP, tmem_O + lane_addr, nch, brow, p, c2, m_ref, m_new, km0, km1, k0, i, row_ok, l_run, ls, dkey);
-          m_ref = m_new;
-        }
-        l_run += ls;
       }
-      tmem_st_wait();
-      tc_fence_before();
+      tc_fence_before();  // the accumulator columns may be overwritten by the next head's first P V
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_ready + (kb & 1));
+      if (lane == 0) mbar_arrive(o_free);
+      if (row_ok) p.lse[((int64_t)b * p.H + h) * p.Tq + i] = l_run > 0.f ? (m_ref + __log2f(l_run)) * kLn2 : -INFINITY;
     }
-    mbar_wait(o_done, 0);
-    tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-#pragma unroll
-    for (int hf = 0; hf < 2; ++hf) {
-      uint32_t r[32];
-      tmem_ld32(tmem_O + lane_addr + hf * 32, r);
-      if (row_ok) {
-        bf16* op = p.o + (int64_t)b * p.o_bs + (int64_t)i * p.o_rs + h * 64 + hf * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          f8 v;
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v.v[e] = __uint_as_float(r[j + e]) * inv;
-          store8(op + j, v);
-        }
-      }
-    }
-    if (row_ok) p.lse[((int64_t)b * p.H + h) * p.Tq + i] = l_run > 0.f ? (m_ref + __log2f(l_run)) * kLn2 : -INFINITY;
   }
   tc_fence_before();
   __syncthreads();
@@ -1260,8 +1291,22 @@ int ofab_attn_tc_fwd(const ofab_attn_fwd_args* a, ofab_stream_t stream) {
   if (!make_map3(&mk, a->k, a->H * 64, a->Tk, a->B, a->k_rs, a->k_bs, 64)) return 1;  // 64-key blocks
   if (!make_map3(&mv, a->v, a->H * 64, a->Tk, a->B, a->v_rs, a->v_bs, 64)) return 1;
   const int nkb = (a->Tk + 63) / 64;
-  const int smem = 1024 + 128 * 128 + 2 * 4 * 64 * 128 + 16 * 8 + 16 + (nkb + 1) * 2 * 4;
-  dim3 grid((a->Tq + 127) / 128, a->H, a->B);
+  const int smem = 1024 + 2 * 128 * 128 + 2 * 4 * 64 * 128 + 24 * 8 + 16 + (nkb + 1) * 2 * 4;
+  // heads per CTA: minimise waves x (set-up + heads x work), set-up being about two heads' worth of work (ncu, profiles/README)
+  const int qtiles = (a->Tq + 127) / 128;
+  int hpc = 1;
+  if (const char* ov = getenv("OFAB_ATTN_HPC")) hpc = atoi(ov) > 0 ? atoi(ov) : 1;
+  else {
+    const int64_t slots = 2 * (int64_t)ofab_sm_count();
+    int64_t best = INT64_MAX;
+    for (int c = 1; c <= 6 && c <= a->H; ++c) {
+      const int64_t ctas = (int64_t)qtiles * ((a->H + c - 1) / c) * a->B;
+      const int64_t cost = ((ctas + slots - 1) / slots) * (2 + c);
+      if (cost < best) best = cost, hpc = c;
+    }
+  }
+  p.hpc = hpc;
+  dim3 grid(qtiles, (a->H + hpc - 1) / hpc, a->B);
   cudaStream_t st = (cudaStream_t)stream;
   const bool hb = a->bias != nullptr;
   if (hb && drop_on) return tc_launch(attn_tc_fwd_kernel<true, true>, grid, smem, st, mq, mk, mv, p);
