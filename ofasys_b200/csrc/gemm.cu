@@ -785,9 +785,20 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ ws, int splits, i
   const int64_t nvec = M * (N / 4);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / (N / 4), c = (i % (N / 4)) * 4;
-    float4 acc = *reinterpret_cast<const float4*>(ws + r * N + c);
-    for (int sp = 1; sp < splits; ++sp) {
-      const float4 v = *reinterpret_cast<const float4*>(ws + (int64_t)sp * slab + r * N + c);
+    const float* src = ws + r * N + c;
+    float4 acc = *reinterpret_cast<const float4*>(src);
+    int sp = 1;
+    for (; sp + 4 <= splits; sp += 4) {  // four slabs in flight (the adds keep the slab order: the sum does not depend on the unrolling)
+      float4 v[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) v[k] = *reinterpret_cast<const float4*>(src + (int64_t)(sp + k) * slab);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc.x += v[k].x; acc.y += v[k].y; acc.z += v[k].z; acc.w += v[k].w;
+      }
+    }
+    for (; sp < splits; ++sp) {
+      const float4 v = *reinterpret_cast<const float4*>(src + (int64_t)sp * slab);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     if (sizeof(TO) == 4) {

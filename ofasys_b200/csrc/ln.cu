@@ -602,8 +602,17 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int co
   const int c = blockIdx.x * 32 + threadIdx.x;
   const float* base = partial + (int64_t)blockIdx.y * OFAB_LN_PARTIAL_ROWS * cols;
   float s = 0.f;
-  if (c < cols)
-    for (int r = threadIdx.y; r < OFAB_LN_PARTIAL_ROWS; r += 32) s += base[(int64_t)r * cols + c];
+  if (c < cols) {
+    constexpr int NR = (OFAB_LN_PARTIAL_ROWS + 31) / 32;
+    float v[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {  // every load in flight before the first add (same order of adds as a plain loop)
+      const int r = threadIdx.y + 32 * k;
+      v[k] = r < OFAB_LN_PARTIAL_ROWS ? base[(int64_t)r * cols + c] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NR; ++k) s += v[k];
+  }
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {
@@ -623,7 +632,16 @@ __global__ void reduce_rows_kernel(const float* __restrict__ partial, int64_t ro
   const float* base = partial + (int64_t)blockIdx.y * rows * cols;
   float s = 0.f;
   if (c < cols)
-    for (int64_t r = threadIdx.y; r < rows; r += 32) s += base[r * cols + c];
+    for (int64_t r0 = threadIdx.y; r0 < rows; r0 += 32 * 8) {  // eight loads in flight per thread
+      float v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int64_t r = r0 + 32 * k;
+        v[k] = r < rows ? base[r * cols + c] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += v[k];
+    }
   sm[threadIdx.y][threadIdx.x] = s;
   __syncthreads();
   if (threadIdx.y == 0 && c < cols) {

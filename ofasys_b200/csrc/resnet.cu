@@ -155,45 +155,121 @@ __global__ void maxpool_bwd_kernel(const bf16* __restrict__ dy, const uint8_t* _
 }
 
 // ---- BatchNorm (training): per-channel statistics over the R = B*H*W rows of x [R, C]
-// stage 1: partial (sum, sum of squares) of (x - shift[c]) per row chunk; shift = first row (conditioning)
-#define BN_CHUNKS 64
-__global__ void bn_stats_stage1(const bf16* __restrict__ x, int64_t R, int C, float* __restrict__ part /* [2][CHUNKS][C] */) {
-  pdl_launch();
-  pdl_wait();  // PDL: no global access above
-  __shared__ float s1[4][64], s2[4][64];
-  const int c = blockIdx.x * 64 + threadIdx.x;
-  const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
-  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(R, r0 + per);
-  float a = 0.f, q = 0.f;
-  if (c < C) {
-    const float sh = __bfloat162float(x[c]);
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
-      const float v = __bfloat162float(x[r * C + c]) - sh;
-      a += v;
-      q += v * v;
+// Thread layout of the per-channel reductions (statistics, backward sums): a block of 256 threads is `tx` threads across
+// the channels (one 16-byte vector of 8 channels each, tx = largest power of two <= min(C/8, 32)) by ty = 256 / tx rows;
+// grid = (channel blocks, row chunks) with as many row chunks as it takes to fill the machine whatever C is (the 64-channel
+// layers have ONE channel block).  Every block leaves one partial row per sum; stage 2 reduces the chunks 32 at a time.
+struct BnRed {
+  int tx, ty, gx, nch;
+};
+inline int bn_tx(int C) {
+  const int c8 = C / 8;
+  int tx = 1;
+  while (tx * 2 <= c8 && tx < 32) tx *= 2;
+  return tx;
+}
+inline int bn_max_chunks(int C) {
+  const int tx = bn_tx(C), gx = (C / 8 + tx - 1) / tx;
+  return (2 * ofab_sm_count() + gx - 1) / gx;
+}
+inline BnRed bn_red(int C, int64_t R) {
+  BnRed r;
+  r.tx = bn_tx(C);
+  r.ty = 256 / r.tx;
+  r.gx = (C / 8 + r.tx - 1) / r.tx;
+  const int64_t by_rows = R / (2 * r.ty);  // at least two rows per thread
+  const int64_t nch = std::min<int64_t>(bn_max_chunks(C), by_rows < 1 ? 1 : by_rows);
+  r.nch = (int)nch;
+  return r;
+}
+// block-level finish of a two-sum reduction: a, q of every thread -> one value per channel of the block and sum
+// (var != NULL: the second sum is scaled by rstd of its channel)
+__device__ __forceinline__ void bn_block_finish(const f8& a, const f8& q, const float* __restrict__ var, float eps, int C, float* __restrict__ part,
+                                                int nch) {
+  __shared__ float red[2][256 * 8];
+  const int tx = blockDim.x, ty = blockDim.y;
+  const int t = threadIdx.y * tx + threadIdx.x;
+  store8(&red[0][t * 8], a);
+  store8(&red[1][t * 8], q);
+  __syncthreads();
+  const int wch = tx * 8;  // channels of this block
+  if (t < wch) {
+    const int c = blockIdx.x * wch + t;
+    if (c < C) {
+      float sa = 0.f, sq = 0.f;
+      for (int y = 0; y < ty; ++y) {
+        sa += red[0][y * wch + t];
+        sq += red[1][y * wch + t];
+      }
+      if (var != nullptr) sq *= rsqrtf(var[c] + eps);  // backward: sum g (x - mean) -> sum g xhat
+      part[(int64_t)blockIdx.y * C + c] = sa;
+      part[((int64_t)nch + blockIdx.y) * C + c] = sq;
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = q;
+}
+// reduce the chunks of both sums for 32 channels: block (32 channels, 32 chunk lanes)
+__device__ __forceinline__ void bn_chunk_sums(const float* __restrict__ part, int nch, int C, int c, float& a, float& q) {
+  __shared__ float ra[32][33], rq[32][33];
+  float sa = 0.f, sq = 0.f;
+  if (c < C)
+    for (int k = threadIdx.y; k < nch; k += 32) {
+      sa += part[(int64_t)k * C + c];
+      sq += part[((int64_t)nch + k) * C + c];
+    }
+  ra[threadIdx.y][threadIdx.x] = sa;
+  rq[threadIdx.y][threadIdx.x] = sq;
   __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    part[(int64_t)blockIdx.y * C + c] = s1[0][threadIdx.x] + s1[1][threadIdx.x] + s1[2][threadIdx.x] + s1[3][threadIdx.x];
-    part[((int64_t)BN_CHUNKS + blockIdx.y) * C + c] = s2[0][threadIdx.x] + s2[1][threadIdx.x] + s2[2][threadIdx.x] + s2[3][threadIdx.x];
+  a = 0.f;
+  q = 0.f;
+  if (threadIdx.y == 0) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+      a += ra[k][threadIdx.x];
+      q += rq[k][threadIdx.x];
+    }
   }
+}
+
+// stage 1: partial (sum, sum of squares) of (x - shift[c]) per row chunk; shift = first row (conditioning)
+__global__ void __launch_bounds__(256) bn_stats_stage1(const bf16* __restrict__ x, int64_t R, int C, float* __restrict__ part /* [2][nch][C] */) {
+  pdl_launch();
+  pdl_wait();  // PDL: no global access above
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = c8 < C / 8;
+  const int nch = gridDim.y;
+  const int64_t per = (R + nch - 1) / nch;
+  const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(R, r0 + per);
+  f8 a, q;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a.v[j] = q.v[j] = 0.f;
+  if (ok) {
+    const f8 sh = load8(x + c8 * 8);
+    const bf16* xp = x + c8 * 8;
+    const int ty = blockDim.y;
+#pragma unroll 4
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += ty) {
+      const f8 v = load8(xp + r * C);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float d = v.v[j] - sh.v[j];
+        a.v[j] += d;
+        q.v[j] = fmaf(d, d, q.v[j]);
+      }
+    }
+  }
+  bn_block_finish(a, q, nullptr, 0.f, C, part, nch);
 }
 // stage 2: mean / biased variance; momentum update of the running statistics (unbiased variance), as nn.BatchNorm2d
 template <typename TR>
-__global__ void bn_stats_stage2(const bf16* __restrict__ x, const float* __restrict__ part, int64_t R, int C, float* __restrict__ mean,
-                                float* __restrict__ var, TR* __restrict__ run_mean, TR* __restrict__ run_var, float momentum) {
+__global__ void __launch_bounds__(1024) bn_stats_stage2(const bf16* __restrict__ x, const float* __restrict__ part, int nch, int64_t R, int C,
+                                                        float* __restrict__ mean, float* __restrict__ var, TR* __restrict__ run_mean,
+                                                        TR* __restrict__ run_var, float momentum) {
   pdl_launch();
   pdl_wait();  // PDL: no global access above
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f, q = 0.f;
-  for (int k = 0; k < BN_CHUNKS; ++k) {
-    a += part[(int64_t)k * C + c];
-    q += part[((int64_t)BN_CHUNKS + k) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a, q;
+  bn_chunk_sums(part, nch, C, c, a, q);
+  if (threadIdx.y != 0 || c >= C) return;
   const float sh = __bfloat162float(x[c]);
   const float m = a / (float)R;
   const float v = fmaxf(q / (float)R - m * m, 0.f);
@@ -205,22 +281,39 @@ __global__ void bn_stats_stage2(const bf16* __restrict__ x, const float* __restr
     run_var[c] = (TR)((1.f - momentum) * (float)run_var[c] + momentum * unb);
   }
 }
-// y = relu?( (x - mean) * rstd * gamma + beta (+ residual) )
-__global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var, const bf16* __restrict__ gamma,
-                                const bf16* __restrict__ beta, const bf16* __restrict__ res, bf16* __restrict__ y, int64_t R, int C, float eps, int relu) {
+// y = relu?( (x - mean) * rstd * gamma + beta (+ residual) ).  The grid stride is a multiple of C / 8 whenever C / 8 divides the
+// block size (every ResNet width), so a thread keeps ITS 8 channels for the whole loop and the per-channel constants stay
+// in registers; other widths reload them per vector.
+__global__ void __launch_bounds__(256) bn_apply_kernel(const bf16* __restrict__ x, const float* __restrict__ mean, const float* __restrict__ var,
+                                                       const bf16* __restrict__ gamma, const bf16* __restrict__ beta, const bf16* __restrict__ res,
+                                                       bf16* __restrict__ y, int64_t R, int C, float eps, int relu) {
   pdl_launch();
   pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = R * C8;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8) * 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool fixed = stride % C8 == 0;
+  f8 mu, sc, sf;
+  auto consts = [&](int c) {
+    const f8 g = load8(gamma + c);
+    sf = load8(beta + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      mu.v[j] = mean[c + j];
+      sc.v[j] = rsqrtf(var[c + j] + eps) * g.v[j];
+    }
+  };
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 < total) consts((int)(i0 % C8) * 8);
+#pragma unroll 2
+  for (int64_t i = i0; i < total; i += stride) {
+    if (!fixed) consts((int)(i % C8) * 8);
     f8 v = load8(x + i * 8);
-    const f8 g = load8(gamma + c), b = load8(beta + c);
     f8 rr;
     if (res != nullptr) rr = load8(res + i * 8);
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      float o = (v.v[j] - mean[c + j]) * rsqrtf(var[c + j] + eps) * g.v[j] + b.v[j];
+      float o = fmaf(v.v[j] - mu.v[j], sc.v[j], sf.v[j]);
       if (res != nullptr) o += rr.v[j];
       v.v[j] = relu ? fmaxf(o, 0.f) : o;
     }
@@ -228,58 +321,86 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, const float* __restr
   }
 }
 // backward stage 1: per-channel partial sums of g and g*xhat, g = dy * (y > 0 if relu)
-__global__ void bn_bwd_stage1(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
-                              const float* __restrict__ var, int64_t R, int C, float eps, int relu, float* __restrict__ part) {
+__global__ void __launch_bounds__(256) bn_bwd_stage1(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                     const float* __restrict__ mean, const float* __restrict__ var, int64_t R, int C, float eps,
+                                                     int relu, float* __restrict__ part) {
   pdl_launch();
   pdl_wait();  // PDL: no global access above
-  __shared__ float s1[4][64], s2[4][64];
-  const int c = blockIdx.x * 64 + threadIdx.x;
-  const int64_t per = (R + BN_CHUNKS - 1) / BN_CHUNKS;
+  const int c8 = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool ok = c8 < C / 8;
+  const int nch = gridDim.y;
+  const int64_t per = (R + nch - 1) / nch;
   const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(R, r0 + per);
-  float a = 0.f, q = 0.f;
-  if (c < C) {
-    const float m = mean[c], rs = rsqrtf(var[c] + eps);
-    for (int64_t r = r0 + threadIdx.y; r < r1; r += 4) {
-      float g = __bfloat162float(dy[r * C + c]);
-      if (relu && !(__bfloat162float(y[r * C + c]) > 0.f)) g = 0.f;
-      a += g;
-      q += g * (__bfloat162float(x[r * C + c]) - m) * rs;
+  f8 a, q;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) a.v[j] = q.v[j] = 0.f;
+  if (ok) {
+    f8 m;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m.v[j] = mean[c8 * 8 + j];
+    const int ty = blockDim.y;
+#pragma unroll 2
+    for (int64_t r = r0 + threadIdx.y; r < r1; r += ty) {
+      const int64_t o = r * C + c8 * 8;
+      f8 g = load8(dy + o);
+      const f8 xv = load8(x + o);
+      if (relu) {
+        const f8 yv = load8(y + o);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.v[j] = yv.v[j] > 0.f ? g.v[j] : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        a.v[j] += g.v[j];
+        q.v[j] = fmaf(g.v[j], xv.v[j] - m.v[j], q.v[j]);  // times rstd in the block finish
+      }
     }
   }
-  s1[threadIdx.y][threadIdx.x] = a;
-  s2[threadIdx.y][threadIdx.x] = q;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < C) {
-    part[(int64_t)blockIdx.y * C + c] = s1[0][threadIdx.x] + s1[1][threadIdx.x] + s1[2][threadIdx.x] + s1[3][threadIdx.x];
-    part[((int64_t)BN_CHUNKS + blockIdx.y) * C + c] = s2[0][threadIdx.x] + s2[1][threadIdx.x] + s2[2][threadIdx.x] + s2[3][threadIdx.x];
-  }
+  bn_block_finish(a, q, var, eps, C, part, nch);
 }
-__global__ void bn_bwd_stage2(const float* __restrict__ part, int C, float* __restrict__ sums /* [2][C]: sum g, sum g*xhat */) {
+__global__ void __launch_bounds__(1024) bn_bwd_stage2(const float* __restrict__ part, int nch, int C, float* __restrict__ sums /* [2][C]: sum g, sum g*xhat */) {
   pdl_launch();
   pdl_wait();  // PDL: no global access above
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float a = 0.f, q = 0.f;
-  for (int k = 0; k < BN_CHUNKS; ++k) {
-    a += part[(int64_t)k * C + c];
-    q += part[((int64_t)BN_CHUNKS + k) * C + c];
-  }
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float a, q;
+  bn_chunk_sums(part, nch, C, c, a, q);
+  if (threadIdx.y != 0 || c >= C) return;
   sums[c] = a;
   sums[C + c] = q;
 }
-// dx = gamma * rstd * (g - sum_g/R - xhat * sum_gxhat/R);  dres = g
-__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y, const float* __restrict__ mean,
-                                    const float* __restrict__ var, const bf16* __restrict__ gamma, const float* __restrict__ sums, bf16* __restrict__ dx,
-                                    bf16* __restrict__ dres, int64_t R, int C, float eps, int relu, int frozen_stats) {
+// dx = gamma * rstd * (g - sum_g/R - xhat * sum_gxhat/R);  dres = g.  Per-channel constants in registers as in bn_apply_kernel.
+__global__ void __launch_bounds__(256) bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const bf16* __restrict__ y,
+                                                           const float* __restrict__ mean, const float* __restrict__ var, const bf16* __restrict__ gamma,
+                                                           const float* __restrict__ sums, bf16* __restrict__ dx, bf16* __restrict__ dres, int64_t R, int C,
+                                                           float eps, int relu, int frozen_stats) {
   pdl_launch();
   pdl_wait();  // PDL: no global access above
   const int C8 = C / 8;
   const int64_t total = R * C8;
   const float invR = 1.0f / (float)R;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % C8) * 8;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const bool fixed = stride % C8 == 0;
+  f8 mu, ka, kb, kc;  // dx = ka * (g - kb - (x - mu) * kc):  ka = gamma rstd, kb = sum_g / R, kc = rstd sum_gxhat / R
+  auto consts = [&](int c) {
+    const f8 gm = load8(gamma + c);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float rs = rsqrtf(var[c + j] + eps);
+      mu.v[j] = mean[c + j];
+      ka.v[j] = gm.v[j] * rs;
+      // frozen_stats (eval-mode BatchNorm: mean / var are the running buffers, constants of the graph): dx = gamma * rstd * g
+      kb.v[j] = frozen_stats ? 0.f : sums[c + j] * invR;
+      kc.v[j] = frozen_stats ? 0.f : rs * sums[C + c + j] * invR;
+    }
+  };
+  const int64_t i0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i0 < total) consts((int)(i0 % C8) * 8);
+#pragma unroll 2
+  for (int64_t i = i0; i < total; i += stride) {
+    if (!fixed) consts((int)(i % C8) * 8);
     f8 g = load8(dy + i * 8);
-    const f8 xv = load8(x + i * 8), gm = load8(gamma + c);
+    f8 xv;
+    if (!frozen_stats) xv = load8(x + i * 8);
     if (relu) {
       const f8 yv = load8(y + i * 8);
 #pragma unroll
@@ -288,12 +409,8 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, const bf16* __r
     if (dres != nullptr) store8(dres + i * 8, g);
     f8 o;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float rs = rsqrtf(var[c + j] + eps);
-      const float xh = (xv.v[j] - mean[c + j]) * rs;
-      // frozen_stats (eval-mode BatchNorm: mean / var are the running buffers, constants of the graph): dx = gamma * rstd * g
-      o.v[j] = frozen_stats ? gm.v[j] * rs * g.v[j] : gm.v[j] * rs * (g.v[j] - sums[c + j] * invR - xh * sums[C + c + j] * invR);
-    }
+    for (int j = 0; j < 8; ++j)
+      o.v[j] = frozen_stats ? ka.v[j] * g.v[j] : ka.v[j] * fmaf(-(xv.v[j] - mu.v[j]), kc.v[j], g.v[j] - kb.v[j]);
     store8(dx + i * 8, o);
   }
 }
@@ -387,19 +504,20 @@ extern "C" int ofab_maxpool3x3s2_bwd(const void* dy, const uint8_t* argmax, int 
   OFAB_LAUNCH_CHECK("ofab_maxpool3x3s2_bwd");
   return OFAB_OK;
 }
-extern "C" int64_t ofab_bn_scratch_elems(int C) { return (int64_t)2 * BN_CHUNKS * C; }
+extern "C" int64_t ofab_bn_scratch_elems(int C) { return (int64_t)2 * bn_max_chunks(C) * C; }
 
 extern "C" int ofab_bn_stats(const void* x, int64_t R, int C, float* mean, float* var, void* run_mean, void* run_var, int run_dt,
                              float momentum, float* scratch, ofab_stream_t stream) {
-  OFAB_REQUIRE(R > 0 && C > 0 && scratch != nullptr, "ofab_bn_stats: bad arguments");
+  OFAB_REQUIRE(R > 0 && C > 0 && C % 8 == 0 && scratch != nullptr, "ofab_bn_stats: bad arguments (C %% 8 == 0)");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+  const BnRed rd = bn_red(C, R);
+  dim3 grid(rd.gx, rd.nch), block(rd.tx, rd.ty);
   ofab_launch(bn_stats_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)x, R, C, scratch);
   OFAB_LAUNCH_CHECK("ofab_bn_stats stage1");
   if (run_dt == OFAB_F32)
-    ofab_launch(bn_stats_stage2<float>, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, (const bf16*)x, scratch, R, C, mean, var, (float*)run_mean, (float*)run_var, momentum);
+    ofab_launch(bn_stats_stage2<float>, dim3((C + 31) / 32), dim3(32, 32), (size_t)(0), st, (const bf16*)x, (const float*)scratch, rd.nch, R, C, mean, var, (float*)run_mean, (float*)run_var, momentum);
   else
-    ofab_launch(bn_stats_stage2<bf16>, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, (const bf16*)x, scratch, R, C, mean, var, (bf16*)run_mean, (bf16*)run_var, momentum);
+    ofab_launch(bn_stats_stage2<bf16>, dim3((C + 31) / 32), dim3(32, 32), (size_t)(0), st, (const bf16*)x, (const float*)scratch, rd.nch, R, C, mean, var, (bf16*)run_mean, (bf16*)run_var, momentum);
   OFAB_LAUNCH_CHECK("ofab_bn_stats stage2");
   return OFAB_OK;
 }
@@ -416,10 +534,11 @@ extern "C" int ofab_bn_bwd(const void* dy, const void* x, const void* y, const f
   OFAB_REQUIRE(C % 8 == 0 && scratch != nullptr && sums != nullptr, "ofab_bn_bwd: bad arguments");
   OFAB_REQUIRE(!relu || y != nullptr, "ofab_bn_bwd: relu needs the forward output");
   cudaStream_t st = (cudaStream_t)stream;
-  dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+  const BnRed rd = bn_red(C, R);
+  dim3 grid(rd.gx, rd.nch), block(rd.tx, rd.ty);
   ofab_launch(bn_bwd_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd stage1");
-  ofab_launch(bn_bwd_stage2, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, scratch, C, sums);
+  ofab_launch(bn_bwd_stage2, dim3((C + 31) / 32), dim3(32, 32), (size_t)(0), st, (const float*)scratch, rd.nch, C, sums);
   OFAB_LAUNCH_CHECK("ofab_bn_bwd stage2");
   ofab_launch(bn_bwd_apply_kernel, dim3(ew_grid(R * (C / 8), 256)), dim3(256), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
                                                                 (bf16*)dx, (bf16*)dres, R, C, eps, relu, 0);
@@ -435,10 +554,11 @@ extern "C" int ofab_bn_bwd_eval(const void* dy, const void* x, const void* y, co
   OFAB_REQUIRE(sums == nullptr || scratch != nullptr, "ofab_bn_bwd_eval: parameter gradients need scratch");
   cudaStream_t st = (cudaStream_t)stream;
   if (sums != nullptr) {  // dbeta / dgamma wanted (BatchNorm affine parameters not frozen)
-    dim3 grid((C + 63) / 64, BN_CHUNKS), block(64, 4);
+    const BnRed rd = bn_red(C, R);
+    dim3 grid(rd.gx, rd.nch), block(rd.tx, rd.ty);
     ofab_launch(bn_bwd_stage1, dim3(grid), dim3(block), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, R, C, eps, relu, scratch);
     OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage1");
-    ofab_launch(bn_bwd_stage2, dim3((C + 127) / 128), dim3(128), (size_t)(0), st, scratch, C, sums);
+    ofab_launch(bn_bwd_stage2, dim3((C + 31) / 32), dim3(32, 32), (size_t)(0), st, (const float*)scratch, rd.nch, C, sums);
     OFAB_LAUNCH_CHECK("ofab_bn_bwd_eval stage2");
   }
   ofab_launch(bn_bwd_apply_kernel, dim3(ew_grid(R * (C / 8), 256)), dim3(256), (size_t)(0), st, (const bf16*)dy, (const bf16*)x, (const bf16*)y, mean, var, (const bf16*)gamma, sums,
