@@ -153,6 +153,67 @@ __device__ __forceinline__ float gelu_grad_f(float x) {
   return cdf + px;
 }
 
+// ---- packed fp32 (Blackwell FFMA2: two fp32 FMAs per issued instruction) ---------------------------------------------
+// The HBM-bound row kernels with a transcendental per element (GELU + LayerNorm) are ISSUE-bound with scalar fp32 math
+// (ncu, profiles/r02_ncu_ln_gelu.csv: 69-74 % issue-active at 36 % of HBM peak); pairs of neighbouring columns go through
+// fma.rn.f32x2 instead.  Results are bit-identical to the scalar fmaf / * / + on each half (same IEEE operation).
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+  asm("{\n\t.reg .b64 ra, rb, rc, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmov.b64 rc, {%6, %7};\n\t"
+      "fma.rn.f32x2 rd, ra, rb, rc;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1), "f"(c0), "f"(c1));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tmul.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+__device__ __forceinline__ void add2(float& d0, float& d1, float a0, float a1, float b0, float b1) {
+  asm("{\n\t.reg .b64 ra, rb, rd;\n\tmov.b64 ra, {%2, %3};\n\tmov.b64 rb, {%4, %5};\n\tadd.rn.f32x2 rd, ra, rb;\n\tmov.b64 {%0, %1}, rd;\n\t}"
+      : "=f"(d0), "=f"(d1)
+      : "f"(a0), "f"(a1), "f"(b0), "f"(b1));
+}
+// q = 0.5 erfc(|x| / sqrt 2) and e = exp(-x^2 / 2) for a pair (same polynomial as gelu_parts)
+__device__ __forceinline__ void gelu_qe2(float x0, float x1, float& q0, float& q1, float& e0, float& e1, float& nax0, float& nax1) {
+  nax0 = __uint_as_float(__float_as_uint(x0) | 0x80000000u);  // -|x|
+  nax1 = __uint_as_float(__float_as_uint(x1) | 0x80000000u);
+  float d0, d1, s0, s1, t0, t1, p0, p1;
+  const float nk = -0.3275911f * 0.70710678118654752f;
+  fma2(d0, d1, nax0, nax1, nk, nk, 1.0f, 1.0f);
+  t0 = fast_rcp(d0);
+  t1 = fast_rcp(d1);
+  mul2(s0, s1, x0, x1, x0, x1);
+  const float c = -0.5f * 1.4426950408889634f;
+  mul2(s0, s1, s0, s1, c, c);
+  e0 = fast_ex2(s0);  // exp(-x^2/2)
+  e1 = fast_ex2(s1);
+  const float a5 = 0.5f * 1.061405429f, a4 = 0.5f * -1.453152027f, a3 = 0.5f * 1.421413741f, a2 = 0.5f * -0.284496736f,
+              a1 = 0.5f * 0.254829592f;
+  fma2(p0, p1, t0, t1, a5, a5, a4, a4);
+  fma2(p0, p1, t0, t1, p0, p1, a3, a3);
+  fma2(p0, p1, t0, t1, p0, p1, a2, a2);
+  fma2(p0, p1, t0, t1, p0, p1, a1, a1);
+  mul2(p0, p1, t0, t1, p0, p1);
+  mul2(q0, q1, p0, p1, e0, e1);
+}
+// gelu(x) = max(x, 0) - |x| q for a pair of values (value-identical to gelu_f)
+__device__ __forceinline__ void gelu2(float& x0, float& x1) {
+  float q0, q1, e0, e1, n0, n1;
+  gelu_qe2(x0, x1, q0, q1, e0, e1, n0, n1);
+  fma2(x0, x1, n0, n1, q0, q1, fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+}
+// cdf and x * pdf for a pair (value-identical to gelu_parts)
+__device__ __forceinline__ void gelu_parts2(float x0, float x1, float& cdf0, float& cdf1, float& px0, float& px1) {
+  float q0, q1, e0, e1, n0, n1, m0, m1;
+  gelu_qe2(x0, x1, q0, q1, e0, e1, n0, n1);
+  fma2(m0, m1, q0, q1, -1.0f, -1.0f, 1.0f, 1.0f);  // 1 - q
+  cdf0 = x0 >= 0.f ? m0 : q0;
+  cdf1 = x1 >= 0.f ? m1 : q1;
+  const float k = 0.39894228040143268f;
+  mul2(px0, px1, e0, e1, k, k);
+  mul2(px0, px1, px0, px1, x0, x1);
+}
+
 // ---- dropout / drop-path masks: counter-based RNG (Philox4x32, 7 rounds), no mask tensor in HBM --------------------
 // The mask of the 8-column vector starting at column c of row r is a pure function of (seed, step, site, r, c / 8),
 // so forward and backward kernels regenerate the same bits whatever their thread layout.  `state` lives in device

@@ -40,24 +40,26 @@ __device__ __forceinline__ RowCtx row_ctx(int tpr, int cols) {
 }
 
 // Sums over the threads of one row group; all threads of the block call these together.  Cross-warp step: one
-// partial per warp goes to shared memory, then every thread reads the partial of warp (lane & 15) of its row and
-// finishes with a 16-lane butterfly (wpr <= 16).  `red` is double-buffered ([2][256] values) so ONE __syncthreads per
-// call suffices: a buffer is rewritten two calls later, after every thread has passed the barrier in between.
+// partial per warp goes to shared memory (slot [row group][warp in row], 16 slots per group, unused slots stay zero
+// from red_init), then every thread adds the partials of its row, read directly with 16-byte loads in a fixed order (so
+// every thread of the row gets the same bits).  This replaced a second 16-lane shuffle butterfly: the 768 / 1024 column
+// kernels are bound by the latency of exactly this chain (ncu: short-scoreboard stalls), and keeping both forms
+// in one kernel cost registers.  `red` is double-buffered ([2][256] values) so ONE __syncthreads per call suffices: a
+// buffer is rewritten two calls later, after every thread has passed the barrier in between.
 // `sync_always`: barrier even when rows are one warp wide (callers use it to release a pipeline stage).
-__device__ __forceinline__ float group_sum(float v, float* red, int& flip, const RowCtx& r, bool sync_always) {
-  v = warp_sum(v);
-  if (r.wpr == 1) {
-    if (sync_always) __syncthreads();
-    return v;
-  }
-  float* buf = red + flip * 256;
-  flip ^= 1;
-  if ((threadIdx.x & 31) == 0) buf[r.rib * 16 + r.wir] = v;
-  __syncthreads();
-  const int l = threadIdx.x & 15;
-  float s = l < r.wpr ? buf[r.rib * 16 + l] : 0.f;
+template <typename T>
+__device__ __forceinline__ void red_init(T* red) {  // call before the first __syncthreads of the kernel
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) red[i] = T{};
+}
+// rows wider than 4 warps (GELU / ffn_layernorm kernels: 12 or 16 warps): the partials of the row, outside the caller's
+// register allocation (kernels sit at their register cap; this path inlined cost spills in every variant)
+__device__ __noinline__ float2 group_sum2_wide(const float2* buf) {
+  float2 s = buf[threadIdx.x & 15];  // slots past the row's warp count are zero (red_init)
 #pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  for (int o = 8; o > 0; o >>= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
+    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+  }
   return s;
 }
 __device__ __forceinline__ void group_sum2(float& a, float& b, float2* red, int& flip, const RowCtx& r, bool sync_always) {
@@ -71,15 +73,15 @@ __device__ __forceinline__ void group_sum2(float& a, float& b, float2* red, int&
   flip ^= 1;
   if ((threadIdx.x & 31) == 0) buf[r.rib * 16 + r.wir] = make_float2(a, b);
   __syncthreads();
-  const int l = threadIdx.x & 15;
-  float2 s = l < r.wpr ? buf[r.rib * 16 + l] : make_float2(0.f, 0.f);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
-    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+  if (r.wpr <= 4) {
+    const float4 p = *reinterpret_cast<const float4*>(buf + r.rib * 16), q = *reinterpret_cast<const float4*>(buf + r.rib * 16 + 2);
+    a = (p.x + p.z) + (q.x + q.z);
+    b = (p.y + p.w) + (q.y + q.w);
+  } else {
+    const float2 s = group_sum2_wide(buf + r.rib * 16);
+    a = s.x;
+    b = s.y;
   }
-  a = s.x;
-  b = s.y;
 }
 
 // ---- persistent schedule + async input ring --------------------------------------------------------------
@@ -153,7 +155,8 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
   extern __shared__ __align__(128) uint8_t dsm[];
   pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
   pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
-  __shared__ float red[512];
+  __shared__ __align__(16) float2 red[512];
+  red_init(red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
@@ -173,36 +176,41 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
   }
   int stage = 0, flip = 0;
   uint32_t phase = 0;
+  // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
+  const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
+  int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
   for (int64_t it = 0; it < my_n; ++it) {
-    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
+    row += row_step;
+    eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
     rowpipe::wait(bars + stage, phase);
     f8 v;
-    float s = 0.f;
+    float s = 0.f, q = 0.f;
     if (live) {
       v = load8(reinterpret_cast<const TX*>(ring + (size_t)stage * in.stage_bytes) + r.rib * cols + r.c);
+      if (GELU) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        if (GELU) v.v[j] = gelu_f(v.v[j]);
+        for (int j = 0; j < 8; j += 2) gelu2(v.v[j], v.v[j + 1]);
+      }
       if (DROP) {
         const f8 m = drop_mask8(da, dk, row, r.c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v.v[j] *= m.v[j];
+        for (int j = 0; j < 8; j += 2) mul2(v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], m.v[j], m.v[j + 1]);
       }
+      // one pass: sum and sum of squares (fp32; the variance is E[v^2] - mean^2, clamped at 0)
+      float s1 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v.v[j];
+      for (int j = 0; j < 8; j += 2) {
+        add2(s, s1, s, s1, v.v[j], v.v[j + 1]);
+        fma2(q, q1, v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], q, q1);
+      }
+      s += s1;
+      q += q1;
     }
-    const float mu = group_sum(s, red, flip, r, true) * inv_n;  // barrier: every thread has consumed the stage
+    group_sum2(s, q, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<1>(in, ring, bars, stage, it + NST, rows, r.rpb);
-    float q = 0.f;
-    if (live) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v.v[j] -= mu;
-        q = fmaf(v.v[j], v.v[j], q);
-      }
-    }
-    const float rs = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
+    const float mu = s * inv_n;
+    const float rs = rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_n), 0.f) + eps);
     if (live) {
       if (r.lane_in_row == 0) {
         mean[row] = mu;
@@ -210,8 +218,13 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
       }
       f8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(v.v[j] * rs, g.v[j], b.v[j]);
-      store8(y + row * cols + r.c, o);
+      for (int j = 0; j < 8; j += 2) {
+        float t0, t1;
+        add2(t0, t1, v.v[j], v.v[j + 1], -mu, -mu);
+        mul2(t0, t1, t0, t1, rs, rs);
+        fma2(o.v[j], o.v[j + 1], t0, t1, g.v[j], g.v[j + 1], b.v[j], b.v[j + 1]);
+      }
+      store8(y + eoff, o);
     }
     if (++stage == NST) {
       stage = 0;
@@ -229,7 +242,8 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
   extern __shared__ __align__(128) uint8_t dsm[];
   pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
   pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
-  __shared__ float2 red[512];
+  __shared__ __align__(16) float2 red[512];
+  red_init(red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
@@ -254,8 +268,12 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
   int stage = 0, flip = 0;
   uint32_t phase = 0;
+  // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
+  const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
+  int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
   for (int64_t it = 0; it < my_n; ++it) {
-    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
+    row += row_step;
+    eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
     rowpipe::wait(bars + stage, phase);
     float rs = 0.f;
@@ -269,42 +287,51 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
       const float nmr = -mean[row] * rs;
       f8 m;
       if (DROP) m = drop_mask8(da, dk, row, r.c);
+      float s1b = 0.f, s2b = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float a = pre.v[j];
+      for (int j = 0; j < 8; j += 2) {  // pairs of columns through the packed fp32 pipe
+        float a0 = pre.v[j], a1 = pre.v[j + 1];
         if (GELU) {  // one erf evaluation serves both gelu(x) and gelu'(x)
-          float cdf, px;
-          gelu_parts(a, cdf, px);
-          gp.v[j] = cdf + px;
-          a *= cdf;
+          float c0, c1, p0, p1;
+          gelu_parts2(a0, a1, c0, c1, p0, p1);
+          add2(gp.v[j], gp.v[j + 1], c0, c1, p0, p1);
+          mul2(a0, a1, a0, a1, c0, c1);
           if (DROP) {  // LN input = m * gelu(x): the mask scales the value and the chain-rule factor alike
-            a *= m.v[j];
-            gp.v[j] *= m.v[j];
+            mul2(a0, a1, a0, a1, m.v[j], m.v[j + 1]);
+            mul2(gp.v[j], gp.v[j + 1], gp.v[j], gp.v[j + 1], m.v[j], m.v[j + 1]);
           }
         }
-        xh.v[j] = fmaf(a, rs, nmr);
-        acc[0].v[j] = fmaf(d.v[j], xh.v[j], acc[0].v[j]);
-        acc[1].v[j] += d.v[j];
-        const float gg = d.v[j] * g.v[j];
-        d.v[j] = gg;
-        s1 = fmaf(gg, xh.v[j], s1);
-        s2 += gg;
+        fma2(xh.v[j], xh.v[j + 1], a0, a1, rs, rs, nmr, nmr);
+        fma2(acc[0].v[j], acc[0].v[j + 1], d.v[j], d.v[j + 1], xh.v[j], xh.v[j + 1], acc[0].v[j], acc[0].v[j + 1]);
+        add2(acc[1].v[j], acc[1].v[j + 1], acc[1].v[j], acc[1].v[j + 1], d.v[j], d.v[j + 1]);
+        mul2(d.v[j], d.v[j + 1], d.v[j], d.v[j + 1], g.v[j], g.v[j + 1]);
+        fma2(s1, s1b, d.v[j], d.v[j + 1], xh.v[j], xh.v[j + 1], s1, s1b);
+        add2(s2, s2b, s2, s2b, d.v[j], d.v[j + 1]);
       }
+      s1 += s1b;
+      s2 += s2b;
     }
     group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<2>(in, ring, bars, stage, it + NST, rows, r.rpb);
     if (live) {
       const float c1 = -s1 * inv_n * rs, c2 = -s2 * inv_n * rs;
       f8 o;
-      if (ACCUM) o = load8(reinterpret_cast<const TDX*>(dx) + row * cols + r.c);
+      if (ACCUM) o = load8(reinterpret_cast<const TDX*>(dx) + eoff);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float t = fmaf(xh.v[j], c1, fmaf(d.v[j], rs, c2));  // rs * (d - mean(d) - xh * mean(d xh))
-        if (GELU) t *= gp.v[j];
-        acc[2].v[j] += t;
-        o.v[j] = ACCUM ? o.v[j] + t : t;
+      for (int j = 0; j < 8; j += 2) {
+        float t0, t1;
+        fma2(t0, t1, d.v[j], d.v[j + 1], rs, rs, c2, c2);
+        fma2(t0, t1, xh.v[j], xh.v[j + 1], c1, c1, t0, t1);  // rs * (d - mean(d) - xh * mean(d xh))
+        if (GELU) mul2(t0, t1, t0, t1, gp.v[j], gp.v[j + 1]);
+        add2(acc[2].v[j], acc[2].v[j + 1], acc[2].v[j], acc[2].v[j + 1], t0, t1);
+        if (ACCUM) {
+          add2(o.v[j], o.v[j + 1], o.v[j], o.v[j + 1], t0, t1);
+        } else {
+          o.v[j] = t0;
+          o.v[j + 1] = t1;
+        }
       }
-      store8(dx + row * cols + r.c, o);
+      store8(dx + eoff, o);
     }
     if (++stage == NST) {
       stage = 0;
@@ -327,7 +354,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
   extern __shared__ __align__(128) uint8_t dsm[];
   pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
   pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
-  __shared__ float red[512];
+  __shared__ __align__(16) float2 red[512];
+  red_init(red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
@@ -354,61 +382,67 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
   }
   int stage = 0, flip = 0;
   uint32_t phase = 0;
+  // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
+  const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
+  int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
   for (int64_t it = 0; it < my_n; ++it) {
-    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
+    row += row_step;
+    eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
     rowpipe::wait(bars + stage, phase);
     f8 v, xx;
-    float s = 0.f;
+    float s = 0.f, q = 0.f;
     if (live) {
       const uint8_t* st = ring + (size_t)stage * in.stage_bytes;
       xx = load8(reinterpret_cast<const float*>(st) + r.rib * cols + r.c);
       v = load8(reinterpret_cast<const bf16*>(st + in.off[1]) + r.rib * cols + r.c);
+      if (HAS_LN1) {  // one pass: sum and sum of squares of the branch
+        float s1 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) s += v.v[j];
+        for (int j = 0; j < 8; j += 2) {
+          add2(s, s1, s, s1, v.v[j], v.v[j + 1]);
+          fma2(q, q1, v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], q, q1);
+        }
+        s += s1;
+        q += q1;
+      }
     }
     // (first) barrier of the iteration: every thread has consumed the stage -> refill it
     float m1 = 0.f, r1 = 1.f;
     if (HAS_LN1) {
-      m1 = group_sum(s, red, flip, r, true) * inv_n;
+      group_sum2(s, q, red, flip, r, true);
+      m1 = s * inv_n;
+      r1 = rsqrtf(fmaxf(fmaf(-m1, m1, q * inv_n), 0.f) + eps);
     } else {
       __syncthreads();
     }
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<2>(in, ring, bars, stage, it + NST, rows, r.rpb);
-    if (HAS_LN1) {
-      float q = 0.f;
-      if (live) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v.v[j] -= m1;
-          q = fmaf(v.v[j], v.v[j], q);
-        }
-      }
-      r1 = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
-    }
     s = 0.f;
+    q = 0.f;
     if (live) {
       f8 m;
       if (DROP) m = drop_mask8(da, dk, row, r.c);
+      float s1 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float br = HAS_LN1 ? fmaf(v.v[j] * r1, gg1.v[j], bb1.v[j]) : v.v[j];
-        if (DROP) br *= m.v[j];
-        v.v[j] = xx.v[j] + br;
-        s += v.v[j];
+      for (int j = 0; j < 8; j += 2) {
+        float b0 = v.v[j], b1v = v.v[j + 1];
+        if (HAS_LN1) {
+          add2(b0, b1v, b0, b1v, -m1, -m1);
+          mul2(b0, b1v, b0, b1v, r1, r1);
+          fma2(b0, b1v, b0, b1v, gg1.v[j], gg1.v[j + 1], bb1.v[j], bb1.v[j + 1]);
+        }
+        if (DROP) mul2(b0, b1v, b0, b1v, m.v[j], m.v[j + 1]);
+        add2(v.v[j], v.v[j + 1], xx.v[j], xx.v[j + 1], b0, b1v);
+        add2(s, s1, s, s1, v.v[j], v.v[j + 1]);
+        fma2(q, q1, v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], q, q1);
       }
-      store8(x_new + row * cols + r.c, v);
+      s += s1;
+      q += q1;
+      store8(x_new + eoff, v);
     }
-    const float m2 = group_sum(s, red, flip, r, false) * inv_n;
-    float q = 0.f;
-    if (live) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        v.v[j] -= m2;
-        q = fmaf(v.v[j], v.v[j], q);
-      }
-    }
-    const float r2 = rsqrtf(group_sum(q, red, flip, r, false) * inv_n + eps);
+    group_sum2(s, q, red, flip, r, false);
+    const float m2 = s * inv_n;
+    const float r2 = rsqrtf(fmaxf(fmaf(-m2, m2, q * inv_n), 0.f) + eps);
     if (live) {
       if (r.lane_in_row == 0) {
         stats[row] = m1;
@@ -418,8 +452,13 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
       }
       f8 o;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) o.v[j] = fmaf(v.v[j] * r2, gg2.v[j], bb2.v[j]);
-      store8(y + row * cols + r.c, o);
+      for (int j = 0; j < 8; j += 2) {
+        float t0, t1;
+        add2(t0, t1, v.v[j], v.v[j + 1], -m2, -m2);
+        mul2(t0, t1, t0, t1, r2, r2);
+        fma2(o.v[j], o.v[j + 1], t0, t1, gg2.v[j], gg2.v[j + 1], bb2.v[j], bb2.v[j + 1]);
+      }
+      store8(y + eoff, o);
     }
     if (++stage == NST) {
       stage = 0;
@@ -439,7 +478,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
   extern __shared__ __align__(128) uint8_t dsm[];
   pdl_launch();  // the next kernel's CTAs may become resident once all of ours have started ...
   pdl_wait();    // ... and we touch global memory only after the previous kernel has completed
-  __shared__ float2 red[512];
+  __shared__ __align__(16) float2 red[512];
+  red_init(red);
   uint64_t* bars = reinterpret_cast<uint64_t*>(dsm);
   uint8_t* ring = dsm + kLnBarBytes;
   const RowCtx r = row_ctx(tpr, cols);
@@ -474,8 +514,12 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
     for (int j = 0; j < 8; ++j) acc[s].v[j] = 0.f;
   int stage = 0, flip = 0;
   uint32_t phase = 0;
+  // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
+  const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
+  int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
   for (int64_t it = 0; it < my_n; ++it) {
-    const int64_t row = ((int64_t)blockIdx.x + it * gridDim.x) * r.rpb + r.rib;
+    row += row_step;
+    eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
     rowpipe::wait(bars + stage, phase);
     float m1 = 0.f, r1 = 0.f, r2 = 0.f;
@@ -493,16 +537,18 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
       r1 = stats[rows + row];
       r2 = stats[3 * rows + row];
       const float nmr = -stats[2 * rows + row] * r2;
+      float s1b = 0.f, s2b = 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        xh.v[j] = fmaf(xx.v[j], r2, nmr);
-        acc[2].v[j] = fmaf(d.v[j], xh.v[j], acc[2].v[j]);
-        acc[3].v[j] += d.v[j];
-        const float t = d.v[j] * gg2.v[j];
-        d.v[j] = t;
-        s1 = fmaf(t, xh.v[j], s1);
-        s2 += t;
+      for (int j = 0; j < 8; j += 2) {
+        fma2(xh.v[j], xh.v[j + 1], xx.v[j], xx.v[j + 1], r2, r2, nmr, nmr);
+        fma2(acc[2].v[j], acc[2].v[j + 1], d.v[j], d.v[j + 1], xh.v[j], xh.v[j + 1], acc[2].v[j], acc[2].v[j + 1]);
+        add2(acc[3].v[j], acc[3].v[j + 1], acc[3].v[j], acc[3].v[j + 1], d.v[j], d.v[j + 1]);
+        mul2(d.v[j], d.v[j + 1], d.v[j], d.v[j + 1], gg2.v[j], gg2.v[j + 1]);
+        fma2(s1, s1b, d.v[j], d.v[j + 1], xh.v[j], xh.v[j + 1], s1, s1b);
+        add2(s2, s2b, s2, s2b, d.v[j], d.v[j + 1]);
       }
+      s1 += s1b;
+      s2 += s2b;
     }
     group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<NIN>(in, ring, bars, stage, it + NST, rows, r.rpb);
@@ -510,30 +556,37 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
     if (live) {
       const float c1 = -s1 * inv_n * r2, c2 = -s2 * inv_n * r2;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) tot.v[j] += fmaf(xh.v[j], c1, fmaf(d.v[j], r2, c2));  // + LN2'(dy)
-      store8(dxt + row * cols + r.c, tot);
+      for (int j = 0; j < 8; j += 2) {  // + LN2'(dy)
+        float u0, u1;
+        fma2(u0, u1, d.v[j], d.v[j + 1], r2, r2, c2, c2);
+        fma2(u0, u1, xh.v[j], xh.v[j + 1], c1, c1, u0, u1);
+        add2(tot.v[j], tot.v[j + 1], tot.v[j], tot.v[j + 1], u0, u1);
+      }
+      store8(dxt + eoff, tot);
       if (DROP) {  // gradient of the residual branch = mask * d x_new
         const f8 m = drop_mask8(dra, dk, row, r.c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) tot.v[j] *= m.v[j];
+        for (int j = 0; j < 8; j += 2) mul2(tot.v[j], tot.v[j + 1], tot.v[j], tot.v[j + 1], m.v[j], m.v[j + 1]);
       }
       if (HAS_LN1) {
         const f8 aa = unpack8(a_raw);
         const float nm1 = -m1 * r1;
+        float t1b = 0.f, t2b = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          xh.v[j] = fmaf(aa.v[j], r1, nm1);
-          acc[0].v[j] = fmaf(tot.v[j], xh.v[j], acc[0].v[j]);
-          acc[1].v[j] += tot.v[j];
-          const float t = tot.v[j] * gg1.v[j];
-          d.v[j] = t;
-          t1 = fmaf(t, xh.v[j], t1);
-          t2 += t;
+        for (int j = 0; j < 8; j += 2) {
+          fma2(xh.v[j], xh.v[j + 1], aa.v[j], aa.v[j + 1], r1, r1, nm1, nm1);
+          fma2(acc[0].v[j], acc[0].v[j + 1], tot.v[j], tot.v[j + 1], xh.v[j], xh.v[j + 1], acc[0].v[j], acc[0].v[j + 1]);
+          add2(acc[1].v[j], acc[1].v[j + 1], acc[1].v[j], acc[1].v[j + 1], tot.v[j], tot.v[j + 1]);
+          mul2(d.v[j], d.v[j + 1], tot.v[j], tot.v[j + 1], gg1.v[j], gg1.v[j + 1]);
+          fma2(t1, t1b, d.v[j], d.v[j + 1], xh.v[j], xh.v[j + 1], t1, t1b);
+          add2(t2, t2b, t2, t2b, d.v[j], d.v[j + 1]);
         }
+        t1 += t1b;
+        t2 += t2b;
       } else {
-        store8(da + row * cols + r.c, tot);  // d a = d x_new
+        store8(da + eoff, tot);  // d a = d x_new
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[4].v[j] += tot.v[j];
+        for (int j = 0; j < 8; j += 2) add2(acc[4].v[j], acc[4].v[j + 1], acc[4].v[j], acc[4].v[j + 1], tot.v[j], tot.v[j + 1]);
       }
     }
     if (HAS_LN1) {
@@ -542,11 +595,12 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
         const float c1 = -t1 * inv_n * r1, c2 = -t2 * inv_n * r1;
         f8 o;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o.v[j] = fmaf(xh.v[j], c1, fmaf(d.v[j], r1, c2));
-          acc[4].v[j] += o.v[j];
+        for (int j = 0; j < 8; j += 2) {
+          fma2(o.v[j], o.v[j + 1], d.v[j], d.v[j + 1], r1, r1, c2, c2);
+          fma2(o.v[j], o.v[j + 1], xh.v[j], xh.v[j + 1], c1, c1, o.v[j], o.v[j + 1]);
+          add2(acc[4].v[j], acc[4].v[j + 1], acc[4].v[j], acc[4].v[j + 1], o.v[j], o.v[j + 1]);
         }
-        store8(da + row * cols + r.c, o);
+        store8(da + eoff, o);
       }
     }
     if (++stage == NST) {
@@ -812,12 +866,12 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
     if (has_drop) RBWD(true); else RBWD(false);
 #undef RBWD
   } else {
-    const LnLaunch l = ln_launch(cols);
+    const LnLaunch l = ln_launch(cols, has_drop ? 288 : 384);  // the dropout form needs the mask registers: 288-thread CTAs
     const int smem = ln_smem(l, cols, 10, 2, true);
-#define RBWD(D)                                                                                                                       \
-  LN_GO(grid, smem, 384, (ln_res_ln_bwd_kernel<false, 384, D>), (ln_res_ln_bwd_kernel<false, 512, D>), dx_new, (const bf16*)dy,           \
+#define RBWD(D, T)                                                                                                                    \
+  LN_GO(grid, smem, T, (ln_res_ln_bwd_kernel<false, T, D>), (ln_res_ln_bwd_kernel<false, 512, D>), dx_new, (const bf16*)dy,             \
         (const bf16*)nullptr, x_new, (const bf16*)nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr, dra)
-    if (has_drop) RBWD(true); else RBWD(false);
+    if (has_drop) RBWD(true, 288); else RBWD(false, 384);
 #undef RBWD
   }
   OFAB_LAUNCH_CHECK("ofab_ln_res_ln_bwd");

@@ -32,7 +32,7 @@ def time_it(fn, iters=20):
 
 def main():
     out = []
-    for tag, rows in (("enc", 8480), ("dec", 2048), ("b128", 33920)):
+    for tag, rows in (("enc32", 8480), ("enc64", 16960), ("dec64", 4096)):
         # GELU + ffn_layernorm
         cols = 3072
         x = torch.randn(rows, cols, device=dev).bfloat16().requires_grad_(True)

@@ -40,12 +40,18 @@ elif which == "attn_modeA":  # encoder self-attention with OFA's position biases
         o = ops.attention(qkv, None, H, 0.0884, ops.PositionBias(pq, pk, idx.contiguous(), tab), kpm, False)
         o.backward(torch.randn_like(o))
 elif which == "ln":  # GELU + ffn_layernorm of the benchmark step: rows 8480 x 3072
-    x = torch.randn(8480, 3072, device=dev).bfloat16().requires_grad_(True)
+    rows = int(os.environ.get("LN_ROWS", "8480"))
+    x = torch.randn(rows, 3072, device=dev).bfloat16().requires_grad_(True)
     w = torch.ones(3072, device=dev).bfloat16().requires_grad_(True)
     b = torch.zeros(3072, device=dev).bfloat16().requires_grad_(True)
+    a = torch.randn(rows, 768, device=dev).bfloat16().requires_grad_(True)
+    xr = torch.randn(rows, 768, device=dev).requires_grad_(True)
+    ws = [(torch.rand(768, device=dev) + 0.5).bfloat16().requires_grad_(True) for _ in range(4)]
     for _ in range(3):
         y = ops.layer_norm(x, w, b, gelu=True)
         y.backward(torch.randn_like(y))
+        xn, yy = ops.ln_res_ln(a, xr, ws[0], ws[1], ws[2], ws[3])  # the LN -> +residual -> LN junction
+        torch.autograd.backward((xn, yy), (torch.randn_like(xn), torch.randn_like(yy)))
 elif which == "adam":  # optimizer step over 200 M elements in 300 tensors (OFA-base sized)
     from ofasys_b200 import FusedAdam
 
