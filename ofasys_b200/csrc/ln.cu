@@ -147,7 +147,10 @@ __device__ __forceinline__ void flush_partials(f8 (&acc)[NS], float* __restrict_
 
 // ------------------------------------------------------------------------------------ forward
 // DROP (GELU form only): activation dropout between GELU and the LayerNorm (transformer_layer.py:195).
-template <typename TX, typename TY, bool GELU, int MAXT, bool DROP = false>
+// VPT: 8-column vectors per thread.  2 for the wide GELU rows (3072 / 4096 columns: `tpr` = cols / 16 threads per row, the
+// thread's second vector sits tpr * 8 columns to the right): the per-iteration overhead (reduction, pipeline wait, loop) is
+// paid once per 16 elements, which matters because this kernel is issue-bound (ncu: profiles/r02_ncu_ln_before_packed.csv).
+template <typename TX, typename TY, bool GELU, int MAXT, bool DROP = false, int VPT = 1>
 __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                               TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int cols,
                                               float eps, int tpr, const DropArgs da) {
@@ -169,10 +172,16 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
   const float inv_n = 1.0f / (float)cols;
   DropCtx dk;
   if (DROP) dk = drop_ctx(da);
-  f8 g, b;
-  if (r.col_ok) {
-    g = load8(gamma + r.c);
-    b = load8(beta + r.c);
+  const int vstep = tpr * 8;  // columns between a thread's vectors
+  bool ok[VPT];
+  f8 g[VPT], b[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    ok[k] = r.rib < r.rpb && r.c + k * vstep < cols;
+    if (ok[k]) {
+      g[k] = load8(gamma + r.c + k * vstep);
+      b[k] = load8(beta + r.c + k * vstep);
+    }
   }
   int stage = 0, flip = 0;
   uint32_t phase = 0;
@@ -182,49 +191,54 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
   for (int64_t it = 0; it < my_n; ++it) {
     row += row_step;
     eoff += eoff_step;
-    const bool live = r.col_ok && row < rows;
+    const bool row_live = row < rows;
     rowpipe::wait(bars + stage, phase);
-    f8 v;
-    float s = 0.f, q = 0.f;
-    if (live) {
-      v = load8(reinterpret_cast<const TX*>(ring + (size_t)stage * in.stage_bytes) + r.rib * cols + r.c);
-      if (GELU) {
+    f8 v[VPT];
+    float s = 0.f, q = 0.f, s1 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) gelu2(v.v[j], v.v[j + 1]);
-      }
-      if (DROP) {
-        const f8 m = drop_mask8(da, dk, row, r.c);
+    for (int k = 0; k < VPT; ++k) {
+      if (ok[k] && row_live) {
+        v[k] = load8(reinterpret_cast<const TX*>(ring + (size_t)stage * in.stage_bytes) + r.rib * cols + r.c + k * vstep);
+        if (GELU) {
 #pragma unroll
-        for (int j = 0; j < 8; j += 2) mul2(v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], m.v[j], m.v[j + 1]);
-      }
-      // one pass: sum and sum of squares (fp32; the variance is E[v^2] - mean^2, clamped at 0)
-      float s1 = 0.f, q1 = 0.f;
+          for (int j = 0; j < 8; j += 2) gelu2(v[k].v[j], v[k].v[j + 1]);
+        }
+        if (DROP) {
+          const f8 m = drop_mask8(da, dk, row, r.c + k * vstep);
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        add2(s, s1, s, s1, v.v[j], v.v[j + 1]);
-        fma2(q, q1, v.v[j], v.v[j + 1], v.v[j], v.v[j + 1], q, q1);
+          for (int j = 0; j < 8; j += 2) mul2(v[k].v[j], v[k].v[j + 1], v[k].v[j], v[k].v[j + 1], m.v[j], m.v[j + 1]);
+        }
+        // one pass: sum and sum of squares (fp32; the variance is E[v^2] - mean^2, clamped at 0)
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          add2(s, s1, s, s1, v[k].v[j], v[k].v[j + 1]);
+          fma2(q, q1, v[k].v[j], v[k].v[j + 1], v[k].v[j], v[k].v[j + 1], q, q1);
+        }
       }
-      s += s1;
-      q += q1;
     }
+    s += s1;
+    q += q1;
     group_sum2(s, q, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<1>(in, ring, bars, stage, it + NST, rows, r.rpb);
     const float mu = s * inv_n;
     const float rs = rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_n), 0.f) + eps);
-    if (live) {
-      if (r.lane_in_row == 0) {
-        mean[row] = mu;
-        rstd[row] = rs;
-      }
-      f8 o;
+    if (ok[0] && row_live && r.lane_in_row == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        float t0, t1;
-        add2(t0, t1, v.v[j], v.v[j + 1], -mu, -mu);
-        mul2(t0, t1, t0, t1, rs, rs);
-        fma2(o.v[j], o.v[j + 1], t0, t1, g.v[j], g.v[j + 1], b.v[j], b.v[j + 1]);
+    for (int k = 0; k < VPT; ++k) {
+      if (ok[k] && row_live) {
+        f8 o;
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float t0, t1;
+          add2(t0, t1, v[k].v[j], v[k].v[j + 1], -mu, -mu);
+          mul2(t0, t1, t0, t1, rs, rs);
+          fma2(o.v[j], o.v[j + 1], t0, t1, g[k].v[j], g[k].v[j + 1], b[k].v[j], b[k].v[j + 1]);
+        }
+        store8(y + eoff + k * vstep, o);
       }
-      store8(y + eoff, o);
     }
     if (++stage == NST) {
       stage = 0;
@@ -271,10 +285,22 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
   // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
   const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
   int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
+  // the row statistics of the NEXT iteration are requested before this iteration's wait: their L2 latency used to sit at
+  // the head of every iteration's dependency chain (ncu source view: 17 % of the stall samples on the first use)
+  float nx_mean = 0.f, nx_rstd = 0.f;
+  if (r.col_ok && row + row_step < rows) {
+    nx_mean = mean[row + row_step];
+    nx_rstd = rstd[row + row_step];
+  }
   for (int64_t it = 0; it < my_n; ++it) {
     row += row_step;
     eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
+    const float cur_mean = nx_mean, cur_rstd = nx_rstd;
+    if (r.col_ok && row + row_step < rows) {
+      nx_mean = mean[row + row_step];
+      nx_rstd = rstd[row + row_step];
+    }
     rowpipe::wait(bars + stage, phase);
     float rs = 0.f;
     f8 xh, d, gp;
@@ -283,8 +309,8 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
       const uint8_t* st = ring + (size_t)stage * in.stage_bytes;
       const f8 pre = load8(reinterpret_cast<const TX*>(st) + r.rib * cols + r.c);
       d = load8(reinterpret_cast<const TDY*>(st + in.off[1]) + r.rib * cols + r.c);
-      rs = rstd[row];
-      const float nmr = -mean[row] * rs;
+      rs = cur_rstd;
+      const float nmr = -cur_mean * rs;
       f8 m;
       if (DROP) m = drop_mask8(da, dk, row, r.c);
       float s1b = 0.f, s2b = 0.f;
@@ -517,10 +543,25 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
   // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
   const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
   int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
+  // row statistics one iteration ahead (see ln_bwd_kernel)
+  float nx[4] = {0.f, 0.f, 0.f, 0.f};
+  auto fetch_stats = [&](int64_t rw) {
+    if (r.col_ok && rw < rows) {
+      if (HAS_LN1) {
+        nx[0] = stats[rw];
+        nx[1] = stats[rows + rw];
+      }
+      nx[2] = stats[2 * rows + rw];
+      nx[3] = stats[3 * rows + rw];
+    }
+  };
+  fetch_stats(row + row_step);
   for (int64_t it = 0; it < my_n; ++it) {
     row += row_step;
     eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
+    const float cur0 = nx[0], cur1 = nx[1], cur2 = nx[2], cur3 = nx[3];
+    fetch_stats(row + row_step);
     rowpipe::wait(bars + stage, phase);
     float m1 = 0.f, r1 = 0.f, r2 = 0.f;
     f8 xh, d, tot;
@@ -533,10 +574,10 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
       tot = load8(reinterpret_cast<const float*>(st + in.off[1]) + e);  // upstream d x_new
       d = load8(reinterpret_cast<const bf16*>(st + in.off[2]) + e);
       if (HAS_LN1) a_raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(st + in.off[NIN - 1]) + e);
-      m1 = stats[row];
-      r1 = stats[rows + row];
-      r2 = stats[3 * rows + row];
-      const float nmr = -stats[2 * rows + row] * r2;
+      m1 = cur0;
+      r1 = cur1;
+      r2 = cur3;
+      const float nmr = -cur2 * r2;
       float s1b = 0.f, s2b = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
@@ -765,13 +806,24 @@ extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const voi
   OFAB_REQUIRE(LN_ALIGNED16(x) && LN_ALIGNED16(y) && LN_ALIGNED16(gamma) && LN_ALIGNED16(beta), "ofab_ln_fwd: x / y / gamma / beta must be 16-byte aligned");
   if (rows == 0) return OFAB_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  const LnLaunch l = ln_launch(cols);
+  // wide GELU rows (ffn_layernorm over 4d): two vectors per thread, half as many threads per row
+  const bool two = gelu && x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && cols >= 2048 && cols % 16 == 0 && !getenv("OFAB_LN_VPT1");
+  LnLaunch l = ln_launch(cols);
+  if (two) {
+    l.tpr = ((cols / 16) + 31) / 32 * 32;
+    l.rpb = l.tpr >= 384 ? 1 : 384 / l.tpr;
+    l.block = l.rpb * l.tpr;
+    l.grid = ofab_sm_count() * 2;
+    if (l.grid > OFAB_LN_PARTIAL_ROWS) l.grid = OFAB_LN_PARTIAL_ROWS;
+  }
   const int64_t ngroups = (rows + l.rpb - 1) / l.rpb;
   const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
   const int smem = ln_smem(l, cols, x_dt == OFAB_F32 ? 4 : 2, 6, false);
 #define ARGS(TX, TY) (const TX*)x, (const bf16*)gamma, (const bf16*)beta, (TY*)y, mean, rstd, rows, cols, eps, l.tpr, da
 #define FWD(TX, TY, G) LN_GO(grid, smem, 384, (ln_fwd_kernel<TX, TY, G, 384>), (ln_fwd_kernel<TX, TY, G, 512>), ARGS(TX, TY))
-  if (has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
+  if (two && has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true, 2>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
+  else if (two) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, false, 2>), (ln_fwd_kernel<bf16, bf16, true, 512>), ARGS(bf16, bf16));
+  else if (has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
   else if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) FWD(float, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && !gelu) FWD(bf16, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && gelu) FWD(bf16, bf16, true);
