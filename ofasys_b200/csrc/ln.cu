@@ -51,17 +51,9 @@ template <typename T>
 __device__ __forceinline__ void red_init(T* red) {  // call before the first __syncthreads of the kernel
   for (int i = threadIdx.x; i < 512; i += blockDim.x) red[i] = T{};
 }
-// rows wider than 4 warps (GELU / ffn_layernorm kernels: 12 or 16 warps): the partials of the row, outside the caller's
-// register allocation (kernels sit at their register cap; this path inlined cost spills in every variant)
-__device__ __noinline__ float2 group_sum2_wide(const float2* buf) {
-  float2 s = buf[threadIdx.x & 15];  // slots past the row's warp count are zero (red_init)
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) {
-    s.x += __shfl_xor_sync(0xffffffffu, s.x, o);
-    s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
-  }
-  return s;
-}
+// NARROW (rows at most 4 warps wide, chosen at dispatch): two 16-byte loads of the row's partials; otherwise the 16-lane
+// butterfly.  A compile-time choice: both forms in one kernel cost registers (spills) in kernels that sit at their cap.
+template <bool NARROW>
 __device__ __forceinline__ void group_sum2(float& a, float& b, float2* red, int& flip, const RowCtx& r, bool sync_always) {
   a = warp_sum(a);
   b = warp_sum(b);
@@ -73,14 +65,19 @@ __device__ __forceinline__ void group_sum2(float& a, float& b, float2* red, int&
   flip ^= 1;
   if ((threadIdx.x & 31) == 0) buf[r.rib * 16 + r.wir] = make_float2(a, b);
   __syncthreads();
-  if (r.wpr <= 4) {
+  if (NARROW) {
     const float4 p = *reinterpret_cast<const float4*>(buf + r.rib * 16), q = *reinterpret_cast<const float4*>(buf + r.rib * 16 + 2);
     a = (p.x + p.z) + (q.x + q.z);
     b = (p.y + p.w) + (q.y + q.w);
   } else {
-    const float2 s = group_sum2_wide(buf + r.rib * 16);
-    a = s.x;
-    b = s.y;
+    float2 s2 = buf[r.rib * 16 + (threadIdx.x & 15)];  // slots past the row's warp count are zero (red_init)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+      s2.x += __shfl_xor_sync(0xffffffffu, s2.x, o);
+      s2.y += __shfl_xor_sync(0xffffffffu, s2.y, o);
+    }
+    a = s2.x;
+    b = s2.y;
   }
 }
 
@@ -150,7 +147,7 @@ __device__ __forceinline__ void flush_partials(f8 (&acc)[NS], float* __restrict_
 // VPT: 8-column vectors per thread.  2 for the wide GELU rows (3072 / 4096 columns: `tpr` = cols / 16 threads per row, the
 // thread's second vector sits tpr * 8 columns to the right): the per-iteration overhead (reduction, pipeline wait, loop) is
 // paid once per 16 elements, which matters because this kernel is issue-bound (ncu: profiles/r02_ncu_ln_before_packed.csv).
-template <typename TX, typename TY, bool GELU, int MAXT, bool DROP = false, int VPT = 1>
+template <typename TX, typename TY, bool GELU, int MAXT, bool DROP = false, int VPT = 1, bool NARROW = false>
 __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf16* __restrict__ gamma, const bf16* __restrict__ beta,
                                               TY* __restrict__ y, float* __restrict__ mean, float* __restrict__ rstd, int64_t rows, int cols,
                                               float eps, int tpr, const DropArgs da) {
@@ -218,7 +215,7 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
     }
     s += s1;
     q += q1;
-    group_sum2(s, q, red, flip, r, true);  // barrier: every thread has consumed the stage
+    group_sum2<NARROW>(s, q, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<1>(in, ring, bars, stage, it + NST, rows, r.rpb);
     const float mu = s * inv_n;
     const float rs = rsqrtf(fmaxf(fmaf(-mu, mu, q * inv_n), 0.f) + eps);
@@ -248,7 +245,7 @@ __global__ void LN_BOUNDS(MAXT) ln_fwd_kernel(const TX* __restrict__ x, const bf
 }
 
 // ----------------------------------------------------------------------------------- backward
-template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM, int MAXT, bool DROP = false>
+template <typename TDY, typename TX, typename TDX, bool GELU, bool ACCUM, int MAXT, bool DROP = false, bool NARROW = false>
 __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const TX* __restrict__ x, const bf16* __restrict__ gamma,
                                               const float* __restrict__ mean, const float* __restrict__ rstd, TDX* __restrict__ dx,
                                               float* __restrict__ partial, int64_t rows, int cols, int tpr, const DropArgs da) {
@@ -337,7 +334,7 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
       s1 += s1b;
       s2 += s2b;
     }
-    group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
+    group_sum2<NARROW>(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<2>(in, ring, bars, stage, it + NST, rows, r.rpb);
     if (live) {
       const float c1 = -s1 * inv_n * rs, c2 = -s2 * inv_n * rs;
@@ -371,7 +368,7 @@ __global__ void LN_BOUNDS(MAXT) ln_bwd_kernel(const TDY* __restrict__ dy, const 
 // HAS_LN1 = false: x_new = x + a (no first LayerNorm): the deferred residual add of an FFN output fused
 // with the next block's pre-LayerNorm.
 // DROP: x_new = x + mask * branch  (residual dropout + drop-path of the block, transformer_layer.py:181,87)
-template <bool HAS_LN1, int MAXT, bool DROP = false>
+template <bool HAS_LN1, int MAXT, bool DROP = false, bool NARROW = false>
 __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a, const float* __restrict__ x, const bf16* __restrict__ g1,
                                                      const bf16* __restrict__ b1, const bf16* __restrict__ g2, const bf16* __restrict__ b2,
                                                      float* __restrict__ x_new, bf16* __restrict__ y, float* __restrict__ stats,
@@ -436,7 +433,7 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
     // (first) barrier of the iteration: every thread has consumed the stage -> refill it
     float m1 = 0.f, r1 = 1.f;
     if (HAS_LN1) {
-      group_sum2(s, q, red, flip, r, true);
+      group_sum2<NARROW>(s, q, red, flip, r, true);
       m1 = s * inv_n;
       r1 = rsqrtf(fmaxf(fmaf(-m1, m1, q * inv_n), 0.f) + eps);
     } else {
@@ -466,7 +463,7 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
       q += q1;
       store8(x_new + eoff, v);
     }
-    group_sum2(s, q, red, flip, r, false);
+    group_sum2<NARROW>(s, q, red, flip, r, false);
     const float m2 = s * inv_n;
     const float r2 = rsqrtf(fmaxf(fmaf(-m2, m2, q * inv_n), 0.f) + eps);
     if (live) {
@@ -493,7 +490,7 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_fwd_kernel(const bf16* __restrict__ a,
   }
 }
 
-template <bool HAS_LN1, int MAXT, bool DROP = false>
+template <bool HAS_LN1, int MAXT, bool DROP = false, bool NARROW = false>
 __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ dxn, const bf16* __restrict__ dy, const bf16* __restrict__ a,
                                                      const float* __restrict__ x_new, const bf16* __restrict__ g1,
                                                      const bf16* __restrict__ g2, const float* __restrict__ stats,
@@ -524,14 +521,39 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
     in.off[NIN - 1] = (uint32_t)r.rpb * (uint32_t)cols * 10u;
   }
   in.stage_bytes = (uint32_t)r.rpb * (uint32_t)cols * (HAS_LN1 ? 12u : 10u);
+  // Row statistics (mean / rstd of both LayerNorms) travel global -> shared by 4-byte cp.async two iterations ahead of their
+  // use, issued by the first thread of each row group.  Loading them at the point of use put an L2 round trip at the head of
+  // every iteration's dependency chain (ncu source view: 17 % of the stall samples); prefetching into registers did not fit
+  // under the register cap (ptxas parked the values in local memory, whose store waits for the load just the same).
+  __shared__ __align__(16) float st_s[3][16][4];
+  const bool leader = r.lane_in_row == 0 && r.rib < r.rpb && r.rib < 16;
+  auto stats_issue = [&](int slot, int64_t rw) {
+    if (rw < rows) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (HAS_LN1 || q >= 2)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(rowpipe::s32(&st_s[slot][r.rib][q])), "l"(stats + q * rows + rw) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  {
+    const int64_t first = (int64_t)blockIdx.x * r.rpb + r.rib, step = (int64_t)gridDim.x * r.rpb;
+    if (leader) {
+      stats_issue(0, first);
+      stats_issue(1, first + step);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");  // row(0)'s are in; ring_start's __syncthreads publishes them
+    }
+  }
   const int64_t my_n = ring_start<NIN, NST>(in, ring, bars, rows, r.rpb);
   const float inv_n = 1.0f / (float)cols;
   DropCtx dk;
   if (DROP) dk = drop_ctx(dra);
-  f8 gg1, gg2;
+  // gamma vectors stay packed (bf16, 4 registers each) and are unpacked where used: the kernel sits at its register cap and
+  // is bound by latency, not by issue slots
+  uint4 g1_raw = make_uint4(0u, 0u, 0u, 0u), g2_raw = make_uint4(0u, 0u, 0u, 0u);
   if (r.col_ok) {
-    if (HAS_LN1) gg1 = load8(g1 + r.c);
-    gg2 = load8(g2 + r.c);
+    if (HAS_LN1) g1_raw = *reinterpret_cast<const uint4*>(g1 + r.c);
+    g2_raw = *reinterpret_cast<const uint4*>(g2 + r.c);
   }
   f8 acc[5];  // dg1, db1, dg2, db2, column sums of da (bias gradient of the Linear that produced a)
 #pragma unroll
@@ -543,25 +565,14 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
   // row and element offset of this thread advance by a constant per iteration (no 64-bit multiplies in the loop)
   const int64_t row_step = (int64_t)gridDim.x * r.rpb, eoff_step = row_step * cols;
   int64_t row = (int64_t)blockIdx.x * r.rpb + r.rib - row_step, eoff = row * cols + r.c;
-  // row statistics one iteration ahead (see ln_bwd_kernel)
-  float nx[4] = {0.f, 0.f, 0.f, 0.f};
-  auto fetch_stats = [&](int64_t rw) {
-    if (r.col_ok && rw < rows) {
-      if (HAS_LN1) {
-        nx[0] = stats[rw];
-        nx[1] = stats[rows + rw];
-      }
-      nx[2] = stats[2 * rows + rw];
-      nx[3] = stats[3 * rows + rw];
-    }
-  };
-  fetch_stats(row + row_step);
   for (int64_t it = 0; it < my_n; ++it) {
     row += row_step;
     eoff += eoff_step;
     const bool live = r.col_ok && row < rows;
-    const float cur0 = nx[0], cur1 = nx[1], cur2 = nx[2], cur3 = nx[3];
-    fetch_stats(row + row_step);
+    // the statistics of row(it + 2) start their way into shared memory now; row(it)'s were published by the barrier of the
+    // previous iteration (or of the prologue)
+    if (leader) stats_issue((int)((it + 2) % 3), row + 2 * row_step);
+    const float4 cur = *reinterpret_cast<const float4*>(&st_s[it % 3][r.rib < 16 ? r.rib : 0][0]);
     rowpipe::wait(bars + stage, phase);
     float m1 = 0.f, r1 = 0.f, r2 = 0.f;
     f8 xh, d, tot;
@@ -574,11 +585,12 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
       tot = load8(reinterpret_cast<const float*>(st + in.off[1]) + e);  // upstream d x_new
       d = load8(reinterpret_cast<const bf16*>(st + in.off[2]) + e);
       if (HAS_LN1) a_raw = *reinterpret_cast<const uint4*>(reinterpret_cast<const bf16*>(st + in.off[NIN - 1]) + e);
-      m1 = cur0;
-      r1 = cur1;
-      r2 = cur3;
-      const float nmr = -cur2 * r2;
+      m1 = cur.x;
+      r1 = cur.y;
+      r2 = cur.w;
+      const float nmr = -cur.z * r2;
       float s1b = 0.f, s2b = 0.f;
+      const f8 gg2 = unpack8(g2_raw);
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         fma2(xh.v[j], xh.v[j + 1], xx.v[j], xx.v[j + 1], r2, r2, nmr, nmr);
@@ -591,7 +603,8 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
       s1 += s1b;
       s2 += s2b;
     }
-    group_sum2(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
+    if (leader) asm volatile("cp.async.wait_group 1;" ::: "memory");  // row(it + 1)'s statistics have landed; the barrier publishes them
+    group_sum2<NARROW>(s1, s2, red, flip, r, true);  // barrier: every thread has consumed the stage
     if (threadIdx.x == 0 && it + NST < my_n) ring_issue<NIN>(in, ring, bars, stage, it + NST, rows, r.rpb);
     float t1 = 0.f, t2 = 0.f;
     if (live) {
@@ -610,7 +623,7 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
         for (int j = 0; j < 8; j += 2) mul2(tot.v[j], tot.v[j + 1], tot.v[j], tot.v[j + 1], m.v[j], m.v[j + 1]);
       }
       if (HAS_LN1) {
-        const f8 aa = unpack8(a_raw);
+        const f8 aa = unpack8(a_raw), gg1 = unpack8(g1_raw);
         const float nm1 = -m1 * r1;
         float t1b = 0.f, t2b = 0.f;
 #pragma unroll
@@ -631,7 +644,7 @@ __global__ void LN_BOUNDS(MAXT) ln_res_ln_bwd_kernel(const float* __restrict__ d
       }
     }
     if (HAS_LN1) {
-      group_sum2(t1, t2, red, flip, r, false);
+      group_sum2<NARROW>(t1, t2, red, flip, r, false);
       if (live) {
         const float c1 = -t1 * inv_n * r1, c2 = -t2 * inv_n * r1;
         f8 o;
@@ -786,14 +799,17 @@ static int ln_configure(const void* kern) {  // opt in to > 48 KB dynamic shared
   const bool has_drop = drop != nullptr && (drop->p > 0.f || drop->drop_path > 0.f); \
   if (has_drop && !ofab_drop_args(drop, da, who)) return OFAB_ERR_ARG
 // launch kernel template K<..., 384> or K<..., 512> by block size
-#define LN_GO(GRID, SMEM, TARGET, K384, K512, ...)                              \
+#define LN_GO(GRID, SMEM, TARGET, K384N, K384, K512, ...)                       \
   do {                                                                          \
+    auto k384n = K384N; /* rows at most 4 warps wide */                         \
     auto k384 = K384;                                                           \
     auto k512 = K512;                                                           \
-    const void* kp = l.block > (TARGET) ? (const void*)k512 : (const void*)k384; \
+    const bool narrow_ = l.tpr <= 128;                                          \
+    const void* kp = l.block > (TARGET) ? (const void*)k512 : (narrow_ ? (const void*)k384n : (const void*)k384); \
     int rc_ = ln_configure(kp);                                                 \
     if (rc_) return rc_;                                                        \
     if (l.block > (TARGET)) ofab_launch(k512, dim3(GRID), dim3(l.block), SMEM, st, __VA_ARGS__); \
+    else if (narrow_) ofab_launch(k384n, dim3(GRID), dim3(l.block), SMEM, st, __VA_ARGS__); \
     else ofab_launch(k384, dim3(GRID), dim3(l.block), SMEM, st, __VA_ARGS__);   \
   } while (0)
 
@@ -820,10 +836,10 @@ extern "C" int ofab_ln_fwd(const void* x, int x_dt, const void* gamma, const voi
   const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
   const int smem = ln_smem(l, cols, x_dt == OFAB_F32 ? 4 : 2, 6, false);
 #define ARGS(TX, TY) (const TX*)x, (const bf16*)gamma, (const bf16*)beta, (TY*)y, mean, rstd, rows, cols, eps, l.tpr, da
-#define FWD(TX, TY, G) LN_GO(grid, smem, 384, (ln_fwd_kernel<TX, TY, G, 384>), (ln_fwd_kernel<TX, TY, G, 512>), ARGS(TX, TY))
-  if (two && has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true, 2>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
-  else if (two) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, false, 2>), (ln_fwd_kernel<bf16, bf16, true, 512>), ARGS(bf16, bf16));
-  else if (has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
+#define FWD(TX, TY, G) LN_GO(grid, smem, 384, (ln_fwd_kernel<TX, TY, G, 384, false, 1, true>), (ln_fwd_kernel<TX, TY, G, 384>), (ln_fwd_kernel<TX, TY, G, 512>), ARGS(TX, TY))
+  if (two && has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true, 2>), (ln_fwd_kernel<bf16, bf16, true, 384, true, 2>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
+  else if (two) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, false, 2>), (ln_fwd_kernel<bf16, bf16, true, 384, false, 2>), (ln_fwd_kernel<bf16, bf16, true, 512>), ARGS(bf16, bf16));
+  else if (has_drop) LN_GO(grid, smem, 384, (ln_fwd_kernel<bf16, bf16, true, 384, true, 1, true>), (ln_fwd_kernel<bf16, bf16, true, 384, true>), (ln_fwd_kernel<bf16, bf16, true, 512, true>), ARGS(bf16, bf16));
   else if (x_dt == OFAB_F32 && y_dt == OFAB_BF16 && !gelu) FWD(float, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && !gelu) FWD(bf16, bf16, false);
   else if (x_dt == OFAB_BF16 && y_dt == OFAB_BF16 && gelu) FWD(bf16, bf16, true);
@@ -853,8 +869,8 @@ extern "C" int ofab_ln_bwd(const void* dy, int dy_dt, const void* x, int x_dt, c
   const int grid = OFAB_LN_PARTIAL_ROWS;  // every partial row is written (idle CTAs write zeros)
   const int smem = ln_smem(l, cols, (x_dt == OFAB_F32 ? 4 : 2) + (dy_dt == OFAB_F32 ? 4 : 2), 4, true);
 #define ARGS(TDY, TX, TDX) (const TDY*)dy, (const TX*)x, (const bf16*)gamma, mean, rstd, (TDX*)dx, dgb_partial, rows, cols, l.tpr, da
-#define BWD(TDY, TX, TDX, G, A) LN_GO(grid, smem, 384, (ln_bwd_kernel<TDY, TX, TDX, G, A, 384>), (ln_bwd_kernel<TDY, TX, TDX, G, A, 512>), ARGS(TDY, TX, TDX))
-  if (has_drop) LN_GO(grid, smem, 384, (ln_bwd_kernel<bf16, bf16, bf16, true, false, 384, true>), (ln_bwd_kernel<bf16, bf16, bf16, true, false, 512, true>), ARGS(bf16, bf16, bf16));
+#define BWD(TDY, TX, TDX, G, A) LN_GO(grid, smem, 384, (ln_bwd_kernel<TDY, TX, TDX, G, A, 384, false, true>), (ln_bwd_kernel<TDY, TX, TDX, G, A, 384>), (ln_bwd_kernel<TDY, TX, TDX, G, A, 512>), ARGS(TDY, TX, TDX))
+  if (has_drop) LN_GO(grid, smem, 384, (ln_bwd_kernel<bf16, bf16, bf16, true, false, 384, true, true>), (ln_bwd_kernel<bf16, bf16, bf16, true, false, 384, true>), (ln_bwd_kernel<bf16, bf16, bf16, true, false, 512, true>), ARGS(bf16, bf16, bf16));
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && dx_accum) BWD(bf16, float, float, false, true);
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_F32 && dx_dt == OFAB_F32 && !gelu && !dx_accum) BWD(bf16, float, float, false, false);
   else if (dy_dt == OFAB_BF16 && x_dt == OFAB_BF16 && dx_dt == OFAB_BF16 && gelu) BWD(bf16, bf16, bf16, true, false);
@@ -884,7 +900,7 @@ extern "C" int ofab_ln_res_ln_fwd(const void* a, const float* x, const void* g1,
   const int grid = (int)(ngroups < l.grid ? ngroups : l.grid);
   const int smem = ln_smem(l, cols, 6, 3, false);
 #define RFWD(L1, D)                                                                                                                     \
-  LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<L1, 384, D>), (ln_res_ln_fwd_kernel<L1, 512, D>), (const bf16*)a, x, (const bf16*)g1, \
+  LN_GO(grid, smem, 384, (ln_res_ln_fwd_kernel<L1, 384, D, true>), (ln_res_ln_fwd_kernel<L1, 384, D>), (ln_res_ln_fwd_kernel<L1, 512, D>), (const bf16*)a, x, (const bf16*)g1, \
         (const bf16*)b1, (const bf16*)g2, (const bf16*)b2, x_new, (bf16*)y, stats, rows, cols, eps, l.tpr, da)
   if (g1 != nullptr) {
     if (has_drop) RFWD(true, true); else RFWD(true, false);
@@ -913,7 +929,7 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
     const LnLaunch l = ln_launch(cols, 288);  // 5 accumulator slabs: ~110 registers -> 288-thread CTAs, still two per SM
     const int smem = ln_smem(l, cols, 12, 2, true);
 #define RBWD(D)                                                                                                                          \
-  LN_GO(grid, smem, 288, (ln_res_ln_bwd_kernel<true, 288, D>), (ln_res_ln_bwd_kernel<true, 512, D>), dx_new, (const bf16*)dy, (const bf16*)a, \
+  LN_GO(grid, smem, 288, (ln_res_ln_bwd_kernel<true, 288, D, true>), (ln_res_ln_bwd_kernel<true, 288, D>), (ln_res_ln_bwd_kernel<true, 512, D>), dx_new, (const bf16*)dy, (const bf16*)a, \
         x_new, (const bf16*)g1, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr, dra)
     if (has_drop) RBWD(true); else RBWD(false);
 #undef RBWD
@@ -921,7 +937,7 @@ extern "C" int ofab_ln_res_ln_bwd(const float* dx_new, const void* dy, const voi
     const LnLaunch l = ln_launch(cols, has_drop ? 288 : 384);  // the dropout form needs the mask registers: 288-thread CTAs
     const int smem = ln_smem(l, cols, 10, 2, true);
 #define RBWD(D, T)                                                                                                                    \
-  LN_GO(grid, smem, T, (ln_res_ln_bwd_kernel<false, T, D>), (ln_res_ln_bwd_kernel<false, 512, D>), dx_new, (const bf16*)dy,             \
+  LN_GO(grid, smem, T, (ln_res_ln_bwd_kernel<false, T, D, true>), (ln_res_ln_bwd_kernel<false, T, D>), (ln_res_ln_bwd_kernel<false, 512, D>), dx_new, (const bf16*)dy, \
         (const bf16*)nullptr, x_new, (const bf16*)nullptr, (const bf16*)g2, stats, dx_tot, (bf16*)da, dgb_partial, rows, cols, l.tpr, dra)
     if (has_drop) RBWD(true, 288); else RBWD(false, 384);
 #undef RBWD
