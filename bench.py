@@ -626,6 +626,7 @@ def run_gpu(args, rank, world, local_rank):
     # ---- the other BASELINE.json workloads (configs[2..4]: ASR, co-training, OFA-large video + grounding), same method, at
     # this N -- every rank runs them (their steps end with the gradient exchange); see workloads.py
     extra, dp_check = [], None
+    peak_mem_gb = torch.cuda.max_memory_allocated(dev) / 1e9  # of the headline workload (before the other workloads allocate)
     if not args.no_workloads:
         import workloads as wl
 
@@ -673,6 +674,8 @@ def run_gpu(args, rank, world, local_rank):
             "e2e": {"value": gb / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e,
                     "how": "pinned-host batch -> H2D on a copy stream (prefetch of the next step's batch) -> D2D into the graph's input buffers -> fwd+bwd -> loss.item()"},
             "gpu_launches": launches,
+            "peak_mem_gb": peak_mem_gb,
+            "ce_chunk_rows": int(os.environ.get("OFAB_CE_CHUNK_ROWS", "0")) or None,
             "model_tflops": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world,
             "model_frac_of_bf16_peak": value * 3 * FWD_GFLOP_PER_SEQ / 1e3 / world / pk["tf_sustained"],
             "roofline": roof,

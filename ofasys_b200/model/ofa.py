@@ -179,14 +179,16 @@ class GeneralistModel(nn.Module):
             return_encoder_out=return_encoder_out, return_hf_dict=return_hf_dict,
             return_all_attention_weights=return_all_attention_weights)
 
-    def forward_loss(self, slots: List[Slot], target: torch.Tensor, ignore_index: Optional[int] = None, label_smoothing: float = 0.0):
+    def forward_loss(self, slots: List[Slot], target: torch.Tensor, ignore_index: Optional[int] = None, label_smoothing: float = 0.0,
+                     ce_chunk_rows: Optional[int] = None):
         """fwd of the measured path in one call: model + sum-CE criterion (cross_entropy.py:50-67) with the
         tied output projection fused into the loss, so the [B, T, V] logits are never kept in fp32.
         label_smoothing > 0: the label-smoothed criterion (label_smoothed_cross_entropy.py:62-92,175-191).
-        Returns (loss_sum, sample_size = ntokens is left to the caller)."""
+        ce_chunk_rows: run projection + criterion that many target rows at a time (no [B * T, V] scratch at all; see
+        ops.linear_cross_entropy).  Returns (loss_sum, sample_size = ntokens is left to the caller)."""
         feats, _ = self.forward(slots, features_only=True)
         pad = self.global_dict.pad() if ignore_index is None else ignore_index
-        return ops.linear_cross_entropy(feats, self.decoder.adaptor.embed_tokens.weight, target, pad, label_smoothing)
+        return ops.linear_cross_entropy(feats, self.decoder.adaptor.embed_tokens.weight, target, pad, label_smoothing, chunk_rows=ce_chunk_rows)
 
     def forward_backward_split(self, slots: List[Slot], target: torch.Tensor, ignore_index: Optional[int] = None):
         """fwd + bwd of the measured path with the backward cut at the encoder/decoder boundary, for data-parallel

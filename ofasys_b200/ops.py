@@ -5,6 +5,7 @@ walk; every kernel that runs is ours.  All functions require CUDA tensors and ra
 there is no CPU or eager fallback.
 """
 import ctypes
+import os
 import weakref
 
 import torch
@@ -970,9 +971,71 @@ class _LinearCrossEntropyFn(torch.autograd.Function):
         return dx, dE, None, None, None, None
 
 
-def linear_cross_entropy(x, E, target, ignore_index=1, label_smoothing=0.0, nll_out=None):
+class _ChunkedLinearCrossEntropyFn(torch.autograd.Function):
+    """Same value and gradients as _LinearCrossEntropyFn without a [rows, V] scratch: the rows go through the projection and
+    the criterion `chunk_rows` at a time, so only a [chunk_rows, V] bf16 tile ever exists (it stays in the 126 MB L2 between
+    the kernels that touch it for chunk_rows <= 1024 at V ~ 59 k).  Forward keeps the per-row log-sum-exp only; backward
+    recomputes each chunk's logits (one extra projection GEMM, the usual price of not storing them), turns them into their
+    gradient in place and feeds the dX / dE GEMMs.  dE accumulates over the chunks in fp32 (the GEMM's residual input) and is
+    rounded to bf16 once, like the one-shot form."""
+
+    @staticmethod
+    def forward(ctx, x, E, target, ignore_index, label_smoothing, chunk_rows, nll_out):
+        _need_cuda(x, E, target)
+        x2 = _as2d(x)
+        M, K = x2.shape
+        V = E.shape[0]
+        Vp = (V + 7) // 8 * 8
+        E = _c(E)
+        dev = x.device
+        R = max(8, min(int(chunk_rows), M))
+        tile = torch.empty((R, Vp), dtype=torch.bfloat16, device=dev)
+        tgt = _c(target.reshape(-1))
+        lse = torch.empty(M, dtype=torch.float32, device=dev)
+        loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        eps = float(label_smoothing)
+        for r0 in range(0, M, R):
+            m = min(R, M - r0)
+            gemm(m, Vp, K, x2[r0:r0 + m], x2.stride(0), 0, E, K, 0, tile, Vp)  # pad columns [V, Vp) = 0 (TMA zero-fills rows of E beyond V)
+            _lib.call("ofab_ce_fwd", _p(tile), m, V, Vp, _p(tgt[r0:r0 + m]), ignore_index, _p(lse[r0:r0 + m]), _p(loss), eps, _p(nll_out), _s())  # sums accumulate
+        ctx.save_for_backward(x2, E, tgt, lse)
+        ctx.meta = (ignore_index, x.shape, eps, R)
+        return loss[0]
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, E, tgt, lse = ctx.saved_tensors
+        ignore_index, xshape, eps, R = ctx.meta
+        M, K = x2.shape
+        V = E.shape[0]
+        Vp = (V + 7) // 8 * 8
+        dev = x2.device
+        need_dx, need_dE = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        gs = _c(g.reshape(1).to(torch.float32))
+        tile = torch.empty((R, Vp), dtype=torch.bfloat16, device=dev)
+        dx = torch.empty((M, K), dtype=torch.bfloat16, device=dev) if need_dx else None
+        dE32 = torch.empty((V, K), dtype=torch.float32, device=dev) if need_dE else None
+        for r0 in range(0, M, R):
+            m = min(R, M - r0)
+            xs, ts = x2[r0:r0 + m], tgt[r0:r0 + m]
+            gemm(m, Vp, K, xs, x2.stride(0), 0, E, K, 0, tile, Vp)
+            _lib.call("ofab_ce_bwd", _p(tile), m, V, Vp, _p(ts), ignore_index, _p(lse[r0:r0 + m]), _p(gs), _p(tile), eps, _s())  # in place
+            if need_dx:
+                gemm_splitk(m, K, V, tile, Vp, 0, E, K, 1, dx[r0:r0 + m], K)  # few output tiles, contraction over the vocabulary
+            if need_dE:
+                gemm(V, K, m, tile, Vp, 1, xs, x2.stride(0), 1, dE32, K, residual=dE32 if r0 > 0 else None, ldr=K)
+        return (None if dx is None else dx.view(xshape)), (cast_bf16(dE32) if need_dE else None), None, None, None, None, None
+
+
+def linear_cross_entropy(x, E, target, ignore_index=1, label_smoothing=0.0, nll_out=None, chunk_rows=None):
     """loss = sum-CE(x E^T, target), optionally label-smoothed (label_smoothed_cross_entropy.py:62-92).  nll_out: optional
-    zeroed fp32 [1] tensor that receives the plain nll sum (the reference logs it next to the loss)."""
+    zeroed fp32 [1] tensor that receives the plain nll sum (the reference logs it next to the loss).
+    chunk_rows (or env OFAB_CE_CHUNK_ROWS): process the rows in chunks of that many so that no [rows, V] scratch is allocated
+    (412 MB at B=64, T=64, V=50265); default: one shot."""
+    if chunk_rows is None and os.environ.get("OFAB_CE_CHUNK_ROWS"):
+        chunk_rows = int(os.environ["OFAB_CE_CHUNK_ROWS"])
+    if chunk_rows:
+        return _ChunkedLinearCrossEntropyFn.apply(x, E, target, ignore_index, label_smoothing, int(chunk_rows), nll_out)
     return _LinearCrossEntropyFn.apply(x, E, target, ignore_index, label_smoothing, nll_out)
 
 

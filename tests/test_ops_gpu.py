@@ -563,6 +563,38 @@ def test_cross_entropy_and_fused_projection(V):
     assert rel_l2(lg.grad, lgr.grad) <= TOL16
 
 
+@pytest.mark.parametrize("V,chunk", [(512, 32), (50265, 40)])
+def test_chunked_fused_projection_criterion_matches_the_one_shot_form(V, chunk):
+    """Row-chunked projection + criterion (no [rows, V] scratch): same loss, nll and gradients as the
+    one-shot fused form and as torch fp32, label smoothing on, ragged last chunk."""
+    from ofasys_b200 import ops
+
+    gen = g()
+    M, d, eps = 77, 128, 0.1
+    x0 = rnd(M, d, gen=gen)
+    E0 = rnd(V, d, gen=gen, scale=0.3)
+    tgt = torch.randint(2, V, (M,), generator=gen)
+    tgt[::7] = 1
+    tgt = tgt.to(dev())
+    out = []
+    for ch in (None, chunk):
+        x, E = x0.clone().requires_grad_(True), E0.clone().requires_grad_(True)
+        nll = torch.zeros(1, device=dev())
+        loss = ops.linear_cross_entropy(x, E, tgt, 1, eps, nll, chunk_rows=ch)
+        (loss * 0.37).backward()
+        out.append((loss.item(), nll.item(), x.grad, E.grad))
+    (l1, n1, dx1, dE1), (l2, n2, dx2, dE2) = out
+    assert abs(l1 - l2) <= 1e-6 * abs(l1) and abs(n1 - n2) <= 1e-6 * abs(n1)
+    assert rel_l2(dx2, dx1) <= 3e-3 and rel_l2(dE2, dE1) <= 3e-3  # same bf16 gradient tile; split-K / fp32-accumulated sums
+    from oracle import oracle_model as om
+
+    xr, Er = x0.float().cpu().requires_grad_(True), E0.float().cpu().requires_grad_(True)
+    lref, nref, _ = om.label_smoothed_cross_entropy_sum(xr @ Er.t(), tgt.cpu(), eps)  # label_smoothed_cross_entropy.py:62-92
+    (lref * 0.37).backward()
+    assert abs(l2 - lref.item()) <= 3e-3 * abs(lref.item()) and abs(n2 - nref.item()) <= 3e-3 * abs(nref.item())
+    assert rel_l2(dx2, xr.grad) <= 1e-2 and rel_l2(dE2, Er.grad) <= 1e-2
+
+
 def test_scale_cols():
     from ofasys_b200 import ops
 
