@@ -46,17 +46,19 @@ def bench(name, M, N, K, a_mn, b_mn, out_dtype=torch.bfloat16):
 
 def main():
     rows = []
-    for tag, M in (("enc", 8480), ("dec", 2048)):
+    BS = int(os.environ.get("GEMM_B", "32"))  # per-GPU batch: rows = BS x 265 (encoder) / BS x 64 (decoder)
+    ME, MD = BS * 265, BS * 64
+    for tag, M in (("enc", ME), ("dec", MD)):
         for lname, N, K in (("qkv", 2304, 768), ("out", 768, 768), ("fc1", 3072, 768), ("fc2", 768, 3072)):
             rows.append(bench(f"{tag}.{lname}.fwd", M, N, K, 0, 0))
             rows.append(bench(f"{tag}.{lname}.dgrad", M, K, N, 0, 1))
             rows.append(bench(f"{tag}.{lname}.wgrad", N, K, M, 1, 1))
-    rows.append(bench("dec.crosskv.fwd", 8480, 1536, 768, 0, 0))
-    rows.append(bench("dec.crosskv.dgrad", 8480, 768, 1536, 0, 1))
-    rows.append(bench("dec.crosskv.wgrad", 1536, 768, 8480, 1, 1))
-    rows.append(bench("logits.fwd", 2048, 50264, 768, 0, 0))
-    rows.append(bench("logits.dgrad", 2048, 768, 50264, 0, 1))
-    rows.append(bench("logits.wgrad", 50264, 768, 2048, 1, 1))
+    rows.append(bench("dec.crosskv.fwd", ME, 1536, 768, 0, 0))
+    rows.append(bench("dec.crosskv.dgrad", ME, 768, 1536, 0, 1))
+    rows.append(bench("dec.crosskv.wgrad", 1536, 768, ME, 1, 1))
+    rows.append(bench("logits.fwd", MD, 50264, 768, 0, 0))
+    rows.append(bench("logits.dgrad", MD, 768, 50264, 0, 1))
+    rows.append(bench("logits.wgrad", 50264, 768, MD, 1, 1))
     tot = sum(r["us"] for r in rows if not r["name"].startswith("logits") and "crosskv" not in r["name"]) * 12
     tot += sum(r["us"] for r in rows if "crosskv" in r["name"]) * 12 + sum(r["us"] for r in rows if r["name"].startswith("logits"))
     for r in rows:

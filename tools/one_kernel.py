@@ -10,7 +10,7 @@ from ofasys_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 which = sys.argv[1] if len(sys.argv) > 1 else "gemm"
 if which == "gemm":  # encoder fc1 forward of the benchmark step: M=8480 N=3072 K=768 (+bias)
-    M, N, K = 8480, 3072, 768
+    M, N, K = int(os.environ.get("GEMM_M", "8480")), 3072, 768
     A = torch.randn(M, K, device=dev).bfloat16()
     B = torch.randn(N, K, device=dev).bfloat16()
     bias = torch.randn(N, device=dev).bfloat16()
