@@ -699,8 +699,12 @@ int gemm_run(int64_t M, int64_t N, int64_t K, const void* A, int64_t lda, int a_
   CUtensorMap ta, tb;
   int rc;
   // K-major operands are loaded as 64-wide (128 B) K atoms x rows; MN-major operands as 64-wide MN atoms x BK rows
-  uint32_t BK = CG == 2 ? 128 : 64;
-  if (const char* ov = getenv("OFAB_GEMM_BK")) {  // development: 64-deep stages (twice as many) for CTA pairs
+  // CTA pairs: 64-deep stages (six of them) by default -- measured 2.7 % less GEMM time over the headline step's shapes than
+  // three 128-deep stages (profiles/r02_gemm_shapes_b64.txt vs r02_gemm_shapes_b64_bk64.txt: the deeper ring keeps the TMA
+  // latency covered on the long-K shapes); split-K work items keep 128-deep stages (their k-block bookkeeping is in units of 128).
+  uint32_t BK = (CG == 2 && splits > 1) ? 128 : 64;
+  if (const char* ov = getenv("OFAB_GEMM_BK")) {  // development / tests: force the stage depth of CTA pairs
+    if (atoi(ov) == 128 && CG == 2) BK = 128;
     if (atoi(ov) == 64 && CG == 2 && splits <= 1) BK = 64;
   }
   if (!a_mn_major) rc = make_map(&ta, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 64, BLOCK_M);

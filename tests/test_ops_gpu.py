@@ -170,7 +170,7 @@ def test_gemm_forced_tile_configs(monkeypatch, a_mn, b_mn, bn, cg, cl, bk):
     monkeypatch.setenv("OFAB_GEMM_BN", str(bn))
     monkeypatch.setenv("OFAB_GEMM_CG", str(cg))
     monkeypatch.setenv("OFAB_GEMM_CL", str(cl))
-    monkeypatch.setenv("OFAB_GEMM_BK", str(bk))  # CTA pairs: 128-deep stages (default) or twice as many 64-deep ones
+    monkeypatch.setenv("OFAB_GEMM_BK", str(bk))  # CTA pairs: 64-deep stages (six, the default) or three 128-deep ones
     gen = g()
     for (M, N, K) in [(1000, 776, 200), (8480 // 4, 2304, 768), (300, 136, 3072), (2048 + 24, 1024, 520)]:
         if a_mn:
